@@ -1,0 +1,192 @@
+"""ctypes binding of the CPU oracle (oracle/_build/libcvb_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (cv_b200/) never imports this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libcvb_oracle.so")
+
+
+class AkazeCfg(C.Structure):
+    """mirrors akaze::Akaze (akaze/src/lib.rs:109-142)"""
+    _fields_ = [
+        ("maximum_features", C.c_int64),
+        ("num_sublevels", C.c_uint32),
+        ("max_octave_evolution", C.c_uint32),
+        ("base_scale_offset", C.c_double),
+        ("initial_contrast", C.c_double),
+        ("contrast_percentile", C.c_double),
+        ("contrast_factor_num_bins", C.c_uint64),
+        ("derivative_factor", C.c_double),
+        ("detector_threshold", C.c_double),
+        ("descriptor_channels", C.c_uint64),
+        ("descriptor_pattern_size", C.c_uint64),
+    ]
+
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("response", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("octave", "<u4"), ("class_id", "<u4")])
+
+PLANES = {"Lt": 0, "Lsmooth": 1, "Lx": 2, "Ly": 3, "Lflow": 4, "Ldet": 5, "Lxx": 6, "Lyy": 7, "Lxy": 8}
+STAGES = {"candidates": 0, "extrema": 1, "refined": 2, "sorted": 3, "final": 4}
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h")) or f == "Makefile"]
+    if (not force and os.path.exists(_LIB_PATH)
+            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-s", "-C", _HERE], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        fp = C.POINTER(C.c_float)
+        L.ref_akaze_default_cfg.argtypes = [C.POINTER(AkazeCfg)]
+        L.ref_akaze_create.restype = C.c_void_p
+        L.ref_akaze_create.argtypes = [C.POINTER(AkazeCfg)]
+        L.ref_akaze_destroy.argtypes = [C.c_void_p]
+        L.ref_akaze_extract.argtypes = [C.c_void_p, fp, C.c_int, C.c_int]
+        L.ref_akaze_num_evolutions.argtypes = [C.c_void_p]
+        L.ref_akaze_evolution_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                               C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                               C.POINTER(C.c_double)]
+        L.ref_akaze_contrast_factor.restype = C.c_double
+        L.ref_akaze_contrast_factor.argtypes = [C.c_void_p]
+        L.ref_akaze_plane.restype = fp
+        L.ref_akaze_plane.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ref_akaze_stage.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.ref_akaze_descriptors.restype = C.POINTER(C.c_uint8)
+        L.ref_akaze_descriptors.argtypes = [C.c_void_p]
+        L.ref_horizontal_filter.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, fp]
+        L.ref_vertical_filter.argtypes = [fp, C.c_int, C.c_int, fp, C.c_int, fp]
+        L.ref_gaussian_kernel.argtypes = [C.c_float, C.c_int, fp]
+        L.ref_half_size.argtypes = [fp, C.c_int, C.c_int, fp]
+        L.ref_fed_tau.argtypes = [C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int]
+        for f in ("ref_sinf", "ref_cosf"):
+            getattr(L, f).restype = C.c_float
+            getattr(L, f).argtypes = [C.c_float]
+        for f in ("ref_atan2f", "ref_fast_atan2_equiv"):
+            getattr(L, f).restype = C.c_float
+            getattr(L, f).argtypes = [C.c_float, C.c_float]
+        L.ref_hamming_knn.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
+                                      C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def default_cfg(**kw):
+    c = AkazeCfg()
+    lib().ref_akaze_default_cfg(C.byref(c))
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+class Akaze:
+    """Oracle counterpart of akaze::Akaze::extract_from_gray_float_image (akaze/src/lib.rs:309-339)."""
+
+    def __init__(self, cfg=None, **kw):
+        self.cfg = cfg if cfg is not None else default_cfg(**kw)
+        self._h = lib().ref_akaze_create(C.byref(self.cfg))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().ref_akaze_destroy(self._h)
+            self._h = None
+
+    def extract(self, image):
+        image = np.ascontiguousarray(image, dtype=np.float32)
+        h, w = image.shape
+        self._shape = (h, w)
+        n = lib().ref_akaze_extract(self._h, _fp(image), w, h)
+        kps = self.stage("final")
+        d = np.ctypeslib.as_array(lib().ref_akaze_descriptors(self._h), shape=(max(n, 1), 64))[:n].copy()
+        return kps, d
+
+    def num_evolutions(self):
+        return lib().ref_akaze_num_evolutions(self._h)
+
+    def evolution_info(self, i):
+        w, h, nt = C.c_int(), C.c_int(), C.c_int()
+        o, es = C.c_uint32(), C.c_double()
+        tau = (C.c_double * 256)()
+        r = lib().ref_akaze_evolution_info(self._h, i, C.byref(w), C.byref(h), C.byref(o), C.byref(es), C.byref(nt), tau)
+        assert r == 0
+        return dict(w=w.value, h=h.value, octave=o.value, esigma=es.value, tau=[tau[j] for j in range(nt.value)])
+
+    def contrast_factor(self):
+        return lib().ref_akaze_contrast_factor(self._h)
+
+    def plane(self, i, name):
+        info = self.evolution_info(i)
+        p = lib().ref_akaze_plane(self._h, i, PLANES[name])
+        if not p:
+            return None
+        return np.ctypeslib.as_array(p, shape=(info["h"], info["w"])).copy()
+
+    def stage(self, name):
+        ptr = C.c_void_p()
+        n = lib().ref_akaze_stage(self._h, STAGES[name], C.byref(ptr))
+        if n <= 0 or not ptr.value:
+            return np.zeros(0, dtype=KP_DTYPE)
+        buf = (C.c_uint8 * (n * KP_DTYPE.itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=KP_DTYPE, count=n).copy()
+
+
+def horizontal_filter(img, kernel):
+    img = np.ascontiguousarray(img, np.float32); k = np.ascontiguousarray(kernel, np.float32)
+    out = np.empty_like(img)
+    lib().ref_horizontal_filter(_fp(img), img.shape[1], img.shape[0], _fp(k), len(k), _fp(out))
+    return out
+
+
+def vertical_filter(img, kernel):
+    img = np.ascontiguousarray(img, np.float32); k = np.ascontiguousarray(kernel, np.float32)
+    out = np.empty_like(img)
+    lib().ref_vertical_filter(_fp(img), img.shape[1], img.shape[0], _fp(k), len(k), _fp(out))
+    return out
+
+
+def gaussian_kernel(r, ks):
+    out = np.empty(ks, np.float32)
+    lib().ref_gaussian_kernel(r, ks, _fp(out))
+    return out
+
+
+def half_size(img):
+    img = np.ascontiguousarray(img, np.float32)
+    out = np.zeros((img.shape[0] // 2, img.shape[1] // 2), np.float32)
+    lib().ref_half_size(_fp(img), img.shape[1], img.shape[0], _fp(out))
+    return out
+
+
+def fed_tau(T, tau_max=0.25):
+    out = (C.c_double * 256)()
+    n = lib().ref_fed_tau(T, tau_max, out, 256)
+    return [out[i] for i in range(n)]
+
+
+def hamming_knn(q, db, k=2):
+    """space::LinearKnn{Hamming}.knn for every query: (idx[n,k], dist[n,k]) uint32."""
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 64); db = np.ascontiguousarray(db, np.uint8).reshape(-1, 64)
+    idx = np.empty((len(q), k), np.uint32); dist = np.empty((len(q), k), np.uint32)
+    lib().ref_hamming_knn(q.ctypes.data, len(q), db.ctypes.data, len(db), k, idx.ctypes.data, dist.ctypes.data)
+    return idx, dist
