@@ -1,0 +1,17 @@
+"""cv_b200 -- B200-native (sm_100a) drop-in for rust-cv's AKAZE -> Hamming match -> RANSAC hot path.
+
+Host-side mirror of the reference's interfaces for this path, over the C ABI in include/cvb200.h:
+
+  Akaze                 <- akaze::Akaze                       (akaze/src/lib.rs:109-185, 295-366)
+  KeyPoint dtype        <- akaze::KeyPoint                    (akaze/src/lib.rs:71-93)
+  LinearKnn / hamming_knn <- space::LinearKnn + bitarray::Hamming (call sites akaze/tests/estimate_pose.rs:78-97)
+  matching / symmetric_matching <- cv-sfm/src/lib.rs:3097-3133, tutorial-code chapter4 main.rs:91-137
+
+There is no CPU fallback: every call runs CUDA kernels from cv_b200/libcvb200.so and raises
+CvbError when the library or a Blackwell GPU is missing.
+"""
+from ._lib import CvbError, Context, KP_DTYPE, lib_path, load_library  # noqa: F401
+from .akaze import Akaze, AkazeConfig  # noqa: F401
+from .knn import LinearKnn, hamming_knn, matching, symmetric_matching  # noqa: F401
+
+__version__ = "0.1.0"

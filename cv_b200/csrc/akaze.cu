@@ -1,0 +1,641 @@
+// cv_b200/csrc/akaze.cu -- host orchestration + C ABI of the AKAZE extractor.
+// Mirrors akaze::Akaze::extract_from_gray_float_image (akaze/src/lib.rs:309-339): allocate_evolutions
+// (evolution.rs:80-126) and the FED schedule (fed_tau.rs:26-93) run on the host exactly as in the
+// reference (tiny f64 scalar work); every per-pixel and per-keypoint stage is a CUDA kernel.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "akaze_kernels.cuh"
+#include "common.cuh"
+
+using namespace akz;
+
+namespace {
+
+struct EvoHost {
+    int w = 0, h = 0;
+    uint32_t octave = 0, sublevel = 0;
+    double esigma = 0, etime = 0;
+    uint32_t sigma = 0;       // detector_response.rs:13  round(esigma*derivative_factor/ratio)
+    float quat = 0;           // sigma^4 as f32            detector_response.rs:39
+    float norm = 0, middle = 0;  // derivatives.rs:57-61
+    std::vector<double> tau;  // fed_tau_steps
+    size_t off = 0;           // offset of the level inside a pyramid plane (floats)
+    bool new_octave = false;
+};
+
+bool is_prime_u64(uint64_t n) {
+    if (n < 2) return false;
+    for (uint64_t d = 2; d * d <= n; d++)
+        if (n % d == 0) return false;
+    return true;
+}
+
+// fed_tau.rs:26-93 (M = 1, reordering = true)
+std::vector<double> fed_tau_by_process_time(double T, double tau_max) {
+    double t = T / 1.0;
+    long n = (long)(ceil(sqrt(3.0 * t / tau_max + 0.25) - 0.5 - 1.0e-8) + 0.5);
+    std::vector<double> out;
+    if (n <= 0) return out;
+    double scale = 3.0 * t / (tau_max * (double)(n * (n + 1)));
+    std::vector<double> tau((size_t)n);
+    for (long k = 0; k < n; k++) {
+        double c = 1.0 / (4.0 * (double)n + 2.0);
+        double d = scale * tau_max / 2.0;
+        double hh = cos(3.14159265358979323846 * (2.0 * (double)k + 1.0) * c);
+        tau[(size_t)k] = d / (hh * hh);
+    }
+    long kappa = n / 2, prime = n + 1;
+    while (!is_prime_u64((uint64_t)prime)) prime++;
+    long k = 0;
+    for (long i = 0; i < n; i++) {
+        long index = ((k + 1) * kappa) % prime - 1;
+        while (index >= n || index < 0) {   // usize wrap-around of `x % prime - 1` when the remainder is 0
+            k++;
+            index = ((k + 1) * kappa) % prime - 1;
+        }
+        k++;
+        out.push_back(tau[(size_t)index]);
+    }
+    return out;
+}
+
+// image.rs:349-374
+void gaussian_kernel_host(float r, int ks, float *out) {
+    int half = ks / 2;
+    float sum = 0.f;
+    for (int i = -half; i <= half; i++) {
+        float x = (float)i;
+        volatile float denom = sqrtf(2.0f * 3.14159265358979323846f) * r;
+        volatile float e = expf(-(x * x) / (2.0f * (r * r)));
+        float val = (1.0f / denom) * e;
+        out[i + half] = val;
+        sum += val;
+    }
+    for (int i = 0; i < ks; i++) out[i] /= sum;
+}
+
+int make_gauss_taps(float r, Taps *t) {
+    int radius = (int)ceilf(2.0f * r);   // image.rs:385
+    int ks = radius * 2 + 1;
+    if (ks > MAXK) return -1;
+    t->ks = ks;
+    memset(t->k, 0, sizeof(t->k));
+    gaussian_kernel_host(r, ks, t->k);
+    return 0;
+}
+
+}  // namespace
+
+struct AkazeWorkspace {
+    cvb_akaze_cfg cfg{};
+    uint32_t w = 0, h = 0, batch = 0;
+    std::vector<EvoHost> evo;
+    EvoTable table{};
+    size_t plane_floats = 0;   // sum of level sizes
+    size_t p0 = 0;             // w*h
+    unsigned capc = 0, capk = 0;
+    Taps g0{}, g1{};
+    // device memory
+    float *img = nullptr;
+    float *Lt = nullptr, *Lsm = nullptr, *Lx = nullptr, *Ly = nullptr, *Lflow = nullptr, *Ldet = nullptr;
+    float *tmpA = nullptr, *tmpB = nullptr, *tmpC = nullptr;
+    double *g2 = nullptr;
+    unsigned long long *gmax = nullptr;
+    unsigned *hist = nullptr, *npoints = nullptr;
+    double *kc = nullptr;
+    float *inv_k = nullptr;
+    int *evo_octave = nullptr;
+    unsigned *rowcount = nullptr, *rowoff = nullptr, *ncand = nullptr;
+    Cand *cand = nullptr;
+    cvb_keypoint *cache = nullptr, *refined = nullptr, *sorted = nullptr;
+    unsigned *ncache = nullptr, *nsorted = nullptr;
+    unsigned char *keep = nullptr, *valid = nullptr, *ok = nullptr, *desc_tmp = nullptr;
+    unsigned *overflow = nullptr;
+    OrientTables *ot = nullptr;
+    DescTables *dt = nullptr;
+    // outputs owned by the workspace for the host-pointer API
+    cvb_keypoint *kp_out = nullptr;
+    unsigned char *desc_out = nullptr;
+    unsigned *n_out = nullptr;
+    unsigned cap_out = 0;
+    std::vector<void *> allocs;
+    bool has_run = false;
+};
+
+void akaze_workspace_free(AkazeWorkspace *ws) {
+    if (!ws) return;
+    for (void *p : ws->allocs) cudaFree(p);
+    delete ws;
+}
+
+namespace {
+
+template <typename T>
+int dalloc(cvb_ctx *ctx, AkazeWorkspace *ws, T **p, size_t n) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return cvb_set_error(ctx, CVB_ENOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+    ws->allocs.push_back(q);
+    *p = (T *)q;
+    return 0;
+}
+
+bool same_cfg(const cvb_akaze_cfg &a, const cvb_akaze_cfg &b) { return memcmp(&a, &b, sizeof(a)) == 0; }
+
+// evolution.rs:46-58,80-126 + per-level sizes from the half_size chain (image.rs:155-156, lib.rs:219-221)
+int plan_evolutions(cvb_ctx *ctx, AkazeWorkspace *ws) {
+    const cvb_akaze_cfg &c = ws->cfg;
+    ws->evo.clear();
+    for (uint32_t octave = 0; octave < c.max_octave_evolution; octave++) {
+        double rfactor = 1.0 / (double)(1ull << octave);   // 2.0f64.powi(-octave)
+        uint32_t lh = (uint32_t)((double)ws->h * rfactor), lw = (uint32_t)((double)ws->w * rfactor);
+        uint32_t smallest = std::min(lw, lh);
+        if (smallest < 40) continue;
+        uint32_t sub = smallest < 80 ? 1 : c.num_sublevels;
+        for (uint32_t s = 0; s < sub; s++) {
+            EvoHost e;
+            e.octave = octave; e.sublevel = s;
+            e.esigma = c.base_scale_offset * pow(2.0, (double)s / (double)c.num_sublevels + (double)octave);
+            e.etime = 0.5 * (e.esigma * e.esigma);
+            ws->evo.push_back(e);
+        }
+    }
+    if (ws->evo.empty()) return 0;
+    if (ws->evo.size() > (size_t)MAX_EVO) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "more than %d evolutions", MAX_EVO);
+    int lw = (int)ws->w, lh = (int)ws->h;
+    size_t off = 0;
+    int rowbase = 0;
+    for (size_t i = 0; i < ws->evo.size(); i++) {
+        EvoHost &e = ws->evo[i];
+        e.new_octave = i > 0 && e.octave > ws->evo[i - 1].octave;
+        if (e.new_octave) { lw /= 2; lh /= 2; }
+        e.w = lw; e.h = lh; e.off = off;
+        off += (size_t)lw * lh;
+        off = (off + 63) & ~(size_t)63;   // 256-byte aligned levels
+        if (i > 0) {
+            e.tau = fed_tau_by_process_time(e.etime - ws->evo[i - 1].etime, 0.25);
+            if (e.tau.size() > (size_t)MAX_TAU) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "too many FED steps");
+        }
+        double ratio = (double)(1ull << e.octave);
+        double ss = round(e.esigma * c.derivative_factor / ratio);
+        e.sigma = (uint32_t)ss;
+        e.quat = (float)(ss * ss * ss * ss);
+        double wv = 10.0 / 3.0;
+        e.norm = (float)(1.0 / (2.0 * (double)e.sigma * (wv + 2.0)));
+        e.middle = e.norm * (float)wv;
+        if (e.sigma < 1 || e.sigma > 16) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "derivative sigma %u out of range", e.sigma);
+        EvoDev &d = ws->table.e[i];
+        d.w = e.w; d.h = e.h; d.off = e.off; d.octave = (int)e.octave;
+        d.size = (float)(e.esigma * c.derivative_factor);
+        d.rowbase = rowbase; d.pad = 0;
+        rowbase += e.h;
+    }
+    ws->table.n = (int)ws->evo.size();
+    ws->table.total_rows = rowbase;
+    ws->plane_floats = off;
+    return 0;
+}
+
+int build_tables(cvb_ctx *ctx, AkazeWorkspace *ws) {
+    // orientation tables (scale_space_extrema.rs:233-287)
+    OrientTables ot;
+    memset(&ot, 0, sizeof(ot));
+    static const float GAUSS25[7][7] = {
+        {0.02546481f, 0.02350698f, 0.01849125f, 0.01239505f, 0.00708017f, 0.00344629f, 0.00142946f},
+        {0.02350698f, 0.02169968f, 0.01706957f, 0.01144208f, 0.00653582f, 0.00318132f, 0.00131956f},
+        {0.01849125f, 0.01706957f, 0.01342740f, 0.00900066f, 0.00514126f, 0.00250252f, 0.00103800f},
+        {0.01239505f, 0.01144208f, 0.00900066f, 0.00603332f, 0.00344629f, 0.00167749f, 0.00069579f},
+        {0.00708017f, 0.00653582f, 0.00514126f, 0.00344629f, 0.00196855f, 0.00095820f, 0.00039744f},
+        {0.00344629f, 0.00318132f, 0.00250252f, 0.00167749f, 0.00095820f, 0.00046640f, 0.00019346f},
+        {0.00142946f, 0.00131956f, 0.00103800f, 0.00069579f, 0.00039744f, 0.00019346f, 0.00008024f},
+    };
+    static const int id[13] = {6, 5, 4, 3, 2, 1, 0, 1, 2, 3, 4, 5, 6};
+    int idx = 0;
+    for (int j = -6; j <= 6; j++)
+        for (int i = -6; i <= 6; i++)
+            if (i * i + j * j < 36) {
+                ot.di[idx] = (signed char)i; ot.dj[idx] = (signed char)j;
+                ot.gw[idx] = GAUSS25[id[j + 6]][id[i + 6]];
+                idx++;
+            }
+    {
+        volatile float ang1 = 0.f;   // f32 accumulation exactly as the reference loop (:259-287)
+        const float two_pi = 2.0f * 3.14159265358979323846f;
+        int n = 0;
+        while (ang1 < two_pi && n < 64) { ot.ang1[n++] = ang1; ang1 = ang1 + 0.15f; }
+        ot.nwin = n;
+    }
+    CVB_CUDA(ctx, cudaMemcpyAsync(ws->ot, &ot, sizeof(ot), cudaMemcpyHostToDevice, ctx->stream));
+    // descriptor tables (descriptors.rs:64-96,117-124,188-201)
+    DescTables dt;
+    memset(&dt, 0, sizeof(dt));
+    const int pattern = (int)ws->cfg.descriptor_pattern_size, nch = (int)ws->cfg.descriptor_channels;
+    const float size_mult[3] = {1.0f, 2.0f / 3.0f, 1.0f / 2.0f};
+    int base[3], ncell = 0;
+    for (int lvl = 0; lvl < 3; lvl++) {
+        int step = (int)ceilf((float)pattern * size_mult[lvl]);
+        base[lvl] = ncell;
+        int per_axis = 0;
+        for (int i = -pattern; i < pattern; i += step) per_axis++;
+        if (per_axis != lvl + 2) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "descriptor_pattern_size %d: grid %d has %d cells per axis", pattern, lvl, per_axis);
+        for (int i = -pattern; i < pattern; i += step)
+            for (int j = -pattern; j < pattern; j += step) {
+                dt.ci[ncell] = (short)i; dt.cj[ncell] = (short)j; dt.cstep[ncell] = (short)step;
+                ncell++;
+            }
+    }
+    dt.ncells = ncell;
+    int bit = 0;
+    for (int lvl = 0; lvl < 3; lvl++) {
+        int count = (lvl + 2) * (lvl + 2);
+        for (int pos = 0; pos < nch; pos++)
+            for (int a = 0; a < count; a++)
+                for (int b2 = a + 1; b2 < count; b2++) {
+                    dt.ba[bit] = (unsigned char)(base[lvl] + a); dt.bb[bit] = (unsigned char)(base[lvl] + b2);
+                    dt.bch[bit] = (unsigned char)pos;
+                    bit++;
+                }
+    }
+    dt.nbits = bit;
+    CVB_CUDA(ctx, cudaMemcpyAsync(ws->dt, &dt, sizeof(dt), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<int> oct(MAX_EVO, 0);
+    for (size_t i = 0; i < ws->evo.size(); i++) oct[i] = (int)ws->evo[i].octave;
+    CVB_CUDA(ctx, cudaMemcpyAsync(ws->evo_octave, oct.data(), sizeof(int) * MAX_EVO, cudaMemcpyHostToDevice, ctx->stream));
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int ensure_workspace(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, uint32_t batch, uint32_t w, uint32_t h, unsigned cap_out) {
+    AkazeWorkspace *ws = ctx->akaze;
+    if (ws && same_cfg(ws->cfg, *cfg) && ws->w == w && ws->h == h && ws->batch >= batch && ws->cap_out >= cap_out) return 0;
+    if (ws) { cudaStreamSynchronize(ctx->stream); akaze_workspace_free(ws); ctx->akaze = nullptr; }
+    if (cfg->descriptor_channels < 1 || cfg->descriptor_channels > 3) return cvb_set_error(ctx, CVB_EINVAL, "descriptor_channels must be 1..3");
+    if (cfg->contrast_factor_num_bins < 1 || cfg->contrast_factor_num_bins > 8192) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "contrast_factor_num_bins must be 1..8192");
+    if (cfg->num_sublevels < 1) return cvb_set_error(ctx, CVB_EINVAL, "num_sublevels must be >= 1");
+    if (!(cfg->base_scale_offset > 0.0)) return cvb_set_error(ctx, CVB_EINVAL, "sigma must be > 0.0");   // image.rs:384
+    ws = new AkazeWorkspace();
+    ctx->akaze = ws;
+    ws->cfg = *cfg; ws->w = w; ws->h = h; ws->batch = batch; ws->cap_out = cap_out;
+    int rc = plan_evolutions(ctx, ws);
+    if (rc) return rc;
+    if (make_gauss_taps((float)cfg->base_scale_offset, &ws->g0)) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "base_scale_offset too large");
+    make_gauss_taps(1.0f, &ws->g1);
+    ws->p0 = (size_t)w * h;
+    // capacities: every strict 3x3 maximum needs a 2-pixel pitch -> at most P/4 per level; bound generously
+    ws->capc = (unsigned)std::min<size_t>(std::max<size_t>(ws->p0 / 8, 4096), 1u << 20);
+    ws->capk = (unsigned)std::min<size_t>(std::max<size_t>(ws->p0 / 32, 4096), 1u << 17);
+    const size_t B = batch, PF = ws->plane_floats, R = (size_t)std::max(ws->table.total_rows, 1);
+#define DA(p, n) do { rc = dalloc(ctx, ws, &ws->p, (n)); if (rc) return rc; } while (0)
+    DA(img, B * ws->p0);
+    DA(Lt, B * PF); DA(Lsm, B * PF); DA(Lx, B * PF); DA(Ly, B * PF); DA(Lflow, B * PF); DA(Ldet, B * PF);
+    DA(tmpA, B * ws->p0); DA(tmpB, B * ws->p0); DA(tmpC, B * ws->p0);
+    DA(g2, B * ws->p0);
+    DA(gmax, B); DA(hist, B * cfg->contrast_factor_num_bins); DA(npoints, B); DA(kc, B); DA(inv_k, B * MAX_EVO);
+    DA(evo_octave, MAX_EVO);
+    DA(rowcount, B * R); DA(rowoff, B * R); DA(ncand, B);
+    DA(cand, B * ws->capc);
+    DA(cache, B * ws->capk); DA(refined, B * ws->capk); DA(sorted, B * ws->capk);
+    DA(ncache, B); DA(nsorted, B);
+    DA(keep, B * ws->capk); DA(valid, B * ws->capk); DA(ok, B * ws->capk); DA(desc_tmp, B * ws->capk * 64);
+    DA(overflow, 1);
+    DA(ot, 1); DA(dt, 1);
+    DA(kp_out, B * (size_t)cap_out); DA(desc_out, B * (size_t)cap_out * 64); DA(n_out, B);
+#undef DA
+    CVB_CUDA(ctx, cudaMemsetAsync(ws->overflow, 0, sizeof(unsigned), ctx->stream));
+    CVB_CUDA(ctx, cudaMemsetAsync(ws->inv_k, 0, sizeof(float) * B * MAX_EVO, ctx->stream));
+    // opt in to large dynamic shared memory where a configuration needs it
+    cudaFuncSetAttribute(k_separable, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_deriv1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_deriv1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_deriv1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_deriv1<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_deriv2_det<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_deriv2_det<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_deriv2_det<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_deriv2_det<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    return build_tables(ctx, ws);
+}
+
+inline dim3 tile_grid(int w, int h, unsigned B) { return dim3(cdiv((unsigned)w, TW), cdiv((unsigned)h, TH), B); }
+
+int launch_separable(cvb_ctx *ctx, const float *in, size_t in_bs, float *out, size_t out_bs, int w, int h, unsigned B,
+                     const Taps &hk, const Taps &vk) {
+    int rx = hk.ks / 2, ry = vk.ks / 2;
+    size_t smem = sizeof(float) * ((size_t)(TH + 2 * ry) * (TW + 2 * rx) + (size_t)(TH + 2 * ry) * TW);
+    k_separable<<<tile_grid(w, h, B), NT, smem, ctx->stream>>>(in, out, w, h, in_bs, out_bs, hk, vk);
+    CVB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int launch_deriv1(cvb_ctx *ctx, const EvoHost &e, const float *Ls, float *Lx, float *Ly, size_t bs, unsigned B) {
+    int s = (int)e.sigma;
+    size_t smem = sizeof(float) * ((size_t)(TH + 2 * s) * (TW + 2 * s) + 2 * (size_t)(TH + 2 * s) * TW);
+    dim3 g = tile_grid(e.w, e.h, B);
+    switch (s & 3) {
+    case 0: k_deriv1<0><<<g, NT, smem, ctx->stream>>>(Ls, Lx, Ly, e.w, e.h, bs, s, e.norm, e.middle); break;
+    case 1: k_deriv1<1><<<g, NT, smem, ctx->stream>>>(Ls, Lx, Ly, e.w, e.h, bs, s, e.norm, e.middle); break;
+    case 2: k_deriv1<2><<<g, NT, smem, ctx->stream>>>(Ls, Lx, Ly, e.w, e.h, bs, s, e.norm, e.middle); break;
+    default: k_deriv1<3><<<g, NT, smem, ctx->stream>>>(Ls, Lx, Ly, e.w, e.h, bs, s, e.norm, e.middle); break;
+    }
+    CVB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int launch_deriv2(cvb_ctx *ctx, const EvoHost &e, const float *Lx, const float *Ly, float *Ldet, size_t bs, unsigned B) {
+    int s = (int)e.sigma;
+    size_t smem = sizeof(float) * (2 * (size_t)(TH + 2 * s) * (TW + 2 * s) + 3 * (size_t)(TH + 2 * s) * TW);
+    dim3 g = tile_grid(e.w, e.h, B);
+    switch (s & 3) {
+    case 0: k_deriv2_det<0><<<g, NT, smem, ctx->stream>>>(Lx, Ly, Ldet, e.w, e.h, bs, s, e.norm, e.middle, e.quat); break;
+    case 1: k_deriv2_det<1><<<g, NT, smem, ctx->stream>>>(Lx, Ly, Ldet, e.w, e.h, bs, s, e.norm, e.middle, e.quat); break;
+    case 2: k_deriv2_det<2><<<g, NT, smem, ctx->stream>>>(Lx, Ly, Ldet, e.w, e.h, bs, s, e.norm, e.middle, e.quat); break;
+    default: k_deriv2_det<3><<<g, NT, smem, ctx->stream>>>(Lx, Ly, Ldet, e.w, e.h, bs, s, e.norm, e.middle, e.quat); break;
+    }
+    CVB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// The whole extractor for `B` frames already resident in `images` (device).  Asynchronous.
+int run_extract(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoint *kp_out, unsigned char *desc_out,
+                unsigned cap_out, unsigned *n_out) {
+    AkazeWorkspace *ws = ctx->akaze;
+    cudaStream_t st = ctx->stream;
+    const size_t PF = ws->plane_floats, P0 = ws->p0;
+    const int W = (int)ws->w, H = (int)ws->h;
+    const int E = (int)ws->evo.size();
+    if (E == 0) {   // image too small for a single octave: the reference returns no keypoints
+        CVB_CUDA(ctx, cudaMemsetAsync(n_out, 0, sizeof(unsigned) * B, st));
+        ws->has_run = true;
+        return 0;
+    }
+    const int nbins = (int)ws->cfg.contrast_factor_num_bins;
+    // ---- create_nonlinear_scale_space (lib.rs:193-258)
+    // evolution 0: Lt = gaussian_blur(image, base_scale_offset); Lsmooth = Lt
+    int rc = launch_separable(ctx, images, P0, ws->Lt + ws->evo[0].off, PF, W, H, B, ws->g0, ws->g0);
+    if (rc) return rc;
+    CVB_CUDA(ctx, cudaMemcpy2DAsync(ws->Lsm + ws->evo[0].off, PF * sizeof(float), ws->Lt + ws->evo[0].off, PF * sizeof(float),
+                                    P0 * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+    // contrast factor (contrast_factor.rs:16-64)
+    CVB_CUDA(ctx, cudaMemsetAsync(ws->gmax, 0, sizeof(unsigned long long) * B, st));
+    CVB_CUDA(ctx, cudaMemsetAsync(ws->hist, 0, sizeof(unsigned) * B * nbins, st));
+    CVB_CUDA(ctx, cudaMemsetAsync(ws->npoints, 0, sizeof(unsigned) * B, st));
+    rc = launch_separable(ctx, images, P0, ws->tmpA, P0, W, H, B, ws->g1, ws->g1);
+    if (rc) return rc;
+    k_scharr_pm<1><<<tile_grid(W, H, B), NT, 0, st>>>(ws->tmpA, nullptr, ws->g2, ws->gmax, W, H, P0, P0, nullptr, 0);
+    CVB_LAUNCH_CHECK(ctx);
+    {
+        unsigned blocks = std::min<unsigned>(cdiv((unsigned)P0, NT), (unsigned)ctx->num_sms * 8);
+        k_contrast_hist<<<dim3(blocks, 1, B), NT, sizeof(unsigned) * nbins, st>>>(ws->g2, ws->gmax, ws->hist, ws->npoints, (int)P0, P0, nbins);
+        CVB_LAUNCH_CHECK(ctx);
+        k_contrast_final<<<B, 32, 0, st>>>(ws->gmax, ws->hist, ws->npoints, nbins, ws->cfg.contrast_percentile, ws->evo_octave, E, ws->kc, ws->inv_k);
+        CVB_LAUNCH_CHECK(ctx);
+    }
+    for (int i = 1; i < E; i++) {
+        const EvoHost &e = ws->evo[i];
+        const EvoHost &pe = ws->evo[i - 1];
+        const float *src = ws->Lt + pe.off;   // previous evolution's final Lt
+        size_t src_bs = PF;
+        if (e.new_octave) {
+            dim3 blk(32, 8), grd(cdiv((unsigned)e.w, 32), cdiv((unsigned)e.h, 8), B);
+            k_half_size<<<grd, blk, 0, st>>>(src, ws->tmpC, pe.w, pe.h, src_bs, P0);
+            CVB_LAUNCH_CHECK(ctx);
+            src = ws->tmpC; src_bs = P0;
+        }
+        // Lsmooth = gaussian_blur(Lt, 1.0)
+        rc = launch_separable(ctx, src, src_bs, ws->Lsm + e.off, PF, e.w, e.h, B, ws->g1, ws->g1);
+        if (rc) return rc;
+        // Lflow = pm_g2(simple_scharr_x(Lsmooth), simple_scharr_y(Lsmooth), contrast)
+        k_scharr_pm<0><<<tile_grid(e.w, e.h, B), NT, 0, st>>>(ws->Lsm + e.off, ws->Lflow + e.off, nullptr, nullptr, e.w, e.h, PF, PF,
+                                                             ws->inv_k + i, MAX_EVO);
+        CVB_LAUNCH_CHECK(ctx);
+        // FED steps, FED_SMAX per launch; the chain ends in Lt_i
+        const int n = (int)e.tau.size();
+        const int nl = (n + FED_SMAX - 1) / FED_SMAX;
+        if (nl == 0) {
+            CVB_CUDA(ctx, cudaMemcpy2DAsync(ws->Lt + e.off, PF * sizeof(float), src, src_bs * sizeof(float),
+                                            (size_t)e.w * e.h * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+        }
+        const float *cur = src; size_t cur_bs = src_bs;
+        for (int l = 0; l < nl; l++) {
+            FedSteps fs;
+            fs.n = std::min(FED_SMAX, n - l * FED_SMAX);
+            for (int t = 0; t < fs.n; t++) fs.tau[t] = (float)e.tau[(size_t)(l * FED_SMAX + t)];
+            // destinations alternate tmpA/tmpB so that the last one is Lt_i
+            float *dst; size_t dst_bs;
+            if (l == nl - 1) { dst = ws->Lt + e.off; dst_bs = PF; }
+            else if (((nl - 1 - l) & 1) == 1) { dst = ws->tmpA; dst_bs = P0; }
+            else { dst = ws->tmpB; dst_bs = P0; }
+            size_t smem = sizeof(float) * 3 * (size_t)(TW + 2 * fs.n) * (TH + 2 * fs.n);
+            k_fed<<<tile_grid(e.w, e.h, B), NT, smem, st>>>(cur, ws->Lflow + e.off, dst, e.w, e.h, cur_bs, PF, dst_bs, fs);
+            CVB_LAUNCH_CHECK(ctx);
+            cur = dst; cur_bs = dst_bs;
+        }
+    }
+    // ---- detector_response (detector_response.rs:8-85)
+    for (int i = 0; i < E; i++) {
+        const EvoHost &e = ws->evo[i];
+        rc = launch_deriv1(ctx, e, ws->Lsm + e.off, ws->Lx + e.off, ws->Ly + e.off, PF, B);
+        if (rc) return rc;
+        rc = launch_deriv2(ctx, e, ws->Lx + e.off, ws->Ly + e.off, ws->Ldet + e.off, PF, B);
+        if (rc) return rc;
+    }
+    // ---- detect_keypoints (scale_space_extrema.rs)
+    const int R = ws->table.total_rows;
+    const float thr = (float)ws->cfg.detector_threshold;
+    {
+        dim3 g(cdiv((unsigned)R * 32u, NT), 1, B);
+        k_extrema<false><<<g, NT, 0, st>>>(ws->Ldet, PF, ws->table, thr, ws->rowcount, nullptr, nullptr, 0, ws->overflow);
+        CVB_LAUNCH_CHECK(ctx);
+        k_scan_rows<<<B, 1024, 0, st>>>(ws->rowcount, ws->rowoff, ws->ncand, R);
+        CVB_LAUNCH_CHECK(ctx);
+        k_extrema<true><<<g, NT, 0, st>>>(ws->Ldet, PF, ws->table, thr, nullptr, ws->rowoff, ws->cand, ws->capc, ws->overflow);
+        CVB_LAUNCH_CHECK(ctx);
+    }
+    k_suppress<<<B, 1024, 0, st>>>(ws->cand, ws->ncand, ws->capc, ws->table, ws->cache, ws->ncache, ws->capk, ws->overflow);
+    CVB_LAUNCH_CHECK(ctx);
+    const unsigned kp_blocks = (unsigned)ctx->num_sms * 2;
+    k_filter_upper<<<dim3(kp_blocks, B), NT, 0, st>>>(ws->cache, ws->ncache, ws->capk, ws->keep);
+    CVB_LAUNCH_CHECK(ctx);
+    k_refine_orient<<<dim3(kp_blocks, B), NT, 0, st>>>(ws->cache, ws->ncache, ws->capk, ws->keep, ws->table, ws->Ldet, ws->Lx, ws->Ly, PF,
+                                                       ws->ot, ws->refined, ws->valid);
+    CVB_LAUNCH_CHECK(ctx);
+    // ---- sort + truncate (lib.rs:326-327)
+    k_rank_sort<<<dim3(kp_blocks, B), NT, 0, st>>>(ws->refined, ws->valid, ws->ncache, ws->capk, (long long)ws->cfg.maximum_features,
+                                                   ws->sorted, ws->nsorted);
+    CVB_LAUNCH_CHECK(ctx);
+    // ---- extract_descriptors (descriptors.rs:16-45)
+    k_descriptors<<<dim3(kp_blocks, B), NT, 0, st>>>(ws->sorted, ws->nsorted, ws->capk, ws->table, ws->Lt, ws->Lx, ws->Ly, PF, ws->dt,
+                                                     (int)ws->cfg.descriptor_channels, ws->desc_tmp, ws->ok);
+    CVB_LAUNCH_CHECK(ctx);
+    k_compact_final<<<B, 1024, 0, st>>>(ws->sorted, ws->desc_tmp, ws->ok, ws->nsorted, ws->capk, kp_out, desc_out, cap_out, n_out,
+                                        ws->overflow);
+    CVB_LAUNCH_CHECK(ctx);
+    ws->has_run = true;
+    return 0;
+}
+
+int check_args(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, const void *img, uint32_t batch, uint32_t w, uint32_t h) {
+    if (!ctx) return CVB_EINVAL;
+    if (!cfg || !img) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    if (batch == 0 || w == 0 || h == 0) return cvb_set_error(ctx, CVB_EINVAL, "empty image or batch");
+    if ((uint64_t)w * h > (1ull << 28)) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "image too large");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void cvb_akaze_default_cfg(cvb_akaze_cfg *c) {
+    if (!c) return;
+    c->maximum_features = -1;
+    c->num_sublevels = 4; c->max_octave_evolution = 4;
+    c->base_scale_offset = 1.6; c->initial_contrast = 0.001; c->contrast_percentile = 0.7;
+    c->contrast_factor_num_bins = 300; c->derivative_factor = 1.5; c->detector_threshold = 0.001;
+    c->descriptor_channels = 3; c->descriptor_pattern_size = 10;
+}
+
+int cvb_akaze_extract_batch_dev(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, const float *images_dev, uint32_t batch, uint32_t w,
+                                uint32_t h, cvb_keypoint *kp_out_dev, uint8_t *desc_out_dev, uint32_t cap, uint32_t *n_out_dev) {
+    int rc = check_args(ctx, cfg, images_dev, batch, w, h);
+    if (rc) return rc;
+    if (!kp_out_dev || !desc_out_dev || !n_out_dev) return cvb_set_error(ctx, CVB_EINVAL, "null output");
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    rc = ensure_workspace(ctx, cfg, batch, w, h, ctx->akaze ? ctx->akaze->cap_out : 1);
+    if (rc) return rc;
+    return run_extract(ctx, images_dev, batch, kp_out_dev, desc_out_dev, cap, n_out_dev);
+}
+
+int cvb_akaze_extract_batch(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, const float *images, uint32_t batch, uint32_t w, uint32_t h,
+                            cvb_keypoint *kp_out, uint8_t *desc_out, uint32_t cap, uint32_t *n_out) {
+    int rc = check_args(ctx, cfg, images, batch, w, h);
+    if (rc) return rc;
+    if (!n_out || (cap && (!kp_out || !desc_out))) return cvb_set_error(ctx, CVB_EINVAL, "null output");
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    rc = ensure_workspace(ctx, cfg, batch, w, h, std::max<uint32_t>(cap, 1));
+    if (rc) return rc;
+    AkazeWorkspace *ws = ctx->akaze;
+    cudaStream_t st = ctx->stream;
+    CVB_CUDA(ctx, cudaMemcpyAsync(ws->img, images, sizeof(float) * ws->p0 * batch, cudaMemcpyHostToDevice, st));
+    const unsigned cap_dev = ws->cap_out;
+    rc = run_extract(ctx, ws->img, batch, ws->kp_out, ws->desc_out, cap_dev, ws->n_out);
+    if (rc) return rc;
+    unsigned ovf = 0;
+    CVB_CUDA(ctx, cudaMemcpyAsync(n_out, ws->n_out, sizeof(unsigned) * batch, cudaMemcpyDeviceToHost, st));
+    CVB_CUDA(ctx, cudaMemcpyAsync(&ovf, ws->overflow, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CVB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (ovf) {
+        cudaMemsetAsync(ws->overflow, 0, sizeof(unsigned), st);
+        if (ovf == 3) return cvb_set_error(ctx, CVB_ECAP, "output capacity %u too small", cap);
+        return cvb_set_error(ctx, CVB_ECAP, "internal keypoint capacity exceeded (stage %u)", ovf);
+    }
+    for (uint32_t b = 0; b < batch; b++) {
+        unsigned n = std::min<unsigned>(n_out[b], cap);
+        if (!n) continue;
+        CVB_CUDA(ctx, cudaMemcpyAsync(kp_out + (size_t)b * cap, ws->kp_out + (size_t)b * cap_dev, sizeof(cvb_keypoint) * n,
+                                      cudaMemcpyDeviceToHost, st));
+        CVB_CUDA(ctx, cudaMemcpyAsync(desc_out + (size_t)b * cap * 64, ws->desc_out + (size_t)b * cap_dev * 64, (size_t)n * 64,
+                                      cudaMemcpyDeviceToHost, st));
+    }
+    CVB_CUDA(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int cvb_akaze_extract(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, const float *image, uint32_t w, uint32_t h, cvb_keypoint *kp_out,
+                      uint8_t *desc_out, uint32_t cap, uint32_t *n_out) {
+    return cvb_akaze_extract_batch(ctx, cfg, image, 1, w, h, kp_out, desc_out, cap, n_out);
+}
+
+// ---- introspection for the parity tests ------------------------------------------------------
+int cvb_akaze_debug_num_evolutions(cvb_ctx *ctx, uint32_t *n_out) {
+    if (!ctx || !n_out) return CVB_EINVAL;
+    if (!ctx->akaze || !ctx->akaze->has_run) return cvb_set_error(ctx, CVB_EINVAL, "no extract call yet");
+    *n_out = (uint32_t)ctx->akaze->evo.size();
+    return 0;
+}
+
+int cvb_akaze_debug_evolution(cvb_ctx *ctx, uint32_t i, uint32_t *w, uint32_t *h, uint32_t *octave, uint32_t *sigma_size,
+                              uint32_t *n_fed_steps) {
+    if (!ctx) return CVB_EINVAL;
+    if (!ctx->akaze || !ctx->akaze->has_run || i >= ctx->akaze->evo.size()) return cvb_set_error(ctx, CVB_EINVAL, "bad evolution");
+    const EvoHost &e = ctx->akaze->evo[i];
+    if (w) *w = (uint32_t)e.w;
+    if (h) *h = (uint32_t)e.h;
+    if (octave) *octave = e.octave;
+    if (sigma_size) *sigma_size = e.sigma;
+    if (n_fed_steps) *n_fed_steps = (uint32_t)e.tau.size();
+    return 0;
+}
+
+int cvb_akaze_debug_plane(cvb_ctx *ctx, uint32_t frame, uint32_t i, uint32_t plane, float *out) {
+    if (!ctx || !out) return CVB_EINVAL;
+    AkazeWorkspace *ws = ctx->akaze;
+    if (!ws || !ws->has_run || i >= ws->evo.size() || frame >= ws->batch) return cvb_set_error(ctx, CVB_EINVAL, "bad frame/evolution");
+    const float *planes[6] = {ws->Lt, ws->Lsm, ws->Lx, ws->Ly, ws->Lflow, ws->Ldet};
+    if (plane >= 6) return cvb_set_error(ctx, CVB_EINVAL, "bad plane");
+    const EvoHost &e = ws->evo[i];
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cudaMemcpy(out, planes[plane] + (size_t)frame * ws->plane_floats + e.off, sizeof(float) * (size_t)e.w * e.h,
+                             cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int cvb_akaze_debug_contrast(cvb_ctx *ctx, uint32_t frame, double *k_out) {
+    if (!ctx || !k_out) return CVB_EINVAL;
+    AkazeWorkspace *ws = ctx->akaze;
+    if (!ws || !ws->has_run || frame >= ws->batch) return cvb_set_error(ctx, CVB_EINVAL, "bad frame");
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cudaMemcpy(k_out, ws->kc + frame, sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int cvb_akaze_debug_stage(cvb_ctx *ctx, uint32_t frame, uint32_t stage, cvb_keypoint *out, uint32_t cap, uint32_t *n_out) {
+    if (!ctx || !n_out) return CVB_EINVAL;
+    AkazeWorkspace *ws = ctx->akaze;
+    if (!ws || !ws->has_run || frame >= ws->batch) return cvb_set_error(ctx, CVB_EINVAL, "bad frame");
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<cvb_keypoint> res;
+    if (stage == 0) {
+        unsigned n = 0;
+        CVB_CUDA(ctx, cudaMemcpy(&n, ws->ncand + frame, sizeof(unsigned), cudaMemcpyDeviceToHost));
+        n = std::min(n, ws->capc);
+        std::vector<Cand> c(n);
+        if (n) CVB_CUDA(ctx, cudaMemcpy(c.data(), ws->cand + (size_t)frame * ws->capc, sizeof(Cand) * n, cudaMemcpyDeviceToHost));
+        for (unsigned i = 0; i < n; i++) {
+            cvb_keypoint k{};
+            const EvoHost &e = ws->evo[(size_t)c[i].e];
+            k.x = (float)c[i].x; k.y = (float)c[i].y; k.response = fabsf(c[i].v);
+            k.size = (float)(e.esigma * ws->cfg.derivative_factor); k.angle = 0.f; k.octave = e.octave; k.class_id = (uint32_t)c[i].e;
+            res.push_back(k);
+        }
+    } else if (stage == 1 || stage == 2) {
+        unsigned n = 0;
+        CVB_CUDA(ctx, cudaMemcpy(&n, ws->ncache + frame, sizeof(unsigned), cudaMemcpyDeviceToHost));
+        std::vector<cvb_keypoint> k(n);
+        std::vector<unsigned char> f(n);
+        const cvb_keypoint *src = stage == 1 ? ws->cache : ws->refined;
+        const unsigned char *flg = stage == 1 ? ws->keep : ws->valid;
+        if (n) {
+            CVB_CUDA(ctx, cudaMemcpy(k.data(), src + (size_t)frame * ws->capk, sizeof(cvb_keypoint) * n, cudaMemcpyDeviceToHost));
+            CVB_CUDA(ctx, cudaMemcpy(f.data(), flg + (size_t)frame * ws->capk, n, cudaMemcpyDeviceToHost));
+        }
+        for (unsigned i = 0; i < n; i++)
+            if (f[i]) res.push_back(k[i]);
+    } else if (stage == 3) {
+        unsigned n = 0;
+        CVB_CUDA(ctx, cudaMemcpy(&n, ws->nsorted + frame, sizeof(unsigned), cudaMemcpyDeviceToHost));
+        res.resize(n);
+        if (n) CVB_CUDA(ctx, cudaMemcpy(res.data(), ws->sorted + (size_t)frame * ws->capk, sizeof(cvb_keypoint) * n, cudaMemcpyDeviceToHost));
+    } else return cvb_set_error(ctx, CVB_EINVAL, "bad stage");
+    *n_out = (uint32_t)res.size();
+    if (out)
+        for (size_t i = 0; i < res.size() && i < cap; i++) out[i] = res[i];
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,823 @@
+// cv_b200/csrc/akaze_kernels.cuh -- sm_100a kernels of the AKAZE extractor.
+//
+// Parity contract: every f32 value produced here is bit-identical to what rust-cv `akaze` 0.7.0
+// computes on a default x86-64 build (unfused multiply-add, wide::f32x4 lane sums reduced as
+// (l0+l2)+(l1+l3)).  Stages may be FUSED (intermediates live in shared memory, never in HBM) but
+// each intermediate is rounded to f32 exactly where the reference materialises it.
+// Compile with -fmad=false.  Reference line numbers are relative to /root/reference/akaze/src.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "device_libm.cuh"
+#include "../../include/cvb200.h"
+
+namespace akz {
+
+constexpr int TW = 32;        // tile width  (outputs)
+constexpr int TH = 32;        // tile height (outputs)
+constexpr int NT = 256;       // threads per CTA for tile kernels (32 x 8)
+constexpr int MAXK = 33;      // max taps of a generic separable kernel (sigma <= 8)
+constexpr int MAX_EVO = 32;
+constexpr int MAX_TAU = 64;
+constexpr int FED_SMAX = 8;   // diffusion steps fused per launch (halo = steps)
+
+struct Taps { int ks; float k[MAXK]; };
+
+// per-evolution description used by the keypoint kernels
+struct EvoDev {
+    int w, h;
+    unsigned long long off;   // offset (floats) of this level inside a per-frame pyramid plane
+    int octave;
+    float size;               // (esigma * derivative_factor) as f32      scale_space_extrema.rs:63
+    int rowbase;              // first global row index of this evolution (extrema scan)
+    int pad;
+};
+struct EvoTable { int n; int total_rows; EvoDev e[MAX_EVO]; };
+
+struct Cand { int x, y, e; float v; };
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// wide::f32x4 lane-ordered correlation (image.rs:242-247 / 320-325): lane j&3 accumulates taps
+// j, j+4, ... as (w*k)+acc from +0; reduce_add = (l0+l2)+(l1+l3).
+__device__ __forceinline__ float lane_dot(const float *w, int stride, const float *k, int ks) {
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+    int j = 0;
+    for (; j + 4 <= ks; j += 4) {
+        l0 = w[(j + 0) * stride] * k[j + 0] + l0;
+        l1 = w[(j + 1) * stride] * k[j + 1] + l1;
+        l2 = w[(j + 2) * stride] * k[j + 2] + l2;
+        l3 = w[(j + 3) * stride] * k[j + 3] + l3;
+    }
+    if (j < ks) l0 = w[j * stride] * k[j] + l0;
+    if (j + 1 < ks) l1 = w[(j + 1) * stride] * k[j + 1] + l1;
+    if (j + 2 < ks) l2 = w[(j + 2) * stride] * k[j + 2] + l2;
+    return (l0 + l2) + (l1 + l3);
+}
+
+// Sparse 2-/3-tap versions of the same sum for the Scharr kernels (derivatives.rs:3-11, 54-79).
+// Zero taps contribute (w*0)+acc == acc (acc is never -0), so only the non-zero taps are evaluated,
+// each in its own lane JA/JB/JC = tap index & 3, in increasing tap order.
+template <int JA, int JB>
+__device__ __forceinline__ float dot2(float a, float ka, float b, float kb) {
+    float l[4] = {0.f, 0.f, 0.f, 0.f};
+    l[JA] = a * ka + l[JA];
+    l[JB] = b * kb + l[JB];
+    return (l[0] + l[2]) + (l[1] + l[3]);
+}
+template <int JA, int JB, int JC>
+__device__ __forceinline__ float dot3(float a, float ka, float b, float kb, float c, float kc) {
+    float l[4] = {0.f, 0.f, 0.f, 0.f};
+    l[JA] = a * ka + l[JA];
+    l[JB] = b * kb + l[JB];
+    l[JC] = c * kc + l[JC];
+    return (l[0] + l[2]) + (l[1] + l[3]);
+}
+// Scharr "main" kernel [-1, 0.., 1] of size 2s+1: taps 0 and 2s.  SM = s & 3.
+template <int SM>
+__device__ __forceinline__ float scharr_main(float first, float last) {
+    return dot2<0, (2 * SM) & 3>(first, -1.0f, last, 1.0f);
+}
+// Scharr "off" kernel [norm, 0.., middle, 0.., norm]: taps 0, s, 2s.
+template <int SM>
+__device__ __forceinline__ float scharr_off(float first, float mid, float last, float norm, float middle) {
+    return dot3<0, SM & 3, (2 * SM) & 3>(first, norm, mid, middle, last, norm);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic separable filter, H then V in one pass through shared memory (image.rs:333-340).
+// grid = (ceil(w/TW), ceil(h/TH), B).
+__global__ void __launch_bounds__(NT) k_separable(const float *__restrict__ in, float *__restrict__ out, int w, int h,
+                                                  size_t in_bstride, size_t out_bstride, Taps hk, Taps vk) {
+    extern __shared__ float sm[];
+    const int rx = hk.ks / 2, ry = vk.ks / 2;
+    const int sw = TW + 2 * rx, sh = TH + 2 * ry;
+    float *s_in = sm;            // sh x sw
+    float *s_h = sm + sh * sw;   // sh x TW
+    const float *src = in + (size_t)blockIdx.z * in_bstride;
+    float *dst = out + (size_t)blockIdx.z * out_bstride;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    for (int i = threadIdx.x; i < sw * sh; i += NT) {
+        int ly = i / sw, lx = i - ly * sw;
+        int gx = clampi(x0 + lx - rx, 0, w - 1), gy = clampi(y0 + ly - ry, 0, h - 1);
+        s_in[i] = src[(size_t)gy * w + gx];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TW * sh; i += NT) {
+        int ly = i / TW, lx = i - ly * TW;
+        s_h[i] = lane_dot(s_in + ly * sw + lx, 1, hk.k, hk.ks);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TW * TH; i += NT) {
+        int ly = i / TW, lx = i - ly * TW;
+        int gx = x0 + lx, gy = y0 + ly;
+        if (gx < w && gy < h) dst[(size_t)gy * w + gx] = lane_dot(s_h + ly * TW + lx, TW, vk.k, vk.ks);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// half_size (image.rs:154-199): 2x2 box (row sums first) * 0.25; odd tail rows/cols * 0.5; corner copy.
+__global__ void k_half_size(const float *__restrict__ in, float *__restrict__ out, int w, int h, size_t in_bstride,
+                            size_t out_bstride) {
+    const int hw = w / 2, hh = h / 2;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= hw || y >= hh) return;
+    const float *p = in + (size_t)blockIdx.z * in_bstride;
+    const bool oddw = hw * 2 != w, oddh = hh * 2 != h;
+    float v;
+    if (oddw && oddh && x == hw - 1 && y == hh - 1) v = p[(size_t)(h - 1) * w + (w - 1)];
+    else if (oddw && x == hw - 1) v = (p[(size_t)(2 * y) * w + (w - 1)] + p[(size_t)(2 * y + 1) * w + (w - 1)]) * 0.5f;
+    else if (oddh && y == hh - 1) v = (p[(size_t)(h - 1) * w + 2 * x] + p[(size_t)(h - 1) * w + 2 * x + 1]) * 0.5f;
+    else {
+        const float *q = p + (size_t)(2 * y) * w + 2 * x;
+        v = ((q[0] + q[1]) + (q[w] + q[w + 1])) * 0.25f;
+    }
+    out[(size_t)blockIdx.z * out_bstride + (size_t)y * hw + x] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Simple Scharr (x and y) of Lsmooth fused with pm_g2 -> Lflow.
+// lib.rs:236-248, derivatives.rs:3-11, nonlinear_diffusion.rs:70-83.  Lx/Ly are never written to HBM.
+// Also used (MODE 1) for the contrast-factor gradient: writes g2 = (f64)lx^2 + (f64)ly^2 on interior
+// pixels and a per-frame max (contrast_factor.rs:24-34).
+__device__ __forceinline__ void simple_scharr_at(const float *s, int sw, float &lx, float &ly) {
+    // s points at the centre of a 3x3 neighbourhood inside a shared tile of row stride sw
+    // H pass [-1,0,1] then V pass [3,10,3] for Lx; H [3,10,3] then V [-1,0,1] for Ly.
+    float hm_m = dot2<0, 2>(s[-sw - 1], -1.0f, s[-sw + 1], 1.0f);
+    float hm_0 = dot2<0, 2>(s[-1], -1.0f, s[1], 1.0f);
+    float hm_p = dot2<0, 2>(s[sw - 1], -1.0f, s[sw + 1], 1.0f);
+    lx = dot3<0, 1, 2>(hm_m, 3.0f, hm_0, 10.0f, hm_p, 3.0f);
+    float ho_m = dot3<0, 1, 2>(s[-sw - 1], 3.0f, s[-sw], 10.0f, s[-sw + 1], 3.0f);
+    float ho_p = dot3<0, 1, 2>(s[sw - 1], 3.0f, s[sw], 10.0f, s[sw + 1], 3.0f);
+    ly = dot2<0, 2>(ho_m, -1.0f, ho_p, 1.0f);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NT) k_scharr_pm(const float *__restrict__ in, float *__restrict__ out_flow,
+                                                  double *__restrict__ out_g2, unsigned long long *__restrict__ gmax,
+                                                  int w, int h, size_t in_bstride, size_t out_bstride,
+                                                  const float *__restrict__ inv_k, int inv_k_stride) {
+    __shared__ float s_in[(TH + 2) * (TW + 2)];
+    __shared__ unsigned long long s_max;
+    const int sw = TW + 2;
+    const float *src = in + (size_t)blockIdx.z * in_bstride;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    if (MODE == 1 && threadIdx.x == 0) s_max = 0ull;
+    for (int i = threadIdx.x; i < sw * (TH + 2); i += NT) {
+        int ly = i / sw, lx = i - ly * sw;
+        int gx = clampi(x0 + lx - 1, 0, w - 1), gy = clampi(y0 + ly - 1, 0, h - 1);
+        s_in[i] = src[(size_t)gy * w + gx];
+    }
+    __syncthreads();
+    float ik = 0.f;
+    if (MODE == 0) ik = inv_k[(size_t)blockIdx.z * inv_k_stride];
+    unsigned long long lmax = 0ull;
+    for (int i = threadIdx.x; i < TW * TH; i += NT) {
+        int ly = i / TW, lx = i - ly * TW;
+        int gx = x0 + lx, gy = y0 + ly;
+        if (gx >= w || gy >= h) continue;
+        float dx, dy;
+        simple_scharr_at(s_in + (ly + 1) * sw + (lx + 1), sw, dx, dy);
+        if (MODE == 0) {
+            out_flow[(size_t)blockIdx.z * out_bstride + (size_t)gy * w + gx] = 1.0f / (1.0f + ik * (dx * dx + dy * dy));
+        } else {
+            double g2 = -1.0;   // marks non-interior
+            if (gx >= 1 && gx < w - 1 && gy >= 1 && gy < h - 1) {
+                g2 = (double)(dx * dx) + (double)(dy * dy);
+                unsigned long long bits = (unsigned long long)__double_as_longlong(g2);
+                lmax = bits > lmax ? bits : lmax;   // g2 >= 0: bit pattern is order preserving
+            }
+            out_g2[(size_t)blockIdx.z * out_bstride + (size_t)gy * w + gx] = g2;
+        }
+    }
+    if (MODE == 1) {
+        atomicMax(&s_max, lmax);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_max) atomicMax(gmax + blockIdx.z, s_max);
+    }
+}
+
+// contrast_factor.rs:35-48 histogram of floor(nbins * modg/hmax) over interior pixels with modg != 0
+__global__ void __launch_bounds__(NT) k_contrast_hist(const double *__restrict__ g2, const unsigned long long *gmax,
+                                                      unsigned *hist, unsigned *npoints, int n, size_t bstride, int nbins) {
+    extern __shared__ unsigned s_hist[];
+    for (int i = threadIdx.x; i < nbins; i += NT) s_hist[i] = 0;
+    __syncthreads();
+    const double hmax = sqrt(__longlong_as_double((long long)gmax[blockIdx.z]));
+    const double *p = g2 + (size_t)blockIdx.z * bstride;
+    unsigned cnt = 0;
+    for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT) {
+        double v = p[i];
+        if (v < 0.0) continue;
+        double modg = sqrt(v);
+        if (modg != 0.0) {
+            long long bin = (long long)floor((double)nbins * (modg / hmax));
+            if (bin == nbins) bin -= 1;
+            if (bin >= 0 && bin < nbins) atomicAdd(&s_hist[bin], 1u);
+            cnt++;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nbins; i += NT)
+        if (s_hist[i]) atomicAdd(&hist[(size_t)blockIdx.z * nbins + i], s_hist[i]);
+    // warp-aggregate the point count
+    for (int o = 16; o; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&npoints[blockIdx.z], cnt);
+}
+
+// contrast_factor.rs:49-63 + lib.rs:222,248: k, then per-evolution inverse_k = (1/(k_i*k_i)) as f32 with
+// k_i = k * 0.75^(octave changes so far), multiplied sequentially in f64 as the reference does.
+__global__ void k_contrast_final(const unsigned long long *gmax, const unsigned *hist, const unsigned *npoints, int nbins,
+                                 double percentile, const int *evo_octave, int nevo, double *kc, float *inv_k) {
+    const int b = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const double hmax = sqrt(__longlong_as_double((long long)gmax[b]));
+    const double num_points = (double)npoints[b];
+    const unsigned long long threshold = (unsigned long long)(num_points * percentile);
+    unsigned long long k = 0, nel = 0;
+    while (nel < threshold && k < (unsigned long long)nbins) { nel += hist[(size_t)b * nbins + k]; k++; }
+    double c = (nel >= threshold) ? hmax * (double)k / (double)nbins : 0.03;
+    kc[b] = c;
+    for (int i = 1; i < nevo; i++) {
+        if (evo_octave[i] > evo_octave[i - 1]) c *= 0.75;
+        inv_k[(size_t)b * MAX_EVO + i] = (float)(1.0 / (c * c));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FED diffusion: `nsteps` explicit steps fused in one launch (temporal blocking, halo = nsteps).
+// nonlinear_diffusion.rs:14-58: flows from the OLD image; L += hf[x]; L -= hf[x-1]; L += vf[y]; L -= vf[y-1]
+// in that order; flow = ((0.5*step)*(ca+cb))*(b-a); image borders by omission.
+struct FedSteps { int n; float tau[FED_SMAX]; };
+
+__global__ void __launch_bounds__(NT) k_fed(const float *__restrict__ Lin, const float *__restrict__ C,
+                                            float *__restrict__ Lout, int w, int h, size_t lin_bstride, size_t c_bstride,
+                                            size_t lout_bstride, FedSteps steps) {
+    extern __shared__ float sm[];
+    const int S = steps.n;
+    const int sw = TW + 2 * S, sh = TH + 2 * S;
+    float *bufA = sm, *bufB = sm + sw * sh, *sc = sm + 2 * sw * sh;
+    const float *lin = Lin + (size_t)blockIdx.z * lin_bstride;
+    const float *cc = C + (size_t)blockIdx.z * c_bstride;
+    const int X0 = blockIdx.x * TW - S, Y0 = blockIdx.y * TH - S;
+    // loaded region clipped to the image
+    const int cx0 = max(X0, 0), cy0 = max(Y0, 0), cx1 = min(X0 + sw, w), cy1 = min(Y0 + sh, h);
+    for (int i = threadIdx.x; i < sw * sh; i += NT) {
+        int ly = i / sw, lx = i - ly * sw;
+        int gx = X0 + lx, gy = Y0 + ly;
+        bool in = gx >= cx0 && gx < cx1 && gy >= cy0 && gy < cy1;
+        size_t g = (size_t)gy * w + gx;
+        bufA[i] = in ? lin[g] : 0.f;
+        sc[i] = in ? cc[g] : 0.f;
+    }
+    __syncthreads();
+    float *cur = bufA, *nxt = bufB;
+    for (int t = 1; t <= S; t++) {
+        const float hs = 0.5f * steps.tau[t - 1];
+        // region whose dependency cone is inside the loaded data (no shrink on true image borders)
+        const int vx0 = cx0 + (cx0 > 0 ? t : 0), vx1 = cx1 - (cx1 < w ? t : 0);
+        const int vy0 = cy0 + (cy0 > 0 ? t : 0), vy1 = cy1 - (cy1 < h ? t : 0);
+        const int vw = vx1 - vx0, vh = vy1 - vy0;
+        if (vw > 0 && vh > 0) {
+            for (int i = threadIdx.x; i < vw * vh; i += NT) {
+                int yy = i / vw, xx = i - yy * vw;
+                int gx = vx0 + xx, gy = vy0 + yy;
+                int li = (gy - Y0) * sw + (gx - X0);
+                float l = cur[li], c0 = sc[li];
+                float v = l;
+                if (gx < w - 1) v += (hs * (c0 + sc[li + 1])) * (cur[li + 1] - l);
+                if (gx > 0) v -= (hs * (sc[li - 1] + c0)) * (l - cur[li - 1]);
+                if (gy < h - 1) v += (hs * (c0 + sc[li + sw])) * (cur[li + sw] - l);
+                if (gy > 0) v -= (hs * (sc[li - sw] + c0)) * (l - cur[li - sw]);
+                nxt[li] = v;
+            }
+        }
+        __syncthreads();
+        float *tmp = cur; cur = nxt; nxt = tmp;
+    }
+    float *dst = Lout + (size_t)blockIdx.z * lout_bstride;
+    for (int i = threadIdx.x; i < TW * TH; i += NT) {
+        int ly = i / TW, lx = i - ly * TW;
+        int gx = blockIdx.x * TW + lx, gy = blockIdx.y * TH + ly;
+        if (gx < w && gy < h) dst[(size_t)gy * w + gx] = cur[(ly + S) * sw + (lx + S)];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multiscale first derivatives from Lsmooth (detector_response.rs:60-65, derivatives.rs:23-49):
+//   Lx = V_off(H_main(Ls)),  Ly = V_main(H_off(Ls)),  kernel size 2*sigma+1.
+template <int SM>
+__global__ void __launch_bounds__(NT) k_deriv1(const float *__restrict__ Ls, float *__restrict__ Lx,
+                                               float *__restrict__ Ly, int w, int h, size_t bstride, int sigma,
+                                               float norm, float middle) {
+    extern __shared__ float sm[];
+    const int sw = TW + 2 * sigma, sh = TH + 2 * sigma;
+    float *s_in = sm;                 // sh x sw
+    float *s_hm = sm + sh * sw;       // sh x TW   H_main
+    float *s_ho = s_hm + sh * TW;     // sh x TW   H_off
+    const float *src = Ls + (size_t)blockIdx.z * bstride;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    for (int i = threadIdx.x; i < sw * sh; i += NT) {
+        int ly = i / sw, lx = i - ly * sw;
+        int gx = clampi(x0 + lx - sigma, 0, w - 1), gy = clampi(y0 + ly - sigma, 0, h - 1);
+        s_in[i] = src[(size_t)gy * w + gx];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TW * sh; i += NT) {
+        int ly = i / TW, lx = i - ly * TW;
+        const float *p = s_in + ly * sw + lx;   // p[0] = x - sigma, p[sigma] = x, p[2 sigma] = x + sigma
+        s_hm[i] = scharr_main<SM>(p[0], p[2 * sigma]);
+        s_ho[i] = scharr_off<SM>(p[0], p[sigma], p[2 * sigma], norm, middle);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TW * TH; i += NT) {
+        int ly = i / TW, lx = i - ly * TW;
+        int gx = x0 + lx, gy = y0 + ly;
+        if (gx >= w || gy >= h) continue;
+        const float *pm = s_hm + ly * TW + lx, *po = s_ho + ly * TW + lx;
+        size_t g = (size_t)blockIdx.z * bstride + (size_t)gy * w + gx;
+        Lx[g] = scharr_off<SM>(pm[0], pm[sigma * TW], pm[2 * sigma * TW], norm, middle);
+        Ly[g] = scharr_main<SM>(po[0], po[2 * sigma * TW]);
+    }
+}
+
+// Second derivatives + determinant of Hessian (detector_response.rs:40-47,66-68):
+//   Lxx = V_off(H_main(Lx)), Lyy = V_main(H_off(Ly)), Lxy = V_main(H_off(Lx)),
+//   Ldet = (Lxx*Lyy - Lxy*Lxy) * sigma^4.   Lxx/Lyy/Lxy never reach HBM.
+template <int SM>
+__global__ void __launch_bounds__(NT) k_deriv2_det(const float *__restrict__ Lx, const float *__restrict__ Ly,
+                                                   float *__restrict__ Ldet, int w, int h, size_t bstride, int sigma,
+                                                   float norm, float middle, float quat) {
+    extern __shared__ float sm[];
+    const int sw = TW + 2 * sigma, sh = TH + 2 * sigma;
+    float *s_x = sm;                  // Lx tile sh x sw
+    float *s_y = sm + sh * sw;        // Ly tile
+    float *s_a = s_y + sh * sw;       // H_main(Lx)  sh x TW
+    float *s_b = s_a + sh * TW;       // H_off(Ly)
+    float *s_c = s_b + sh * TW;       // H_off(Lx)
+    const float *px = Lx + (size_t)blockIdx.z * bstride, *py = Ly + (size_t)blockIdx.z * bstride;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    for (int i = threadIdx.x; i < sw * sh; i += NT) {
+        int ly = i / sw, lx = i - ly * sw;
+        int gx = clampi(x0 + lx - sigma, 0, w - 1), gy = clampi(y0 + ly - sigma, 0, h - 1);
+        size_t g = (size_t)gy * w + gx;
+        s_x[i] = px[g];
+        s_y[i] = py[g];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TW * sh; i += NT) {
+        int ly = i / TW, lx = i - ly * TW;
+        const float *p = s_x + ly * sw + lx, *q = s_y + ly * sw + lx;
+        s_a[i] = scharr_main<SM>(p[0], p[2 * sigma]);
+        s_b[i] = scharr_off<SM>(q[0], q[sigma], q[2 * sigma], norm, middle);
+        s_c[i] = scharr_off<SM>(p[0], p[sigma], p[2 * sigma], norm, middle);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TW * TH; i += NT) {
+        int ly = i / TW, lx = i - ly * TW;
+        int gx = x0 + lx, gy = y0 + ly;
+        if (gx >= w || gy >= h) continue;
+        const float *pa = s_a + ly * TW + lx, *pb = s_b + ly * TW + lx, *pc = s_c + ly * TW + lx;
+        float lxx = scharr_off<SM>(pa[0], pa[sigma * TW], pa[2 * sigma * TW], norm, middle);
+        float lyy = scharr_main<SM>(pb[0], pb[2 * sigma * TW]);
+        float lxy = scharr_main<SM>(pc[0], pc[2 * sigma * TW]);
+        Ldet[(size_t)blockIdx.z * bstride + (size_t)gy * w + gx] = (lxx * lyy - lxy * lxy) * quat;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scale-space extrema candidates (scale_space_extrema.rs:34-60): strict 3x3 maximum above threshold on
+// interior pixels, emitted in the reference's order: evolution ascending, raster within evolution.
+// One warp per image row (all evolutions of a frame form one global row index space).
+__device__ __forceinline__ bool is_extremum(const float *D, int w, int x, int y, float thr) {
+    const float *p = D + (size_t)y * w + x;
+    float v = *p;
+    return v > thr && v > p[-w - 1] && v > p[-w] && v > p[-w + 1] && v > p[-1] && v > p[1] && v > p[w - 1] &&
+           v > p[w] && v > p[w + 1];
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(NT) k_extrema(const float *__restrict__ Ldet, size_t bstride, EvoTable T, float thr,
+                                                unsigned *__restrict__ rowcount, const unsigned *__restrict__ rowoff,
+                                                Cand *__restrict__ cand, unsigned cap, unsigned *overflow) {
+    const int warp = (blockIdx.x * NT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= T.total_rows) return;
+    int e = 0;
+    while (e + 1 < T.n && warp >= T.e[e + 1].rowbase) e++;
+    const int y = warp - T.e[e].rowbase, w = T.e[e].w, h = T.e[e].h;
+    const float *D = Ldet + (size_t)blockIdx.z * bstride + T.e[e].off;
+    unsigned count = 0;
+    unsigned base = WRITE ? rowoff[(size_t)blockIdx.z * T.total_rows + warp] : 0;
+    if (y >= 1 && y < h - 1) {
+        for (int xb = 1; xb < w - 1; xb += 32) {
+            int x = xb + lane;
+            bool hit = x < w - 1 && is_extremum(D, w, x, y, thr);
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (WRITE && hit) {
+                unsigned pos = base + count + __popc(m & ((1u << lane) - 1u));
+                if (pos < cap) {
+                    Cand c; c.x = x; c.y = y; c.e = e; c.v = D[(size_t)y * w + x];
+                    cand[(size_t)blockIdx.z * cap + pos] = c;
+                } else *overflow = 1u;
+            }
+            count += __popc(m);
+        }
+    }
+    if (!WRITE && lane == 0) rowcount[(size_t)blockIdx.z * T.total_rows + warp] = count;
+}
+
+// exclusive scan of per-row counts; one CTA of 1024 threads per frame
+__global__ void __launch_bounds__(1024) k_scan_rows(const unsigned *__restrict__ rowcount, unsigned *__restrict__ rowoff,
+                                                    unsigned *__restrict__ total, int n) {
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_carry;
+    const unsigned *in = rowcount + (size_t)blockIdx.x * n;
+    unsigned *out = rowoff + (size_t)blockIdx.x * n;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        int i = base + threadIdx.x;
+        unsigned v = i < n ? in[i] : 0u, x = v;
+        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned y = s_warp[lane], z = y;
+            for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += t; }
+            s_warp[lane] = z - y;
+        }
+        __syncthreads();
+        unsigned excl = s_carry + s_warp[wid] + x - v;
+        if (i < n) out[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total[blockIdx.x] = s_carry;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sequential-equivalent duplicate suppression (scale_space_extrema.rs:61-117).  One CTA per frame walks
+// the candidates in reference order; for each one the whole CTA searches the keypoint cache in parallel
+// for the FIRST (lowest slot) cached keypoint of the same or previous class within `size`, then thread 0
+// applies the reference's replace / drop / append rule.  Candidates failing the border test never modify
+// the cache (:95-116) and are skipped up front.
+__global__ void __launch_bounds__(1024) k_suppress(const Cand *__restrict__ cand, const unsigned *__restrict__ ncand,
+                                                   unsigned capc, EvoTable T, cvb_keypoint *__restrict__ cache,
+                                                   unsigned *__restrict__ ncache, unsigned capk, unsigned *overflow) {
+    __shared__ unsigned s_min[32];
+    __shared__ unsigned s_n;
+    __shared__ unsigned s_kmin;
+    const int b = blockIdx.x;
+    const Cand *cd = cand + (size_t)b * capc;
+    cvb_keypoint *kc = cache + (size_t)b * capk;
+    const unsigned n = min(ncand[b], capc);
+    const float smax = 10.0f * sqrtf(2.0f);
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (unsigned ci = 0; ci < n; ci++) {
+        const Cand c = cd[ci];
+        const EvoDev ev = T.e[c.e];
+        const float ratio = (float)(1 << ev.octave);
+        const float size = ev.size;
+        const float sigma_size = roundf(size / ratio);
+        const float px = (float)c.x, py = (float)c.y;
+        // border test (:97-104), evaluated first: a failing candidate has no effect on the cache
+        const float left_x = roundf(px - smax * sigma_size) - 1.f, right_x = roundf(px + smax * sigma_size) + 1.f;
+        const float up_y = roundf(py - smax * sigma_size) - 1.f, down_y = roundf(py + smax * sigma_size) + 1.f;
+        const bool is_out = left_x < 0.f || right_x >= (float)ev.w || up_y < 0.f || down_y >= (float)ev.h;
+        if (is_out) continue;   // uniform across the CTA
+        const unsigned nc = s_n;
+        const float fx = px * ratio, fy = py * ratio, s2 = size * size;
+        unsigned kmin = 0xffffffffu;
+        for (unsigned k = threadIdx.x; k < nc; k += 1024) {
+            const cvb_keypoint p = kc[k];
+            if ((unsigned)c.e == p.class_id || (c.e != 0 && (unsigned)(c.e - 1) == p.class_id)) {
+                float dx = fx - p.x, dy = fy - p.y;
+                float dist = dx * dx + dy * dy;
+                if (dist <= s2) { kmin = k; break; }
+            }
+        }
+        for (int o = 16; o; o >>= 1) kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        if (lane == 0) s_min[wid] = kmin;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned m = s_min[lane];
+            for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) {
+                const float resp = fabsf(c.v);
+                bool is_repeated = false, is_extremum = true;
+                if (m != 0xffffffffu) {
+                    if (resp > kc[m].response) is_repeated = true; else is_extremum = false;
+                }
+                if (is_extremum) {
+                    cvb_keypoint kp;
+                    kp.x = px * ratio + 0.5f * (ratio - 1.0f);
+                    kp.y = py * ratio + 0.5f * (ratio - 1.0f);
+                    kp.response = resp; kp.size = size; kp.angle = 0.f;
+                    kp.octave = (uint32_t)ev.octave; kp.class_id = (uint32_t)c.e;
+                    if (is_repeated) kc[m] = kp;
+                    else if (nc < capk) { kc[nc] = kp; s_n = nc + 1; }
+                    else *overflow = 2u;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ncache[b] = s_n;
+}
+
+// Upper-scale filter (:120-140): cache[i] is dropped when a LATER cache entry of class+1 lies within
+// size_i and is at least as strong.  Thread per i; keep flags preserve order.
+__global__ void __launch_bounds__(NT) k_filter_upper(const cvb_keypoint *__restrict__ cache,
+                                                     const unsigned *__restrict__ ncache, unsigned capk,
+                                                     unsigned char *__restrict__ keep) {
+    const int b = blockIdx.y;
+    const unsigned n = ncache[b];
+    const cvb_keypoint *kc = cache + (size_t)b * capk;
+    for (unsigned i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT) {
+        const cvb_keypoint a = kc[i];
+        bool rep = false;
+        for (unsigned j = i + 1; j < n; j++) {
+            const cvb_keypoint q = kc[j];
+            if (a.class_id + 1 == q.class_id) {
+                float dx = a.x - q.x, dy = a.y - q.y;
+                float dist = dx * dx + dy * dy;
+                if (dist <= a.size * a.size && a.response <= q.response) { rep = true; break; }
+            }
+        }
+        keep[(size_t)b * capk + i] = rep ? 0 : 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sub-pixel refinement + main orientation, one warp per keypoint (scale_space_extrema.rs:229-362).
+struct OrientTables {
+    int nwin;                 // number of sliding windows (ang1 = 0, += 0.15f while < 2pi)
+    float ang1[64];
+    signed char di[109], dj[109];
+    float gw[109];            // GAUSS25[id[j+6]][id[i+6]]
+};
+
+__global__ void __launch_bounds__(NT) k_refine_orient(const cvb_keypoint *__restrict__ cache,
+                                                      const unsigned *__restrict__ ncache, unsigned capk,
+                                                      const unsigned char *__restrict__ keep, EvoTable T,
+                                                      const float *__restrict__ Ldet, const float *__restrict__ Lx,
+                                                      const float *__restrict__ Ly, size_t bstride,
+                                                      const OrientTables *__restrict__ OT,
+                                                      cvb_keypoint *__restrict__ refined,
+                                                      unsigned char *__restrict__ valid) {
+    __shared__ float s_rx[NT / 32][112], s_ry[NT / 32][112], s_an[NT / 32][112];
+    const int b = blockIdx.y;
+    const unsigned n = ncache[b];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const float PI = 3.14159265358979323846f;
+    const float two_pi = 2.0f * PI;
+    for (unsigned q = blockIdx.x * (NT / 32) + wid; q < n; q += gridDim.x * (NT / 32)) {
+        const size_t gi = (size_t)b * capk + q;
+        if (!keep[gi]) { if (lane == 0) valid[gi] = 0; continue; }
+        cvb_keypoint kp = cache[gi];
+        const EvoDev ev = T.e[kp.class_id];
+        const size_t poff = (size_t)b * bstride + ev.off;
+        const float *D = Ldet + poff;
+        const int w = ev.w;
+        float ratio = (float)(1u << kp.octave);
+        // `as usize` saturates negatives to 0
+        float rxf = roundf(kp.x / ratio), ryf = roundf(kp.y / ratio);
+        long long x = rxf > 0.f ? (long long)rxf : 0, y = ryf > 0.f ? (long long)ryf : 0;
+        float x_i = D[y * w + x], x_p = D[y * w + x + 1], x_m = D[y * w + x - 1];
+        float y_p = D[(y + 1) * w + x], y_m = D[(y - 1) * w + x];
+        float x_p_y_p = D[(y + 1) * w + x + 1], x_p_y_m = D[(y - 1) * w + x + 1];
+        float x_m_y_p = D[(y + 1) * w + x - 1], x_m_y_m = D[(y - 1) * w + x - 1];
+        float d_x = 0.5f * (x_p - x_m), d_y = 0.5f * (y_p - y_m);
+        float d_xx = x_p + x_m - 2.f * x_i;
+        float d_yy = y_p + y_m - 2.f * x_i;
+        float d_xy = 0.25f * (x_p_y_p + x_m_y_m) - 0.25f * (x_p_y_m + x_m_y_p);
+        float inv_det = 1.0f / (d_xx * d_yy - d_xy * d_xy);
+        float a0 = inv_det * d_yy, a1 = inv_det * -d_xy, a2 = inv_det * -d_xy, a3 = inv_det * d_xx;
+        float dst0 = -d_x * a0 + -d_y * a1;
+        float dst1 = -d_x * a2 + -d_y * a3;
+        if (!(fabsf(dst0) <= 1.0f && fabsf(dst1) <= 1.0f)) { if (lane == 0) valid[gi] = 0; continue; }
+        kp.x = (float)x + dst0; kp.y = (float)y + dst1;
+        float power = (float)(1u << ev.octave);
+        kp.x = kp.x * power + 0.5f * (power - 1.f);
+        kp.y = kp.y * power + 0.5f * (power - 1.f);
+        kp.size *= 2.f;
+        // ---- compute_main_orientation (:229-288)
+        const float *PX = Lx + poff, *PY = Ly + poff;
+        ratio = (float)(1 << ev.octave);
+        const float s = roundf(0.5f * kp.size / ratio);
+        const float xf = kp.x / ratio, yf = kp.y / ratio;
+        for (int idx = lane; idx < 109; idx += 32) {
+            float fy = roundf(yf + (float)OT->dj[idx] * s), fx = roundf(xf + (float)OT->di[idx] * s);
+            long long iy = fy > 0.f ? (long long)fy : 0, ix = fx > 0.f ? (long long)fx : 0;
+            ix = ix > ev.w - 1 ? ev.w - 1 : ix;   // the reference would panic here; never taken after the border test
+            iy = iy > ev.h - 1 ? ev.h - 1 : iy;
+            float gwt = OT->gw[idx];
+            float rx = gwt * PX[iy * w + ix], ry = gwt * PY[iy * w + ix];
+            s_rx[wid][idx] = rx; s_ry[wid][idx] = ry;
+            s_an[wid][idx] = dlm::fast_atan2_equiv(ry, rx);
+        }
+        __syncwarp();
+        float best_val = 0.f, best_sx = 0.f, best_sy = 0.f;
+        int best_w = 0x7fffffff;
+        for (int wi = lane; wi < OT->nwin; wi += 32) {
+            const float ang1 = OT->ang1[wi];
+            const float ang2 = (ang1 + PI / 3.0f > two_pi) ? ang1 - 5.0f * PI / 3.0f : ang1 + PI / 3.0f;
+            float sum_x = 0.f, sum_y = 0.f;
+            for (int k = 0; k < 109; k++) {
+                float ang = s_an[wid][k];
+                if ((ang1 < ang2 && ang1 < ang && ang < ang2) ||
+                    (ang2 < ang1 && ((ang > 0.f && ang < ang2) || (ang > ang1 && ang < two_pi)))) {
+                    sum_x += s_rx[wid][k];
+                    sum_y += s_ry[wid][k];
+                }
+            }
+            float val = sum_x * sum_x + sum_y * sum_y;
+            if (val > best_val) { best_val = val; best_sx = sum_x; best_sy = sum_y; best_w = wi; }
+        }
+        // sequential `if val > max` == first window attaining the maximum (when > 0)
+        for (int o = 16; o; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, best_val, o);
+            float osx = __shfl_xor_sync(0xffffffffu, best_sx, o), osy = __shfl_xor_sync(0xffffffffu, best_sy, o);
+            int ow = __shfl_xor_sync(0xffffffffu, best_w, o);
+            if (ov > best_val || (ov == best_val && ow < best_w)) { best_val = ov; best_sx = osx; best_sy = osy; best_w = ow; }
+        }
+        if (lane == 0) {
+            kp.angle = best_val > 0.f ? dlm::fast_atan2_equiv(best_sy, best_sx) : 0.f;
+            refined[gi] = kp;
+            valid[gi] = 1;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sort by descending response + truncate (lib.rs:326-327) as a rank sort over the valid refined
+// keypoints: rank = #{ j valid : r_j > r_i  or (r_j == r_i and j < i) }.  (The reference sort is
+// unstable; ties keep their original order here and in the oracle.)
+__global__ void __launch_bounds__(NT) k_rank_sort(const cvb_keypoint *__restrict__ refined,
+                                                  const unsigned char *__restrict__ valid,
+                                                  const unsigned *__restrict__ ncache, unsigned capk,
+                                                  long long max_features, cvb_keypoint *__restrict__ sorted,
+                                                  unsigned *__restrict__ nsorted) {
+    __shared__ float s_r[NT];
+    const int b = blockIdx.y;
+    const unsigned n = ncache[b];
+    const cvb_keypoint *kp = refined + (size_t)b * capk;
+    const unsigned char *vl = valid + (size_t)b * capk;
+    unsigned nvalid = 0;
+    for (unsigned base = blockIdx.x * NT; base < ((n + NT - 1) / NT) * NT; base += gridDim.x * NT) {
+        const unsigned i = base + threadIdx.x;
+        const bool vi = i < n && vl[i];
+        const float ri = vi ? kp[i].response : 0.f;
+        unsigned rank = 0;
+        nvalid = 0;
+        for (unsigned t = 0; t < n; t += NT) {
+            unsigned j = t + threadIdx.x;
+            __syncthreads();
+            s_r[threadIdx.x] = (j < n && vl[j]) ? kp[j].response : -1.0f;   // responses are |v| >= 0
+            __syncthreads();
+            unsigned lim = min((unsigned)NT, n - t);
+            for (unsigned u = 0; u < lim; u++) {
+                float rj = s_r[u];
+                if (rj < 0.f) continue;
+                nvalid++;
+                if (rj > ri || (rj == ri && (t + u) < i)) rank++;
+            }
+        }
+        if (vi && (max_features < 0 || (long long)rank < max_features)) sorted[(size_t)b * capk + rank] = kp[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (n == 0) nvalid = 0;
+        unsigned keepn = nvalid;
+        if (max_features >= 0 && (long long)keepn > max_features) keepn = (unsigned)max_features;
+        nsorted[b] = keepn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// M-LDB descriptor, one warp per keypoint, one lane per grid cell (descriptors.rs:55-202).
+struct DescTables {
+    // 29 cells: 2x2 (step 10), 3x3 (step ceil(10*2/3)=7), 4x4 (step 5) over [-pattern, pattern)
+    int ncells;
+    short ci[32], cj[32], cstep[32];
+    int nbits;
+    unsigned char ba[512], bb[512], bch[512];   // bit t = values[ba][ch] > values[bb][ch]
+};
+
+__global__ void __launch_bounds__(NT) k_descriptors(const cvb_keypoint *__restrict__ sorted,
+                                                    const unsigned *__restrict__ nsorted, unsigned capk, EvoTable T,
+                                                    const float *__restrict__ Lt, const float *__restrict__ Lx,
+                                                    const float *__restrict__ Ly, size_t bstride,
+                                                    const DescTables *__restrict__ DT, int nch,
+                                                    unsigned char *__restrict__ desc_tmp,
+                                                    unsigned char *__restrict__ ok) {
+    __shared__ float s_val[NT / 32][32][3];
+    const int b = blockIdx.y;
+    const unsigned n = nsorted[b];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (unsigned q = blockIdx.x * (NT / 32) + wid; q < n; q += gridDim.x * (NT / 32)) {
+        const size_t gi = (size_t)b * capk + q;
+        const cvb_keypoint kp = sorted[gi];
+        const EvoDev ev = T.e[kp.class_id];
+        const size_t poff = (size_t)b * bstride + ev.off;
+        const float *PT = Lt + poff, *PX = Lx + poff, *PY = Ly + poff;
+        const int W = ev.w, H = ev.h;
+        const float ratio = (float)(1u << kp.octave);
+        const float scale = roundf(0.5f * kp.size / ratio);
+        const float xf = kp.x / ratio, yf = kp.y / ratio;
+        const float co = dlm::cosf_glibc(kp.angle), si = dlm::sinf_glibc(kp.angle);
+        bool oob = false;
+        if (lane < DT->ncells) {
+            const int i0 = DT->ci[lane], j0 = DT->cj[lane], step = DT->cstep[lane];
+            float di = 0.f, dx = 0.f, dy = 0.f;
+            int ns = 0;
+            for (int k = i0; k < i0 + step && !oob; k++)
+                for (int l = j0; l < j0 + step; l++) {
+                    const float lf = (float)l, kf = (float)k;
+                    const float sample_y = yf + (lf * co * scale + kf * si * scale);
+                    const float sample_x = xf + (-lf * si * scale + kf * co * scale);
+                    const float ry_ = roundf(sample_y), rx_ = roundf(sample_x);
+                    if (!(rx_ >= 0.f && rx_ < (float)W) || !(ry_ >= 0.f && ry_ < (float)H)) { oob = true; break; }
+                    const size_t p = (size_t)(int)ry_ * W + (int)rx_;
+                    di += PT[p];
+                    if (nch > 1) {
+                        const float rx = PX[p], ry = PY[p];
+                        if (nch == 2) dx += sqrtf(rx * rx + ry * ry);
+                        else {
+                            const float rry = rx * co + ry * si;
+                            const float rrx = -rx * si + ry * co;
+                            dx += rrx; dy += rry;
+                        }
+                    }
+                    ns++;
+                }
+            di /= (float)ns; dx /= (float)ns; dy /= (float)ns;
+            s_val[wid][lane][0] = di; s_val[wid][lane][1] = dx; s_val[wid][lane][2] = dy;
+        }
+        const bool any_oob = __any_sync(0xffffffffu, oob);
+        __syncwarp();
+        // 512 output bits, 16 per lane
+        unsigned bits = 0;
+        if (!any_oob) {
+            for (int t = 0; t < 16; t++) {
+                int bit = lane * 16 + t;
+                if (bit < DT->nbits) {
+                    float a = s_val[wid][DT->ba[bit]][DT->bch[bit]], c = s_val[wid][DT->bb[bit]][DT->bch[bit]];
+                    bits |= (a > c ? 1u : 0u) << t;
+                }
+            }
+        }
+        ((unsigned short *)(desc_tmp + gi * 64))[lane] = (unsigned short)bits;
+        if (lane == 0) ok[gi] = any_oob ? 0 : 1;
+        __syncwarp();
+    }
+}
+
+// Ordered compaction of the surviving keypoints/descriptors into the caller's output arrays.
+__global__ void __launch_bounds__(1024) k_compact_final(const cvb_keypoint *__restrict__ sorted,
+                                                        const unsigned char *__restrict__ desc_tmp,
+                                                        const unsigned char *__restrict__ ok,
+                                                        const unsigned *__restrict__ nsorted, unsigned capk,
+                                                        cvb_keypoint *__restrict__ kp_out,
+                                                        unsigned char *__restrict__ desc_out, unsigned cap_out,
+                                                        unsigned *__restrict__ n_out, unsigned *overflow) {
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_carry;
+    const int b = blockIdx.x;
+    const unsigned n = nsorted[b];
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (unsigned base = 0; base < n; base += 1024) {
+        unsigned i = base + threadIdx.x;
+        unsigned v = (i < n && ok[(size_t)b * capk + i]) ? 1u : 0u, x = v;
+        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned y = s_warp[lane], z = y;
+            for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += t; }
+            s_warp[lane] = z - y;
+        }
+        __syncthreads();
+        unsigned pos = s_carry + s_warp[wid] + x - v;
+        if (v) {
+            if (pos < cap_out) {
+                kp_out[(size_t)b * cap_out + pos] = sorted[(size_t)b * capk + i];
+                const uint4 *s = (const uint4 *)(desc_tmp + ((size_t)b * capk + i) * 64);
+                uint4 *d = (uint4 *)(desc_out + ((size_t)b * cap_out + pos) * 64);
+                d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+            } else *overflow = 3u;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = pos + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_out[b] = s_carry;
+}
+
+}  // namespace akz

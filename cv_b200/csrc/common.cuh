@@ -1,0 +1,45 @@
+// cv_b200/csrc/common.cuh -- shared declarations for libcvb200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/cvb200.h"
+
+struct AkazeWorkspace;
+struct MatchWorkspace;
+
+struct cvb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::string err;
+    uint64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int num_sms = 148;
+    AkazeWorkspace *akaze = nullptr;
+    MatchWorkspace *match = nullptr;
+};
+
+int cvb_set_error(cvb_ctx *ctx, int code, const char *fmt, ...);
+void akaze_workspace_free(AkazeWorkspace *ws);
+void match_workspace_free(MatchWorkspace *ws);
+
+#define CVB_CUDA(ctx, call)                                                                          \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return cvb_set_error((ctx), CVB_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,        \
+                                 cudaGetErrorString(e__));                                           \
+    } while (0)
+
+#define CVB_LAUNCH_CHECK(ctx)                                                                        \
+    do {                                                                                             \
+        (ctx)->launches++;                                                                           \
+        cudaError_t e__ = cudaPeekAtLastError();                                                     \
+        if (e__ != cudaSuccess)                                                                      \
+            return cvb_set_error((ctx), CVB_ECUDA, "%s:%d launch: %s", __FILE__, __LINE__,           \
+                                 cudaGetErrorString(e__));                                           \
+    } while (0)
+
+static inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }

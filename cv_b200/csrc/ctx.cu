@@ -1,0 +1,79 @@
+// cv_b200/csrc/ctx.cu -- context, error reporting, stream/event plumbing of libcvb200.so.
+#include <stdarg.h>
+#include <stdio.h>
+#include "common.cuh"
+
+int cvb_set_error(cvb_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+extern "C" {
+
+const char *cvb_version(void) { return "cvb200 0.1.0 (sm_100a)"; }
+
+int cvb_ctx_create_on_stream(int device, void *cuda_stream, cvb_ctx **out) {
+    if (!out) return CVB_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return CVB_ENODEV;   // no CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess) return CVB_ENODEV;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return CVB_ENODEV;
+    if (prop.major < 10) return CVB_ENODEV;   // kernels are built for sm_100a only
+    cvb_ctx *ctx = new cvb_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
+    else if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CVB_ECUDA; }
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    *out = ctx;
+    return CVB_OK;
+}
+
+int cvb_ctx_create(int device, cvb_ctx **out) { return cvb_ctx_create_on_stream(device, nullptr, out); }
+
+void cvb_ctx_destroy(cvb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    akaze_workspace_free(ctx->akaze);
+    match_workspace_free(ctx->match);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int cvb_ctx_sync(cvb_ctx *ctx) {
+    if (!ctx) return CVB_EINVAL;
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+const char *cvb_last_error(const cvb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+uint64_t cvb_ctx_launch_count(const cvb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int cvb_ctx_timer_begin(cvb_ctx *ctx) {
+    if (!ctx) return CVB_EINVAL;
+    CVB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    return 0;
+}
+
+int cvb_ctx_timer_end(cvb_ctx *ctx, float *ms_out) {
+    if (!ctx || !ms_out) return CVB_EINVAL;
+    CVB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CVB_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    CVB_CUDA(ctx, cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,333 @@
+// cv_b200/csrc/match.cu -- brute-force Hamming k-NN over 64-byte descriptors (sm_100a).
+//
+// Replaces `space::LinearKnn{metric: bitarray::Hamming, iter}.knn(query, k)` (external crates space 0.17 /
+// bitarray 0.9; call sites /root/reference/akaze/tests/estimate_pose.rs:78-97, tutorial-code/
+// chapter4-feature-matching/src/main.rs:91-106, cv-sfm/src/lib.rs:3097-3114) for ALL queries at once.
+// Semantics kept bit-exact: distance = popcount(a ^ b) over 512 bits; the k smallest in ascending
+// distance; among equal distances the lower database index comes first.
+//
+// Kernel: one query per thread held in registers (8 x u64); the database streams through shared memory
+// in 8 KB tiles fetched by the TMA engine (cp.async.bulk + mbarrier, double buffered) and is read by all
+// threads at the same address (broadcast).  (distance, index) is packed into one 32-bit key
+// (distance << 22 | local index) so the running best-k is maintained with integer min/max only.  The
+// database is split across gridDim.y so that the grid covers all SMs; a second small kernel merges the
+// per-split lists in index order.  The bound is the integer popc pipe, not HBM (working set is L2 resident).
+#include <stdio.h>
+#include <algorithm>
+#include <vector>
+#include "common.cuh"
+
+namespace {
+
+constexpr int QT = 128;          // queries per CTA (1 per thread)
+constexpr int DTILE = 128;       // database descriptors per shared-memory tile (8 KB)
+constexpr int MAXKNN = 8;
+constexpr unsigned IDX_BITS = 22;
+constexpr unsigned IDX_MASK = (1u << IDX_BITS) - 1u;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit, completion signalled on an mbarrier
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int K>
+__device__ __forceinline__ void insert_key(uint32_t (&best)[K], uint32_t key) {
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        uint32_t lo = min(best[i], key);
+        key = max(best[i], key);
+        best[i] = lo;
+    }
+}
+
+// grid = (ceil(n_max/QT), splits); partial[(q * splits + s) * K + i] = key with split-local index
+template <int K>
+__global__ void __launch_bounds__(QT) k_hamming_knn(const uint8_t *__restrict__ queries, const uint32_t *__restrict__ n_dev,
+                                                    uint32_t n_host, const uint8_t *__restrict__ db,
+                                                    const uint32_t *__restrict__ m_dev, uint32_t m_host, uint32_t chunk,
+                                                    uint32_t *__restrict__ partial) {
+    __shared__ __align__(128) uint8_t s_db[2][DTILE * 64];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    const uint32_t n = n_dev ? *n_dev : n_host, m = m_dev ? *m_dev : m_host;
+    const uint32_t q = blockIdx.x * QT + threadIdx.x;
+    if (blockIdx.x * QT >= n) return;
+    const uint32_t lo = min(blockIdx.y * chunk, m), hi = min(lo + chunk, m);
+    const uint32_t cnt = hi - lo;
+    uint64_t qa[8];
+    {
+        const uint4 *p = (const uint4 *)(queries + (size_t)min(q, n - 1) * 64);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint4 v = p[i];
+            qa[2 * i] = ((uint64_t)v.y << 32) | v.x;
+            qa[2 * i + 1] = ((uint64_t)v.w << 32) | v.z;
+        }
+    }
+    uint32_t best[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) best[i] = 0xffffffffu;
+    const uint32_t ntiles = (cnt + DTILE - 1) / DTILE;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](uint32_t t) {
+        const uint32_t first = t * DTILE, rows = min((uint32_t)DTILE, cnt - first), bytes = rows * 64u;
+        mbar_expect_tx(&s_bar[t & 1], bytes);
+        tma_load_1d(s_db[t & 1], db + (size_t)(lo + first) * 64, bytes, &s_bar[t & 1]);
+    };
+    if (threadIdx.x == 0) {
+        if (ntiles > 0) issue(0);
+        if (ntiles > 1) issue(1);
+    }
+    for (uint32_t t = 0; t < ntiles; t++) {
+        mbar_wait(&s_bar[t & 1], (t >> 1) & 1);
+        const uint32_t first = t * DTILE, rows = min((uint32_t)DTILE, cnt - first);
+        const uint64_t *tile = (const uint64_t *)s_db[t & 1];
+#pragma unroll 4
+        for (uint32_t r = 0; r < rows; r++) {
+            const ulonglong2 *d = (const ulonglong2 *)(tile + r * 8);
+            uint32_t dist = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                ulonglong2 v = d[i];   // same address for every thread: shared-memory broadcast
+                dist += __popcll(qa[2 * i] ^ v.x) + __popcll(qa[2 * i + 1] ^ v.y);
+            }
+            insert_key<K>(best, (dist << IDX_BITS) | (first + r));
+        }
+        __syncthreads();   // everyone is done with buffer t&1
+        if (threadIdx.x == 0 && t + 2 < ntiles) issue(t + 2);
+    }
+    if (q < n) {
+        uint32_t *out = partial + ((size_t)q * gridDim.y + blockIdx.y) * K;
+#pragma unroll
+        for (int i = 0; i < K; i++) out[i] = best[i];
+    }
+}
+
+// merge the per-split lists (split order == index order) into global (idx, dist)
+template <int K>
+__global__ void k_knn_merge(const uint32_t *__restrict__ partial, const uint32_t *__restrict__ n_dev, uint32_t n_host,
+                            uint32_t splits, uint32_t chunk, uint32_t *__restrict__ idx_out, uint32_t *__restrict__ dist_out) {
+    const uint32_t n = n_dev ? *n_dev : n_host;
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    uint64_t best[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) best[i] = ~0ull;
+    for (uint32_t s = 0; s < splits; s++) {
+        const uint32_t *p = partial + ((size_t)q * splits + s) * K;
+#pragma unroll
+        for (int i = 0; i < K; i++) {
+            uint32_t key = p[i];
+            if (key == 0xffffffffu) continue;
+            uint64_t g = ((uint64_t)(key >> IDX_BITS) << 32) | (uint64_t)((key & IDX_MASK) + s * chunk);
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                uint64_t lo = min(best[j], g);
+                g = max(best[j], g);
+                best[j] = lo;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        idx_out[(size_t)q * K + i] = best[i] == ~0ull ? 0xffffffffu : (uint32_t)(best[i] & 0xffffffffu);
+        dist_out[(size_t)q * K + i] = best[i] == ~0ull ? 0xffffffffu : (uint32_t)(best[i] >> 32);
+    }
+}
+
+// cv-sfm symmetric_matching (cv-sfm/src/lib.rs:3097-3133) on the two 2-NN tables
+__global__ void k_symmetric(const uint32_t *__restrict__ fidx, const uint32_t *__restrict__ fdist,
+                            const uint32_t *__restrict__ ridx, const uint32_t *__restrict__ rdist, uint32_t n, uint32_t m,
+                            uint32_t better_by, uint32_t *__restrict__ flag) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    uint32_t f = 0xffffffffu;
+    if (n >= 2 && m >= 2) {
+        if (fdist[2 * a] + better_by <= fdist[2 * a + 1]) {
+            uint32_t bix = fidx[2 * a];
+            if (rdist[2 * bix] + better_by <= rdist[2 * bix + 1] && ridx[2 * bix] == a) f = bix;
+        }
+    }
+    flag[a] = f;
+}
+
+}  // namespace
+
+struct MatchWorkspace {
+    uint32_t *partial = nullptr;
+    size_t partial_elems = 0;
+    uint8_t *q = nullptr, *db = nullptr;
+    size_t q_bytes = 0, db_bytes = 0;
+    uint32_t *idx = nullptr, *dist = nullptr, *idx2 = nullptr, *dist2 = nullptr, *flag = nullptr;
+    size_t idx_elems = 0, dist_elems = 0, idx2_elems = 0, dist2_elems = 0, flag_elems = 0;
+};
+
+void match_workspace_free(MatchWorkspace *ws) {
+    if (!ws) return;
+    cudaFree(ws->partial); cudaFree(ws->q); cudaFree(ws->db); cudaFree(ws->idx); cudaFree(ws->dist);
+    cudaFree(ws->idx2); cudaFree(ws->dist2); cudaFree(ws->flag);
+    delete ws;
+}
+
+namespace {
+
+template <typename T>
+int grow(cvb_ctx *ctx, T **p, size_t *have, size_t need) {
+    if (*have >= need && *p) return 0;
+    if (*p) { cudaStreamSynchronize(ctx->stream); cudaFree(*p); *p = nullptr; }
+    size_t n = std::max<size_t>(need, 1);
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e != cudaSuccess) { *have = 0; return cvb_set_error(ctx, CVB_ENOMEM, "cudaMalloc(%zu): %s", n * sizeof(T), cudaGetErrorString(e)); }
+    *have = n;
+    return 0;
+}
+
+template <int K>
+int launch_knn(cvb_ctx *ctx, const uint8_t *q, const uint32_t *n_dev, uint32_t n, const uint8_t *db, const uint32_t *m_dev,
+               uint32_t m, uint32_t splits, uint32_t chunk, uint32_t *partial, uint32_t *idx, uint32_t *dist) {
+    dim3 grid(cdiv(n, QT), splits);
+    k_hamming_knn<K><<<grid, QT, 0, ctx->stream>>>(q, n_dev, n, db, m_dev, m, chunk, partial);
+    CVB_LAUNCH_CHECK(ctx);
+    k_knn_merge<K><<<cdiv(n, 128), 128, 0, ctx->stream>>>(partial, n_dev, n, splits, chunk, idx, dist);
+    CVB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int knn_dev(cvb_ctx *ctx, const uint8_t *q, const uint32_t *n_dev, uint32_t n, const uint8_t *db, const uint32_t *m_dev,
+            uint32_t m, uint32_t k, uint32_t *idx, uint32_t *dist) {
+    if (k < 1 || k > MAXKNN) return cvb_set_error(ctx, CVB_EINVAL, "k must be 1..%d", MAXKNN);
+    if (n == 0) return 0;
+    if (((uintptr_t)q & 15) || ((uintptr_t)db & 15)) return cvb_set_error(ctx, CVB_EINVAL, "descriptor arrays must be 16-byte aligned");
+    if (!ctx->match) ctx->match = new MatchWorkspace();
+    MatchWorkspace *ws = ctx->match;
+    // split the database so that the grid covers the machine (>= 2 CTAs per SM) and chunks fit IDX_BITS
+    uint32_t qblocks = cdiv(n, QT);
+    uint32_t splits = std::max<uint32_t>(1, cdiv((uint32_t)ctx->num_sms * 4u, qblocks));
+    splits = std::min<uint32_t>(splits, std::max<uint32_t>(1, cdiv(std::max<uint32_t>(m, 1), DTILE * 2)));
+    uint32_t chunk = cdiv(std::max<uint32_t>(m, 1), splits);
+    chunk = cdiv(chunk, DTILE) * DTILE;
+    while (chunk > IDX_MASK) { splits *= 2; chunk = cdiv(cdiv(m, splits), DTILE) * DTILE; }
+    splits = cdiv(std::max<uint32_t>(m, 1), chunk);
+    int rc = grow(ctx, &ws->partial, &ws->partial_elems, (size_t)n * splits * k);
+    if (rc) return rc;
+    switch (k) {
+    case 1: return launch_knn<1>(ctx, q, n_dev, n, db, m_dev, m, splits, chunk, ws->partial, idx, dist);
+    case 2: return launch_knn<2>(ctx, q, n_dev, n, db, m_dev, m, splits, chunk, ws->partial, idx, dist);
+    case 3: return launch_knn<3>(ctx, q, n_dev, n, db, m_dev, m, splits, chunk, ws->partial, idx, dist);
+    case 4: return launch_knn<4>(ctx, q, n_dev, n, db, m_dev, m, splits, chunk, ws->partial, idx, dist);
+    case 5: return launch_knn<5>(ctx, q, n_dev, n, db, m_dev, m, splits, chunk, ws->partial, idx, dist);
+    case 6: return launch_knn<6>(ctx, q, n_dev, n, db, m_dev, m, splits, chunk, ws->partial, idx, dist);
+    case 7: return launch_knn<7>(ctx, q, n_dev, n, db, m_dev, m, splits, chunk, ws->partial, idx, dist);
+    default: return launch_knn<8>(ctx, q, n_dev, n, db, m_dev, m, splits, chunk, ws->partial, idx, dist);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int cvb_hamming_knn_dev(cvb_ctx *ctx, const uint8_t *q, uint32_t n, const uint8_t *db, uint32_t m, uint32_t k, uint32_t *idx,
+                        uint32_t *dist) {
+    if (!ctx) return CVB_EINVAL;
+    if ((n && !q) || (m && !db) || (n && (!idx || !dist))) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return knn_dev(ctx, q, nullptr, n, db, nullptr, m, k, idx, dist);
+}
+
+int cvb_hamming_knn_dev_counts(cvb_ctx *ctx, const uint8_t *q, const uint32_t *n_dev, uint32_t n_max, const uint8_t *db,
+                               const uint32_t *m_dev, uint32_t m_max, uint32_t k, uint32_t *idx, uint32_t *dist) {
+    if (!ctx) return CVB_EINVAL;
+    if (!q || !db || !idx || !dist || !n_dev || !m_dev) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return knn_dev(ctx, q, n_dev, n_max, db, m_dev, m_max, k, idx, dist);
+}
+
+int cvb_hamming_knn(cvb_ctx *ctx, const uint8_t *q, uint32_t n, const uint8_t *db, uint32_t m, uint32_t k, uint32_t *idx,
+                    uint32_t *dist) {
+    if (!ctx) return CVB_EINVAL;
+    if ((n && !q) || (m && !db) || (n && (!idx || !dist))) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    if (k < 1 || k > MAXKNN) return cvb_set_error(ctx, CVB_EINVAL, "k must be 1..%d", MAXKNN);
+    if (n == 0) return 0;
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->match) ctx->match = new MatchWorkspace();
+    MatchWorkspace *ws = ctx->match;
+    int rc;
+    if ((rc = grow(ctx, &ws->q, &ws->q_bytes, (size_t)n * 64))) return rc;
+    if ((rc = grow(ctx, &ws->db, &ws->db_bytes, (size_t)std::max<uint32_t>(m, 1) * 64))) return rc;
+    if ((rc = grow(ctx, &ws->idx, &ws->idx_elems, (size_t)n * k))) return rc;
+    if ((rc = grow(ctx, &ws->dist, &ws->dist_elems, (size_t)n * k))) return rc;
+    cudaStream_t st = ctx->stream;
+    CVB_CUDA(ctx, cudaMemcpyAsync(ws->q, q, (size_t)n * 64, cudaMemcpyHostToDevice, st));
+    if (m) CVB_CUDA(ctx, cudaMemcpyAsync(ws->db, db, (size_t)m * 64, cudaMemcpyHostToDevice, st));
+    rc = knn_dev(ctx, ws->q, nullptr, n, ws->db, nullptr, m, k, ws->idx, ws->dist);
+    if (rc) return rc;
+    CVB_CUDA(ctx, cudaMemcpyAsync(idx, ws->idx, sizeof(uint32_t) * (size_t)n * k, cudaMemcpyDeviceToHost, st));
+    CVB_CUDA(ctx, cudaMemcpyAsync(dist, ws->dist, sizeof(uint32_t) * (size_t)n * k, cudaMemcpyDeviceToHost, st));
+    CVB_CUDA(ctx, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int cvb_match_symmetric(cvb_ctx *ctx, const uint8_t *a, uint32_t n, const uint8_t *b, uint32_t m, uint32_t better_by,
+                        uint32_t *pairs_out, uint32_t cap, uint32_t *n_out) {
+    if (!ctx) return CVB_EINVAL;
+    if (!n_out || (n && !a) || (m && !b)) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    *n_out = 0;
+    if (n < 2 || m < 2) return 0;   // cv-sfm/src/lib.rs:3099-3101
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->match) ctx->match = new MatchWorkspace();
+    MatchWorkspace *ws = ctx->match;
+    int rc;
+    if ((rc = grow(ctx, &ws->q, &ws->q_bytes, (size_t)n * 64))) return rc;
+    if ((rc = grow(ctx, &ws->db, &ws->db_bytes, (size_t)m * 64))) return rc;
+    if ((rc = grow(ctx, &ws->idx, &ws->idx_elems, (size_t)n * 2))) return rc;
+    if ((rc = grow(ctx, &ws->dist, &ws->dist_elems, (size_t)n * 2))) return rc;
+    if ((rc = grow(ctx, &ws->idx2, &ws->idx2_elems, (size_t)m * 2))) return rc;
+    if ((rc = grow(ctx, &ws->dist2, &ws->dist2_elems, (size_t)m * 2))) return rc;
+    if ((rc = grow(ctx, &ws->flag, &ws->flag_elems, (size_t)n))) return rc;
+    cudaStream_t st = ctx->stream;
+    CVB_CUDA(ctx, cudaMemcpyAsync(ws->q, a, (size_t)n * 64, cudaMemcpyHostToDevice, st));
+    CVB_CUDA(ctx, cudaMemcpyAsync(ws->db, b, (size_t)m * 64, cudaMemcpyHostToDevice, st));
+    if ((rc = knn_dev(ctx, ws->q, nullptr, n, ws->db, nullptr, m, 2, ws->idx, ws->dist))) return rc;
+    if ((rc = knn_dev(ctx, ws->db, nullptr, m, ws->q, nullptr, n, 2, ws->idx2, ws->dist2))) return rc;
+    k_symmetric<<<cdiv(n, 256), 256, 0, st>>>(ws->idx, ws->dist, ws->idx2, ws->dist2, n, m, better_by, ws->flag);
+    CVB_LAUNCH_CHECK(ctx);
+    std::vector<uint32_t> flag(n);
+    CVB_CUDA(ctx, cudaMemcpyAsync(flag.data(), ws->flag, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    CVB_CUDA(ctx, cudaStreamSynchronize(st));
+    uint32_t cnt = 0;
+    for (uint32_t i = 0; i < n; i++)
+        if (flag[i] != 0xffffffffu) {
+            if (cnt < cap && pairs_out) { pairs_out[2 * cnt] = i; pairs_out[2 * cnt + 1] = flag[i]; }
+            cnt++;
+        }
+    *n_out = cnt;
+    if (cnt > cap) return cvb_set_error(ctx, CVB_ECAP, "pair capacity %u too small (%u needed)", cap, cnt);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+/* include/cvb200.h -- C ABI of libcvb200.so: the B200-native drop-in for rust-cv's
+ * AKAZE -> brute-force Hamming match -> RANSAC hot path.
+ *
+ * The reference (rust-cv/cv @ 82a25ee3) has no FFI; its boundary is the Rust-level API listed
+ * below.  Each entry point here is what a thin Rust shim crate would bind with `extern "C"`
+ *  to keep those Rust surfaces unchanged:
+ *
+ *   cvb_akaze_extract*      <- akaze::Akaze::extract_from_gray_float_image   akaze/src/lib.rs:309-339
+ *                              (and Akaze::extract / extract_path :295,361 after GrayFloatImage::from_dynamic)
+ *   cvb_akaze_cfg           <- akaze::Akaze (11 pub fields)                   akaze/src/lib.rs:109-142
+ *   cvb_keypoint            <- akaze::KeyPoint                                akaze/src/lib.rs:71-93
+ *   cvb_hamming_knn*        <- space::Knn::knn on LinearKnn<Hamming, BitArray<64>>
+ *                              call sites akaze/tests/estimate_pose.rs:78-97,
+ *                              tutorial-code/chapter4-feature-matching/src/main.rs:91-106
+ *   cvb_match_symmetric*    <- cv-sfm symmetric_matching (d0 + better_by <= d1, cross-check)
+ *                              cv-sfm/src/lib.rs:3097-3133
+ *
+ * Conventions: every function returns 0 on success or a negative CVB_E* code and never throws
+ * or aborts across the boundary; `cvb_last_error` gives the message for the last failure on a
+ * context.  The caller owns every buffer.  Functions without a `_dev` suffix take HOST pointers
+ * and perform the host<->device copies themselves; `_dev` variants take DEVICE pointers on the
+ * context's device and are asynchronous on the context's stream until `cvb_ctx_sync`.
+ * A context owns one CUDA stream and its workspaces; it is not thread-safe, distinct contexts
+ * are.  There is NO CPU fallback: without a CUDA device `cvb_ctx_create` fails with CVB_ENODEV.
+ */
+#ifndef CVB200_H
+#define CVB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVB_OK 0
+#define CVB_EINVAL (-1)   /* bad argument */
+#define CVB_ENODEV (-2)   /* no usable CUDA device */
+#define CVB_ECUDA (-3)    /* CUDA runtime error (see cvb_last_error) */
+#define CVB_ENOMEM (-4)   /* allocation failed */
+#define CVB_ECAP (-5)     /* output capacity too small; *n_out holds the required count */
+#define CVB_EUNSUPPORTED (-6)
+
+typedef struct cvb_ctx cvb_ctx;
+
+/* akaze::Akaze, akaze/src/lib.rs:109-142.  maximum_features < 0 means usize::MAX. */
+typedef struct {
+    int64_t maximum_features;
+    uint32_t num_sublevels;
+    uint32_t max_octave_evolution;
+    double base_scale_offset;
+    double initial_contrast;      /* present for layout parity; never read (lib.rs:123,176) */
+    double contrast_percentile;
+    uint64_t contrast_factor_num_bins;
+    double derivative_factor;
+    double detector_threshold;
+    uint64_t descriptor_channels;
+    uint64_t descriptor_pattern_size;
+} cvb_akaze_cfg;
+
+/* akaze::KeyPoint, akaze/src/lib.rs:71-93 (point.0, point.1, response, size, angle, octave, class_id) */
+typedef struct {
+    float x, y;
+    float response;
+    float size;
+    float angle;
+    uint32_t octave;
+    uint32_t class_id;
+} cvb_keypoint;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int cvb_ctx_create(int device, cvb_ctx **out);
+/* Same, but all work is enqueued on an existing CUDA stream (a cudaStream_t passed as void*),
+ * e.g. torch.cuda.current_stream().cuda_stream, so the caller can time it with its own events. */
+int cvb_ctx_create_on_stream(int device, void *cuda_stream, cvb_ctx **out);
+void cvb_ctx_destroy(cvb_ctx *ctx);
+int cvb_ctx_sync(cvb_ctx *ctx);
+const char *cvb_last_error(const cvb_ctx *ctx);
+const char *cvb_version(void);
+/* kernels launched by this context since creation (the `gpu_launches` evidence in bench.py) */
+uint64_t cvb_ctx_launch_count(const cvb_ctx *ctx);
+/* CUDA-event timing on the context's own stream: begin/end bracket, elapsed in milliseconds. */
+int cvb_ctx_timer_begin(cvb_ctx *ctx);
+int cvb_ctx_timer_end(cvb_ctx *ctx, float *ms_out);
+
+/* ---- AKAZE ------------------------------------------------------------------------------ */
+void cvb_akaze_default_cfg(cvb_akaze_cfg *cfg);      /* Akaze::default(), lib.rs:169-185 */
+
+/* One frame, host buffers.  image: w*h row-major f32 in [0,1] (a GrayFloatImage).  Writes at most
+ * `cap` keypoints / 64-byte descriptors, in the reference's output order (descending response,
+ * out-of-bounds descriptors dropped).  *n_out = number produced. */
+int cvb_akaze_extract(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, const float *image, uint32_t w, uint32_t h,
+                      cvb_keypoint *kp_out, uint8_t *desc_out, uint32_t cap, uint32_t *n_out);
+
+/* B frames of identical size in one pass (frames are independent: this is the data-parallel axis).
+ * images: B contiguous w*h planes.  kp_out: B*cap, desc_out: B*cap*64, n_out: B. */
+int cvb_akaze_extract_batch(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, const float *images, uint32_t batch,
+                            uint32_t w, uint32_t h, cvb_keypoint *kp_out, uint8_t *desc_out, uint32_t cap,
+                            uint32_t *n_out);
+
+/* Device-resident variant: images_dev / kp_out_dev / desc_out_dev / n_out_dev are device pointers.
+ * Asynchronous on the context stream.  Results stay in HBM (feed cvb_hamming_knn_dev directly). */
+int cvb_akaze_extract_batch_dev(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, const float *images_dev, uint32_t batch,
+                                uint32_t w, uint32_t h, cvb_keypoint *kp_out_dev, uint8_t *desc_out_dev,
+                                uint32_t cap, uint32_t *n_out_dev);
+
+/* Introspection of the last extract call (parity tests): copies one plane of one evolution of one
+ * frame to host.  plane: 0 Lt, 1 Lsmooth, 2 Lx, 3 Ly, 4 Lflow, 5 Ldet.  out must hold w*h floats of
+ * that evolution's level (query sizes with cvb_akaze_debug_evolution). */
+int cvb_akaze_debug_num_evolutions(cvb_ctx *ctx, uint32_t *n_out);
+int cvb_akaze_debug_evolution(cvb_ctx *ctx, uint32_t evolution, uint32_t *w, uint32_t *h, uint32_t *octave,
+                              uint32_t *sigma_size, uint32_t *n_fed_steps);
+int cvb_akaze_debug_plane(cvb_ctx *ctx, uint32_t frame, uint32_t evolution, uint32_t plane, float *out);
+int cvb_akaze_debug_contrast(cvb_ctx *ctx, uint32_t frame, double *k_out);
+/* stage: 0 candidates (3x3 maxima, raster order), 1 extrema (after duplicate suppression),
+ * 2 refined (sub-pixel + orientation), 3 sorted.  Returns count in *n_out (<= cap written). */
+int cvb_akaze_debug_stage(cvb_ctx *ctx, uint32_t frame, uint32_t stage, cvb_keypoint *out, uint32_t cap,
+                          uint32_t *n_out);
+
+/* ---- brute-force Hamming k-NN (space::LinearKnn + bitarray::Hamming) ---------------------- */
+/* For each of n queries (64-byte descriptors) the k nearest of m database descriptors, ascending
+ * distance, ties -> lower database index first.  idx_out/dist_out: n*k.  If m < k the missing slots
+ * hold 0xffffffff.  k <= 8. */
+int cvb_hamming_knn(cvb_ctx *ctx, const uint8_t *queries, uint32_t n, const uint8_t *database, uint32_t m,
+                    uint32_t k, uint32_t *idx_out, uint32_t *dist_out);
+int cvb_hamming_knn_dev(cvb_ctx *ctx, const uint8_t *queries_dev, uint32_t n, const uint8_t *database_dev,
+                        uint32_t m, uint32_t k, uint32_t *idx_out_dev, uint32_t *dist_out_dev);
+/* n and m read from device memory (e.g. the n_out_dev of cvb_akaze_extract_batch_dev); n_max/m_max
+ * bound the launch.  Rows >= *n_dev are left untouched. */
+int cvb_hamming_knn_dev_counts(cvb_ctx *ctx, const uint8_t *queries_dev, const uint32_t *n_dev, uint32_t n_max,
+                               const uint8_t *database_dev, const uint32_t *m_dev, uint32_t m_max, uint32_t k,
+                               uint32_t *idx_out_dev, uint32_t *dist_out_dev);
+
+/* cv-sfm symmetric_matching (cv-sfm/src/lib.rs:3097-3133): forward and reverse 2-NN, keep a->b when
+ * d0 + better_by <= d1 in both directions and the best matches agree.  pairs_out: up to cap (a,b)
+ * index pairs in ascending a. */
+int cvb_match_symmetric(cvb_ctx *ctx, const uint8_t *desc_a, uint32_t n, const uint8_t *desc_b, uint32_t m,
+                        uint32_t better_by, uint32_t *pairs_out, uint32_t cap, uint32_t *n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVB200_H */

@@ -1,0 +1,67 @@
+"""GPU parity of the brute-force Hamming k-NN against the CPU oracle (bit-exact indices and distances)."""
+import numpy as np
+import pytest
+
+import cv_b200
+from oracle import pyoracle as O
+from tests.common import GOLDEN, lowe_matches
+from tests.synth import random_descriptors
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,m,k", [(1, 1, 1), (3, 2, 2), (5, 1, 2), (130, 257, 2), (1000, 999, 3), (77, 5000, 8), (5000, 5000, 2)])
+def test_knn_matches_oracle(n, m, k):
+    q, db = random_descriptors(n, 10 + n), random_descriptors(m, 20 + m)
+    idx, dist = cv_b200.hamming_knn(q, db, k)
+    oi, od = O.hamming_knn(q, db, k)
+    assert np.array_equal(dist, od)
+    assert np.array_equal(idx, oi)
+
+
+def test_ties_resolve_to_lower_index():
+    # many duplicates -> many equal distances; the earlier database index must come first
+    base = random_descriptors(16, 3)
+    db = np.concatenate([base] * 40)           # every descriptor appears 40 times
+    q = random_descriptors(64, 4)
+    q[:16] = base
+    idx, dist = cv_b200.hamming_knn(q, db, 4)
+    oi, od = O.hamming_knn(q, db, 4)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+    assert (dist[:16, 0] == 0).all() and (idx[:16, 0] == np.arange(16)).all() and (idx[:16, 1] == np.arange(16) + 16).all()
+
+
+def test_reference_golden_match_count():
+    import os
+    g = np.load(os.path.join(GOLDEN, "oracle_kitti_sparse.npz"))
+    idx, dist = cv_b200.hamming_knn(g["desc0"], g["desc14"], 2)
+    assert lowe_matches(dist) == 11            # akaze/tests/estimate_pose.rs:59
+    assert np.array_equal(idx, g["knn_idx"]) and np.array_equal(dist, g["knn_dist"])
+
+
+def test_linear_knn_interface_and_symmetric_matching():
+    a, b = random_descriptors(700, 1), random_descriptors(650, 2)
+    b[:300] = a[100:400]
+    b[:300, 5] ^= 1                             # near-duplicates -> confident matches
+    knn = cv_b200.LinearKnn(b)
+    nb = knn.knn(a[100], 2)
+    assert nb[0] == (0, 1) and len(nb) == 2
+    pairs = cv_b200.symmetric_matching(a, b, 24)
+    # host restatement of cv-sfm/src/lib.rs:3097-3133 on oracle k-NN tables
+    fi, fd = O.hamming_knn(a, b, 2)
+    ri, rd = O.hamming_knn(b, a, 2)
+    fwd = np.where(fd[:, 0] + 24 <= fd[:, 1], fi[:, 0].astype(np.int64), -1)
+    rev = np.where(rd[:, 0] + 24 <= rd[:, 1], ri[:, 0].astype(np.int64), -1)
+    want = [[i, int(j)] for i, j in enumerate(fwd) if j >= 0 and rev[j] == i]
+    assert pairs.tolist() == want and len(want) >= 300
+    assert np.array_equal(cv_b200.matching(a, b, 24), fwd)
+
+
+def test_large_problem_properties():
+    # full BASELINE size through properties: distances ascending, self-match distance 0 at own index
+    d = random_descriptors(20000, 9)
+    idx, dist = cv_b200.hamming_knn(d[:5000], d, 2)
+    assert (dist[:, 0] == 0).all() and (idx[:, 0] == np.arange(5000)).all()
+    assert (dist[:, 1] >= dist[:, 0]).all()
+    x = np.unpackbits(d[:5000] ^ d[idx[:, 1]], axis=1).sum(1)
+    assert np.array_equal(x.astype(np.uint32), dist[:, 1])
