@@ -118,7 +118,9 @@ class Akaze:
         self._shape = (h, w)
         n = lib().ref_akaze_extract(self._h, _fp(image), w, h)
         kps = self.stage("final")
-        d = np.ctypeslib.as_array(lib().ref_akaze_descriptors(self._h), shape=(max(n, 1), 64))[:n].copy()
+        if n <= 0:
+            return kps, np.zeros((0, 64), np.uint8)
+        d = np.ctypeslib.as_array(lib().ref_akaze_descriptors(self._h), shape=(n, 64)).copy()
         return kps, d
 
     def num_evolutions(self):
