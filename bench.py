@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json configs[1]).
+
+Workload ("step"): one frame PAIR of synthetic 1920x1080 f32 images, ~5k keypoints each:
+  AKAZE extract on both frames (one batched pass) -> symmetric brute-force Hamming 2-NN match
+  (forward + reverse, cv-sfm rule d0 + 24 <= d1 with cross-check).
+metric = frames/s (2 frames per step per GPU).  N>1: every rank runs its own frame pairs
+(frames are independent -> weak scaling, no data-path collective).
+
+  value : device-resident inputs/outputs (inputs already in HBM), CUDA-event timed, max over ranks
+  e2e   : the same step through the reference-facing host API (pinned HOST buffers in, keypoints /
+          descriptors / match pairs back on the host), copies inside the timed region
+  roofline : dominant kernel, algorithmic bytes / CUDA-event duration from an instrumented pass
+  cpu_baseline : the CPU oracle (restated reference) timed on this box's host cores, bounded sample
+
+`--impl reference` times the reference's CPU implementation (the oracle port; the Rust original cannot
+be built: no cargo/rustc in the image) on the same config and prints the same JSON line.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+MAXF = 5000            # maximum_features -> exactly "~5k keypoints" per frame
+BETTER_BY = 24         # cv-sfm/src/settings.rs:397-399
+POOL_PAIRS = 8         # 16 distinct frames = 133 MB > 126 MB L2: step inputs are never L2-resident
+ALG_BYTES_PER_FRAME = 4 * (13 * 11016000 + 3 * 40759200 + 4 * 2073600)   # 1.095 GB
+
+
+def make_pool(npairs, seed0=0):
+    from tests.synth import synth_frame, warp_frame
+    frames = []
+    for i in range(npairs):
+        a = synth_frame(seed0 + i)
+        frames.append(np.stack([a, warp_frame(a, 1000 + seed0 + i)]))
+    return frames
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples if len(s) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_reference_step(frames, reps):
+    """The reference's CPU path (oracle port): extract both frames, symmetric 2-NN match. Returns seconds/step."""
+    from oracle import pyoracle as O
+    t0 = time.perf_counter()
+    for r in range(reps):
+        pair = frames[r % len(frames)]
+        ds = []
+        for f in pair:
+            ak = O.Akaze(maximum_features=MAXF)
+            _, d = ak.extract(f)
+            ds.append(d)
+        fi, fd = O.hamming_knn(ds[0], ds[1], 2)
+        ri, rd = O.hamming_knn(ds[1], ds[0], 2)
+        fwd = np.where(fd[:, 0] + BETTER_BY <= fd[:, 1], fi[:, 0].astype(np.int64), -1)
+        rev = np.where(rd[:, 0] + BETTER_BY <= rd[:, 1], ri[:, 0].astype(np.int64), -1)
+        _ = [(i, j) for i, j in enumerate(fwd) if j >= 0 and rev[j] == i]
+    return (time.perf_counter() - t0) / reps
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    frames = make_pool(1)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step(frames, 1)
+    steps = max(1, min(args.steps, 3))       # bounded sample: ~5 s of CPU work per step
+    sec = cpu_reference_step(frames, steps)
+    fps = 2.0 / sec
+    cores = os.cpu_count()
+    line = {"metric": "vSLAM frames/s (AKAZE+match, 1080p ~5k kp)", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "configs[1]: AKAZE extract x2 + symmetric Hamming 2-NN, 2 frames 1920x1080 f32, ~5k kp/frame",
+                       "maximum_features": MAXF, "detector_threshold": 0.001, "better_by": BETTER_BY},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps} frame pair(s); C restatement of rust-cv akaze/space (oracle/), OpenMP at the reference's rayon sites"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cvb200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    import cv_b200
+    from cv_b200._lib import KP_DTYPE
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    frames = make_pool(POOL_PAIRS, seed0=100 * rank)
+    # the context owns its CUDA stream; all timing uses CUDA events recorded on THAT stream (cvb_ctx_timer_*)
+    ctx = cv_b200.Context(local_rank)
+    lib = ctx.lib
+    cfg = cv_b200.AkazeConfig(maximum_features=MAXF).to_c()
+    cap = 8192
+    # ---- device-resident buffers
+    d_pool = [torch.from_numpy(p).to(dev) for p in frames]
+    d_kp = torch.empty(2 * cap * KP_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_desc = torch.zeros(2 * cap * 64, dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(2, dtype=torch.int32, device=dev)
+    d_fi = torch.empty(cap * 2, dtype=torch.int32, device=dev); d_fd = torch.empty_like(d_fi)
+    d_ri = torch.empty(cap * 2, dtype=torch.int32, device=dev); d_rd = torch.empty_like(d_ri)
+
+    def step_dev(i):
+        img = d_pool[i % POOL_PAIRS]
+        ctx.check(lib.cvb_akaze_extract_batch_dev(ctx.handle, C.byref(cfg), img.data_ptr(), 2, W, H, d_kp.data_ptr(),
+                                                  d_desc.data_ptr(), cap, d_n.data_ptr()))
+        da, db = d_desc.data_ptr(), d_desc.data_ptr() + cap * 64
+        na, nb = d_n.data_ptr(), d_n.data_ptr() + 4
+        ctx.check(lib.cvb_hamming_knn_dev_counts(ctx.handle, da, na, MAXF, db, nb, MAXF, 2, d_fi.data_ptr(), d_fd.data_ptr()))
+        ctx.check(lib.cvb_hamming_knn_dev_counts(ctx.handle, db, nb, MAXF, da, na, MAXF, 2, d_ri.data_ptr(), d_rd.data_ptr()))
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(Wm):
+        step_dev(i)
+    barrier()
+    n_kp = d_n.cpu().numpy().tolist()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    ctx.timer_begin()
+    for i in range(K):
+        step_dev(Wm + i)
+    ms = ctx.timer_end()          # CUDA events on the launching stream; timer_end waits for the end event
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    assert ms > 0.5 * wall_ms or wall_ms < 1.0, f"device timer {ms} ms disagrees with wall clock {wall_ms} ms"
+    launches = ctx.launch_count() - l0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * 2.0 * K / (ms_max * 1e-3)
+
+    # ---- e2e: host API with pinned host buffers (H2D frames, D2H keypoints/descriptors, H2D descriptors, D2H pairs)
+    h_pool = [torch.from_numpy(p).pin_memory() for p in frames]
+    h_kp = torch.empty(2 * cap * KP_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    h_desc = torch.empty(2 * cap * 64, dtype=torch.uint8).pin_memory()
+    h_n = torch.zeros(2, dtype=torch.int32).pin_memory()
+    h_pairs = torch.empty(cap * 2, dtype=torch.int32).pin_memory()
+    npairs = C.c_uint32()
+    h2d = d2h = 0
+
+    def step_host(i):
+        nonlocal h2d, d2h
+        img = h_pool[i % POOL_PAIRS]
+        ctx.check(lib.cvb_akaze_extract_batch(ctx.handle, C.byref(cfg), img.data_ptr(), 2, W, H, h_kp.data_ptr(), h_desc.data_ptr(),
+                                              cap, h_n.data_ptr()))
+        na, nb = int(h_n[0]), int(h_n[1])
+        ctx.check(lib.cvb_match_symmetric(ctx.handle, h_desc.data_ptr(), na, h_desc.data_ptr() + cap * 64, nb, BETTER_BY,
+                                          h_pairs.data_ptr(), cap, C.byref(npairs)))
+        h2d = 2 * W * H * 4 + (na + nb) * 64
+        d2h = 8 + 4 + (na + nb) * (KP_DTYPE.itemsize + 64) + na * 4
+        return npairs.value
+
+    for i in range(Wm):
+        nm = step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    ctx.timer_begin()
+    for i in range(K):
+        step_host(Wm + i)
+    ms_dev = ctx.timer_end()
+    ms_e2e = max(ms_dev, (time.perf_counter() - t0) * 1e3)   # host-blocking API: wall clock bounds it from above
+    barrier()
+    t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * 2.0 * K / (float(t.item()) * 1e-3)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- roofline: instrumented pass (per-kernel CUDA events on the launching stream)
+    ctx.profile(True)
+    PK = min(K, 10)
+    for i in range(PK):
+        step_dev(i)
+    rep = ctx.profile_report()
+    ctx.profile(False)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    tot_ms = sum(v["ms"] for v in rep.values())
+    top = max(rep.items(), key=lambda kv: kv[1]["ms"]) if rep else (None, None)
+    kernels = {k: {"launches_per_step": v["launches"] / PK, "ms_per_step": v["ms"] / PK, "share": v["ms"] / tot_ms if tot_ms else 0,
+                   "alg_GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] > 0 else None} for k, v in rep.items()}
+    # dominant kernel among those with an HBM-traffic model
+    hb = {k: v for k, v in rep.items() if v["bytes"] > 0}
+    dom = max(hb.items(), key=lambda kv: kv[1]["ms"])
+    achieved = dom[1]["bytes"] / (dom[1]["ms"] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src,
+                "launch_ms": dom[1]["ms"] / dom[1]["launches"], "bytes_per_launch": dom[1]["bytes"] / dom[1]["launches"],
+                "timing": "per-kernel CUDA events on the launching stream, separate instrumented pass of the same steps",
+                "pipeline_alg_GBps": value / world * ALG_BYTES_PER_FRAME / 1e9, "pipeline_frac": value / world * ALG_BYTES_PER_FRAME / 1e9 / hbm_peak,
+                "top_kernel_by_time": top[0], "kernels": kernels}
+    knn = rep.get("k_hamming_knn")
+    gcmp = (knn["bytes"] / 64.0) / (knn["ms"] * 1e-3) / 1e9 if knn and knn["ms"] > 0 else None
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        sec = cpu_reference_step(frames[:1], 2)     # ~10 s of CPU work
+        cpu = {"value": 2.0 / sec, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "2 frame pairs (4 extracts + 2 symmetric matches) of the same workload; C restatement of the reference (oracle/), "
+                         "OpenMP only at the reference's rayon sites"}
+    if rank == 0:
+        line = {"metric": "vSLAM frames/s (AKAZE+match, 1080p ~5k kp)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "configs[1]: AKAZE extract x2 + symmetric Hamming 2-NN, 2 frames 1920x1080 f32, ~5k kp/frame",
+                           "frames_per_step_per_gpu": 2, "keypoints_per_frame": n_kp, "matches": int(nm), "maximum_features": MAXF,
+                           "detector_threshold": 0.001, "better_by": BETTER_BY,
+                           "l2": f"inputs rotate over a pool of {2 * POOL_PAIRS} distinct frames ({2 * POOL_PAIRS * W * H * 4 / 1e6:.0f} MB > 126 MB L2)"},
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "roofline": roofline, "hamming_Gcmp_per_s": gcmp, "cpu_baseline": cpu,
+                "clocks": sampler.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -41,7 +41,7 @@ KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("response", "<f4"), ("size", "
 # every symbol include/cvb200.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "cvb_ctx_create", "cvb_ctx_create_on_stream", "cvb_ctx_destroy", "cvb_ctx_sync", "cvb_last_error", "cvb_version",
-    "cvb_ctx_launch_count", "cvb_ctx_timer_begin", "cvb_ctx_timer_end",
+    "cvb_ctx_launch_count", "cvb_ctx_timer_begin", "cvb_ctx_timer_end", "cvb_ctx_profile", "cvb_ctx_profile_report",
     "cvb_akaze_default_cfg", "cvb_akaze_extract", "cvb_akaze_extract_batch", "cvb_akaze_extract_batch_dev",
     "cvb_akaze_debug_num_evolutions", "cvb_akaze_debug_evolution", "cvb_akaze_debug_plane", "cvb_akaze_debug_contrast",
     "cvb_akaze_debug_stage",
@@ -76,6 +76,8 @@ def load_library():
     L.cvb_ctx_launch_count.restype = u64
     L.cvb_ctx_timer_begin.argtypes = [vp]
     L.cvb_ctx_timer_end.argtypes = [vp, C.POINTER(C.c_float)]
+    L.cvb_ctx_profile.argtypes = [vp, C.c_int]
+    L.cvb_ctx_profile_report.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.cvb_akaze_default_cfg.argtypes = [C.POINTER(AkazeCfg)]
     L.cvb_akaze_default_cfg.restype = None
     L.cvb_akaze_extract.argtypes = [vp, C.POINTER(AkazeCfg), vp, u32, u32, vp, vp, u32, C.POINTER(u32)]
@@ -126,6 +128,19 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.cvb_ctx_launch_count(self.handle))
+
+    def profile(self, enable=True):
+        self.check(self.lib.cvb_ctx_profile(self.handle, 1 if enable else 0))
+
+    def profile_report(self):
+        """{kernel: dict(launches, ms, bytes)} accumulated since profile(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        self.check(self.lib.cvb_ctx_profile_report(self.handle, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms, by = line.split()
+            out[name] = dict(launches=int(n), ms=float(ms), bytes=float(by))
+        return out
 
     def timer_begin(self):
         self.check(self.lib.cvb_ctx_timer_begin(self.handle))

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -115,6 +116,8 @@ struct AkazeWorkspace {
     unsigned *ncache = nullptr, *nsorted = nullptr;
     unsigned char *keep = nullptr, *valid = nullptr, *ok = nullptr, *desc_tmp = nullptr;
     unsigned *overflow = nullptr;
+    SupScratch sup{};
+    bool suppress_seq = false;   // CVB_SUPPRESS_SEQ=1: serial reference kernel (debug / A-B check)
     OrientTables *ot = nullptr;
     DescTables *dt = nullptr;
     // outputs owned by the workspace for the host-pointer API
@@ -187,6 +190,7 @@ int plan_evolutions(cvb_ctx *ctx, AkazeWorkspace *ws) {
         double wv = 10.0 / 3.0;
         e.norm = (float)(1.0 / (2.0 * (double)e.sigma * (wv + 2.0)));
         e.middle = e.norm * (float)wv;
+        if (e.sigma == 1) { e.norm = 3.0f; e.middle = 10.0f; }   // derivatives.rs:24-26,43-45: sigma 1 -> simple (un-normalised) Scharr
         if (e.sigma < 1 || e.sigma > 16) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "derivative sigma %u out of range", e.sigma);
         EvoDev &d = ws->table.e[i];
         d.w = e.w; d.h = e.h; d.off = e.off; d.octave = (int)e.octave;
@@ -302,6 +306,21 @@ int ensure_workspace(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, uint32_t batch, uin
     DA(ncache, B); DA(nsorted, B);
     DA(keep, B * ws->capk); DA(valid, B * ws->capk); DA(ok, B * ws->capk); DA(desc_tmp, B * ws->capk * 64);
     DA(overflow, 1);
+    {   // scratch of the parallel duplicate suppression; bins sized for the finest class grid
+        unsigned nbmax = 1;
+        for (size_t i = 0; i < ws->evo.size(); i++) {
+            float ratio = (float)(1u << ws->evo[i].octave), off = 0.5f * (ratio - 1.0f), size = ws->table.e[i].size;
+            float cell = fmaxf(16.0f, ceilf(2.0f * size + 2.0f * off + 2.0f));
+            unsigned nbx = (unsigned)((float)w / cell) + 3, nby = (unsigned)((float)h / cell) + 3;
+            nbmax = std::max(nbmax, nbx * nby);
+        }
+        ws->sup.nbmax = nbmax;
+        DA(sup.state, B * ws->capc); DA(sup.alive, B * ws->capc); DA(sup.rdy, B * ws->capc);
+        DA(sup.key, B * ws->capc); DA(sup.rank, B * ws->capc); DA(sup.next, B * ws->capc);
+        DA(sup.binA, B * nbmax); DA(sup.binB, B * nbmax);
+        const char *env = getenv("CVB_SUPPRESS_SEQ");
+        ws->suppress_seq = env && env[0] == '1';
+    }
     DA(ot, 1); DA(dt, 1);
     DA(kp_out, B * (size_t)cap_out); DA(desc_out, B * (size_t)cap_out * 64); DA(n_out, B);
 #undef DA
@@ -327,13 +346,15 @@ int launch_separable(cvb_ctx *ctx, const float *in, size_t in_bs, float *out, si
                      const Taps &hk, const Taps &vk) {
     int rx = hk.ks / 2, ry = vk.ks / 2;
     size_t smem = sizeof(float) * ((size_t)(TH + 2 * ry) * (TW + 2 * rx) + (size_t)(TH + 2 * ry) * TW);
+    { CVB_PROF(ctx, "k_separable", 8.0 * w * h * B);
     k_separable<<<tile_grid(w, h, B), NT, smem, ctx->stream>>>(in, out, w, h, in_bs, out_bs, hk, vk);
-    CVB_LAUNCH_CHECK(ctx);
+    CVB_LAUNCH_CHECK(ctx); }
     return 0;
 }
 
 int launch_deriv1(cvb_ctx *ctx, const EvoHost &e, const float *Ls, float *Lx, float *Ly, size_t bs, unsigned B) {
     int s = (int)e.sigma;
+    CVB_PROF(ctx, "k_deriv1", 12.0 * e.w * e.h * B);
     size_t smem = sizeof(float) * ((size_t)(TH + 2 * s) * (TW + 2 * s) + 2 * (size_t)(TH + 2 * s) * TW);
     dim3 g = tile_grid(e.w, e.h, B);
     switch (s & 3) {
@@ -348,6 +369,7 @@ int launch_deriv1(cvb_ctx *ctx, const EvoHost &e, const float *Ls, float *Lx, fl
 
 int launch_deriv2(cvb_ctx *ctx, const EvoHost &e, const float *Lx, const float *Ly, float *Ldet, size_t bs, unsigned B) {
     int s = (int)e.sigma;
+    CVB_PROF(ctx, "k_deriv2_det", 12.0 * e.w * e.h * B);
     size_t smem = sizeof(float) * (2 * (size_t)(TH + 2 * s) * (TW + 2 * s) + 3 * (size_t)(TH + 2 * s) * TW);
     dim3 g = tile_grid(e.w, e.h, B);
     switch (s & 3) {
@@ -386,14 +408,17 @@ int run_extract(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoint *kp_
     CVB_CUDA(ctx, cudaMemsetAsync(ws->npoints, 0, sizeof(unsigned) * B, st));
     rc = launch_separable(ctx, images, P0, ws->tmpA, P0, W, H, B, ws->g1, ws->g1);
     if (rc) return rc;
+    { CVB_PROF(ctx, "k_contrast_grad", 4.0 * W * H * B);
     k_scharr_pm<1><<<tile_grid(W, H, B), NT, 0, st>>>(ws->tmpA, nullptr, ws->g2, ws->gmax, W, H, P0, P0, nullptr, 0);
-    CVB_LAUNCH_CHECK(ctx);
+    CVB_LAUNCH_CHECK(ctx); }
     {
         unsigned blocks = std::min<unsigned>(cdiv((unsigned)P0, NT), (unsigned)ctx->num_sms * 8);
+        { CVB_PROF(ctx, "k_contrast_hist", 4.0 * W * H * B);
         k_contrast_hist<<<dim3(blocks, 1, B), NT, sizeof(unsigned) * nbins, st>>>(ws->g2, ws->gmax, ws->hist, ws->npoints, (int)P0, P0, nbins);
-        CVB_LAUNCH_CHECK(ctx);
+        CVB_LAUNCH_CHECK(ctx); }
+        { CVB_PROF(ctx, "k_contrast_final", 0);
         k_contrast_final<<<B, 32, 0, st>>>(ws->gmax, ws->hist, ws->npoints, nbins, ws->cfg.contrast_percentile, ws->evo_octave, E, ws->kc, ws->inv_k);
-        CVB_LAUNCH_CHECK(ctx);
+        CVB_LAUNCH_CHECK(ctx); }
     }
     for (int i = 1; i < E; i++) {
         const EvoHost &e = ws->evo[i];
@@ -402,17 +427,19 @@ int run_extract(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoint *kp_
         size_t src_bs = PF;
         if (e.new_octave) {
             dim3 blk(32, 8), grd(cdiv((unsigned)e.w, 32), cdiv((unsigned)e.h, 8), B);
+            { CVB_PROF(ctx, "k_half_size", 4.0 * ((double)pe.w * pe.h + (double)e.w * e.h) * B);
             k_half_size<<<grd, blk, 0, st>>>(src, ws->tmpC, pe.w, pe.h, src_bs, P0);
-            CVB_LAUNCH_CHECK(ctx);
+            CVB_LAUNCH_CHECK(ctx); }
             src = ws->tmpC; src_bs = P0;
         }
         // Lsmooth = gaussian_blur(Lt, 1.0)
         rc = launch_separable(ctx, src, src_bs, ws->Lsm + e.off, PF, e.w, e.h, B, ws->g1, ws->g1);
         if (rc) return rc;
         // Lflow = pm_g2(simple_scharr_x(Lsmooth), simple_scharr_y(Lsmooth), contrast)
+        { CVB_PROF(ctx, "k_scharr_pm", 8.0 * e.w * e.h * B);
         k_scharr_pm<0><<<tile_grid(e.w, e.h, B), NT, 0, st>>>(ws->Lsm + e.off, ws->Lflow + e.off, nullptr, nullptr, e.w, e.h, PF, PF,
                                                              ws->inv_k + i, MAX_EVO);
-        CVB_LAUNCH_CHECK(ctx);
+        CVB_LAUNCH_CHECK(ctx); }
         // FED steps, FED_SMAX per launch; the chain ends in Lt_i
         const int n = (int)e.tau.size();
         const int nl = (n + FED_SMAX - 1) / FED_SMAX;
@@ -431,8 +458,9 @@ int run_extract(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoint *kp_
             else if (((nl - 1 - l) & 1) == 1) { dst = ws->tmpA; dst_bs = P0; }
             else { dst = ws->tmpB; dst_bs = P0; }
             size_t smem = sizeof(float) * 3 * (size_t)(TW + 2 * fs.n) * (TH + 2 * fs.n);
+            { CVB_PROF(ctx, "k_fed", 12.0 * fs.n * e.w * e.h * B);
             k_fed<<<tile_grid(e.w, e.h, B), NT, smem, st>>>(cur, ws->Lflow + e.off, dst, e.w, e.h, cur_bs, PF, dst_bs, fs);
-            CVB_LAUNCH_CHECK(ctx);
+            CVB_LAUNCH_CHECK(ctx); }
             cur = dst; cur_bs = dst_bs;
         }
     }
@@ -449,32 +477,45 @@ int run_extract(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoint *kp_
     const float thr = (float)ws->cfg.detector_threshold;
     {
         dim3 g(cdiv((unsigned)R * 32u, NT), 1, B);
+        { CVB_PROF(ctx, "k_extrema_count", 4.0 * ws->plane_floats * B);
         k_extrema<false><<<g, NT, 0, st>>>(ws->Ldet, PF, ws->table, thr, ws->rowcount, nullptr, nullptr, 0, ws->overflow);
-        CVB_LAUNCH_CHECK(ctx);
+        CVB_LAUNCH_CHECK(ctx); }
+        { CVB_PROF(ctx, "k_scan_rows", 0);
         k_scan_rows<<<B, 1024, 0, st>>>(ws->rowcount, ws->rowoff, ws->ncand, R);
-        CVB_LAUNCH_CHECK(ctx);
+        CVB_LAUNCH_CHECK(ctx); }
+        { CVB_PROF(ctx, "k_extrema_write", 0);
         k_extrema<true><<<g, NT, 0, st>>>(ws->Ldet, PF, ws->table, thr, nullptr, ws->rowoff, ws->cand, ws->capc, ws->overflow);
-        CVB_LAUNCH_CHECK(ctx);
+        CVB_LAUNCH_CHECK(ctx); }
     }
-    k_suppress<<<B, 1024, 0, st>>>(ws->cand, ws->ncand, ws->capc, ws->table, ws->cache, ws->ncache, ws->capk, ws->overflow);
-    CVB_LAUNCH_CHECK(ctx);
+    { CVB_PROF(ctx, "k_suppress", 0);
+    if (ws->suppress_seq)
+        k_suppress_seq<<<B, 1024, 0, st>>>(ws->cand, ws->ncand, ws->capc, ws->table, ws->cache, ws->ncache, ws->capk, ws->overflow);
+    else
+        k_suppress_par<<<B, 1024, 0, st>>>(ws->cand, ws->ncand, ws->rowoff, ws->capc, ws->table, ws->sup, ws->cache, ws->ncache,
+                                           ws->capk, ws->overflow);
+    CVB_LAUNCH_CHECK(ctx); }
     const unsigned kp_blocks = (unsigned)ctx->num_sms * 2;
+    { CVB_PROF(ctx, "k_filter_upper", 0);
     k_filter_upper<<<dim3(kp_blocks, B), NT, 0, st>>>(ws->cache, ws->ncache, ws->capk, ws->keep);
-    CVB_LAUNCH_CHECK(ctx);
+    CVB_LAUNCH_CHECK(ctx); }
+    { CVB_PROF(ctx, "k_refine_orient", 0);
     k_refine_orient<<<dim3(kp_blocks, B), NT, 0, st>>>(ws->cache, ws->ncache, ws->capk, ws->keep, ws->table, ws->Ldet, ws->Lx, ws->Ly, PF,
                                                        ws->ot, ws->refined, ws->valid);
-    CVB_LAUNCH_CHECK(ctx);
+    CVB_LAUNCH_CHECK(ctx); }
     // ---- sort + truncate (lib.rs:326-327)
+    { CVB_PROF(ctx, "k_rank_sort", 0);
     k_rank_sort<<<dim3(kp_blocks, B), NT, 0, st>>>(ws->refined, ws->valid, ws->ncache, ws->capk, (long long)ws->cfg.maximum_features,
                                                    ws->sorted, ws->nsorted);
-    CVB_LAUNCH_CHECK(ctx);
+    CVB_LAUNCH_CHECK(ctx); }
     // ---- extract_descriptors (descriptors.rs:16-45)
+    { CVB_PROF(ctx, "k_descriptors", 0);
     k_descriptors<<<dim3(kp_blocks, B), NT, 0, st>>>(ws->sorted, ws->nsorted, ws->capk, ws->table, ws->Lt, ws->Lx, ws->Ly, PF, ws->dt,
                                                      (int)ws->cfg.descriptor_channels, ws->desc_tmp, ws->ok);
-    CVB_LAUNCH_CHECK(ctx);
+    CVB_LAUNCH_CHECK(ctx); }
+    { CVB_PROF(ctx, "k_compact_final", 0);
     k_compact_final<<<B, 1024, 0, st>>>(ws->sorted, ws->desc_tmp, ws->ok, ws->nsorted, ws->capk, kp_out, desc_out, cap_out, n_out,
                                         ws->overflow);
-    CVB_LAUNCH_CHECK(ctx);
+    CVB_LAUNCH_CHECK(ctx); }
     ws->has_run = true;
     return 0;
 }

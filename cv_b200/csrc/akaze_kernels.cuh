@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(1024) k_scan_rows(const unsigned *__restrict__
 // for the FIRST (lowest slot) cached keypoint of the same or previous class within `size`, then thread 0
 // applies the reference's replace / drop / append rule.  Candidates failing the border test never modify
 // the cache (:95-116) and are skipped up front.
-__global__ void __launch_bounds__(1024) k_suppress(const Cand *__restrict__ cand, const unsigned *__restrict__ ncand,
+__global__ void __launch_bounds__(1024) k_suppress_seq(const Cand *__restrict__ cand, const unsigned *__restrict__ ncand,
                                                    unsigned capc, EvoTable T, cvb_keypoint *__restrict__ cache,
                                                    unsigned *__restrict__ ncache, unsigned capk, unsigned *overflow) {
     __shared__ unsigned s_min[32];
@@ -529,26 +529,237 @@ __global__ void __launch_bounds__(1024) k_suppress(const Cand *__restrict__ cand
     if (threadIdx.x == 0) ncache[b] = s_n;
 }
 
+// Parallel, provably sequential-equivalent duplicate suppression (scale_space_extrema.rs:61-117).
+//
+// The reference walks all candidates in order against a growing cache: first cached keypoint (lowest
+// slot) of the same or previous class within `size` -> replace it if stronger, else drop; no hit ->
+// append.  Observations that make it parallel without changing a single outcome:
+//  * every cache slot is always occupied by a candidate, so the cache is a per-candidate state
+//    (alive flag + slot key); a class-e candidate only ever matches occupants of class e or e-1;
+//  * candidate c can be influenced by an earlier candidate c' only if c' is within `size` of c or of an
+//    occupant within `size` of c, i.e. |F_c - F_c'| <= 2*size + 2*off (off = 0.5*(ratio-1) shift of the
+//    stored point).  Classes are processed in order; inside a class, in rounds: a candidate is READY
+//    when every earlier unresolved candidate of its class lies beyond that radius; all ready candidates
+//    are mutually independent (they cannot touch a common occupant) and are resolved concurrently with
+//    exactly the reference's comparisons.  The earliest unresolved candidate is always ready, so the
+//    loop terminates; in the worst case (one long dependency chain) it degenerates to the serial order.
+//  * "lowest slot" is decided on slot KEYS: real slot index for slots that existed before the class,
+//    BASE + appender's candidate index for slots appended during the class (same relative order);
+//    keys are turned into real indices by a prefix sum when the class is finished.
+// One CTA per frame.  Uniform-grid bins (cell >= interaction radius) give O(neighbourhood) searches.
+struct SupScratch {
+    unsigned char *state;     // 0 unresolved, 1 resolved            [B][capc]
+    unsigned char *alive;     // currently occupying a cache slot    [B][capc]
+    unsigned char *rdy;       //                                      [B][capc]
+    unsigned *key;            // slot key / final slot index          [B][capc]
+    unsigned *rank;           // exclusive prefix of appended flags   [B][capc]
+    int *next;                // bin linked lists                     [B][capc]
+    int *binA, *binB;         // heads: class e-1 occupants / class e candidates   [B][nbmax]
+    unsigned nbmax;
+};
+
+__device__ __forceinline__ unsigned block_excl_scan_1024(unsigned v, unsigned *s_warp, unsigned *total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned x = v;
+    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned y = s_warp[lane], z = y;
+        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += t; }
+        s_warp[lane] = z - y;
+        if (lane == 31) s_warp[32] = z;
+    }
+    __syncthreads();
+    unsigned excl = s_warp[wid] + x - v;
+    *total = s_warp[32];
+    __syncthreads();
+    return excl;
+}
+
+__global__ void __launch_bounds__(1024) k_suppress_par(const Cand *__restrict__ cand, const unsigned *__restrict__ ncand,
+                                                       const unsigned *__restrict__ rowoff, unsigned capc, EvoTable T,
+                                                       SupScratch S, cvb_keypoint *__restrict__ cache,
+                                                       unsigned *__restrict__ ncache, unsigned capk, unsigned *overflow) {
+    __shared__ unsigned s_warp[33];
+    __shared__ int s_more;
+    const unsigned BASE = 0x40000000u;
+    const int b = blockIdx.x;
+    const Cand *cd = cand + (size_t)b * capc;
+    unsigned char *state = S.state + (size_t)b * capc, *alive = S.alive + (size_t)b * capc, *rdy = S.rdy + (size_t)b * capc;
+    unsigned *key = S.key + (size_t)b * capc, *rank = S.rank + (size_t)b * capc;
+    int *next = S.next + (size_t)b * capc;
+    int *binA = S.binA + (size_t)b * S.nbmax, *binB = S.binB + (size_t)b * S.nbmax;
+    const unsigned ntot = min(ncand[b], capc);
+    const unsigned *ro = rowoff + (size_t)b * T.total_rows;
+    const float smax = 10.0f * sqrtf(2.0f);
+    const float W0 = (float)T.e[0].w, H0 = (float)T.e[0].h;
+    unsigned N = 0;                       // slots so far
+    unsigned prev_cs = 0, prev_ce = 0;    // candidate range of class e-1
+    float prev_off = 0.f, prev_ratio = 1.f;
+    for (int e = 0; e < T.n; e++) {
+        const EvoDev ev = T.e[e];
+        const unsigned cs = min(ro[ev.rowbase], ntot);
+        const unsigned ce = (e + 1 < T.n) ? min(ro[T.e[e + 1].rowbase], ntot) : ntot;
+        const float ratio = (float)(1 << ev.octave), off = 0.5f * (ratio - 1.0f), size = ev.size, s2 = size * size;
+        const float sigma_size = roundf(size / ratio);
+        const float Dr = 2.0f * size + 2.0f * off + 2.0f;
+        const float cell = fmaxf(16.0f, ceilf(Dr));
+        const float inv_cell = 1.0f / cell;
+        const int nbx = (int)(W0 * inv_cell) + 2, nby = (int)(H0 * inv_cell) + 2;
+        const int nb = nbx * nby;
+        for (int t = threadIdx.x; t < nb; t += 1024) { binA[t] = -1; binB[t] = -1; }
+        __syncthreads();
+        // occupants of class e-1 (alive) binned by their stored point
+        for (unsigned g = prev_cs + threadIdx.x; g < prev_ce; g += 1024) {
+            if (!alive[g]) continue;
+            const Cand c = cd[g];
+            float sx = (float)c.x * prev_ratio + prev_off, sy = (float)c.y * prev_ratio + prev_off;
+            int bx = min(max((int)(sx * inv_cell), 0), nbx - 1), by = min(max((int)(sy * inv_cell), 0), nby - 1);
+            next[g] = atomicExch(&binA[by * nbx + bx], (int)g);
+        }
+        // candidates of class e: border test (:97-104); failing ones never touch the cache
+        for (unsigned g = cs + threadIdx.x; g < ce; g += 1024) {
+            const Cand c = cd[g];
+            const float px = (float)c.x, py = (float)c.y;
+            const float left_x = roundf(px - smax * sigma_size) - 1.f, right_x = roundf(px + smax * sigma_size) + 1.f;
+            const float up_y = roundf(py - smax * sigma_size) - 1.f, down_y = roundf(py + smax * sigma_size) + 1.f;
+            const bool is_out = left_x < 0.f || right_x >= (float)ev.w || up_y < 0.f || down_y >= (float)ev.h;
+            alive[g] = 0; key[g] = 0xffffffffu; rank[g] = 0;
+            if (is_out) { state[g] = 1; continue; }
+            state[g] = 0;
+            float fx = px * ratio, fy = py * ratio;
+            int bx = min(max((int)(fx * inv_cell), 0), nbx - 1), by = min(max((int)(fy * inv_cell), 0), nby - 1);
+            next[g] = atomicExch(&binB[by * nbx + bx], (int)g);
+        }
+        __syncthreads();
+        // ---- rounds
+        for (;;) {
+            if (threadIdx.x == 0) s_more = 0;
+            __syncthreads();
+            // phase A: readiness against the state at the start of the round
+            for (unsigned g = cs + threadIdx.x; g < ce; g += 1024) {
+                if (state[g]) continue;
+                const Cand c = cd[g];
+                const float fx = (float)c.x * ratio, fy = (float)c.y * ratio;
+                const int bx = min(max((int)(fx * inv_cell), 0), nbx - 1), by = min(max((int)(fy * inv_cell), 0), nby - 1);
+                bool ready = true;
+                for (int yy = max(by - 1, 0); yy <= min(by + 1, nby - 1) && ready; yy++)
+                    for (int xx = max(bx - 1, 0); xx <= min(bx + 1, nbx - 1) && ready; xx++)
+                        for (int j = binB[yy * nbx + xx]; j >= 0; j = next[j]) {
+                            if ((unsigned)j >= g || state[j]) continue;
+                            const Cand q = cd[j];
+                            if (fabsf((float)q.x * ratio - fx) <= Dr && fabsf((float)q.y * ratio - fy) <= Dr) { ready = false; break; }
+                        }
+                rdy[g] = ready ? 1 : 0;
+                if (!ready) s_more = 1;
+            }
+            __syncthreads();
+            const int more = s_more;
+            // phase B: resolve every ready candidate with the reference's own comparisons
+            for (unsigned g = cs + threadIdx.x; g < ce; g += 1024) {
+                if (state[g] || !rdy[g]) continue;
+                const Cand c = cd[g];
+                const float fx = (float)c.x * ratio, fy = (float)c.y * ratio;
+                const float resp = fabsf(c.v);
+                const int bx = min(max((int)(fx * inv_cell), 0), nbx - 1), by = min(max((int)(fy * inv_cell), 0), nby - 1);
+                unsigned best_key = 0xffffffffu;
+                int best = -1;
+                for (int yy = max(by - 1, 0); yy <= min(by + 1, nby - 1); yy++)
+                    for (int xx = max(bx - 1, 0); xx <= min(bx + 1, nbx - 1); xx++) {
+                        const int bin = yy * nbx + xx;
+                        for (int o = binA[bin]; o >= 0; o = next[o]) {        // occupants of class e-1
+                            if (!alive[o]) continue;
+                            const Cand q = cd[o];
+                            float dx = fx - ((float)q.x * prev_ratio + prev_off), dy = fy - ((float)q.y * prev_ratio + prev_off);
+                            float dist = dx * dx + dy * dy;
+                            if (dist <= s2 && key[o] < best_key) { best_key = key[o]; best = o; }
+                        }
+                        for (int o = binB[bin]; o >= 0; o = next[o]) {        // occupants of class e (earlier candidates)
+                            if ((unsigned)o >= g || !alive[o]) continue;
+                            const Cand q = cd[o];
+                            float dx = fx - ((float)q.x * ratio + off), dy = fy - ((float)q.y * ratio + off);
+                            float dist = dx * dx + dy * dy;
+                            if (dist <= s2 && key[o] < best_key) { best_key = key[o]; best = o; }
+                        }
+                    }
+                if (best >= 0) {
+                    if (resp > fabsf(cd[best].v)) { alive[best] = 0; key[g] = best_key; alive[g] = 1; }   // replace in place
+                } else {
+                    key[g] = BASE + (g - cs); alive[g] = 1; rank[g] = 1;                                   // append
+                }
+                state[g] = 1;
+            }
+            __syncthreads();
+            if (!more) break;
+        }
+        // ---- slot keys -> real slot indices (appended slots keep candidate order)
+        unsigned carry = 0;
+        for (unsigned base = cs; base < ce; base += 1024) {
+            const unsigned g = base + threadIdx.x;
+            const unsigned v = g < ce ? rank[g] : 0u;
+            unsigned tot;
+            const unsigned ex = block_excl_scan_1024(v, s_warp, &tot);
+            if (g < ce) rank[g] = carry + ex;
+            carry += tot;
+        }
+        __syncthreads();
+        for (unsigned g = cs + threadIdx.x; g < ce; g += 1024)
+            if (alive[g] && key[g] >= BASE) key[g] = N + rank[cs + (key[g] - BASE)];
+        N += carry;
+        __syncthreads();
+        prev_cs = cs; prev_ce = ce; prev_off = off; prev_ratio = ratio;
+    }
+    // ---- materialise the cache in slot order
+    for (unsigned g = threadIdx.x; g < ntot; g += 1024) {
+        if (!alive[g]) continue;
+        const unsigned k = key[g];
+        if (k >= capk) { *overflow = 2u; continue; }
+        const Cand c = cd[g];
+        const EvoDev ev = T.e[c.e];
+        const float ratio = (float)(1 << ev.octave);
+        cvb_keypoint kp;
+        kp.x = (float)c.x * ratio + 0.5f * (ratio - 1.0f);
+        kp.y = (float)c.y * ratio + 0.5f * (ratio - 1.0f);
+        kp.response = fabsf(c.v); kp.size = ev.size; kp.angle = 0.f;
+        kp.octave = (uint32_t)ev.octave; kp.class_id = (uint32_t)c.e;
+        cache[(size_t)b * capk + k] = kp;
+    }
+    if (threadIdx.x == 0) ncache[b] = min(N, capk);
+}
+
 // Upper-scale filter (:120-140): cache[i] is dropped when a LATER cache entry of class+1 lies within
-// size_i and is at least as strong.  Thread per i; keep flags preserve order.
+// size_i and is at least as strong (any hit decides, so the scan order is irrelevant).  Thread per i,
+// later entries streamed through shared memory in SoA tiles.
 __global__ void __launch_bounds__(NT) k_filter_upper(const cvb_keypoint *__restrict__ cache,
                                                      const unsigned *__restrict__ ncache, unsigned capk,
                                                      unsigned char *__restrict__ keep) {
+    __shared__ float s_x[NT], s_y[NT], s_r[NT];
+    __shared__ unsigned s_c[NT];
     const int b = blockIdx.y;
     const unsigned n = ncache[b];
     const cvb_keypoint *kc = cache + (size_t)b * capk;
-    for (unsigned i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT) {
-        const cvb_keypoint a = kc[i];
+    for (unsigned base = blockIdx.x * NT; base < n; base += gridDim.x * NT) {
+        const unsigned i = base + threadIdx.x;
+        cvb_keypoint a;
+        a.x = a.y = a.response = a.size = 0.f; a.class_id = 0xfffffff0u;
+        if (i < n) a = kc[i];
+        const float s2 = a.size * a.size;
         bool rep = false;
-        for (unsigned j = i + 1; j < n; j++) {
-            const cvb_keypoint q = kc[j];
-            if (a.class_id + 1 == q.class_id) {
-                float dx = a.x - q.x, dy = a.y - q.y;
+        for (unsigned t = base; t < n; t += NT) {      // only entries after the chunk start can matter
+            const unsigned j = t + threadIdx.x;
+            __syncthreads();
+            if (j < n) { const cvb_keypoint q = kc[j]; s_x[threadIdx.x] = q.x; s_y[threadIdx.x] = q.y; s_r[threadIdx.x] = q.response; s_c[threadIdx.x] = q.class_id; }
+            __syncthreads();
+            const unsigned lim = min((unsigned)NT, n - t);
+            for (unsigned u = 0; u < lim; u++) {
+                if (t + u <= i || s_c[u] != a.class_id + 1) continue;
+                float dx = a.x - s_x[u], dy = a.y - s_y[u];
                 float dist = dx * dx + dy * dy;
-                if (dist <= a.size * a.size && a.response <= q.response) { rep = true; break; }
+                if (dist <= s2 && a.response <= s_r[u]) rep = true;
             }
         }
-        keep[(size_t)b * capk + i] = rep ? 0 : 1;
+        if (i < n) keep[(size_t)b * capk + i] = rep ? 0 : 1;
     }
 }
 

@@ -19,7 +19,26 @@ struct cvb_ctx {
     int num_sms = 148;
     AkazeWorkspace *akaze = nullptr;
     MatchWorkspace *match = nullptr;
+    // optional per-kernel CUDA-event profiling (bench.py roofline pass); off by default
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_pool;
+    size_t prof_used = 0;
+    struct ProfRec { const char *name; cudaEvent_t e0, e1; double bytes; };
+    std::vector<ProfRec> prof_recs;
 };
+
+cudaEvent_t cvb_prof_event(cvb_ctx *ctx);
+struct CvbProfScope {
+    cvb_ctx *ctx; const char *name; double bytes; cudaEvent_t e0 = nullptr;
+    CvbProfScope(cvb_ctx *c, const char *n, double b) : ctx(c), name(n), bytes(b) {
+        if (ctx->prof) { e0 = cvb_prof_event(ctx); cudaEventRecord(e0, ctx->stream); }
+    }
+    ~CvbProfScope() {
+        if (ctx->prof && e0) { cudaEvent_t e1 = cvb_prof_event(ctx); cudaEventRecord(e1, ctx->stream); ctx->prof_recs.push_back({name, e0, e1, bytes}); }
+    }
+};
+// PROF(ctx, "kernel", algorithmic_bytes) brackets the launches that follow in the current scope
+#define CVB_PROF(ctx, name, bytes) CvbProfScope prof_scope__((ctx), (name), (double)(bytes))
 
 int cvb_set_error(cvb_ctx *ctx, int code, const char *fmt, ...);
 void akaze_workspace_free(AkazeWorkspace *ws);

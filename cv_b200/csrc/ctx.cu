@@ -1,6 +1,8 @@
 // cv_b200/csrc/ctx.cu -- context, error reporting, stream/event plumbing of libcvb200.so.
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
+#include <vector>
 #include "common.cuh"
 
 int cvb_set_error(cvb_ctx *ctx, int code, const char *fmt, ...) {
@@ -13,7 +15,51 @@ int cvb_set_error(cvb_ctx *ctx, int code, const char *fmt, ...) {
     return code;
 }
 
+cudaEvent_t cvb_prof_event(cvb_ctx *ctx) {
+    if (ctx->prof_used == ctx->prof_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->prof_pool.push_back(e);
+    }
+    return ctx->prof_pool[ctx->prof_used++];
+}
+
 extern "C" {
+
+int cvb_ctx_profile(cvb_ctx *ctx, int enable) {
+    if (!ctx) return CVB_EINVAL;
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->prof = enable != 0;
+    ctx->prof_recs.clear();
+    ctx->prof_used = 0;
+    return 0;
+}
+
+// Text report: one line per kernel name: "name launches total_ms algorithmic_bytes"
+int cvb_ctx_profile_report(cvb_ctx *ctx, char *buf, size_t cap) {
+    if (!ctx || !buf || !cap) return CVB_EINVAL;
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    struct Agg { const char *name; int n; double ms, bytes; };
+    std::vector<Agg> agg;
+    for (auto &r : ctx->prof_recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        size_t i = 0;
+        for (; i < agg.size(); i++) if (agg[i].name == r.name || !strcmp(agg[i].name, r.name)) break;
+        if (i == agg.size()) agg.push_back({r.name, 0, 0.0, 0.0});
+        agg[i].n++; agg[i].ms += ms; agg[i].bytes += r.bytes;
+    }
+    size_t off = 0;
+    buf[0] = 0;
+    for (auto &a : agg) {
+        int w = snprintf(buf + off, cap - off, "%s %d %.6f %.0f\n", a.name, a.n, a.ms, a.bytes);
+        if (w < 0 || (size_t)w >= cap - off) break;
+        off += (size_t)w;
+    }
+    ctx->prof_recs.clear();
+    ctx->prof_used = 0;
+    return 0;
+}
 
 const char *cvb_version(void) { return "cvb200 0.1.0 (sm_100a)"; }
 
@@ -48,6 +94,7 @@ void cvb_ctx_destroy(cvb_ctx *ctx) {
     match_workspace_free(ctx->match);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

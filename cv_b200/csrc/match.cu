@@ -211,6 +211,7 @@ template <int K>
 int launch_knn(cvb_ctx *ctx, const uint8_t *q, const uint32_t *n_dev, uint32_t n, const uint8_t *db, const uint32_t *m_dev,
                uint32_t m, uint32_t splits, uint32_t chunk, uint32_t *partial, uint32_t *idx, uint32_t *dist) {
     dim3 grid(cdiv(n, QT), splits);
+    CVB_PROF(ctx, "k_hamming_knn", 64.0 * (double)n * (double)m);
     k_hamming_knn<K><<<grid, QT, 0, ctx->stream>>>(q, n_dev, n, db, m_dev, m, chunk, partial);
     CVB_LAUNCH_CHECK(ctx);
     k_knn_merge<K><<<cdiv(n, 128), 128, 0, ctx->stream>>>(partial, n_dev, n, splits, chunk, idx, dist);

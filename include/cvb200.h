@@ -82,6 +82,12 @@ uint64_t cvb_ctx_launch_count(const cvb_ctx *ctx);
 int cvb_ctx_timer_begin(cvb_ctx *ctx);
 int cvb_ctx_timer_end(cvb_ctx *ctx, float *ms_out);
 
+/* Optional per-kernel profiling with CUDA events on the context stream (used by bench.py for the
+ * roofline line; adds event overhead, so never enabled inside a timed throughput region).
+ * cvb_ctx_profile_report writes one text line per kernel: "name launches total_ms algorithmic_bytes". */
+int cvb_ctx_profile(cvb_ctx *ctx, int enable);
+int cvb_ctx_profile_report(cvb_ctx *ctx, char *buf, size_t cap);
+
 /* ---- AKAZE ------------------------------------------------------------------------------ */
 void cvb_akaze_default_cfg(cvb_akaze_cfg *cfg);      /* Akaze::default(), lib.rs:169-185 */
 

@@ -82,6 +82,9 @@ def test_non_default_config():
     img = synth_frame(7, h=240, w=320, nblobs=400)
     _compare_all(img, 0.002, num_sublevels=3, max_octave_evolution=3, descriptor_channels=2, maximum_features=40)
     _compare_all(img, 0.002, descriptor_channels=1, contrast_factor_num_bins=128, contrast_percentile=0.6)
+    # derivative sigma 1 takes the un-normalised simple Scharr path (derivatives.rs:24-26); sigma 5 a wider kernel
+    _compare_all(img, 0.05, derivative_factor=0.7)
+    _compare_all(img, 0.0005, derivative_factor=3.0, base_scale_offset=1.2)
 
 
 def test_batch_equals_single_and_is_deterministic():
