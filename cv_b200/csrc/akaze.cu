@@ -113,11 +113,13 @@ struct AkazeWorkspace {
     unsigned *rowcount = nullptr, *rowoff = nullptr, *ncand = nullptr;
     Cand *cand = nullptr;
     cvb_keypoint *cache = nullptr, *refined = nullptr, *sorted = nullptr;
-    unsigned *ncache = nullptr, *nsorted = nullptr;
+    unsigned *ncache = nullptr, *nsorted = nullptr, *nvalid = nullptr, *rank = nullptr;
     unsigned char *keep = nullptr, *valid = nullptr, *ok = nullptr, *desc_tmp = nullptr;
     unsigned *overflow = nullptr;
     SupScratch sup{};
     bool suppress_seq = false;   // CVB_SUPPRESS_SEQ=1: serial reference kernel (debug / A-B check)
+    bool suppress_par_only = false;   // CVB_SUPPRESS_GLOBAL=1: force the global-memory parallel kernel
+    unsigned *sup_fallback = nullptr;
     OrientTables *ot = nullptr;
     DescTables *dt = nullptr;
     // outputs owned by the workspace for the host-pointer API
@@ -171,7 +173,7 @@ int plan_evolutions(cvb_ctx *ctx, AkazeWorkspace *ws) {
     if (ws->evo.size() > (size_t)MAX_EVO) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "more than %d evolutions", MAX_EVO);
     int lw = (int)ws->w, lh = (int)ws->h;
     size_t off = 0;
-    int rowbase = 0;
+    int rowbase = 0, tilebase = 0;
     for (size_t i = 0; i < ws->evo.size(); i++) {
         EvoHost &e = ws->evo[i];
         e.new_octave = i > 0 && e.octave > ws->evo[i - 1].octave;
@@ -196,10 +198,14 @@ int plan_evolutions(cvb_ctx *ctx, AkazeWorkspace *ws) {
         d.w = e.w; d.h = e.h; d.off = e.off; d.octave = (int)e.octave;
         d.size = (float)(e.esigma * c.derivative_factor);
         d.rowbase = rowbase; d.pad = 0;
+        d.tilebase = tilebase; d.sigma = (int)e.sigma; d.norm = e.norm; d.middle = e.middle; d.quat = e.quat;
         rowbase += e.h;
+        tilebase += (int)(cdiv((unsigned)e.w, TW) * cdiv((unsigned)e.h, TH));
     }
     ws->table.n = (int)ws->evo.size();
     ws->table.total_rows = rowbase;
+    ws->table.total_tiles = tilebase;
+    ws->table.pad = 0;
     ws->plane_floats = off;
     return 0;
 }
@@ -238,6 +244,7 @@ int build_tables(cvb_ctx *ctx, AkazeWorkspace *ws) {
     DescTables dt;
     memset(&dt, 0, sizeof(dt));
     const int pattern = (int)ws->cfg.descriptor_pattern_size, nch = (int)ws->cfg.descriptor_channels;
+
     const float size_mult[3] = {1.0f, 2.0f / 3.0f, 1.0f / 2.0f};
     int base[3], ncell = 0;
     for (int lvl = 0; lvl < 3; lvl++) {
@@ -253,6 +260,10 @@ int build_tables(cvb_ctx *ctx, AkazeWorkspace *ws) {
             }
     }
     dt.ncells = ncell;
+    int kmax = -pattern;
+    for (int c = 0; c < ncell; c++) kmax = std::max(kmax, dt.ci[c] + dt.cstep[c] - 1);
+    dt.nlat = kmax + pattern + 1;
+    if (dt.nlat > DESC_MAXLAT) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "descriptor_pattern_size %d needs a %d-point lattice (max %d)", pattern, dt.nlat, DESC_MAXLAT);
     int bit = 0;
     for (int lvl = 0; lvl < 3; lvl++) {
         int count = (lvl + 2) * (lvl + 2);
@@ -303,7 +314,7 @@ int ensure_workspace(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, uint32_t batch, uin
     DA(rowcount, B * R); DA(rowoff, B * R); DA(ncand, B);
     DA(cand, B * ws->capc);
     DA(cache, B * ws->capk); DA(refined, B * ws->capk); DA(sorted, B * ws->capk);
-    DA(ncache, B); DA(nsorted, B);
+    DA(ncache, B); DA(nsorted, B); DA(nvalid, B); DA(rank, B * ws->capk);
     DA(keep, B * ws->capk); DA(valid, B * ws->capk); DA(ok, B * ws->capk); DA(desc_tmp, B * ws->capk * 64);
     DA(overflow, 1);
     {   // scratch of the parallel duplicate suppression; bins sized for the finest class grid
@@ -320,6 +331,10 @@ int ensure_workspace(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, uint32_t batch, uin
         DA(sup.binA, B * nbmax); DA(sup.binB, B * nbmax);
         const char *env = getenv("CVB_SUPPRESS_SEQ");
         ws->suppress_seq = env && env[0] == '1';
+        env = getenv("CVB_SUPPRESS_GLOBAL");
+        ws->suppress_par_only = env && env[0] == '1';
+        DA(sup_fallback, B);
+        cudaFuncSetAttribute(k_suppress_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SUP_SMEM);
     }
     DA(ot, 1); DA(dt, 1);
     DA(kp_out, B * (size_t)cap_out); DA(desc_out, B * (size_t)cap_out * 64); DA(n_out, B);
@@ -329,6 +344,8 @@ int ensure_workspace(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, uint32_t batch, uin
     // opt in to large dynamic shared memory where a configuration needs it
     cudaFuncSetAttribute(k_separable, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_deriv1_all, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_deriv2_det_all, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_deriv1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_deriv1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_deriv1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -344,6 +361,14 @@ inline dim3 tile_grid(int w, int h, unsigned B) { return dim3(cdiv((unsigned)w, 
 
 int launch_separable(cvb_ctx *ctx, const float *in, size_t in_bs, float *out, size_t out_bs, int w, int h, unsigned B,
                      const Taps &hk, const Taps &vk) {
+    if (hk.ks == vk.ks && (hk.ks == 5 || hk.ks == 9) && memcmp(hk.k, vk.k, sizeof(float) * hk.ks) == 0) {
+        CVB_PROF(ctx, "k_blur", 8.0 * w * h * B);
+        dim3 g(cdiv((unsigned)w, BW), cdiv((unsigned)h, BH), B);
+        if (hk.ks == 5) k_blur<5><<<g, NT, 0, ctx->stream>>>(in, out, w, h, in_bs, out_bs, hk);
+        else k_blur<9><<<g, NT, 0, ctx->stream>>>(in, out, w, h, in_bs, out_bs, hk);
+        CVB_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     int rx = hk.ks / 2, ry = vk.ks / 2;
     size_t smem = sizeof(float) * ((size_t)(TH + 2 * ry) * (TW + 2 * rx) + (size_t)(TH + 2 * ry) * TW);
     { CVB_PROF(ctx, "k_separable", 8.0 * w * h * B);
@@ -409,7 +434,7 @@ int run_extract(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoint *kp_
     rc = launch_separable(ctx, images, P0, ws->tmpA, P0, W, H, B, ws->g1, ws->g1);
     if (rc) return rc;
     { CVB_PROF(ctx, "k_contrast_grad", 4.0 * W * H * B);
-    k_scharr_pm<1><<<tile_grid(W, H, B), NT, 0, st>>>(ws->tmpA, nullptr, ws->g2, ws->gmax, W, H, P0, P0, nullptr, 0);
+    k_scharr_pm2<1><<<dim3(cdiv((unsigned)W, BW), cdiv((unsigned)H, BH), B), NT, 0, st>>>(ws->tmpA, nullptr, ws->g2, ws->gmax, W, H, P0, P0, nullptr, 0);
     CVB_LAUNCH_CHECK(ctx); }
     {
         unsigned blocks = std::min<unsigned>(cdiv((unsigned)P0, NT), (unsigned)ctx->num_sms * 8);
@@ -437,10 +462,10 @@ int run_extract(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoint *kp_
         if (rc) return rc;
         // Lflow = pm_g2(simple_scharr_x(Lsmooth), simple_scharr_y(Lsmooth), contrast)
         { CVB_PROF(ctx, "k_scharr_pm", 8.0 * e.w * e.h * B);
-        k_scharr_pm<0><<<tile_grid(e.w, e.h, B), NT, 0, st>>>(ws->Lsm + e.off, ws->Lflow + e.off, nullptr, nullptr, e.w, e.h, PF, PF,
+        k_scharr_pm2<0><<<dim3(cdiv((unsigned)e.w, BW), cdiv((unsigned)e.h, BH), B), NT, 0, st>>>(ws->Lsm + e.off, ws->Lflow + e.off, nullptr, nullptr, e.w, e.h, PF, PF,
                                                              ws->inv_k + i, MAX_EVO);
         CVB_LAUNCH_CHECK(ctx); }
-        // FED steps, FED_SMAX per launch; the chain ends in Lt_i
+        // FED steps: nl launches of at most FED_SMAX fused steps (balanced split); the chain ends in Lt_i
         const int n = (int)e.tau.size();
         const int nl = (n + FED_SMAX - 1) / FED_SMAX;
         if (nl == 0) {
@@ -448,29 +473,36 @@ int run_extract(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoint *kp_
                                             (size_t)e.w * e.h * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
         }
         const float *cur = src; size_t cur_bs = src_bs;
+        int done = 0;
         for (int l = 0; l < nl; l++) {
             FedSteps fs;
-            fs.n = std::min(FED_SMAX, n - l * FED_SMAX);
-            for (int t = 0; t < fs.n; t++) fs.tau[t] = (float)e.tau[(size_t)(l * FED_SMAX + t)];
+            fs.n = (n - done + (nl - l) - 1) / (nl - l);
+            for (int t = 0; t < fs.n; t++) fs.tau[t] = (float)e.tau[(size_t)(done + t)];
+            done += fs.n;
             // destinations alternate tmpA/tmpB so that the last one is Lt_i
             float *dst; size_t dst_bs;
             if (l == nl - 1) { dst = ws->Lt + e.off; dst_bs = PF; }
             else if (((nl - 1 - l) & 1) == 1) { dst = ws->tmpA; dst_bs = P0; }
             else { dst = ws->tmpB; dst_bs = P0; }
-            size_t smem = sizeof(float) * 3 * (size_t)(TW + 2 * fs.n) * (TH + 2 * fs.n);
             { CVB_PROF(ctx, "k_fed", 12.0 * fs.n * e.w * e.h * B);
-            k_fed<<<tile_grid(e.w, e.h, B), NT, smem, st>>>(cur, ws->Lflow + e.off, dst, e.w, e.h, cur_bs, PF, dst_bs, fs);
+            dim3 grd(cdiv((unsigned)e.w, (unsigned)(FR_W - 2 * fs.n)), cdiv((unsigned)e.h, (unsigned)(FR_H - 2 * fs.n)), B);
+            k_fed2<<<grd, 1024, 0, st>>>(cur, ws->Lflow + e.off, dst, e.w, e.h, cur_bs, PF, dst_bs, fs);
             CVB_LAUNCH_CHECK(ctx); }
             cur = dst; cur_bs = dst_bs;
         }
     }
-    // ---- detector_response (detector_response.rs:8-85)
-    for (int i = 0; i < E; i++) {
-        const EvoHost &e = ws->evo[i];
-        rc = launch_deriv1(ctx, e, ws->Lsm + e.off, ws->Lx + e.off, ws->Ly + e.off, PF, B);
-        if (rc) return rc;
-        rc = launch_deriv2(ctx, e, ws->Lx + e.off, ws->Ly + e.off, ws->Ldet + e.off, PF, B);
-        if (rc) return rc;
+    // ---- detector_response (detector_response.rs:8-85): two launches cover every evolution
+    {
+        int smax = 1;
+        for (const EvoHost &e : ws->evo) smax = std::max(smax, (int)e.sigma);
+        const size_t sh = (size_t)(TH + 2 * smax), sw = (size_t)(TW + 2 * smax);
+        dim3 g((unsigned)ws->table.total_tiles, 1, B);
+        { CVB_PROF(ctx, "k_deriv1_all", 12.0 * (double)ws->plane_floats * B);
+        k_deriv1_all<<<g, NT, sizeof(float) * (sh * sw + 2 * sh * TW), st>>>(ws->Lsm, ws->Lx, ws->Ly, PF, ws->table);
+        CVB_LAUNCH_CHECK(ctx); }
+        { CVB_PROF(ctx, "k_deriv2_det_all", 12.0 * (double)ws->plane_floats * B);
+        k_deriv2_det_all<<<g, NT, sizeof(float) * (2 * sh * sw + 3 * sh * TW), st>>>(ws->Lx, ws->Ly, ws->Ldet, PF, ws->table);
+        CVB_LAUNCH_CHECK(ctx); }
     }
     // ---- detect_keypoints (scale_space_extrema.rs)
     const int R = ws->table.total_rows;
@@ -490,27 +522,40 @@ int run_extract(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoint *kp_
     { CVB_PROF(ctx, "k_suppress", 0);
     if (ws->suppress_seq)
         k_suppress_seq<<<B, 1024, 0, st>>>(ws->cand, ws->ncand, ws->capc, ws->table, ws->cache, ws->ncache, ws->capk, ws->overflow);
-    else
+    else {
+        k_suppress_smem<<<B, 1024, SUP_SMEM, st>>>(ws->cand, ws->ncand, ws->rowoff, ws->capc, ws->table, ws->sup, ws->cache,
+                                                   ws->ncache, ws->capk, ws->overflow, ws->sup_fallback);
+        CVB_LAUNCH_CHECK(ctx);
         k_suppress_par<<<B, 1024, 0, st>>>(ws->cand, ws->ncand, ws->rowoff, ws->capc, ws->table, ws->sup, ws->cache, ws->ncache,
-                                           ws->capk, ws->overflow);
+                                           ws->capk, ws->overflow, ws->suppress_par_only ? nullptr : ws->sup_fallback);
+    }
     CVB_LAUNCH_CHECK(ctx); }
     const unsigned kp_blocks = (unsigned)ctx->num_sms * 2;
+    const unsigned ichunks = std::min<unsigned>(cdiv(ws->capk, NT), 64u);
+    CVB_CUDA(ctx, cudaMemsetAsync(ws->keep, 1, (size_t)B * ws->capk, st));
     { CVB_PROF(ctx, "k_filter_upper", 0);
-    k_filter_upper<<<dim3(kp_blocks, B), NT, 0, st>>>(ws->cache, ws->ncache, ws->capk, ws->keep);
+    k_filter_upper<<<dim3(ichunks, 16, B), NT, 0, st>>>(ws->cache, ws->ncache, ws->capk, ws->keep);
     CVB_LAUNCH_CHECK(ctx); }
     { CVB_PROF(ctx, "k_refine_orient", 0);
     k_refine_orient<<<dim3(kp_blocks, B), NT, 0, st>>>(ws->cache, ws->ncache, ws->capk, ws->keep, ws->table, ws->Ldet, ws->Lx, ws->Ly, PF,
                                                        ws->ot, ws->refined, ws->valid);
     CVB_LAUNCH_CHECK(ctx); }
     // ---- sort + truncate (lib.rs:326-327)
+    CVB_CUDA(ctx, cudaMemsetAsync(ws->rank, 0, sizeof(unsigned) * (size_t)B * ws->capk, st));
+    CVB_CUDA(ctx, cudaMemsetAsync(ws->nvalid, 0, sizeof(unsigned) * B, st));
     { CVB_PROF(ctx, "k_rank_sort", 0);
-    k_rank_sort<<<dim3(kp_blocks, B), NT, 0, st>>>(ws->refined, ws->valid, ws->ncache, ws->capk, (long long)ws->cfg.maximum_features,
-                                                   ws->sorted, ws->nsorted);
+    k_rank_count<<<dim3(ichunks, 16, B), NT, 0, st>>>(ws->refined, ws->valid, ws->ncache, ws->capk, ws->rank);
+    CVB_LAUNCH_CHECK(ctx);
+    k_rank_scatter<<<dim3(ichunks, B), NT, 0, st>>>(ws->refined, ws->valid, ws->ncache, ws->capk, ws->rank,
+                                                    (long long)ws->cfg.maximum_features, ws->sorted, ws->nvalid);
+    CVB_LAUNCH_CHECK(ctx);
+    k_clamp_count<<<cdiv(B, 32), 32, 0, st>>>(ws->nvalid, (long long)ws->cfg.maximum_features, ws->nsorted, (int)B);
     CVB_LAUNCH_CHECK(ctx); }
     // ---- extract_descriptors (descriptors.rs:16-45)
     { CVB_PROF(ctx, "k_descriptors", 0);
-    k_descriptors<<<dim3(kp_blocks, B), NT, 0, st>>>(ws->sorted, ws->nsorted, ws->capk, ws->table, ws->Lt, ws->Lx, ws->Ly, PF, ws->dt,
-                                                     (int)ws->cfg.descriptor_channels, ws->desc_tmp, ws->ok);
+    k_descriptors<<<dim3((unsigned)ctx->num_sms * 8, B), DESC_WARPS * 32, 0, st>>>(ws->sorted, ws->nsorted, ws->capk, ws->table, ws->Lt, ws->Lx,
+                                                     ws->Ly, PF, ws->dt, (int)ws->cfg.descriptor_channels,
+                                                     (int)ws->cfg.descriptor_pattern_size, ws->desc_tmp, ws->ok);
     CVB_LAUNCH_CHECK(ctx); }
     { CVB_PROF(ctx, "k_compact_final", 0);
     k_compact_final<<<B, 1024, 0, st>>>(ws->sorted, ws->desc_tmp, ws->ok, ws->nsorted, ws->capk, kp_out, desc_out, cap_out, n_out,

@@ -102,3 +102,21 @@ def test_full_hd_frame_parity():
     img = synth_frame(0)
     kps, d = _compare_all(img, 0.001, maximum_features=5000)
     assert len(d) > 1000
+
+
+def test_suppression_kernel_variants_agree():
+    """The shared-memory, global-memory and serial duplicate-suppression kernels give identical output."""
+    import hashlib
+    import subprocess
+    import sys
+    code = ("import numpy as np, hashlib, cv_b200; from tests.common import kitti_frame; "
+            "k, d = cv_b200.Akaze().extract_from_gray_float_image(kitti_frame('0000000000')); "
+            "print(len(d), hashlib.sha1(d.tobytes() + k.tobytes()).hexdigest())")
+    outs = []
+    for var in (None, "CVB_SUPPRESS_GLOBAL", "CVB_SUPPRESS_SEQ"):
+        env = dict(os.environ)
+        if var:
+            env[var] = "1"
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=600).stdout.strip())
+    assert outs[0].startswith("3425 ") and outs[0] == outs[1] == outs[2], outs
