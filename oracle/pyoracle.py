@@ -192,3 +192,161 @@ def hamming_knn(q, db, k=2):
     idx = np.empty((len(q), k), np.uint32); dist = np.empty((len(q), k), np.uint32)
     lib().ref_hamming_knn(q.ctypes.data, len(q), db.ctypes.data, len(db), k, idx.ctypes.data, dist.ctypes.data)
     return idx, dist
+
+
+# ---------------------------------------------------------------------------------------------
+# geometry oracle (oracle/ref_geom.c)
+class Pose(C.Structure):
+    _fields_ = [("R", C.c_double * 9), ("t", C.c_double * 3)]
+
+    def numpy(self):
+        return np.array(self.R, dtype=np.float64).reshape(3, 3), np.array(self.t, dtype=np.float64)
+
+
+class Rng(C.Structure):
+    _fields_ = [("kind", C.c_int), ("s", C.c_uint64 * 4)]
+
+
+class ArrsacCfg(C.Structure):
+    _fields_ = [("inlier_threshold", C.c_double), ("initialization_hypotheses", C.c_uint32), ("initialization_blocks", C.c_uint32),
+                ("max_candidate_hypotheses", C.c_uint32), ("estimations_per_block", C.c_uint32), ("block_size", C.c_uint32),
+                ("likelihood_ratio_threshold", C.c_float), ("initial_epsilon", C.c_float), ("initial_delta", C.c_float)]
+
+
+_geom_ready = False
+
+
+def _geom():
+    global _geom_ready
+    L = lib()
+    if not _geom_ready:
+        dp = C.POINTER(C.c_double)
+        L.ref_sym_eigen.argtypes = [C.c_int, dp, C.c_double, C.c_int, dp, dp]
+        L.ref_eight_point_essential.argtypes = [dp, dp, C.c_double, C.c_int, dp]
+        L.ref_essential_poses.argtypes = [dp, C.c_double, C.c_int, C.POINTER(Pose)]
+        L.ref_eight_point.argtypes = [dp, dp, C.POINTER(Pose)]
+        L.ref_essential_residual.restype = C.c_double
+        L.ref_essential_residual.argtypes = [dp, dp, dp]
+        L.ref_residual_c2c.restype = C.c_double
+        L.ref_residual_c2c.argtypes = [C.POINTER(Pose), dp, dp]
+        L.ref_residual_w2c.restype = C.c_double
+        L.ref_residual_w2c.argtypes = [C.POINTER(Pose), dp, dp]
+        L.ref_p3p.argtypes = [dp, dp, C.POINTER(Pose)]
+        L.ref_triangulate_linear_eigen.argtypes = [C.POINTER(Pose), dp, C.c_int, dp]
+        L.ref_calibrate.argtypes = [C.c_double] * 7 + [dp]
+        L.ref_rng_seed_xoshiro.argtypes = [C.POINTER(Rng), C.c_uint64]
+        L.ref_rng_seed_pcg64.argtypes = [C.POINTER(Rng), C.c_char_p]
+        L.ref_rng_next_u32.restype = C.c_uint32
+        L.ref_rng_next_u32.argtypes = [C.POINTER(Rng)]
+        L.ref_arrsac_default_cfg.argtypes = [C.POINTER(ArrsacCfg), C.c_double]
+        L.ref_arrsac.argtypes = [C.POINTER(ArrsacCfg), C.c_int, dp, dp, C.c_uint32, C.POINTER(Rng), C.POINTER(Pose),
+                                 C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        _geom_ready = True
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def make_pose(R, t):
+    p = Pose()
+    p.R[:] = list(np.asarray(R, np.float64).reshape(9))
+    p.t[:] = list(np.asarray(t, np.float64).reshape(3))
+    return p
+
+
+def sym_eigen(A, eps=1e-12, iters=1000):
+    A = np.ascontiguousarray(A, np.float64); n = A.shape[0]
+    d = np.zeros(n); V = np.zeros((n, n))
+    ok = _geom().ref_sym_eigen(n, _dp(A), eps, iters, _dp(d), _dp(V))
+    return ok, d, V
+
+
+def eight_point_essential(a, b, eps=1e-12, iters=1000):
+    a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+    E = np.zeros((3, 3))
+    ok = _geom().ref_eight_point_essential(_dp(a), _dp(b), eps, iters, _dp(E))
+    return E if ok else None
+
+
+def essential_poses(E, eps=1e-12, iters=1000):
+    E = np.ascontiguousarray(E, np.float64)
+    out = (Pose * 4)()
+    n = _geom().ref_essential_poses(_dp(E), eps, iters, out)
+    return [out[i].numpy() for i in range(n)]
+
+
+def eight_point(a, b):
+    a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+    out = (Pose * 4)()
+    n = _geom().ref_eight_point(_dp(a), _dp(b), out)
+    return [out[i].numpy() for i in range(n)]
+
+
+def essential_residual(E, a, b):
+    E = np.ascontiguousarray(E, np.float64); a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+    return _geom().ref_essential_residual(_dp(E), _dp(a), _dp(b))
+
+
+def residual_c2c(R, t, a, b):
+    p = make_pose(R, t); a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+    return _geom().ref_residual_c2c(C.byref(p), _dp(a), _dp(b))
+
+
+def residual_w2c(R, t, bearing, world):
+    p = make_pose(R, t); a = np.ascontiguousarray(bearing, np.float64); b = np.ascontiguousarray(world, np.float64)
+    return _geom().ref_residual_w2c(C.byref(p), _dp(a), _dp(b))
+
+
+def p3p(bearings, world):
+    a = np.ascontiguousarray(bearings, np.float64); b = np.ascontiguousarray(world, np.float64)
+    out = (Pose * 4)()
+    n = _geom().ref_p3p(_dp(a), _dp(b), out)
+    return [out[i].numpy() for i in range(n)]
+
+
+def triangulate_linear_eigen(poses, bearings):
+    arr = (Pose * len(poses))(*[make_pose(R, t) for R, t in poses])
+    b = np.ascontiguousarray(bearings, np.float64)
+    out = np.zeros(4)
+    ok = _geom().ref_triangulate_linear_eigen(arr, _dp(b), len(poses), _dp(out))
+    return out if ok else None
+
+
+def calibrate(fx, fy, cx, cy, skew, px, py):
+    out = np.zeros(3)
+    _geom().ref_calibrate(fx, fy, cx, cy, skew, px, py, _dp(out))
+    return out
+
+
+def rng_xoshiro(seed):
+    r = Rng(); _geom().ref_rng_seed_xoshiro(C.byref(r), seed); return r
+
+
+def rng_pcg64(seed_bytes):
+    r = Rng(); _geom().ref_rng_seed_pcg64(C.byref(r), bytes(seed_bytes)); return r
+
+
+def rng_next_u32(r):
+    return _geom().ref_rng_next_u32(C.byref(r))
+
+
+def arrsac_cfg(threshold, **kw):
+    c = ArrsacCfg(); _geom().ref_arrsac_default_cfg(C.byref(c), threshold)
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def arrsac(cfg, kind, a, b, rng):
+    """kind 0: EightPoint over FeatureMatch(a[n,3], b[n,3]); kind 1: LambdaTwist over (bearing[n,3], world[n,4])."""
+    a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+    n = len(a)
+    model = Pose(); inl = np.zeros(max(n, 1), np.uint32); cnt = C.c_uint32()
+    ok = _geom().ref_arrsac(C.byref(cfg), kind, _dp(a), _dp(b), n, C.byref(rng), C.byref(model),
+                            inl.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(cnt))
+    if not ok:
+        return None
+    R, t = model.numpy()
+    return R, t, inl[:cnt.value].copy()

@@ -1,0 +1,628 @@
+/* oracle/ref_geom.c -- TEST INFRASTRUCTURE: CPU restatement of the geometric-verification half of the
+ * hot path.  Not product code.
+ *
+ * Follows (paths relative to /root/reference):
+ *   eight-point/src/lib.rs:11-84            encode_epipolar_equation (incl. the b/a.z quirk), from_matches, estimate
+ *   cv-pinhole/src/essential.rs:114-231     possible_rotations_unscaled_translation / possible_unscaled_poses
+ *   cv-pinhole/src/essential.rs:266-275     EssentialMatrix::residual
+ *   cv-pinhole/src/lib.rs:108-116           CameraIntrinsics::calibrate (no distortion)
+ *   cv-core/src/pose.rs:194-202, 249-296    WorldToCamera::residual, CameraToCamera::residual
+ *   cv-core/src/point.rs:20-25              Projective::from_homogeneous
+ *   lambda-twist/src/lib.rs:110-317,361-554 compute_poses_nordberg and helpers
+ *   cv-geom/src/triangulation.rs:82-130     LinearEigenTriangulator
+ * and, from crates that are NOT in /root/reference (restated from their published algorithms):
+ *   nalgebra 0.30.1   try_symmetric_eigen / SVD  -> here: cyclic Jacobi (same mathematical result up to the
+ *                     sign/order of eigenvectors, which nalgebra does not specify either); Rotation3::from_matrix_eps
+ *   arrsac 0.10.0     adaptive real-time RANSAC   -> ref_arrsac_* below: restated from the crate's documented
+ *                     parameters and the ARRSAC paper.  PARITY UNPINNED against the real crate (source unavailable;
+ *                     SURVEY.md hard part 4): the in-tree tests only pin "all 11 matches are inliers"
+ *                     (akaze/tests/estimate_pose.rs:75) and "pose from 5 exact points to 1e-6"
+ *                     (lambda-twist/tests/consensus.rs:18-66), both checked in tests/test_oracle_geom.py.
+ *   rand_xoshiro 0.6 / rand 0.8 SmallRng (xoshiro256++, SplitMix64 seeding), rand_pcg 0.3 Pcg64 (Lcg128Xsl64).
+ * All arithmetic is f64; the comparison bar for f64 results is 1e-6 relative (BASELINE.json north_star).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "ref_geom.h"
+
+/* ------------------------------------------------------------------ small linear algebra */
+/* cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (row-major, n <= 9).
+ * d: eigenvalues, V: eigenvectors as COLUMNS (row-major n x n).  Returns 1 when converged. */
+int ref_sym_eigen(int n, const double *Ain, double eps, int max_sweeps, double *d, double *V) {
+    double A[81];
+    memcpy(A, Ain, sizeof(double) * (size_t)n * n);
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) V[i * n + j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < n; i++) {
+            diag += A[i * n + i] * A[i * n + i];
+            for (int j = i + 1; j < n; j++) off += A[i * n + j] * A[i * n + j];
+        }
+        if (off <= eps * eps * diag || off == 0.0) {
+            for (int i = 0; i < n; i++) d[i] = A[i * n + i];
+            return 1;
+        }
+        for (int p = 0; p < n - 1; p++)
+            for (int q = p + 1; q < n; q++) {
+                double apq = A[p * n + q];
+                if (apq == 0.0) continue;
+                double app = A[p * n + p], aqq = A[q * n + q];
+                double theta = (aqq - app) / (2.0 * apq);
+                double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; k++) {
+                    double akp = A[k * n + p], akq = A[k * n + q];
+                    A[k * n + p] = c * akp - s * akq;
+                    A[k * n + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; k++) {
+                    double apk = A[p * n + k], aqk = A[q * n + k];
+                    A[p * n + k] = c * apk - s * aqk;
+                    A[q * n + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < n; k++) {
+                    double vkp = V[k * n + p], vkq = V[k * n + q];
+                    V[k * n + p] = c * vkp - s * vkq;
+                    V[k * n + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < n; i++) d[i] = A[i * n + i];
+    return 0;
+}
+
+static void mat3_mul(const double *a, const double *b, double *o) {
+    double r[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) r[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
+    memcpy(o, r, sizeof(r));
+}
+static double det3(const double *m) {
+    return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+static void cross3(const double *a, const double *b, double *o) {
+    double r[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
+}
+static double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static double norm3(const double *a) { return sqrt(dot3(a, a)); }
+
+/* sorted (descending) SVD of a 3x3 matrix: M = U diag(s) Vt, via the eigen-decomposition of MtM */
+int ref_svd3(const double *M, double eps, int max_iter, double *U, double *s, double *Vt) {
+    double MtM[9], d[3], V[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) MtM[i * 3 + j] = M[i] * M[j] + M[3 + i] * M[3 + j] + M[6 + i] * M[6 + j];
+    if (!ref_sym_eigen(3, MtM, eps, max_iter, d, V)) return 0;
+    int ord[3] = {0, 1, 2};
+    for (int i = 0; i < 2; i++)
+        for (int j = i + 1; j < 3; j++)
+            if (d[ord[j]] > d[ord[i]]) { int t = ord[i]; ord[i] = ord[j]; ord[j] = t; }
+    double v[3][3], u[3][3];
+    for (int k = 0; k < 3; k++) {
+        for (int r = 0; r < 3; r++) v[k][r] = V[r * 3 + ord[k]];
+        s[k] = sqrt(d[ord[k]] > 0.0 ? d[ord[k]] : 0.0);
+    }
+    /* u_k = M v_k / s_k for the two leading triplets; the third left vector is fixed up to sign by
+     * orthogonality and its sign is normalised by the caller's det(U) > 0 rule (essential.rs:139-143),
+     * so u_3 = u_1 x u_2 (robust when s_3 ~ 0, the essential-matrix case). */
+    double tiny = 1e-12 * (s[0] > 0.0 ? s[0] : 1.0);
+    for (int k = 0; k < 2; k++) {
+        if (!(s[k] > tiny)) return 0; /* rank <= 1: no essential-matrix decomposition */
+        for (int r = 0; r < 3; r++) u[k][r] = (M[r * 3] * v[k][0] + M[r * 3 + 1] * v[k][1] + M[r * 3 + 2] * v[k][2]) / s[k];
+    }
+    cross3(u[0], u[1], u[2]);
+    {
+        double nn = norm3(u[2]);
+        if (!(nn > 0.0)) return 0;
+        for (int r = 0; r < 3; r++) u[2][r] /= nn;
+    }
+    for (int k = 0; k < 3; k++)
+        for (int r = 0; r < 3; r++) { U[r * 3 + k] = u[k][r]; Vt[k * 3 + r] = v[k][r]; }
+    return 1;
+}
+
+/* ------------------------------------------------------------------ eight-point */
+/* eight-point/src/lib.rs:11-24,43-58: a, b are unit bearings (8 x 3 each). E is row-major. */
+int ref_eight_point_essential(const double *a, const double *b, double eps, int iters, double *E) {
+    double A[8][9], EtE[81], d[9], V[81];
+    for (int i = 0; i < 8; i++) {
+        const double *pa = a + 3 * i, *pb = b + 3 * i;
+        double ap[3] = {pa[0] / pa[2], pa[1] / pa[2], pa[2] / pa[2]};
+        double bp[3] = {pb[0] / pa[2], pb[1] / pa[2], pb[2] / pa[2]}; /* sic: b is divided by a.z (lib.rs:16) */
+        for (int j = 0; j < 3; j++)
+            for (int k = 0; k < 3; k++) A[i][3 * j + k] = ap[j] * bp[k];
+    }
+    for (int r = 0; r < 9; r++)
+        for (int c = 0; c < 9; c++) {
+            double s = 0.0;
+            for (int i = 0; i < 8; i++) s += A[i][r] * A[i][c];
+            EtE[r * 9 + c] = s;
+        }
+    if (!ref_sym_eigen(9, EtE, eps, iters, d, V)) return 0;
+    int best = 0;
+    for (int i = 1; i < 9; i++)
+        if (d[i] < d[best]) best = i;
+    /* Matrix3::from_iterator fills column-major: e[0..3] is column 0 (lib.rs:56) */
+    for (int k = 0; k < 9; k++) E[(k % 3) * 3 + (k / 3)] = V[k * 9 + best];
+    return 1;
+}
+
+/* cv-pinhole/src/essential.rs:114-162,217-231 -> 4 poses (R row-major, t) in the reference's order */
+int ref_essential_poses(const double *E, double eps, int iters, ref_pose out[4]) {
+    double U[9], s[3], Vt[9];
+    if (!ref_svd3(E, eps, iters, U, s, Vt)) return 0;
+    if (det3(U) < 0.0) for (int r = 0; r < 3; r++) U[r * 3 + 2] *= -1.0;
+    if (det3(Vt) < 0.0) for (int c = 0; c < 3; c++) Vt[6 + c] *= -1.0;
+    const double W[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1}, Wt[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1};
+    double UW[9], Ra[9], Rb[9];
+    mat3_mul(U, W, UW); mat3_mul(UW, Vt, Ra);
+    mat3_mul(U, Wt, UW); mat3_mul(UW, Vt, Rb);
+    double t[3] = {U[2], U[5], U[8]};
+    for (int k = 0; k < 4; k++) {
+        memcpy(out[k].R, (k & 1) ? Rb : Ra, sizeof(double) * 9);
+        for (int r = 0; r < 3; r++) out[k].t[r] = (k & 2) ? -t[r] : t[r];
+    }
+    return 4;
+}
+
+int ref_eight_point(const double *a, const double *b, ref_pose out[4]) { /* Estimator::estimate, eps 1e-12, 1000 */
+    double E[9];
+    if (!ref_eight_point_essential(a, b, 1e-12, 1000, E)) return 0;
+    return ref_essential_poses(E, 1e-12, 1000, out);
+}
+
+/* essential.rs:266-275 */
+double ref_essential_residual(const double *E, const double *a, const double *b) {
+    double na[3] = {a[0] / a[2], a[1] / a[2], a[2] / a[2]}, nb[3] = {b[0] / b[2], b[1] / b[2], b[2] / b[2]};
+    double Ea[3] = {dot3(E, na), dot3(E + 3, na), dot3(E + 6, na)};
+    return fabs(dot3(nb, Ea));
+}
+
+/* ------------------------------------------------------------------ residuals */
+/* point.rs:20-25 Projective::from_homogeneous */
+static void from_homogeneous(double *p) {
+    if (signbit(p[3])) for (int i = 0; i < 4; i++) p[i] = -p[i];
+    double n = norm3(p);
+    for (int i = 0; i < 4; i++) p[i] /= n;
+}
+static void pose_apply(const ref_pose *P, const double *x, double *o) { /* to_homogeneous() * x */
+    for (int r = 0; r < 3; r++) o[r] = dot3(P->R + 3 * r, x) + P->t[r] * x[3];
+    o[3] = x[3];
+}
+/* accumulate (P - b bt P)t (P - b bt P) for a 3x4 pose matrix */
+static void design_add(const ref_pose *P, const double *b, double *D) {
+    double M[3][4], T[3][4];
+    for (int r = 0; r < 3; r++) { M[r][0] = P->R[3 * r]; M[r][1] = P->R[3 * r + 1]; M[r][2] = P->R[3 * r + 2]; M[r][3] = P->t[r]; }
+    for (int c = 0; c < 4; c++) {
+        double btP = b[0] * M[0][c] + b[1] * M[1][c] + b[2] * M[2][c];
+        for (int r = 0; r < 3; r++) T[r][c] = M[r][c] - b[r] * btP;
+    }
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) D[i * 4 + j] += T[0][i] * T[0][j] + T[1][i] * T[1][j] + T[2][i] * T[2][j];
+}
+
+/* cv-core/src/pose.rs:249-296 */
+double ref_residual_c2c(const ref_pose *P, const double *a, const double *b) {
+    double D[16] = {0}, d[4], V[16];
+    ref_pose I = {{1, 0, 0, 0, 1, 0, 0, 0, 1}, {0, 0, 0}};
+    design_add(&I, a, D);
+    design_add(P, b, D);
+    if (!ref_sym_eigen(4, D, 1e-12, 1024, d, V)) return 2.0;
+    int best = 0;
+    for (int i = 1; i < 4; i++)
+        if (fabs(d[i]) < fabs(d[best])) best = i;
+    double p[4] = {V[best], V[4 + best], V[8 + best], V[12 + best]};
+    from_homogeneous(p);
+    for (int i = 0; i < 4; i++) if (!isfinite(p[i])) return 2.0;
+    double q[4];
+    pose_apply(P, p, q);
+    from_homogeneous(q);
+    return 0.5 * (1.0 - dot3(a, p) + 1.0 - dot3(b, q));
+}
+
+/* cv-core/src/pose.rs:194-202; world is a homogeneous WorldPoint (xyz unit, w >= 0) */
+double ref_residual_w2c(const ref_pose *P, const double *bearing, const double *world) {
+    double q[4];
+    pose_apply(P, world, q);
+    from_homogeneous(q);
+    return 1.0 - dot3(bearing, q);
+}
+
+/* ------------------------------------------------------------------ lambda twist */
+static void root2real(double b, double c, double *r1, double *r2) { /* lib.rs:423-435 */
+    double disc = b * b - 4.0 * c;
+    if (disc < 0.0) { *r1 = *r2 = 0.5 * b; }
+    else if (b < 0.0) { double y = sqrt(disc); *r1 = 0.5 * (-b + y); *r2 = 0.5 * (-b - y); }
+    else { double y = sqrt(disc); *r1 = 2.0 * c / (-b + y); *r2 = 2.0 * c / (-b - y); }
+}
+static double cube_root(double b, double c, double d) { /* lib.rs:458-506 */
+    double r0;
+    if (b * b >= 3.0 * c) {
+        double v = sqrt(b * b - 3.0 * c);
+        double t1 = (-b - v) / 3.0;
+        double k = ((t1 + b) * t1 + c) * t1 + d;
+        if (k > 0.0) r0 = t1 - sqrt(-k / (3.0 * t1 + b));
+        else {
+            double t2 = (-b + v) / 3.0;
+            k = ((t2 + b) * t2 + c) * t2 + d;
+            r0 = t2 + sqrt(-k / (3.0 * t2 + b));
+        }
+    } else {
+        r0 = -b / 3.0;
+        if (fabs((3.0 * r0 + 2.0 * b) * r0 + c) < 1e-4) r0 += 1.0;
+    }
+    for (int i = 0; i < 7; i++) {
+        double fx = ((r0 + b) * r0 + c) * r0 + d, fpx = (3.0 * r0 + 2.0 * b) * r0 + c;
+        r0 -= fx / fpx;
+    }
+    for (int i = 0; i < 43; i++) {
+        double fx = ((r0 + b) * r0 + c) * r0 + d;
+        if (fabs(fx) > 1e-13) { double fpx = (3.0 * r0 + 2.0 * b) * r0 + c; r0 -= fx / fpx; }
+        else break;
+    }
+    return r0;
+}
+/* lib.rs:510-554; x row-major symmetric; Ev columns v1 v2 v3 (row-major), ev[0..2] */
+static void eigen_decomposition_singular(const double *x, double *Ev, double *ev) {
+    /* nalgebra linear index is column-major: x[1]=m21 x[2]=m31 x[3]=m12 x[4]=m22 x[5]=m32 */
+    double m11 = x[0], m12 = x[1], m13 = x[2], m21 = x[3], m22 = x[4], m23 = x[5], m31 = x[6], m32 = x[7], m33 = x[8];
+    double v3[3] = {m21 * m32 - m31 * m22, m31 * m12 - m32 * m11, m22 * m11 - m21 * m12};
+    double n = norm3(v3);
+    for (int i = 0; i < 3; i++) v3[i] /= n;
+    double x12_sqr = m12 * m12;
+    double b = -m11 - m22 - m33;
+    double c = -x12_sqr - m13 * m13 - m23 * m23 + m11 * (m22 + m33) + m22 * m33;
+    double e1, e2;
+    root2real(b, c, &e1, &e2);
+    if (fabs(e1) < fabs(e2)) { double t = e1; e1 = e2; e2 = t; }
+    ev[0] = e1; ev[1] = e2; ev[2] = 0.0;
+    double mx0011 = -m11 * m22, prec_0 = m12 * m23 - m13 * m22, prec_1 = m12 * m13 - m11 * m23;
+    double es[2] = {e1, e2}, v[2][3];
+    for (int k = 0; k < 2; k++) {
+        double e = es[k];
+        double tmp = 1.0 / (e * (m11 + m22) + mx0011 - e * e + x12_sqr);
+        double a1 = -(e * m13 + prec_0) * tmp, a2 = -(e * m23 + prec_1) * tmp;
+        double rnorm = 1.0 / sqrt(a1 * a1 + a2 * a2 + 1.0);
+        v[k][0] = a1 * rnorm; v[k][1] = a2 * rnorm; v[k][2] = rnorm;
+    }
+    for (int r = 0; r < 3; r++) { Ev[r * 3] = v[0][r]; Ev[r * 3 + 1] = v[1][r]; Ev[r * 3 + 2] = v3[r]; }
+}
+static double l1n(const double *v) { return fabs(v[0]) + fabs(v[1]) + fabs(v[2]); }
+static void gn_residual(const double *l, double a12, double a13, double a23, double b12, double b13, double b23, double *r) {
+    r[0] = l[0] * l[0] + l[1] * l[1] + b12 * l[0] * l[1] - a12;
+    r[1] = l[0] * l[0] + l[2] * l[2] + b13 * l[0] * l[2] - a13;
+    r[2] = l[1] * l[1] + l[2] * l[2] + b23 * l[1] * l[2] - a23;
+}
+/* lib.rs:361-412 */
+static void gauss_newton_refine_lambda(double *l, int iterations, double a12, double a13, double a23, double b12, double b13, double b23) {
+    double res[3];
+    gn_residual(l, a12, a13, a23, b12, b13, b23, res);
+    for (int it = 0; it < iterations; it++) {
+        if (l1n(res) < 1e-10) break;
+        double l1 = l[0], l2 = l[1], l3 = l[2];
+        double dr1dl1 = 2.0 * l1 + b12 * l2, dr1dl2 = 2.0 * l2 + b12 * l1, dr2dl1 = 2.0 * l1 + b13 * l3;
+        double dr2dl3 = 2.0 * l3 + b13 * l1, dr3dl2 = 2.0 * l2 + b23 * l3, dr3dl3 = 2.0 * l3 + b23 * l2;
+        double det = 1.0 / (-dr1dl1 * dr2dl3 * dr3dl2 - dr1dl2 * dr2dl1 * dr3dl3);
+        double J[9] = {-dr2dl3 * dr3dl2, -dr1dl2 * dr3dl3, dr1dl2 * dr2dl3,
+                       -dr2dl1 * dr3dl3, dr1dl1 * dr3dl3, -dr1dl1 * dr2dl3,
+                       dr2dl1 * dr3dl2, -dr1dl1 * dr3dl2, -dr1dl2 * dr2dl1};
+        double ln[3], rn[3];
+        for (int r = 0; r < 3; r++) ln[r] = l[r] - det * dot3(J + 3 * r, res);
+        gn_residual(ln, a12, a13, a23, b12, b13, b23, rn);
+        if (l1n(rn) > l1n(res)) break;
+        memcpy(l, ln, sizeof(ln)); memcpy(res, rn, sizeof(rn));
+    }
+}
+static int inv3(const double *m, double *o) {
+    double d = det3(m);
+    if (d == 0.0) return 0;
+    double id = 1.0 / d;
+    o[0] = (m[4] * m[8] - m[5] * m[7]) * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+    o[3] = (m[5] * m[6] - m[3] * m[8]) * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+    o[6] = (m[3] * m[7] - m[4] * m[6]) * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+    return 1;
+}
+/* nalgebra Rotation3::from_matrix_eps(m, eps, max_iter, identity): iterative closest rotation */
+static void rotation_from_matrix_eps(const double *m, double eps, int max_iter, double *rot) {
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int it = 0; it < max_iter; it++) {
+        double axis[3] = {0, 0, 0}, denom = 0.0;
+        for (int c = 0; c < 3; c++) {
+            double rc[3] = {R[c], R[3 + c], R[6 + c]}, mc[3] = {m[c], m[3 + c], m[6 + c]}, x[3];
+            cross3(rc, mc, x);
+            for (int k = 0; k < 3; k++) axis[k] += x[k];
+            denom += dot3(rc, mc);
+        }
+        double sc = fabs(denom) + 2.220446049250313e-16;
+        double aa[3] = {axis[0] / sc, axis[1] / sc, axis[2] / sc};
+        double angle = norm3(aa);
+        if (!(angle > eps)) break;
+        double u[3] = {aa[0] / angle, aa[1] / angle, aa[2] / angle};
+        double s = sin(angle), c = cos(angle), omc = 1.0 - c;
+        double Q[9] = {u[0] * u[0] + (1 - u[0] * u[0]) * c, u[0] * u[1] * omc - u[2] * s, u[0] * u[2] * omc + u[1] * s,
+                       u[0] * u[1] * omc + u[2] * s, u[1] * u[1] + (1 - u[1] * u[1]) * c, u[1] * u[2] * omc - u[0] * s,
+                       u[0] * u[2] * omc - u[1] * s, u[1] * u[2] * omc + u[0] * s, u[2] * u[2] + (1 - u[2] * u[2]) * c};
+        mat3_mul(Q, R, R);
+    }
+    memcpy(rot, R, sizeof(R));
+}
+
+/* lambda-twist/src/lib.rs:110-317: samples = 3 x (bearing xyz, world homogeneous xyzw); out: <= 4 WorldToCamera */
+int ref_p3p(const double *bearings, const double *world, ref_pose out[4]) {
+    double wp[3][3];
+    for (int i = 0; i < 3; i++) {
+        const double *w = world + 4 * i;
+        if (w[3] == 0.0) return 0; /* Projective::point() -> None */
+        for (int k = 0; k < 3; k++) wp[i][k] = w[k] / w[3];
+    }
+    const double *y1 = bearings, *y2 = bearings + 3, *y3 = bearings + 6;
+    double d12[3], d13[3], d23[3], d12xd13[3];
+    for (int k = 0; k < 3; k++) { d12[k] = wp[0][k] - wp[1][k]; d13[k] = wp[0][k] - wp[2][k]; d23[k] = wp[1][k] - wp[2][k]; }
+    cross3(d12, d13, d12xd13);
+    double a12 = dot3(d12, d12), a13 = dot3(d13, d13), a23 = dot3(d23, d23);
+    double c12 = dot3(y1, y2), c23 = dot3(y2, y3), c31 = dot3(y3, y1);
+    double blob = c12 * c23 * c31 - 1.0;
+    double s12_sqr = 1.0 - c12 * c12, s23_sqr = 1.0 - c23 * c23, s31_sqr = 1.0 - c31 * c31;
+    double b12 = -2.0 * c12, b13 = -2.0 * c31, b23 = -2.0 * c23;
+    double p3 = a13 * (a23 * s31_sqr - a13 * s23_sqr);
+    double p2 = 2.0 * blob * a23 * a13 + a13 * (2.0 * a12 + a13) * s23_sqr + a23 * (a23 - a12) * s31_sqr;
+    double p1 = a23 * (a13 - a23) * s12_sqr - a12 * a12 * s23_sqr - 2.0 * a12 * (blob * a23 + a13 * s23_sqr);
+    double p0 = a12 * (a12 * s23_sqr - a23 * s12_sqr);
+    double g = cube_root(p2 / p3, p1 / p3, p0 / p3);
+    double d0_00 = a23 * (1.0 - g), d0_01 = -(a23 * c12), d0_02 = a23 * c31 * g, d0_11 = a23 - a12 + a13 * g;
+    double d0_12 = -c23 * (a13 * g - a12), d0_22 = g * (a13 - a23) - a12;
+    double D0[9] = {d0_00, d0_01, d0_02, d0_01, d0_11, d0_12, d0_02, d0_12, d0_22}, Ev[9], ev[3];
+    eigen_decomposition_singular(D0, Ev, ev);
+    double lambdas[4][3];
+    int nl = 0;
+    double eigen_ratio = sqrt(fmax(0.0, -ev[1] / ev[0]));
+    for (int sgn = 0; sgn < 2; sgn++) {
+        double ratio = sgn ? -eigen_ratio : eigen_ratio;
+        /* m11 = Ev[0], m12 = Ev[1], m21 = Ev[3], m22 = Ev[4], m31 = Ev[6], m32 = Ev[7] */
+        double w2 = 1.0 / (ratio * Ev[1] - Ev[0]);
+        double w0 = w2 * (Ev[3] - ratio * Ev[4]);
+        double w1 = w2 * (Ev[6] - ratio * Ev[7]);
+        double a = 1.0 / ((a13 - a12) * w1 * w1 - a12 * b13 * w1 - a12);
+        double b = a * (a13 * b12 * w1 - a12 * b13 * w0 - 2.0 * w0 * w1 * (a12 - a13));
+        double c = a * ((a13 - a12) * w0 * w0 + a13 * b12 * w0 + a13);
+        if (b * b - 4.0 * c >= 0.0) {
+            double tau[2];
+            root2real(b, c, &tau[0], &tau[1]);
+            for (int k = 0; k < 2; k++) {
+                if (tau[k] > 0.0) {
+                    double d = a23 / (tau[k] * (b23 + tau[k]) + 1.0);
+                    if (d > 0.0) {
+                        double l2 = sqrt(d), l3 = tau[k] * l2, l1 = w0 * l2 + w1 * l3;
+                        if (l1 >= 0.0 && nl < 4) { lambdas[nl][0] = l1; lambdas[nl][1] = l2; lambdas[nl][2] = l3; nl++; }
+                    }
+                }
+            }
+        }
+    }
+    double X[9] = {d12[0], d13[0], d12xd13[0], d12[1], d13[1], d12xd13[1], d12[2], d13[2], d12xd13[2]}, Xi[9];
+    if (!inv3(X, Xi)) return 0;
+    for (int s = 0; s < nl; s++) {
+        double l[3] = {lambdas[s][0], lambdas[s][1], lambdas[s][2]};
+        gauss_newton_refine_lambda(l, 5, a12, a13, a23, b12, b13, b23);
+        double ry1[3], ry2[3], ry3[3], yd1[3], yd2[3], yx[3];
+        for (int k = 0; k < 3; k++) { ry1[k] = l[0] * y1[k]; ry2[k] = l[1] * y2[k]; ry3[k] = l[2] * y3[k]; }
+        for (int k = 0; k < 3; k++) { yd1[k] = ry1[k] - ry2[k]; yd2[k] = ry1[k] - ry3[k]; }
+        cross3(yd1, yd2, yx);
+        double Y[9] = {yd1[0], yd2[0], yx[0], yd1[1], yd2[1], yx[1], yd1[2], yd2[2], yx[2]}, rot[9];
+        mat3_mul(Y, Xi, rot);
+        for (int k = 0; k < 3; k++) out[s].t[k] = ry1[k] - dot3(rot + 3 * k, wp[0]);
+        rotation_from_matrix_eps(rot, 1e-12, 100, out[s].R);
+    }
+    return nl;
+}
+
+/* ------------------------------------------------------------------ triangulation */
+/* cv-geom/src/triangulation.rs:82-130: n (pose, bearing) observations -> homogeneous world point; returns 1 = Some */
+int ref_triangulate_linear_eigen(const ref_pose *poses, const double *bearings, int n, double *out) {
+    if (n < 2) return 0;
+    double A[16] = {0}, d[4], V[16];
+    for (int i = 0; i < n; i++) design_add(&poses[i], bearings + 3 * i, A);
+    if (!ref_sym_eigen(4, A, 1e-12, 1000, d, V)) return 0;
+    int best = 0;
+    for (int i = 1; i < 4; i++)
+        if (d[i] < d[best]) best = i;
+    double p[4] = {V[best], V[4 + best], V[8 + best], V[12 + best]};
+    from_homogeneous(p);
+    for (int i = 0; i < 4; i++) if (!isfinite(p[i])) return 0;
+    for (int i = 0; i < n; i++) { /* cheirality: (R^-1 b) . p_bearing must be sign-positive */
+        const double *b = bearings + 3 * i, *R = poses[i].R;
+        double wb[3] = {R[0] * b[0] + R[3] * b[1] + R[6] * b[2], R[1] * b[0] + R[4] * b[1] + R[7] * b[2], R[2] * b[0] + R[5] * b[1] + R[8] * b[2]};
+        if (signbit(dot3(wb, p))) return 0;
+    }
+    memcpy(out, p, sizeof(p));
+    return 1;
+}
+
+/* cv-pinhole/src/lib.rs:108-116 calibrate: pixel -> unit bearing */
+void ref_calibrate(double fx, double fy, double cx, double cy, double skew, double px, double py, double *bearing) {
+    double y = (py - cy) / fy;
+    double x = (px - cx - skew * y) / fx;
+    double n = sqrt(x * x + y * y + 1.0);
+    bearing[0] = x / n; bearing[1] = y / n; bearing[2] = 1.0 / n;
+}
+
+/* ------------------------------------------------------------------ RNGs */
+static uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+void ref_rng_seed_xoshiro(ref_rng *r, uint64_t seed) { /* rand_xoshiro seed_from_u64: SplitMix64 */
+    r->kind = 0;
+    for (int i = 0; i < 4; i++) {
+        seed += 0x9e3779b97f4a7c15ull;
+        uint64_t z = seed;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        r->s[i] = z ^ (z >> 31);
+    }
+}
+void ref_rng_seed_pcg64(ref_rng *r, const uint8_t seed[32]) { /* rand_pcg::Pcg64::from_seed */
+    r->kind = 1;
+    uint64_t w[4];
+    memcpy(w, seed, 32);
+    unsigned __int128 state = (unsigned __int128)w[0] | ((unsigned __int128)w[1] << 64);
+    unsigned __int128 incr = ((unsigned __int128)w[2] | ((unsigned __int128)w[3] << 64)) | 1;
+    const unsigned __int128 MUL = ((unsigned __int128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+    state = state + incr;
+    state = state * MUL + incr;
+    r->s[0] = (uint64_t)state; r->s[1] = (uint64_t)(state >> 64); r->s[2] = (uint64_t)incr; r->s[3] = (uint64_t)(incr >> 64);
+}
+uint32_t ref_rng_next_u32(ref_rng *r) {
+    if (r->kind == 0) { /* xoshiro256++ ; next_u32 = upper half of next_u64 */
+        uint64_t *s = r->s;
+        uint64_t result = rotl64(s[0] + s[3], 23) + s[0];
+        uint64_t t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl64(s[3], 45);
+        return (uint32_t)(result >> 32);
+    }
+    unsigned __int128 state = (unsigned __int128)r->s[0] | ((unsigned __int128)r->s[1] << 64);
+    unsigned __int128 incr = (unsigned __int128)r->s[2] | ((unsigned __int128)r->s[3] << 64);
+    const unsigned __int128 MUL = ((unsigned __int128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+    state = state * MUL + incr;
+    r->s[0] = (uint64_t)state; r->s[1] = (uint64_t)(state >> 64);
+    uint32_t rot = (uint32_t)(state >> 122);
+    uint64_t xsl = (uint64_t)(state >> 64) ^ (uint64_t)state;
+    uint64_t out = (xsl >> rot) | (xsl << ((64 - rot) & 63));
+    return (uint32_t)out;
+}
+
+/* ------------------------------------------------------------------ ARRSAC (restated; parity unpinned, see header) */
+void ref_arrsac_default_cfg(ref_arrsac_cfg *c, double inlier_threshold) {
+    c->inlier_threshold = inlier_threshold;
+    c->initialization_hypotheses = 256; c->initialization_blocks = 4; c->max_candidate_hypotheses = 64;
+    c->estimations_per_block = 64; c->block_size = 64;
+    c->likelihood_ratio_threshold = 1e3f; c->initial_epsilon = 0.1f; c->initial_delta = 0.05f;
+}
+
+typedef struct { ref_pose m; uint32_t inliers; } hyp_t;
+typedef struct { hyp_t *v; size_t n, cap; } hyp_vec;
+static void hv_push(hyp_vec *h, const ref_pose *m, uint32_t inl) {
+    if (h->n == h->cap) { h->cap = h->cap ? h->cap * 2 : 256; h->v = (hyp_t *)realloc(h->v, h->cap * sizeof(hyp_t)); }
+    h->v[h->n].m = *m; h->v[h->n].inliers = inl; h->n++;
+}
+/* stable sort by inliers descending */
+static void hv_sort(hyp_vec *h) {
+    for (size_t i = 1; i < h->n; i++) {
+        hyp_t x = h->v[i];
+        size_t j = i;
+        while (j > 0 && h->v[j - 1].inliers < x.inliers) { h->v[j] = h->v[j - 1]; j--; }
+        h->v[j] = x;
+    }
+}
+
+/* kind: 0 = EightPoint over FeatureMatch (a, b: n x 3 each), 1 = LambdaTwist over FeatureWorldMatch (a = bearings n x 3, b = world n x 4) */
+static double model_residual(int kind, const ref_pose *m, const double *a, const double *b, uint32_t i) {
+    return kind == 0 ? ref_residual_c2c(m, a + 3 * (size_t)i, b + 3 * (size_t)i) : ref_residual_w2c(m, a + 3 * (size_t)i, b + 4 * (size_t)i);
+}
+static int model_estimate(int kind, const double *a, const double *b, const uint32_t *idx, ref_pose out[4]) {
+    if (kind == 0) {
+        double sa[24], sb[24];
+        for (int k = 0; k < 8; k++) { memcpy(sa + 3 * k, a + 3 * (size_t)idx[k], 24); memcpy(sb + 3 * k, b + 3 * (size_t)idx[k], 24); }
+        return ref_eight_point(sa, sb, out);
+    }
+    double sa[9], sb[12];
+    for (int k = 0; k < 3; k++) { memcpy(sa + 3 * k, a + 3 * (size_t)idx[k], 24); memcpy(sb + 4 * k, b + 4 * (size_t)idx[k], 32); }
+    return ref_p3p(sa, sb, out);
+}
+/* MIN_SAMPLES distinct indices: next_u32() % len with rejection of repeats */
+static void populate_samples(ref_rng *rng, uint32_t k, uint32_t len, uint32_t *out) {
+    for (uint32_t c = 0; c < k;) {
+        uint32_t s = ref_rng_next_u32(rng) % len;
+        int dup = 0;
+        for (uint32_t j = 0; j < c; j++) dup |= out[j] == s;
+        if (!dup) out[c++] = s;
+    }
+}
+
+int ref_arrsac(const ref_arrsac_cfg *cfg, int kind, const double *a, const double *b, uint32_t n, ref_rng *rng,
+               ref_pose *model_out, uint32_t *inliers_out, uint32_t *n_inliers) {
+    const uint32_t K = kind == 0 ? 8 : 3;
+    *n_inliers = 0;
+    if (n < K) return 0;
+    const double thr = cfg->inlier_threshold;
+    hyp_vec H = {0};
+    /* ---- initialisation: hypotheses from random minimal samples, adaptive SPRT on the first blocks */
+    float epsilon = cfg->initial_epsilon, delta = cfg->initial_delta;
+    const uint32_t init_n = (uint32_t)(cfg->block_size * cfg->initialization_blocks) < n ? cfg->block_size * cfg->initialization_blocks : n;
+    uint32_t best_inliers = 0;
+    uint64_t rej_inliers = 0, rej_tested = 0;
+    uint32_t idx[8];
+    ref_pose models[4];
+    for (uint32_t h = 0; h < cfg->initialization_hypotheses; h++) {
+        populate_samples(rng, K, n, idx);
+        int nm = model_estimate(kind, a, b, idx, models);
+        for (int m = 0; m < nm; m++) {
+            const float pos = delta / epsilon, neg = (1.0f - delta) / (1.0f - epsilon);
+            float ratio = 1.0f;
+            uint32_t inl = 0, tested = 0;
+            int pass = 1;
+            for (uint32_t i = 0; i < init_n; i++) {
+                tested++;
+                if (model_residual(kind, &models[m], a, b, i) < thr) { inl++; ratio *= pos; }
+                else ratio *= neg;
+                if (ratio > cfg->likelihood_ratio_threshold) { pass = 0; break; }
+            }
+            if (pass) {
+                hv_push(&H, &models[m], inl);
+                if (inl > best_inliers) {
+                    best_inliers = inl;
+                    float e = (float)inl / (float)init_n;
+                    if (e > epsilon && e < 1.0f) epsilon = e; else if (e >= 1.0f) epsilon = 0.999f;
+                }
+            } else {
+                rej_inliers += inl; rej_tested += tested;
+                float d = (float)rej_inliers / (float)rej_tested;
+                if (d > 0.0f && d < epsilon) delta = d;
+            }
+        }
+    }
+    hv_sort(&H);
+    if (H.n > cfg->max_candidate_hypotheses) H.n = cfg->max_candidate_hypotheses;
+    /* ---- main loop over further blocks of data */
+    uint32_t *pool = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)n);
+    for (uint32_t start = init_n; start < n && H.n > 1; start += cfg->block_size) {
+        uint32_t end = start + cfg->block_size < n ? start + cfg->block_size : n;
+        for (size_t h = 0; h < H.n; h++)
+            for (uint32_t i = start; i < end; i++)
+                if (model_residual(kind, &H.v[h].m, a, b, i) < thr) H.v[h].inliers++;
+        hv_sort(&H);
+        size_t keep = H.n / 2 > 1 ? H.n / 2 : 1;
+        H.n = keep;
+        /* new hypotheses from the inliers (so far) of the current best */
+        uint32_t np = 0;
+        for (uint32_t i = 0; i < end; i++)
+            if (model_residual(kind, &H.v[0].m, a, b, i) < thr) pool[np++] = i;
+        if (np >= K) {
+            const uint32_t worst = H.v[H.n - 1].inliers;   /* bar a new hypothesis has to beat */
+            for (uint32_t g = 0; g < cfg->estimations_per_block; g++) {
+                uint32_t loc[8];
+                populate_samples(rng, K, np, loc);
+                for (uint32_t k = 0; k < K; k++) idx[k] = pool[loc[k]];
+                int nm = model_estimate(kind, a, b, idx, models);
+                for (int m = 0; m < nm; m++) {
+                    uint32_t inl = 0;
+                    for (uint32_t i = 0; i < end; i++)
+                        if (model_residual(kind, &models[m], a, b, i) < thr) inl++;
+                    if (inl > worst) hv_push(&H, &models[m], inl);
+                }
+            }
+            hv_sort(&H);
+            if (H.n > cfg->max_candidate_hypotheses) H.n = cfg->max_candidate_hypotheses;
+        }
+    }
+    free(pool);
+    if (H.n == 0) { free(H.v); return 0; }
+    hv_sort(&H);
+    *model_out = H.v[0].m;
+    uint32_t c = 0;
+    for (uint32_t i = 0; i < n; i++)
+        if (model_residual(kind, model_out, a, b, i) < thr) { if (inliers_out) inliers_out[c] = i; c++; }
+    *n_inliers = c;
+    free(H.v);
+    return 1;
+}

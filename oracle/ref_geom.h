@@ -1,0 +1,37 @@
+/* oracle/ref_geom.h -- TEST INFRASTRUCTURE (CPU oracle), not product code. See ref_geom.c. */
+#ifndef REF_GEOM_H
+#define REF_GEOM_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* IsometryMatrix3<f64>: rotation row-major + translation */
+typedef struct { double R[9]; double t[3]; } ref_pose;
+typedef struct { int kind; uint64_t s[4]; } ref_rng;   /* kind 0 xoshiro256++, 1 pcg64 */
+typedef struct {
+    double inlier_threshold;
+    uint32_t initialization_hypotheses, initialization_blocks, max_candidate_hypotheses, estimations_per_block, block_size;
+    float likelihood_ratio_threshold, initial_epsilon, initial_delta;
+} ref_arrsac_cfg;
+
+int ref_sym_eigen(int n, const double *A, double eps, int max_sweeps, double *d, double *V);
+int ref_svd3(const double *M, double eps, int max_iter, double *U, double *s, double *Vt);
+int ref_eight_point_essential(const double *a, const double *b, double eps, int iters, double *E);
+int ref_essential_poses(const double *E, double eps, int iters, ref_pose out[4]);
+int ref_eight_point(const double *a, const double *b, ref_pose out[4]);
+double ref_essential_residual(const double *E, const double *a, const double *b);
+double ref_residual_c2c(const ref_pose *P, const double *a, const double *b);
+double ref_residual_w2c(const ref_pose *P, const double *bearing, const double *world);
+int ref_p3p(const double *bearings, const double *world, ref_pose out[4]);
+int ref_triangulate_linear_eigen(const ref_pose *poses, const double *bearings, int n, double *out);
+void ref_calibrate(double fx, double fy, double cx, double cy, double skew, double px, double py, double *bearing);
+void ref_rng_seed_xoshiro(ref_rng *r, uint64_t seed);
+void ref_rng_seed_pcg64(ref_rng *r, const uint8_t seed[32]);
+uint32_t ref_rng_next_u32(ref_rng *r);
+void ref_arrsac_default_cfg(ref_arrsac_cfg *c, double inlier_threshold);
+int ref_arrsac(const ref_arrsac_cfg *cfg, int kind, const double *a, const double *b, uint32_t n, ref_rng *rng,
+               ref_pose *model_out, uint32_t *inliers_out, uint32_t *n_inliers);
+#ifdef __cplusplus
+}
+#endif
+#endif
