@@ -1351,7 +1351,7 @@ __global__ void __launch_bounds__(NT) k_refine_orient(const cvb_keypoint *__rest
 // ---------------------------------------------------------------------------------------------
 // Sort by descending response + truncate (lib.rs:326-327) as a rank sort over the valid refined
 // keypoints: rank = #{ j valid : r_j > r_i  or (r_j == r_i and j < i) }.  (The reference sort is
-// unstable; ties keep their original order here, the working definition shared with the test oracle.)
+// unstable; ties keep their original order here, the working definition.)
 // k_rank_count: grid = (i-chunks, j-chunks, B) partial ranks accumulated with atomics (rank preset to 0);
 // k_rank_scatter writes sorted[rank] and the surviving count.
 __global__ void __launch_bounds__(NT) k_rank_count(const cvb_keypoint *__restrict__ refined,

@@ -8,6 +8,7 @@
 
 struct AkazeWorkspace;
 struct MatchWorkspace;
+struct GeomWorkspace;
 
 struct cvb_ctx {
     int device = 0;
@@ -19,6 +20,7 @@ struct cvb_ctx {
     int num_sms = 148;
     AkazeWorkspace *akaze = nullptr;
     MatchWorkspace *match = nullptr;
+    GeomWorkspace *geom = nullptr;
     // optional per-kernel CUDA-event profiling (bench.py roofline pass); off by default
     bool prof = false;
     std::vector<cudaEvent_t> prof_pool;
@@ -43,6 +45,7 @@ struct CvbProfScope {
 int cvb_set_error(cvb_ctx *ctx, int code, const char *fmt, ...);
 void akaze_workspace_free(AkazeWorkspace *ws);
 void match_workspace_free(MatchWorkspace *ws);
+void geom_workspace_free(GeomWorkspace *ws);
 
 #define CVB_CUDA(ctx, call)                                                                          \
     do {                                                                                             \

@@ -1,0 +1,863 @@
+// cv_b200/csrc/geom.cu -- batched geometric verification on sm_100a (f64).
+//
+// Every model hypothesis (eight-point / P3P minimal solve) and every (hypothesis, datum) residual runs on
+// the GPU, one thread per hypothesis resp. per (hypothesis, datum) pair; ARRSAC's inherently sequential
+// bookkeeping (likelihood-ratio test over hypotheses, sort / truncate, RNG draws) stays on the host and
+// consumes bit-packed inlier masks.  Reference lines are cited per function (paths relative to /root/reference).
+// The linear algebra that lives in nalgebra upstream (symmetric eigen, SVD, from_matrix_eps) is implemented
+// here as cyclic Jacobi / closed forms; f64 results are held to 1e-6 relative (BASELINE north_star) in the parity tests.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ device math
+template <int N>
+__device__ bool sym_eigen(const double *Ain, double eps, int max_sweeps, double *d, double *V) {
+    double A[N * N];
+#pragma unroll
+    for (int i = 0; i < N * N; i++) A[i] = Ain[i];
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++) V[i * N + j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < N; i++) {
+            diag += A[i * N + i] * A[i * N + i];
+            for (int j = i + 1; j < N; j++) off += A[i * N + j] * A[i * N + j];
+        }
+        if (off <= eps * eps * diag || off == 0.0) {
+            for (int i = 0; i < N; i++) d[i] = A[i * N + i];
+            return true;
+        }
+        for (int p = 0; p < N - 1; p++)
+            for (int q = p + 1; q < N; q++) {
+                const double apq = A[p * N + q];
+                if (apq == 0.0) continue;
+                const double app = A[p * N + p], aqq = A[q * N + q];
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < N; k++) {
+                    const double akp = A[k * N + p], akq = A[k * N + q];
+                    A[k * N + p] = c * akp - s * akq;
+                    A[k * N + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < N; k++) {
+                    const double apk = A[p * N + k], aqk = A[q * N + k];
+                    A[p * N + k] = c * apk - s * aqk;
+                    A[q * N + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < N; k++) {
+                    const double vkp = V[k * N + p], vkq = V[k * N + q];
+                    V[k * N + p] = c * vkp - s * vkq;
+                    V[k * N + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < N; i++) d[i] = A[i * N + i];
+    return false;
+}
+
+__device__ __forceinline__ double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ double norm3(const double *a) { return sqrt(dot3(a, a)); }
+__device__ __forceinline__ void cross3(const double *a, const double *b, double *o) {
+    const double r0 = a[1] * b[2] - a[2] * b[1], r1 = a[2] * b[0] - a[0] * b[2], r2 = a[0] * b[1] - a[1] * b[0];
+    o[0] = r0; o[1] = r1; o[2] = r2;
+}
+__device__ void mat3_mul(const double *a, const double *b, double *o) {
+    double r[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) r[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
+    for (int i = 0; i < 9; i++) o[i] = r[i];
+}
+__device__ __forceinline__ double det3(const double *m) {
+    return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+
+// sorted SVD of a 3x3 matrix through the eigen-decomposition of MtM; u3 = u1 x u2 (its sign is normalised by
+// the det(U) > 0 rule of essential.rs:139-143 anyway)
+__device__ bool svd3(const double *M, double eps, int iters, double *U, double *Vt) {
+    double MtM[9], d[3], V[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) MtM[i * 3 + j] = M[i] * M[j] + M[3 + i] * M[3 + j] + M[6 + i] * M[6 + j];
+    if (!sym_eigen<3>(MtM, eps, iters, d, V)) return false;
+    int ord[3] = {0, 1, 2};
+    for (int i = 0; i < 2; i++)
+        for (int j = i + 1; j < 3; j++)
+            if (d[ord[j]] > d[ord[i]]) { int t = ord[i]; ord[i] = ord[j]; ord[j] = t; }
+    double v[3][3], u[3][3], s[3];
+    for (int k = 0; k < 3; k++) {
+        for (int r = 0; r < 3; r++) v[k][r] = V[r * 3 + ord[k]];
+        s[k] = sqrt(d[ord[k]] > 0.0 ? d[ord[k]] : 0.0);
+    }
+    const double tiny = 1e-12 * (s[0] > 0.0 ? s[0] : 1.0);
+    for (int k = 0; k < 2; k++) {
+        if (!(s[k] > tiny)) return false;
+        for (int r = 0; r < 3; r++) u[k][r] = (M[r * 3] * v[k][0] + M[r * 3 + 1] * v[k][1] + M[r * 3 + 2] * v[k][2]) / s[k];
+    }
+    cross3(u[0], u[1], u[2]);
+    const double nn = norm3(u[2]);
+    if (!(nn > 0.0)) return false;
+    for (int r = 0; r < 3; r++) u[2][r] /= nn;
+    for (int k = 0; k < 3; k++)
+        for (int r = 0; r < 3; r++) { U[r * 3 + k] = u[k][r]; Vt[k * 3 + r] = v[k][r]; }
+    return true;
+}
+
+// eight-point/src/lib.rs:11-24,43-58 (incl. b / a.z) + cv-pinhole/src/essential.rs:114-162,217-231
+__device__ int eight_point(const double *a, const double *b, const uint32_t *idx, cvb_pose *out) {
+    double A[8][9], EtE[81], d[9], V[81];
+    for (int i = 0; i < 8; i++) {
+        const double *pa = a + 3 * (size_t)idx[i], *pb = b + 3 * (size_t)idx[i];
+        const double ap[3] = {pa[0] / pa[2], pa[1] / pa[2], pa[2] / pa[2]};
+        const double bp[3] = {pb[0] / pa[2], pb[1] / pa[2], pb[2] / pa[2]};
+        for (int j = 0; j < 3; j++)
+            for (int k = 0; k < 3; k++) A[i][3 * j + k] = ap[j] * bp[k];
+    }
+    for (int r = 0; r < 9; r++)
+        for (int c = 0; c < 9; c++) {
+            double s = 0.0;
+            for (int i = 0; i < 8; i++) s += A[i][r] * A[i][c];
+            EtE[r * 9 + c] = s;
+        }
+    if (!sym_eigen<9>(EtE, 1e-12, 1000, d, V)) return 0;
+    int best = 0;
+    for (int i = 1; i < 9; i++)
+        if (d[i] < d[best]) best = i;
+    double E[9];
+    for (int k = 0; k < 9; k++) E[(k % 3) * 3 + (k / 3)] = V[k * 9 + best];   // Matrix3::from_iterator is column-major
+    double U[9], Vt[9];
+    if (!svd3(E, 1e-12, 1000, U, Vt)) return 0;
+    if (det3(U) < 0.0) for (int r = 0; r < 3; r++) U[r * 3 + 2] *= -1.0;
+    if (det3(Vt) < 0.0) for (int c = 0; c < 3; c++) Vt[6 + c] *= -1.0;
+    const double W[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1}, Wt[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1};
+    double UW[9], Ra[9], Rb[9];
+    mat3_mul(U, W, UW); mat3_mul(UW, Vt, Ra);
+    mat3_mul(U, Wt, UW); mat3_mul(UW, Vt, Rb);
+    const double t[3] = {U[2], U[5], U[8]};
+    for (int k = 0; k < 4; k++) {
+        for (int i = 0; i < 9; i++) out[k].r[i] = (k & 1) ? Rb[i] : Ra[i];
+        for (int r = 0; r < 3; r++) out[k].t[r] = (k & 2) ? -t[r] : t[r];
+    }
+    return 4;
+}
+
+// cv-core/src/point.rs:20-25
+__device__ __forceinline__ void from_homogeneous(double *p) {
+    if (signbit(p[3])) { p[0] = -p[0]; p[1] = -p[1]; p[2] = -p[2]; p[3] = -p[3]; }
+    const double n = norm3(p);
+    p[0] /= n; p[1] /= n; p[2] /= n; p[3] /= n;
+}
+__device__ __forceinline__ void pose_apply(const cvb_pose &P, const double *x, double *o) {
+    for (int r = 0; r < 3; r++) o[r] = dot3(P.r + 3 * r, x) + P.t[r] * x[3];
+    o[3] = x[3];
+}
+__device__ void design_add(const double *R, const double *t, const double *b, double *D) {
+    double M[3][4], T[3][4];
+    for (int r = 0; r < 3; r++) { M[r][0] = R[3 * r]; M[r][1] = R[3 * r + 1]; M[r][2] = R[3 * r + 2]; M[r][3] = t[r]; }
+    for (int c = 0; c < 4; c++) {
+        const double btP = b[0] * M[0][c] + b[1] * M[1][c] + b[2] * M[2][c];
+        for (int r = 0; r < 3; r++) T[r][c] = M[r][c] - b[r] * btP;
+    }
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) D[i * 4 + j] += T[0][i] * T[0][j] + T[1][i] * T[1][j] + T[2][i] * T[2][j];
+}
+
+// cv-core/src/pose.rs:249-296: two-view linear-eigen triangulation inside the residual
+__device__ double residual_c2c(const cvb_pose &P, const double *a, const double *b) {
+    double D[16], d[4], V[16];
+    for (int i = 0; i < 16; i++) D[i] = 0.0;
+    const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, z[3] = {0, 0, 0};
+    design_add(I, z, a, D);
+    design_add(P.r, P.t, b, D);
+    if (!sym_eigen<4>(D, 1e-12, 1024, d, V)) return 2.0;
+    int best = 0;
+    for (int i = 1; i < 4; i++)
+        if (fabs(d[i]) < fabs(d[best])) best = i;
+    double p[4] = {V[best], V[4 + best], V[8 + best], V[12 + best]};
+    from_homogeneous(p);
+    for (int i = 0; i < 4; i++)
+        if (!isfinite(p[i])) return 2.0;
+    double q[4];
+    pose_apply(P, p, q);
+    from_homogeneous(q);
+    return 0.5 * (1.0 - dot3(a, p) + 1.0 - dot3(b, q));
+}
+
+// cv-core/src/pose.rs:194-202
+__device__ double residual_w2c(const cvb_pose &P, const double *bearing, const double *world) {
+    double q[4];
+    pose_apply(P, world, q);
+    from_homogeneous(q);
+    return 1.0 - dot3(bearing, q);
+}
+
+// ---- lambda twist (lambda-twist/src/lib.rs:110-317, 361-554)
+__device__ void root2real(double b, double c, double *r1, double *r2) {
+    const double disc = b * b - 4.0 * c;
+    if (disc < 0.0) { *r1 = *r2 = 0.5 * b; }
+    else if (b < 0.0) { const double y = sqrt(disc); *r1 = 0.5 * (-b + y); *r2 = 0.5 * (-b - y); }
+    else { const double y = sqrt(disc); *r1 = 2.0 * c / (-b + y); *r2 = 2.0 * c / (-b - y); }
+}
+__device__ double cube_root(double b, double c, double d) {
+    double r0;
+    if (b * b >= 3.0 * c) {
+        const double v = sqrt(b * b - 3.0 * c);
+        const double t1 = (-b - v) / 3.0;
+        double k = ((t1 + b) * t1 + c) * t1 + d;
+        if (k > 0.0) r0 = t1 - sqrt(-k / (3.0 * t1 + b));
+        else {
+            const double t2 = (-b + v) / 3.0;
+            k = ((t2 + b) * t2 + c) * t2 + d;
+            r0 = t2 + sqrt(-k / (3.0 * t2 + b));
+        }
+    } else {
+        r0 = -b / 3.0;
+        if (fabs((3.0 * r0 + 2.0 * b) * r0 + c) < 1e-4) r0 += 1.0;
+    }
+    for (int i = 0; i < 7; i++) {
+        const double fx = ((r0 + b) * r0 + c) * r0 + d, fpx = (3.0 * r0 + 2.0 * b) * r0 + c;
+        r0 -= fx / fpx;
+    }
+    for (int i = 0; i < 43; i++) {
+        const double fx = ((r0 + b) * r0 + c) * r0 + d;
+        if (fabs(fx) > 1e-13) { const double fpx = (3.0 * r0 + 2.0 * b) * r0 + c; r0 -= fx / fpx; }
+        else break;
+    }
+    return r0;
+}
+__device__ void eigen_decomposition_singular(const double *x, double *Ev, double *ev) {
+    const double m11 = x[0], m12 = x[1], m13 = x[2], m21 = x[3], m22 = x[4], m23 = x[5], m31 = x[6], m32 = x[7], m33 = x[8];
+    double v3[3] = {m21 * m32 - m31 * m22, m31 * m12 - m32 * m11, m22 * m11 - m21 * m12};
+    const double n = norm3(v3);
+    for (int i = 0; i < 3; i++) v3[i] /= n;
+    const double x12_sqr = m12 * m12;
+    const double b = -m11 - m22 - m33;
+    const double c = -x12_sqr - m13 * m13 - m23 * m23 + m11 * (m22 + m33) + m22 * m33;
+    double e1, e2;
+    root2real(b, c, &e1, &e2);
+    if (fabs(e1) < fabs(e2)) { const double t = e1; e1 = e2; e2 = t; }
+    ev[0] = e1; ev[1] = e2; ev[2] = 0.0;
+    const double mx0011 = -m11 * m22, prec_0 = m12 * m23 - m13 * m22, prec_1 = m12 * m13 - m11 * m23;
+    const double es[2] = {e1, e2};
+    double v[2][3];
+    for (int k = 0; k < 2; k++) {
+        const double e = es[k];
+        const double tmp = 1.0 / (e * (m11 + m22) + mx0011 - e * e + x12_sqr);
+        const double a1 = -(e * m13 + prec_0) * tmp, a2 = -(e * m23 + prec_1) * tmp;
+        const double rnorm = 1.0 / sqrt(a1 * a1 + a2 * a2 + 1.0);
+        v[k][0] = a1 * rnorm; v[k][1] = a2 * rnorm; v[k][2] = rnorm;
+    }
+    for (int r = 0; r < 3; r++) { Ev[r * 3] = v[0][r]; Ev[r * 3 + 1] = v[1][r]; Ev[r * 3 + 2] = v3[r]; }
+}
+__device__ __forceinline__ double l1n(const double *v) { return fabs(v[0]) + fabs(v[1]) + fabs(v[2]); }
+__device__ void gn_residual(const double *l, double a12, double a13, double a23, double b12, double b13, double b23, double *r) {
+    r[0] = l[0] * l[0] + l[1] * l[1] + b12 * l[0] * l[1] - a12;
+    r[1] = l[0] * l[0] + l[2] * l[2] + b13 * l[0] * l[2] - a13;
+    r[2] = l[1] * l[1] + l[2] * l[2] + b23 * l[1] * l[2] - a23;
+}
+__device__ void gauss_newton_refine_lambda(double *l, int iterations, double a12, double a13, double a23, double b12, double b13, double b23) {
+    double res[3];
+    gn_residual(l, a12, a13, a23, b12, b13, b23, res);
+    for (int it = 0; it < iterations; it++) {
+        if (l1n(res) < 1e-10) break;
+        const double l1 = l[0], l2 = l[1], l3 = l[2];
+        const double dr1dl1 = 2.0 * l1 + b12 * l2, dr1dl2 = 2.0 * l2 + b12 * l1, dr2dl1 = 2.0 * l1 + b13 * l3;
+        const double dr2dl3 = 2.0 * l3 + b13 * l1, dr3dl2 = 2.0 * l2 + b23 * l3, dr3dl3 = 2.0 * l3 + b23 * l2;
+        const double det = 1.0 / (-dr1dl1 * dr2dl3 * dr3dl2 - dr1dl2 * dr2dl1 * dr3dl3);
+        const double J[9] = {-dr2dl3 * dr3dl2, -dr1dl2 * dr3dl3, dr1dl2 * dr2dl3,
+                             -dr2dl1 * dr3dl3, dr1dl1 * dr3dl3, -dr1dl1 * dr2dl3,
+                             dr2dl1 * dr3dl2, -dr1dl1 * dr3dl2, -dr1dl2 * dr2dl1};
+        double ln[3], rn[3];
+        for (int r = 0; r < 3; r++) ln[r] = l[r] - det * dot3(J + 3 * r, res);
+        gn_residual(ln, a12, a13, a23, b12, b13, b23, rn);
+        if (l1n(rn) > l1n(res)) break;
+        for (int r = 0; r < 3; r++) { l[r] = ln[r]; res[r] = rn[r]; }
+    }
+}
+__device__ bool inv3(const double *m, double *o) {
+    const double d = det3(m);
+    if (d == 0.0) return false;
+    const double id = 1.0 / d;
+    o[0] = (m[4] * m[8] - m[5] * m[7]) * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+    o[3] = (m[5] * m[6] - m[3] * m[8]) * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+    o[6] = (m[3] * m[7] - m[4] * m[6]) * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+    return true;
+}
+// nalgebra Rotation3::from_matrix_eps(m, eps, max_iter, identity)
+__device__ void rotation_from_matrix_eps(const double *m, double eps, int max_iter, double *rot) {
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int it = 0; it < max_iter; it++) {
+        double axis[3] = {0, 0, 0}, denom = 0.0;
+        for (int c = 0; c < 3; c++) {
+            const double rc[3] = {R[c], R[3 + c], R[6 + c]}, mc[3] = {m[c], m[3 + c], m[6 + c]};
+            double x[3];
+            cross3(rc, mc, x);
+            for (int k = 0; k < 3; k++) axis[k] += x[k];
+            denom += dot3(rc, mc);
+        }
+        const double sc = fabs(denom) + 2.220446049250313e-16;
+        const double aa[3] = {axis[0] / sc, axis[1] / sc, axis[2] / sc};
+        const double angle = norm3(aa);
+        if (!(angle > eps)) break;
+        const double u[3] = {aa[0] / angle, aa[1] / angle, aa[2] / angle};
+        const double s = sin(angle), c = cos(angle), omc = 1.0 - c;
+        const double Q[9] = {u[0] * u[0] + (1 - u[0] * u[0]) * c, u[0] * u[1] * omc - u[2] * s, u[0] * u[2] * omc + u[1] * s,
+                             u[0] * u[1] * omc + u[2] * s, u[1] * u[1] + (1 - u[1] * u[1]) * c, u[1] * u[2] * omc - u[0] * s,
+                             u[0] * u[2] * omc - u[1] * s, u[1] * u[2] * omc + u[0] * s, u[2] * u[2] + (1 - u[2] * u[2]) * c};
+        mat3_mul(Q, R, R);
+    }
+    for (int i = 0; i < 9; i++) rot[i] = R[i];
+}
+__device__ int p3p(const double *bearings, const double *world, const uint32_t *idx, cvb_pose *out) {
+    double wp[3][3];
+    const double *y[3];
+    for (int i = 0; i < 3; i++) {
+        const double *w = world + 4 * (size_t)idx[i];
+        if (w[3] == 0.0) return 0;
+        for (int k = 0; k < 3; k++) wp[i][k] = w[k] / w[3];
+        y[i] = bearings + 3 * (size_t)idx[i];
+    }
+    double d12[3], d13[3], d23[3], d12xd13[3];
+    for (int k = 0; k < 3; k++) { d12[k] = wp[0][k] - wp[1][k]; d13[k] = wp[0][k] - wp[2][k]; d23[k] = wp[1][k] - wp[2][k]; }
+    cross3(d12, d13, d12xd13);
+    const double a12 = dot3(d12, d12), a13 = dot3(d13, d13), a23 = dot3(d23, d23);
+    const double c12 = dot3(y[0], y[1]), c23 = dot3(y[1], y[2]), c31 = dot3(y[2], y[0]);
+    const double blob = c12 * c23 * c31 - 1.0;
+    const double s12_sqr = 1.0 - c12 * c12, s23_sqr = 1.0 - c23 * c23, s31_sqr = 1.0 - c31 * c31;
+    const double b12 = -2.0 * c12, b13 = -2.0 * c31, b23 = -2.0 * c23;
+    const double p3 = a13 * (a23 * s31_sqr - a13 * s23_sqr);
+    const double p2 = 2.0 * blob * a23 * a13 + a13 * (2.0 * a12 + a13) * s23_sqr + a23 * (a23 - a12) * s31_sqr;
+    const double p1 = a23 * (a13 - a23) * s12_sqr - a12 * a12 * s23_sqr - 2.0 * a12 * (blob * a23 + a13 * s23_sqr);
+    const double p0 = a12 * (a12 * s23_sqr - a23 * s12_sqr);
+    const double g = cube_root(p2 / p3, p1 / p3, p0 / p3);
+    const double d0_00 = a23 * (1.0 - g), d0_01 = -(a23 * c12), d0_02 = a23 * c31 * g, d0_11 = a23 - a12 + a13 * g;
+    const double d0_12 = -c23 * (a13 * g - a12), d0_22 = g * (a13 - a23) - a12;
+    const double D0[9] = {d0_00, d0_01, d0_02, d0_01, d0_11, d0_12, d0_02, d0_12, d0_22};
+    double Ev[9], ev[3];
+    eigen_decomposition_singular(D0, Ev, ev);
+    double lambdas[4][3];
+    int nl = 0;
+    const double eigen_ratio = sqrt(fmax(0.0, -ev[1] / ev[0]));
+    for (int sgn = 0; sgn < 2; sgn++) {
+        const double ratio = sgn ? -eigen_ratio : eigen_ratio;
+        const double w2 = 1.0 / (ratio * Ev[1] - Ev[0]);
+        const double w0 = w2 * (Ev[3] - ratio * Ev[4]);
+        const double w1 = w2 * (Ev[6] - ratio * Ev[7]);
+        const double a = 1.0 / ((a13 - a12) * w1 * w1 - a12 * b13 * w1 - a12);
+        const double b = a * (a13 * b12 * w1 - a12 * b13 * w0 - 2.0 * w0 * w1 * (a12 - a13));
+        const double c = a * ((a13 - a12) * w0 * w0 + a13 * b12 * w0 + a13);
+        if (b * b - 4.0 * c >= 0.0) {
+            double tau[2];
+            root2real(b, c, &tau[0], &tau[1]);
+            for (int k = 0; k < 2; k++) {
+                if (tau[k] > 0.0) {
+                    const double d = a23 / (tau[k] * (b23 + tau[k]) + 1.0);
+                    if (d > 0.0) {
+                        const double l2 = sqrt(d), l3 = tau[k] * l2, l1 = w0 * l2 + w1 * l3;
+                        if (l1 >= 0.0 && nl < 4) { lambdas[nl][0] = l1; lambdas[nl][1] = l2; lambdas[nl][2] = l3; nl++; }
+                    }
+                }
+            }
+        }
+    }
+    const double X[9] = {d12[0], d13[0], d12xd13[0], d12[1], d13[1], d12xd13[1], d12[2], d13[2], d12xd13[2]};
+    double Xi[9];
+    if (!inv3(X, Xi)) return 0;
+    for (int s = 0; s < nl; s++) {
+        double l[3] = {lambdas[s][0], lambdas[s][1], lambdas[s][2]};
+        gauss_newton_refine_lambda(l, 5, a12, a13, a23, b12, b13, b23);
+        double ry1[3], ry2[3], ry3[3], yd1[3], yd2[3], yx[3];
+        for (int k = 0; k < 3; k++) { ry1[k] = l[0] * y[0][k]; ry2[k] = l[1] * y[1][k]; ry3[k] = l[2] * y[2][k]; }
+        for (int k = 0; k < 3; k++) { yd1[k] = ry1[k] - ry2[k]; yd2[k] = ry1[k] - ry3[k]; }
+        cross3(yd1, yd2, yx);
+        const double Y[9] = {yd1[0], yd2[0], yx[0], yd1[1], yd2[1], yx[1], yd1[2], yd2[2], yx[2]};
+        double rot[9];
+        mat3_mul(Y, Xi, rot);
+        for (int k = 0; k < 3; k++) out[s].t[k] = ry1[k] - dot3(rot + 3 * k, wp[0]);
+        rotation_from_matrix_eps(rot, 1e-12, 100, out[s].r);
+    }
+    return nl;
+}
+
+// ------------------------------------------------------------------------------------------ kernels
+template <int KIND>
+__global__ void __launch_bounds__(128) k_estimate(const double *__restrict__ a, const double *__restrict__ b,
+                                                  const uint32_t *__restrict__ samples, uint32_t H, cvb_pose *poses,
+                                                  uint8_t *nposes) {
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    cvb_pose out[4];
+    int n;
+    if (KIND == 0) n = eight_point(a, b, samples + (size_t)h * 8, out);
+    else n = p3p(a, b, samples + (size_t)h * 3, out);
+    for (int k = 0; k < n; k++) poses[(size_t)h * 4 + k] = out[k];
+    nposes[h] = (uint8_t)n;
+}
+
+// one thread per (pose, datum).  MODE 0: write residuals; MODE 1: write bit-packed inlier masks
+// (residual < thr) over data [i0, i1): mask word w of pose p at masks[p * words + w].
+template <int KIND, int MODE>
+__global__ void __launch_bounds__(256) k_residuals(const cvb_pose *__restrict__ poses, uint32_t m,
+                                                   const double *__restrict__ a, const double *__restrict__ b,
+                                                   uint32_t i0, uint32_t i1, double thr, double *__restrict__ out,
+                                                   uint32_t out_stride, uint32_t *__restrict__ masks, uint32_t words) {
+    const uint32_t p = blockIdx.y;
+    const uint32_t i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < i1;
+    double r = 3.0;
+    if (in) {
+        const cvb_pose P = poses[p];
+        r = KIND == 0 ? residual_c2c(P, a + 3 * (size_t)i, b + 3 * (size_t)i) : residual_w2c(P, a + 3 * (size_t)i, b + 4 * (size_t)i);
+    }
+    if (MODE == 0) { if (in) out[(size_t)p * out_stride + i] = r; }
+    else {
+        const unsigned bits = __ballot_sync(0xffffffffu, in && r < thr);
+        if ((threadIdx.x & 31) == 0) masks[(size_t)p * words + ((i - i0) >> 5)] = bits;
+    }
+}
+
+// cv-geom/src/triangulation.rs:82-130, one thread per landmark
+__global__ void __launch_bounds__(128) k_triangulate(const cvb_pose *__restrict__ poses, const double *__restrict__ bearings,
+                                                     const uint32_t *__restrict__ offsets, uint32_t L, double *__restrict__ xyzw,
+                                                     uint8_t *__restrict__ ok) {
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const uint32_t o0 = offsets[l], o1 = offsets[l + 1];
+    uint8_t good = 0;
+    double p[4] = {0, 0, 0, 0};
+    if (o1 - o0 >= 2) {
+        double A[16], d[4], V[16];
+        for (int i = 0; i < 16; i++) A[i] = 0.0;
+        for (uint32_t i = o0; i < o1; i++) design_add(poses[i].r, poses[i].t, bearings + 3 * (size_t)i, A);
+        if (sym_eigen<4>(A, 1e-12, 1000, d, V)) {
+            int best = 0;
+            for (int i = 1; i < 4; i++)
+                if (d[i] < d[best]) best = i;
+            p[0] = V[best]; p[1] = V[4 + best]; p[2] = V[8 + best]; p[3] = V[12 + best];
+            from_homogeneous(p);
+            good = isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]) && isfinite(p[3]);
+            for (uint32_t i = o0; i < o1 && good; i++) {
+                const double *bb = bearings + 3 * (size_t)i, *R = poses[i].r;
+                const double wb[3] = {R[0] * bb[0] + R[3] * bb[1] + R[6] * bb[2], R[1] * bb[0] + R[4] * bb[1] + R[7] * bb[2],
+                                      R[2] * bb[0] + R[5] * bb[1] + R[8] * bb[2]};
+                if (signbit(dot3(wb, p))) good = 0;
+            }
+        }
+    }
+    ok[l] = good;
+    for (int i = 0; i < 4; i++) xyzw[(size_t)l * 4 + i] = good ? p[i] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int ensure(cvb_ctx *ctx, size_t need) {
+        if (need <= bytes && p) return 0;
+        if (p) { cudaStreamSynchronize(ctx->stream); cudaFree(p); p = nullptr; bytes = 0; }
+        size_t n = std::max<size_t>(need, 256);
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) return cvb_set_error(ctx, CVB_ENOMEM, "cudaMalloc(%zu): %s", n, cudaGetErrorString(e));
+        bytes = n;
+        return 0;
+    }
+};
+
+}  // namespace
+
+struct GeomWorkspace {
+    DevBuf a, b, samples, poses, nposes, out, masks, offsets, ok;
+};
+void geom_workspace_free(GeomWorkspace *g) {
+    if (!g) return;
+    DevBuf *bufs[] = {&g->a, &g->b, &g->samples, &g->poses, &g->nposes, &g->out, &g->masks, &g->offsets, &g->ok};
+    for (DevBuf *d : bufs) if (d->p) cudaFree(d->p);
+    delete g;
+}
+
+namespace {
+
+GeomWorkspace *gws(cvb_ctx *ctx) {
+    if (!ctx->geom) ctx->geom = new GeomWorkspace();
+    return ctx->geom;
+}
+
+int upload(cvb_ctx *ctx, DevBuf &d, const void *src, size_t bytes) {
+    int rc = d.ensure(ctx, bytes);
+    if (rc) return rc;
+    if (bytes) CVB_CUDA(ctx, cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+// data stay resident in the workspace (a: n x 3; b: n x 3 or n x 4)
+int upload_data(cvb_ctx *ctx, int kind, const double *a, const double *b, uint32_t n) {
+    GeomWorkspace *g = gws(ctx);
+    int rc = upload(ctx, g->a, a, sizeof(double) * 3 * (size_t)n);
+    if (rc) return rc;
+    return upload(ctx, g->b, b, sizeof(double) * (kind == 0 ? 3 : 4) * (size_t)n);
+}
+
+// estimate H minimal samples (host index lists) -> device poses (H x 4) + host counts
+int estimate_dev(cvb_ctx *ctx, int kind, const uint32_t *samples, uint32_t H, std::vector<uint8_t> &nposes) {
+    GeomWorkspace *g = gws(ctx);
+    const uint32_t K = kind == 0 ? 8 : 3;
+    int rc = upload(ctx, g->samples, samples, sizeof(uint32_t) * K * (size_t)H);
+    if (rc) return rc;
+    if ((rc = g->poses.ensure(ctx, sizeof(cvb_pose) * 4 * (size_t)H))) return rc;
+    if ((rc = g->nposes.ensure(ctx, H))) return rc;
+    {
+        CVB_PROF(ctx, kind == 0 ? "k_estimate_eight_point" : "k_estimate_p3p", 0);
+        if (kind == 0)
+            k_estimate<0><<<cdiv(H, 128), 128, 0, ctx->stream>>>((const double *)g->a.p, (const double *)g->b.p, (const uint32_t *)g->samples.p, H,
+                                                                 (cvb_pose *)g->poses.p, (uint8_t *)g->nposes.p);
+        else
+            k_estimate<1><<<cdiv(H, 128), 128, 0, ctx->stream>>>((const double *)g->a.p, (const double *)g->b.p, (const uint32_t *)g->samples.p, H,
+                                                                 (cvb_pose *)g->poses.p, (uint8_t *)g->nposes.p);
+        CVB_LAUNCH_CHECK(ctx);
+    }
+    nposes.resize(H);
+    CVB_CUDA(ctx, cudaMemcpyAsync(nposes.data(), g->nposes.p, H, cudaMemcpyDeviceToHost, ctx->stream));
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// inlier masks of m device poses over data [i0, i1) -> host (m x words)
+int masks_dev(cvb_ctx *ctx, int kind, const cvb_pose *poses_dev, uint32_t m, uint32_t i0, uint32_t i1, double thr,
+              std::vector<uint32_t> &masks, uint32_t *words_out) {
+    GeomWorkspace *g = gws(ctx);
+    const uint32_t cnt = i1 - i0, words = cdiv(cnt, 32);
+    *words_out = words;
+    masks.assign((size_t)m * words, 0u);
+    if (m == 0 || cnt == 0) return 0;
+    int rc = g->masks.ensure(ctx, sizeof(uint32_t) * (size_t)m * words);
+    if (rc) return rc;
+    for (uint32_t p0 = 0; p0 < m; p0 += 65535) {   // gridDim.y limit
+        const uint32_t pm = std::min<uint32_t>(65535, m - p0);
+        dim3 grid(cdiv(cnt, 256), pm);
+        CVB_PROF(ctx, kind == 0 ? "k_residuals_c2c" : "k_residuals_w2c", (kind == 0 ? 48.0 : 56.0) * pm * cnt);
+        if (kind == 0)
+            k_residuals<0, 1><<<grid, 256, 0, ctx->stream>>>(poses_dev + p0, pm, (const double *)g->a.p, (const double *)g->b.p, i0, i1, thr, nullptr, 0,
+                                                             (uint32_t *)g->masks.p + (size_t)p0 * words, words);
+        else
+            k_residuals<1, 1><<<grid, 256, 0, ctx->stream>>>(poses_dev + p0, pm, (const double *)g->a.p, (const double *)g->b.p, i0, i1, thr, nullptr, 0,
+                                                             (uint32_t *)g->masks.p + (size_t)p0 * words, words);
+        CVB_LAUNCH_CHECK(ctx);
+    }
+    CVB_CUDA(ctx, cudaMemcpyAsync(masks.data(), g->masks.p, sizeof(uint32_t) * (size_t)m * words, cudaMemcpyDeviceToHost, ctx->stream));
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+inline uint32_t popc_range(const uint32_t *row, uint32_t lo, uint32_t hi) {   // bits [lo, hi)
+    uint32_t c = 0;
+    for (uint32_t i = lo; i < hi; i++) c += (row[i >> 5] >> (i & 31)) & 1u;
+    return c;
+}
+
+uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+
+struct Hyp { cvb_pose m; uint32_t inliers; std::vector<uint32_t> mask; };   // mask over ALL n data
+
+void sort_hyps(std::vector<Hyp> &H) {
+    std::stable_sort(H.begin(), H.end(), [](const Hyp &x, const Hyp &y) { return x.inliers > y.inliers; });
+}
+
+void populate_samples(cvb_rng *rng, uint32_t k, uint32_t len, uint32_t *out) {
+    for (uint32_t c = 0; c < k;) {
+        uint32_t s = cvb_rng_next_u32(rng) % len;
+        bool dup = false;
+        for (uint32_t j = 0; j < c; j++) dup |= out[j] == s;
+        if (!dup) out[c++] = s;
+    }
+}
+
+// arrsac::Arrsac::model_inliers, restated (external crate arrsac 0.10.0; see DESIGN.md for what is and is not pinned):
+// initialisation with an adaptive SPRT over the first blocks, then block-wise scoring / halving / re-estimation
+// from the inliers of the current best.  All residuals come from the GPU as bit masks.
+int arrsac_run(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const double *a, const double *b, uint32_t n, cvb_rng *rng,
+               cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers, int32_t *found) {
+    const uint32_t K = kind == 0 ? 8 : 3;
+    *found = 0;
+    if (n_inliers) *n_inliers = 0;
+    if (n < K) return 0;
+    if (cfg->block_size == 0 || cfg->initialization_blocks == 0) return cvb_set_error(ctx, CVB_EINVAL, "block_size / initialization_blocks must be > 0");
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = upload_data(ctx, kind, a, b, n);
+    if (rc) return rc;
+    GeomWorkspace *g = gws(ctx);
+    const double thr = cfg->inlier_threshold;
+    const uint32_t nwords = cdiv(n, 32);
+    // ---- initialisation: all minimal samples are drawn first (the draws do not depend on any result)
+    const uint32_t H0 = cfg->initialization_hypotheses;
+    if (H0 == 0) return 0;
+    std::vector<uint32_t> samples((size_t)H0 * K);
+    for (uint32_t h = 0; h < H0; h++) populate_samples(rng, K, n, samples.data() + (size_t)h * K);
+    std::vector<uint8_t> nposes;
+    if ((rc = estimate_dev(ctx, kind, samples.data(), H0, nposes))) return rc;
+    // inlier masks of every candidate model over the initialisation blocks only (what the SPRT looks at)
+    const uint32_t init_n = std::min<uint32_t>(cfg->block_size * cfg->initialization_blocks, n);
+    std::vector<uint32_t> masks;
+    uint32_t words = 0;
+    if ((rc = masks_dev(ctx, kind, (const cvb_pose *)g->poses.p, H0 * 4, 0, init_n, thr, masks, &words))) return rc;
+    std::vector<cvb_pose> poses_host((size_t)H0 * 4);
+    CVB_CUDA(ctx, cudaMemcpy(poses_host.data(), g->poses.p, sizeof(cvb_pose) * 4 * (size_t)H0, cudaMemcpyDeviceToHost));
+    float epsilon = cfg->initial_epsilon, delta = cfg->initial_delta;
+    uint32_t best_inliers = 0;
+    uint64_t rej_inliers = 0, rej_tested = 0;
+    std::vector<Hyp> H;
+    for (uint32_t h = 0; h < H0; h++)
+        for (uint32_t mi = 0; mi < nposes[h]; mi++) {
+            const uint32_t *row = masks.data() + ((size_t)h * 4 + mi) * words;
+            const float pos = delta / epsilon, neg = (1.0f - delta) / (1.0f - epsilon);
+            float ratio = 1.0f;
+            uint32_t inl = 0, tested = 0;
+            bool pass = true;
+            for (uint32_t i = 0; i < init_n; i++) {
+                tested++;
+                if ((row[i >> 5] >> (i & 31)) & 1u) { inl++; ratio *= pos; }
+                else ratio *= neg;
+                if (ratio > cfg->likelihood_ratio_threshold) { pass = false; break; }
+            }
+            if (pass) {
+                Hyp hy; hy.m = poses_host[(size_t)h * 4 + mi]; hy.inliers = inl; hy.mask.assign(nwords, 0u);
+                for (uint32_t w = 0; w < words; w++) hy.mask[w] = row[w];
+                H.push_back(std::move(hy));
+                if (inl > best_inliers) {
+                    best_inliers = inl;
+                    const float e = (float)inl / (float)init_n;
+                    if (e > epsilon && e < 1.0f) epsilon = e; else if (e >= 1.0f) epsilon = 0.999f;
+                }
+            } else {
+                rej_inliers += inl; rej_tested += tested;
+                const float d = (float)rej_inliers / (float)rej_tested;
+                if (d > 0.0f && d < epsilon) delta = d;
+            }
+        }
+    sort_hyps(H);
+    if (H.size() > cfg->max_candidate_hypotheses) H.resize(cfg->max_candidate_hypotheses);
+    // the surviving candidates are scored on the remaining data in one launch
+    if (init_n < n && !H.empty()) {
+        std::vector<cvb_pose> surv(H.size());
+        for (size_t i = 0; i < H.size(); i++) surv[i] = H[i].m;
+        if ((rc = upload(ctx, g->poses, surv.data(), sizeof(cvb_pose) * surv.size()))) return rc;
+        if ((rc = masks_dev(ctx, kind, (const cvb_pose *)g->poses.p, (uint32_t)surv.size(), init_n, n, thr, masks, &words))) return rc;
+        for (size_t i = 0; i < H.size(); i++) {
+            const uint32_t *row = masks.data() + i * words;
+            for (uint32_t j = init_n; j < n; j++)
+                if ((row[(j - init_n) >> 5] >> ((j - init_n) & 31)) & 1u) H[i].mask[j >> 5] |= 1u << (j & 31);
+        }
+    }
+    sort_hyps(H);
+    if (H.size() > cfg->max_candidate_hypotheses) H.resize(cfg->max_candidate_hypotheses);
+    // ---- main loop over further blocks
+    std::vector<uint32_t> pool, idx((size_t)std::max<uint32_t>(cfg->estimations_per_block, 1) * K);
+    for (uint32_t start = init_n; start < n && H.size() > 1; start += cfg->block_size) {
+        const uint32_t end = std::min<uint32_t>(start + cfg->block_size, n);
+        for (Hyp &h : H) h.inliers += popc_range(h.mask.data(), start, end);
+        sort_hyps(H);
+        H.resize(std::max<size_t>(H.size() / 2, 1));
+        pool.clear();
+        for (uint32_t i = 0; i < end; i++)
+            if ((H[0].mask[i >> 5] >> (i & 31)) & 1u) pool.push_back(i);
+        if (pool.size() >= K && cfg->estimations_per_block > 0) {
+            const uint32_t worst = H.back().inliers;
+            const uint32_t G = cfg->estimations_per_block;
+            for (uint32_t gi = 0; gi < G; gi++) {
+                uint32_t loc[8];
+                populate_samples(rng, K, (uint32_t)pool.size(), loc);
+                for (uint32_t k = 0; k < K; k++) idx[(size_t)gi * K + k] = pool[loc[k]];
+            }
+            if ((rc = estimate_dev(ctx, kind, idx.data(), G, nposes))) return rc;
+            if ((rc = masks_dev(ctx, kind, (const cvb_pose *)g->poses.p, G * 4, 0, n, thr, masks, &words))) return rc;
+            poses_host.resize((size_t)G * 4);
+            CVB_CUDA(ctx, cudaMemcpy(poses_host.data(), g->poses.p, sizeof(cvb_pose) * 4 * (size_t)G, cudaMemcpyDeviceToHost));
+            for (uint32_t gi = 0; gi < G; gi++)
+                for (uint32_t mi = 0; mi < nposes[gi]; mi++) {
+                    const uint32_t *row = masks.data() + ((size_t)gi * 4 + mi) * words;
+                    const uint32_t inl = popc_range(row, 0, end);
+                    if (inl > worst) {
+                        Hyp hy; hy.m = poses_host[(size_t)gi * 4 + mi]; hy.inliers = inl; hy.mask.assign(row, row + words);
+                        H.push_back(std::move(hy));
+                    }
+                }
+            sort_hyps(H);
+            if (H.size() > cfg->max_candidate_hypotheses) H.resize(cfg->max_candidate_hypotheses);
+        }
+    }
+    if (H.empty()) return 0;
+    sort_hyps(H);
+    *model_out = H[0].m;
+    uint32_t c = 0;
+    for (uint32_t i = 0; i < n; i++)
+        if ((H[0].mask[i >> 5] >> (i & 31)) & 1u) { if (inliers_out && c < cap) inliers_out[c] = i; c++; }
+    if (n_inliers) *n_inliers = c;
+    *found = 1;
+    (void)nwords;
+    if (inliers_out && c > cap) return cvb_set_error(ctx, CVB_ECAP, "inlier capacity %u too small (%u needed)", cap, c);
+    return 0;
+}
+
+int residuals_host(cvb_ctx *ctx, int kind, const cvb_pose *poses, uint32_t m, const double *a, const double *b, uint32_t n, double *out) {
+    if (!ctx) return CVB_EINVAL;
+    if ((m && !poses) || (n && (!a || !b)) || (m && n && !out)) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    if (m == 0 || n == 0) return 0;
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = upload_data(ctx, kind, a, b, n);
+    if (rc) return rc;
+    GeomWorkspace *g = gws(ctx);
+    if ((rc = upload(ctx, g->poses, poses, sizeof(cvb_pose) * (size_t)m))) return rc;
+    if ((rc = g->out.ensure(ctx, sizeof(double) * (size_t)m * n))) return rc;
+    for (uint32_t p0 = 0; p0 < m; p0 += 65535) {
+        const uint32_t pm = std::min<uint32_t>(65535, m - p0);
+        dim3 grid(cdiv(n, 256), pm);
+        CVB_PROF(ctx, kind == 0 ? "k_residuals_c2c" : "k_residuals_w2c", (kind == 0 ? 48.0 : 56.0) * pm * n);
+        if (kind == 0)
+            k_residuals<0, 0><<<grid, 256, 0, ctx->stream>>>((const cvb_pose *)g->poses.p + p0, pm, (const double *)g->a.p, (const double *)g->b.p, 0, n, 0.0,
+                                                             (double *)g->out.p + (size_t)p0 * n, n, nullptr, 0);
+        else
+            k_residuals<1, 0><<<grid, 256, 0, ctx->stream>>>((const cvb_pose *)g->poses.p + p0, pm, (const double *)g->a.p, (const double *)g->b.p, 0, n, 0.0,
+                                                             (double *)g->out.p + (size_t)p0 * n, n, nullptr, 0);
+        CVB_LAUNCH_CHECK(ctx);
+    }
+    CVB_CUDA(ctx, cudaMemcpyAsync(out, g->out.p, sizeof(double) * (size_t)m * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int estimate_host(cvb_ctx *ctx, int kind, const double *a, const double *b, uint32_t n, const uint32_t *samples, uint32_t H,
+                  cvb_pose *poses_out, uint8_t *nposes_out) {
+    if (!ctx) return CVB_EINVAL;
+    if (!a || !b || (H && (!samples || !poses_out || !nposes_out))) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    if (H == 0) return 0;
+    const uint32_t K = kind == 0 ? 8 : 3;
+    for (size_t i = 0; i < (size_t)H * K; i++)
+        if (samples[i] >= n) return cvb_set_error(ctx, CVB_EINVAL, "sample index %u out of range (n = %u)", samples[i], n);
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = upload_data(ctx, kind, a, b, n);
+    if (rc) return rc;
+    std::vector<uint8_t> np;
+    if ((rc = estimate_dev(ctx, kind, samples, H, np))) return rc;
+    memcpy(nposes_out, np.data(), H);
+    CVB_CUDA(ctx, cudaMemcpy(poses_out, gws(ctx)->poses.p, sizeof(cvb_pose) * 4 * (size_t)H, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void cvb_arrsac_default_cfg(cvb_arrsac_cfg *c, double inlier_threshold) {
+    if (!c) return;
+    c->inlier_threshold = inlier_threshold;
+    c->initialization_hypotheses = 256; c->initialization_blocks = 4; c->max_candidate_hypotheses = 64;
+    c->estimations_per_block = 64; c->block_size = 64;
+    c->likelihood_ratio_threshold = 1e3f; c->initial_epsilon = 0.1f; c->initial_delta = 0.05f;
+}
+
+void cvb_rng_seed_xoshiro256pp(cvb_rng *r, uint64_t seed) {   // SplitMix64 expansion
+    if (!r) return;
+    r->kind = 0;
+    for (int i = 0; i < 4; i++) {
+        seed += 0x9e3779b97f4a7c15ull;
+        uint64_t z = seed;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        r->s[i] = z ^ (z >> 31);
+    }
+}
+
+void cvb_rng_seed_pcg64(cvb_rng *r, const uint8_t seed[32]) {   // Lcg128Xsl64::from_seed
+    if (!r || !seed) return;
+    r->kind = 1;
+    uint64_t w[4];
+    memcpy(w, seed, 32);
+    unsigned __int128 state = (unsigned __int128)w[0] | ((unsigned __int128)w[1] << 64);
+    unsigned __int128 incr = ((unsigned __int128)w[2] | ((unsigned __int128)w[3] << 64)) | 1;
+    const unsigned __int128 MUL = ((unsigned __int128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+    state = state + incr;
+    state = state * MUL + incr;
+    r->s[0] = (uint64_t)state; r->s[1] = (uint64_t)(state >> 64); r->s[2] = (uint64_t)incr; r->s[3] = (uint64_t)(incr >> 64);
+}
+
+uint32_t cvb_rng_next_u32(cvb_rng *r) {
+    if (!r) return 0;
+    if (r->kind == 0) {
+        uint64_t *s = r->s;
+        const uint64_t result = rotl64(s[0] + s[3], 23) + s[0];
+        const uint64_t t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl64(s[3], 45);
+        return (uint32_t)(result >> 32);
+    }
+    unsigned __int128 state = (unsigned __int128)r->s[0] | ((unsigned __int128)r->s[1] << 64);
+    const unsigned __int128 incr = (unsigned __int128)r->s[2] | ((unsigned __int128)r->s[3] << 64);
+    const unsigned __int128 MUL = ((unsigned __int128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+    state = state * MUL + incr;
+    r->s[0] = (uint64_t)state; r->s[1] = (uint64_t)(state >> 64);
+    const uint32_t rot = (uint32_t)(state >> 122);
+    const uint64_t xsl = (uint64_t)(state >> 64) ^ (uint64_t)state;
+    return (uint32_t)((xsl >> rot) | (xsl << ((64 - rot) & 63)));
+}
+
+int cvb_eight_point_batch(cvb_ctx *ctx, const double *a, const double *b, uint32_t n, const uint32_t *samples, uint32_t H,
+                          cvb_pose *poses_out, uint8_t *nposes_out) {
+    return estimate_host(ctx, 0, a, b, n, samples, H, poses_out, nposes_out);
+}
+int cvb_p3p_batch(cvb_ctx *ctx, const double *bearings, const double *world, uint32_t n, const uint32_t *samples, uint32_t H,
+                  cvb_pose *poses_out, uint8_t *nposes_out) {
+    return estimate_host(ctx, 1, bearings, world, n, samples, H, poses_out, nposes_out);
+}
+int cvb_residuals_camera_to_camera(cvb_ctx *ctx, const cvb_pose *poses, uint32_t m, const double *a, const double *b, uint32_t n, double *out) {
+    return residuals_host(ctx, 0, poses, m, a, b, n, out);
+}
+int cvb_residuals_world_to_camera(cvb_ctx *ctx, const cvb_pose *poses, uint32_t m, const double *bearings, const double *world, uint32_t n,
+                                  double *out) {
+    return residuals_host(ctx, 1, poses, m, bearings, world, n, out);
+}
+
+int cvb_triangulate_linear_eigen(cvb_ctx *ctx, const cvb_pose *poses, const double *bearings, const uint32_t *offsets, uint32_t L,
+                                 double *xyzw_out, uint8_t *ok_out) {
+    if (!ctx) return CVB_EINVAL;
+    if (L == 0) return 0;
+    if (!poses || !bearings || !offsets || !xyzw_out || !ok_out) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    for (uint32_t l = 0; l < L; l++)
+        if (offsets[l + 1] < offsets[l]) return cvb_set_error(ctx, CVB_EINVAL, "offsets must be non-decreasing");
+    const uint32_t nobs = offsets[L];
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    GeomWorkspace *g = gws(ctx);
+    int rc;
+    if ((rc = upload(ctx, g->poses, poses, sizeof(cvb_pose) * (size_t)nobs))) return rc;
+    if ((rc = upload(ctx, g->a, bearings, sizeof(double) * 3 * (size_t)nobs))) return rc;
+    if ((rc = upload(ctx, g->offsets, offsets, sizeof(uint32_t) * ((size_t)L + 1)))) return rc;
+    if ((rc = g->out.ensure(ctx, sizeof(double) * 4 * (size_t)L))) return rc;
+    if ((rc = g->ok.ensure(ctx, L))) return rc;
+    {
+        CVB_PROF(ctx, "k_triangulate", 120.0 * nobs);
+        k_triangulate<<<cdiv(L, 128), 128, 0, ctx->stream>>>((const cvb_pose *)g->poses.p, (const double *)g->a.p, (const uint32_t *)g->offsets.p, L,
+                                                             (double *)g->out.p, (uint8_t *)g->ok.p);
+        CVB_LAUNCH_CHECK(ctx);
+    }
+    CVB_CUDA(ctx, cudaMemcpyAsync(xyzw_out, g->out.p, sizeof(double) * 4 * (size_t)L, cudaMemcpyDeviceToHost, ctx->stream));
+    CVB_CUDA(ctx, cudaMemcpyAsync(ok_out, g->ok.p, L, cudaMemcpyDeviceToHost, ctx->stream));
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int cvb_arrsac_eight_point(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *a, const double *b, uint32_t n, cvb_rng *rng,
+                           cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers, int32_t *found) {
+    if (!ctx) return CVB_EINVAL;
+    if (!cfg || !rng || !model_out || !found || (n && (!a || !b))) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    return arrsac_run(ctx, cfg, 0, a, b, n, rng, model_out, inliers_out, cap, n_inliers, found);
+}
+int cvb_arrsac_p3p(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *bearings, const double *world, uint32_t n, cvb_rng *rng,
+                   cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers, int32_t *found) {
+    if (!ctx) return CVB_EINVAL;
+    if (!cfg || !rng || !model_out || !found || (n && (!bearings || !world))) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    return arrsac_run(ctx, cfg, 1, bearings, world, n, rng, model_out, inliers_out, cap, n_inliers, found);
+}
+
+}  // extern "C"

@@ -142,6 +142,53 @@ int cvb_hamming_knn_dev_counts(cvb_ctx *ctx, const uint8_t *queries_dev, const u
 int cvb_match_symmetric(cvb_ctx *ctx, const uint8_t *desc_a, uint32_t n, const uint8_t *desc_b, uint32_t m,
                         uint32_t better_by, uint32_t *pairs_out, uint32_t cap, uint32_t *n_out);
 
+/* ---- geometric verification ------------------------------------------------------------------
+ * sample_consensus::{Estimator, Model, Consensus} surfaces (external crate sample-consensus 1.0.2, re-exported at
+ * cv-core/src/lib.rs:82) with the solvers and residuals of the reference:
+ *   cvb_eight_point_batch        <- EightPoint::estimate              eight-point/src/lib.rs:70-84 (+ essential.rs:217-231)
+ *   cvb_p3p_batch                <- LambdaTwist::estimate             lambda-twist/src/lib.rs:330-347
+ *   cvb_residuals_camera_to_camera <- CameraToCamera::residual        cv-core/src/pose.rs:249-296
+ *   cvb_residuals_world_to_camera  <- WorldToCamera::residual         cv-core/src/pose.rs:194-202
+ *   cvb_triangulate_linear_eigen <- LinearEigenTriangulator           cv-geom/src/triangulation.rs:82-130
+ *   cvb_arrsac_eight_point / cvb_arrsac_p3p <- arrsac::Arrsac as Consensus<EightPoint, FeatureMatch> /
+ *                                   Consensus<LambdaTwist, FeatureWorldMatch> (call sites akaze/tests/estimate_pose.rs:63-67,
+ *                                   cv-sfm/src/lib.rs:1394-1406,1619-1622, vslam-sandbox/src/main.rs:105-117)
+ * Data: FeatureMatch = two unit bearings (a[i*3..], b[i*3..]); FeatureWorldMatch = unit bearing + homogeneous world
+ * point xyzw (xyz unit, w = 1/distance >= 0).  All pointers are HOST pointers; every model hypothesis and every
+ * (hypothesis, datum) residual is evaluated on the GPU; only ARRSAC's sequential bookkeeping (likelihood-ratio
+ * test, sort/truncate, RNG draws) runs on the host, exactly in the restated reference order. */
+typedef struct { double r[9]; double t[3]; } cvb_pose;      /* IsometryMatrix3<f64>: rotation row-major, translation */
+typedef struct { int32_t kind; uint64_t s[4]; } cvb_rng;   /* kind 0: xoshiro256++ (SmallRng / Xoshiro256PlusPlus), 1: Pcg64 */
+typedef struct {
+    double inlier_threshold;
+    uint32_t initialization_hypotheses, initialization_blocks, max_candidate_hypotheses, estimations_per_block, block_size;
+    float likelihood_ratio_threshold, initial_epsilon, initial_delta;
+} cvb_arrsac_cfg;
+
+void cvb_arrsac_default_cfg(cvb_arrsac_cfg *cfg, double inlier_threshold);   /* Arrsac::new(threshold, rng) defaults */
+void cvb_rng_seed_xoshiro256pp(cvb_rng *rng, uint64_t seed);                 /* Xoshiro256PlusPlus::seed_from_u64 */
+void cvb_rng_seed_pcg64(cvb_rng *rng, const uint8_t seed[32]);               /* Pcg64::from_seed */
+uint32_t cvb_rng_next_u32(cvb_rng *rng);
+
+/* H minimal samples (indices into the n data): samples[h*8..] / samples[h*3..]; up to 4 poses per sample */
+int cvb_eight_point_batch(cvb_ctx *ctx, const double *a, const double *b, uint32_t n, const uint32_t *samples, uint32_t H,
+                          cvb_pose *poses_out, uint8_t *nposes_out);
+int cvb_p3p_batch(cvb_ctx *ctx, const double *bearings, const double *world, uint32_t n, const uint32_t *samples, uint32_t H,
+                  cvb_pose *poses_out, uint8_t *nposes_out);
+/* out[m*n]: residual of pose p for datum i at out[p*n + i] */
+int cvb_residuals_camera_to_camera(cvb_ctx *ctx, const cvb_pose *poses, uint32_t m, const double *a, const double *b,
+                                   uint32_t n, double *out);
+int cvb_residuals_world_to_camera(cvb_ctx *ctx, const cvb_pose *poses, uint32_t m, const double *bearings,
+                                  const double *world, uint32_t n, double *out);
+/* L landmarks; landmark l owns observations offsets[l]..offsets[l+1] of (poses, bearings). ok_out[l] = 1 -> Some(point) */
+int cvb_triangulate_linear_eigen(cvb_ctx *ctx, const cvb_pose *poses, const double *bearings, const uint32_t *offsets,
+                                 uint32_t L, double *xyzw_out, uint8_t *ok_out);
+/* Consensus::model_inliers.  *found = 0 -> None.  inliers_out: ascending datum indices (at most cap written). */
+int cvb_arrsac_eight_point(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *a, const double *b, uint32_t n, cvb_rng *rng,
+                           cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers, int32_t *found);
+int cvb_arrsac_p3p(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *bearings, const double *world, uint32_t n,
+                   cvb_rng *rng, cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers, int32_t *found);
+
 #ifdef __cplusplus
 }
 #endif

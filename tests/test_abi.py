@@ -52,4 +52,4 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
-                assert "oracle" not in src.replace("the oracle", "").replace("and in the oracle", ""), os.path.join(dirpath, f)
+                assert "oracle" not in src.lower(), os.path.join(dirpath, f)
