@@ -190,11 +190,8 @@ def main():
     barrier()
     assert ms > 0.5 * wall_ms or wall_ms < 1.0, f"device timer {ms} ms disagrees with wall clock {wall_ms} ms"
     launches = ctx.launch_count() - l0
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * 2.0 * K / (ms_max * 1e-3)
+    from cv_b200 import dist as D
+    value, ms_max = D.aggregate_throughput(2.0 * K, ms, dev)      # units of all ranks / max-over-ranks device time
 
     # ---- e2e: host API with pinned host buffers (H2D frames, D2H keypoints/descriptors, H2D descriptors, D2H pairs)
     h_pool = [torch.from_numpy(p).pin_memory() for p in frames]
@@ -227,10 +224,7 @@ def main():
     ms_dev = ctx.timer_end()
     ms_e2e = max(ms_dev, (time.perf_counter() - t0) * 1e3)   # host-blocking API: wall clock bounds it from above
     barrier()
-    t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * 2.0 * K / (float(t.item()) * 1e-3)
+    e2e_value, _ = D.aggregate_throughput(2.0 * K, ms_e2e, dev)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
