@@ -141,98 +141,127 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    K, Wm = args.steps, max(args.warmup, 3)
+    # every distinct input buffer gets its CUDA graph captured during warm-up, never inside the timed region
+    K, Wm = args.steps, max(args.warmup, 3, POOL_PAIRS)
 
     frames = make_pool(POOL_PAIRS, seed0=100 * rank)
-    # the context owns its CUDA stream; all timing uses CUDA events recorded on THAT stream (cvb_ctx_timer_*)
-    ctx = cv_b200.Context(local_rank)
+    # Two independent contexts (each owns a CUDA stream + workspace; the ABI makes distinct contexts independent)
+    # alternate steps, so the latency-bound keypoint tail of step i overlaps the image pipeline of step i+1.
+    # Timing: CUDA events on the launching stream of context 0, bracketed by full-device synchronisation.
+    NCTX = 2
+    ctxs = [cv_b200.Context(local_rank) for _ in range(NCTX)]
+    ctx = ctxs[0]
     lib = ctx.lib
     cfg = cv_b200.AkazeConfig(maximum_features=MAXF).to_c()
     cap = 8192
-    # ---- device-resident buffers
+    # ---- device-resident buffers (one output set per context)
     d_pool = [torch.from_numpy(p).to(dev) for p in frames]
-    d_kp = torch.empty(2 * cap * KP_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    d_desc = torch.zeros(2 * cap * 64, dtype=torch.uint8, device=dev)
-    d_n = torch.zeros(2, dtype=torch.int32, device=dev)
-    d_fi = torch.empty(cap * 2, dtype=torch.int32, device=dev); d_fd = torch.empty_like(d_fi)
-    d_ri = torch.empty(cap * 2, dtype=torch.int32, device=dev); d_rd = torch.empty_like(d_ri)
 
-    def step_dev(i):
+    class Out:
+        def __init__(self):
+            self.kp = torch.empty(2 * cap * KP_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+            self.desc = torch.zeros(2 * cap * 64, dtype=torch.uint8, device=dev)
+            self.n = torch.zeros(2, dtype=torch.int32, device=dev)
+            self.fi = torch.empty(cap * 2, dtype=torch.int32, device=dev); self.fd = torch.empty_like(self.fi)
+            self.ri = torch.empty(cap * 2, dtype=torch.int32, device=dev); self.rd = torch.empty_like(self.ri)
+    outs = [Out() for _ in range(NCTX)]
+
+    def step_dev(i, c=None):
+        c = i % NCTX if c is None else c
+        cx, o = ctxs[c], outs[c]
         img = d_pool[i % POOL_PAIRS]
-        ctx.check(lib.cvb_akaze_extract_batch_dev(ctx.handle, C.byref(cfg), img.data_ptr(), 2, W, H, d_kp.data_ptr(),
-                                                  d_desc.data_ptr(), cap, d_n.data_ptr()))
-        da, db = d_desc.data_ptr(), d_desc.data_ptr() + cap * 64
-        na, nb = d_n.data_ptr(), d_n.data_ptr() + 4
-        ctx.check(lib.cvb_hamming_knn_dev_counts(ctx.handle, da, na, MAXF, db, nb, MAXF, 2, d_fi.data_ptr(), d_fd.data_ptr()))
-        ctx.check(lib.cvb_hamming_knn_dev_counts(ctx.handle, db, nb, MAXF, da, na, MAXF, 2, d_ri.data_ptr(), d_rd.data_ptr()))
+        cx.check(lib.cvb_akaze_extract_batch_dev(cx.handle, C.byref(cfg), img.data_ptr(), 2, W, H, o.kp.data_ptr(),
+                                                 o.desc.data_ptr(), cap, o.n.data_ptr()))
+        da, db = o.desc.data_ptr(), o.desc.data_ptr() + cap * 64
+        na, nb = o.n.data_ptr(), o.n.data_ptr() + 4
+        cx.check(lib.cvb_hamming_knn_dev_counts(cx.handle, da, na, MAXF, db, nb, MAXF, 2, o.fi.data_ptr(), o.fd.data_ptr()))
+        cx.check(lib.cvb_hamming_knn_dev_counts(cx.handle, db, nb, MAXF, da, na, MAXF, 2, o.ri.data_ptr(), o.rd.data_ptr()))
 
     def barrier():
-        ctx.sync()
+        for cx in ctxs:
+            cx.sync()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
-    for i in range(Wm):
-        step_dev(i)
+    for c in range(NCTX):                      # every (context, input buffer) pair captures its CUDA graph here
+        for i in range(max(Wm, POOL_PAIRS)):
+            step_dev(i, c)
     barrier()
-    n_kp = d_n.cpu().numpy().tolist()
+    n_kp = outs[0].n.cpu().numpy().tolist()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = ctx.launch_count()
+    l0 = sum(cx.launch_count() for cx in ctxs)
     barrier()
     t0 = time.perf_counter()
     ctx.timer_begin()
     for i in range(K):
         step_dev(Wm + i)
-    ms = ctx.timer_end()          # CUDA events on the launching stream; timer_end waits for the end event
+    for cx in ctxs[1:]:
+        cx.sync()                 # the other stream has drained before the end event is recorded
+    ms = ctx.timer_end()          # CUDA events on context 0's launching stream; waits for the end event
     wall_ms = (time.perf_counter() - t0) * 1e3
     barrier()
     assert ms > 0.5 * wall_ms or wall_ms < 1.0, f"device timer {ms} ms disagrees with wall clock {wall_ms} ms"
-    launches = ctx.launch_count() - l0
+    launches = sum(cx.launch_count() for cx in ctxs) - l0
     from cv_b200 import dist as D
     value, ms_max = D.aggregate_throughput(2.0 * K, ms, dev)      # units of all ranks / max-over-ranks device time
 
-    # ---- e2e: host API with pinned host buffers (H2D frames, D2H keypoints/descriptors, H2D descriptors, D2H pairs)
+    # ---- e2e: host API with pinned host buffers (H2D frames, D2H keypoints/descriptors, H2D descriptors, D2H pairs).
+    # One host thread per context (the blocking C calls release the GIL), steps alternate between them.
     h_pool = [torch.from_numpy(p).pin_memory() for p in frames]
-    h_kp = torch.empty(2 * cap * KP_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-    h_desc = torch.empty(2 * cap * 64, dtype=torch.uint8).pin_memory()
-    h_n = torch.zeros(2, dtype=torch.int32).pin_memory()
-    h_pairs = torch.empty(cap * 2, dtype=torch.int32).pin_memory()
-    npairs = C.c_uint32()
-    h2d = d2h = 0
 
-    def step_host(i):
-        nonlocal h2d, d2h
+    class HostOut:
+        def __init__(self):
+            self.kp = torch.empty(2 * cap * KP_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+            self.desc = torch.empty(2 * cap * 64, dtype=torch.uint8).pin_memory()
+            self.n = torch.zeros(2, dtype=torch.int32).pin_memory()
+            self.pairs = torch.empty(cap * 2, dtype=torch.int32).pin_memory()
+            self.npairs = C.c_uint32()
+            self.h2d = self.d2h = 0
+    houts = [HostOut() for _ in range(NCTX)]
+
+    def step_host(i, c):
+        cx, o = ctxs[c], houts[c]
         img = h_pool[i % POOL_PAIRS]
-        ctx.check(lib.cvb_akaze_extract_batch(ctx.handle, C.byref(cfg), img.data_ptr(), 2, W, H, h_kp.data_ptr(), h_desc.data_ptr(),
-                                              cap, h_n.data_ptr()))
-        na, nb = int(h_n[0]), int(h_n[1])
-        ctx.check(lib.cvb_match_symmetric(ctx.handle, h_desc.data_ptr(), na, h_desc.data_ptr() + cap * 64, nb, BETTER_BY,
-                                          h_pairs.data_ptr(), cap, C.byref(npairs)))
-        h2d = 2 * W * H * 4 + (na + nb) * 64
-        d2h = 8 + 4 + (na + nb) * (KP_DTYPE.itemsize + 64) + na * 4
-        return npairs.value
+        cx.check(lib.cvb_akaze_extract_batch(cx.handle, C.byref(cfg), img.data_ptr(), 2, W, H, o.kp.data_ptr(), o.desc.data_ptr(),
+                                             cap, o.n.data_ptr()))
+        na, nb = int(o.n[0]), int(o.n[1])
+        cx.check(lib.cvb_match_symmetric(cx.handle, o.desc.data_ptr(), na, o.desc.data_ptr() + cap * 64, nb, BETTER_BY,
+                                         o.pairs.data_ptr(), cap, C.byref(o.npairs)))
+        o.h2d = 2 * W * H * 4 + (na + nb) * 64
+        o.d2h = 8 + 4 + (na + nb) * (KP_DTYPE.itemsize + 64) + na * 4
+        return o.npairs.value
 
-    for i in range(Wm):
-        nm = step_host(i)
+    def host_worker(c, first, count):
+        for i in range(first + c, first + count, NCTX):
+            step_host(i, c)
+
+    def run_host(first, count):
+        th = [threading.Thread(target=host_worker, args=(c, first, count)) for c in range(NCTX)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    run_host(0, max(Wm, NCTX))
+    nm = houts[0].npairs.value
     barrier()
     t0 = time.perf_counter()
-    ctx.timer_begin()
-    for i in range(K):
-        step_host(Wm + i)
-    ms_dev = ctx.timer_end()
-    ms_e2e = max(ms_dev, (time.perf_counter() - t0) * 1e3)   # host-blocking API: wall clock bounds it from above
+    run_host(Wm, K)
+    ms_e2e = (time.perf_counter() - t0) * 1e3     # blocking host API: wall clock over the K steps (all results on the host)
     barrier()
+    h2d, d2h = houts[0].h2d, houts[0].d2h
     e2e_value, _ = D.aggregate_throughput(2.0 * K, ms_e2e, dev)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    # ---- roofline: instrumented pass (per-kernel CUDA events on the launching stream)
+    # ---- roofline: instrumented pass (per-kernel CUDA events on the launching stream, one context, no overlap)
     ctx.profile(True)
     PK = min(K, 10)
     for i in range(PK):
-        step_dev(i)
+        step_dev(i, 0)
     rep = ctx.profile_report()
     ctx.profile(False)
     peaks = {}
@@ -271,6 +300,7 @@ def main():
                 "config": {"workload": "configs[1]: AKAZE extract x2 + symmetric Hamming 2-NN, 2 frames 1920x1080 f32, ~5k kp/frame",
                            "frames_per_step_per_gpu": 2, "keypoints_per_frame": n_kp, "matches": int(nm), "maximum_features": MAXF,
                            "detector_threshold": 0.001, "better_by": BETTER_BY,
+                           "pipelining": f"{NCTX} contexts (CUDA streams + workspaces) alternate steps; CUDA graph per context",
                            "l2": f"inputs rotate over a pool of {2 * POOL_PAIRS} distinct frames ({2 * POOL_PAIRS * W * H * 4 / 1e6:.0f} MB > 126 MB L2)"},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "roofline": roofline, "hamming_Gcmp_per_s": gcmp, "cpu_baseline": cpu,

@@ -129,10 +129,23 @@ struct AkazeWorkspace {
     unsigned cap_out = 0;
     std::vector<void *> allocs;
     bool has_run = false;
+    // second stream for the detector response of finished octaves (overlaps the latency-bound coarse octaves)
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork[8] = {}, ev_join = nullptr;
+    // CUDA graphs of the whole extractor, keyed by the caller's buffers
+    struct GraphEntry { const void *img; void *kp, *desc, *n; unsigned B, cap; cudaGraphExec_t exec; };
+    std::vector<GraphEntry> graphs;
+    uint64_t launches_per_graph = 0;
+    bool use_graph = true;       // CVB_NO_GRAPH=1 disables
+    bool use_aux = true;         // CVB_NO_AUX_STREAM=1 disables
 };
 
 void akaze_workspace_free(AkazeWorkspace *ws) {
     if (!ws) return;
+    for (auto &g : ws->graphs) cudaGraphExecDestroy(g.exec);
+    if (ws->aux) cudaStreamDestroy(ws->aux);
+    for (cudaEvent_t e : ws->ev_fork) if (e) cudaEventDestroy(e);
+    if (ws->ev_join) cudaEventDestroy(ws->ev_join);
     for (void *p : ws->allocs) cudaFree(p);
     delete ws;
 }
@@ -334,6 +347,13 @@ int ensure_workspace(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, uint32_t batch, uin
         env = getenv("CVB_SUPPRESS_GLOBAL");
         ws->suppress_par_only = env && env[0] == '1';
         DA(sup_fallback, B);
+        env = getenv("CVB_NO_GRAPH");
+        ws->use_graph = !(env && env[0] == '1');
+        env = getenv("CVB_NO_AUX_STREAM");
+        ws->use_aux = !(env && env[0] == '1');
+        cudaStreamCreateWithFlags(&ws->aux, cudaStreamNonBlocking);
+        for (auto &e : ws->ev_fork) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ws->ev_join, cudaEventDisableTiming);
         cudaFuncSetAttribute(k_suppress_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SUP_SMEM);
     }
     DA(ot, 1); DA(dt, 1);
@@ -408,8 +428,8 @@ int launch_deriv2(cvb_ctx *ctx, const EvoHost &e, const float *Lx, const float *
 }
 
 // The whole extractor for `B` frames already resident in `images` (device).  Asynchronous.
-int run_extract(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoint *kp_out, unsigned char *desc_out,
-                unsigned cap_out, unsigned *n_out) {
+int run_extract_eager(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoint *kp_out, unsigned char *desc_out,
+                      unsigned cap_out, unsigned *n_out) {
     AkazeWorkspace *ws = ctx->akaze;
     cudaStream_t st = ctx->stream;
     const size_t PF = ws->plane_floats, P0 = ws->p0;
@@ -421,12 +441,42 @@ int run_extract(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoint *kp_
         return 0;
     }
     const int nbins = (int)ws->cfg.contrast_factor_num_bins;
+    int smax = 1;
+    for (const EvoHost &e : ws->evo) smax = std::max(smax, (int)e.sigma);
+    const size_t dsh = (size_t)(TH + 2 * smax), dsw = (size_t)(TW + 2 * smax);
+    const bool aux_ok = ws->use_aux && !ctx->prof;
+    bool forked = false;
+    int fork_id = 0;
+    // detector response (derivatives + Ldet) of evolutions [e0, e1): they only depend on Lsmooth of those evolutions
+    auto issue_detector_response = [&](int e0, int e1) -> int {
+        const int t0 = ws->table.e[e0].tilebase;
+        const int t1 = e1 < E ? ws->table.e[e1].tilebase : ws->table.total_tiles;
+        if (t1 <= t0) return 0;
+        cudaStream_t ds = st;
+        if (aux_ok) {
+            CVB_CUDA(ctx, cudaEventRecord(ws->ev_fork[fork_id & 7], st));
+            CVB_CUDA(ctx, cudaStreamWaitEvent(ws->aux, ws->ev_fork[fork_id & 7], 0));
+            fork_id++;
+            forked = true;
+            ds = ws->aux;
+        }
+        double px = 0;
+        for (int e = e0; e < e1; e++) px += (double)ws->evo[e].w * ws->evo[e].h;
+        dim3 g((unsigned)(t1 - t0), 1, B);
+        { CVB_PROF(ctx, "k_deriv1_all", 12.0 * px * B);
+        k_deriv1_all<<<g, NT, sizeof(float) * (dsh * dsw + 2 * dsh * TW), ds>>>(ws->Lsm, ws->Lt, ws->Lx, ws->Ly, PF, ws->table, t0);
+        CVB_LAUNCH_CHECK(ctx); }
+        { CVB_PROF(ctx, "k_deriv2_det_all", 12.0 * px * B);
+        k_deriv2_det_all<<<g, NT, sizeof(float) * (2 * dsh * dsw + 3 * dsh * TW), ds>>>(ws->Lx, ws->Ly, ws->Ldet, PF, ws->table, t0);
+        CVB_LAUNCH_CHECK(ctx); }
+        return 0;
+    };
+    int octave_first = 0;   // first evolution of the octave being built
     // ---- create_nonlinear_scale_space (lib.rs:193-258)
     // evolution 0: Lt = gaussian_blur(image, base_scale_offset); Lsmooth = Lt
     int rc = launch_separable(ctx, images, P0, ws->Lt + ws->evo[0].off, PF, W, H, B, ws->g0, ws->g0);
     if (rc) return rc;
-    CVB_CUDA(ctx, cudaMemcpy2DAsync(ws->Lsm + ws->evo[0].off, PF * sizeof(float), ws->Lt + ws->evo[0].off, PF * sizeof(float),
-                                    P0 * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+    // (Lsmooth_0 is Lt_0 itself, lib.rs:201: the derivative kernels read Lt for evolution 0, no copy)
     // contrast factor (contrast_factor.rs:16-64)
     CVB_CUDA(ctx, cudaMemsetAsync(ws->gmax, 0, sizeof(unsigned long long) * B, st));
     CVB_CUDA(ctx, cudaMemsetAsync(ws->hist, 0, sizeof(unsigned) * B * nbins, st));
@@ -451,6 +501,8 @@ int run_extract(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoint *kp_
         const float *src = ws->Lt + pe.off;   // previous evolution's final Lt
         size_t src_bs = PF;
         if (e.new_octave) {
+            if ((rc = issue_detector_response(octave_first, i))) return rc;
+            octave_first = i;
             dim3 blk(32, 8), grd(cdiv((unsigned)e.w, 32), cdiv((unsigned)e.h, 8), B);
             { CVB_PROF(ctx, "k_half_size", 4.0 * ((double)pe.w * pe.h + (double)e.w * e.h) * B);
             k_half_size<<<grd, blk, 0, st>>>(src, ws->tmpC, pe.w, pe.h, src_bs, P0);
@@ -491,18 +543,11 @@ int run_extract(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoint *kp_
             cur = dst; cur_bs = dst_bs;
         }
     }
-    // ---- detector_response (detector_response.rs:8-85): two launches cover every evolution
-    {
-        int smax = 1;
-        for (const EvoHost &e : ws->evo) smax = std::max(smax, (int)e.sigma);
-        const size_t sh = (size_t)(TH + 2 * smax), sw = (size_t)(TW + 2 * smax);
-        dim3 g((unsigned)ws->table.total_tiles, 1, B);
-        { CVB_PROF(ctx, "k_deriv1_all", 12.0 * (double)ws->plane_floats * B);
-        k_deriv1_all<<<g, NT, sizeof(float) * (sh * sw + 2 * sh * TW), st>>>(ws->Lsm, ws->Lx, ws->Ly, PF, ws->table);
-        CVB_LAUNCH_CHECK(ctx); }
-        { CVB_PROF(ctx, "k_deriv2_det_all", 12.0 * (double)ws->plane_floats * B);
-        k_deriv2_det_all<<<g, NT, sizeof(float) * (2 * sh * sw + 3 * sh * TW), st>>>(ws->Lx, ws->Ly, ws->Ldet, PF, ws->table);
-        CVB_LAUNCH_CHECK(ctx); }
+    if ((rc = issue_detector_response(octave_first, E))) return rc;
+    // ---- detector_response (detector_response.rs:8-85) is issued per octave from inside the loop above
+    if (forked) {   // join the auxiliary stream
+        CVB_CUDA(ctx, cudaEventRecord(ws->ev_join, ws->aux));
+        CVB_CUDA(ctx, cudaStreamWaitEvent(st, ws->ev_join, 0));
     }
     // ---- detect_keypoints (scale_space_extrema.rs)
     const int R = ws->table.total_rows;
@@ -561,6 +606,46 @@ int run_extract(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoint *kp_
     k_compact_final<<<B, 1024, 0, st>>>(ws->sorted, ws->desc_tmp, ws->ok, ws->nsorted, ws->capk, kp_out, desc_out, cap_out, n_out,
                                         ws->overflow);
     CVB_LAUNCH_CHECK(ctx); }
+    ws->has_run = true;
+    return 0;
+}
+
+// Front end: replay the whole extractor as one CUDA graph (captured once per distinct set of caller buffers);
+// falls back to eager launches while profiling or when capture is unavailable.
+int run_extract(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoint *kp_out, unsigned char *desc_out,
+                unsigned cap_out, unsigned *n_out) {
+    AkazeWorkspace *ws = ctx->akaze;
+    if (!ws->use_graph || ctx->prof || ws->evo.empty()) return run_extract_eager(ctx, images, B, kp_out, desc_out, cap_out, n_out);
+    for (auto &g : ws->graphs)
+        if (g.img == images && g.kp == kp_out && g.desc == desc_out && g.n == n_out && g.B == B && g.cap == cap_out) {
+            CVB_CUDA(ctx, cudaGraphLaunch(g.exec, ctx->stream));
+            ctx->launches += ws->launches_per_graph;
+            ws->has_run = true;
+            return 0;
+        }
+    const uint64_t l0 = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    CVB_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = run_extract_eager(ctx, images, B, kp_out, desc_out, cap_out, n_out);
+    cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess || !graph) {   // capture not possible: run eagerly from now on
+        cudaGetLastError();
+        ws->use_graph = false;
+        return run_extract_eager(ctx, images, B, kp_out, desc_out, cap_out, n_out);
+    }
+    ws->launches_per_graph = ctx->launches - l0;
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        ws->use_graph = false;
+        return run_extract_eager(ctx, images, B, kp_out, desc_out, cap_out, n_out);
+    }
+    if (ws->graphs.size() >= 32) { cudaGraphExecDestroy(ws->graphs.front().exec); ws->graphs.erase(ws->graphs.begin()); }
+    ws->graphs.push_back({images, kp_out, desc_out, n_out, B, cap_out, exec});
+    CVB_CUDA(ctx, cudaGraphLaunch(exec, ctx->stream));
     ws->has_run = true;
     return 0;
 }
@@ -665,6 +750,7 @@ int cvb_akaze_debug_plane(cvb_ctx *ctx, uint32_t frame, uint32_t i, uint32_t pla
     const float *planes[6] = {ws->Lt, ws->Lsm, ws->Lx, ws->Ly, ws->Lflow, ws->Ldet};
     if (plane >= 6) return cvb_set_error(ctx, CVB_EINVAL, "bad plane");
     const EvoHost &e = ws->evo[i];
+    if (plane == 1 && i == 0) plane = 0;   // Lsmooth_0 is Lt_0 (lib.rs:201)
     CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     CVB_CUDA(ctx, cudaMemcpy(out, planes[plane] + (size_t)frame * ws->plane_floats + e.off, sizeof(float) * (size_t)e.w * e.h,
                              cudaMemcpyDeviceToHost));

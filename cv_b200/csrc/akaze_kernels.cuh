@@ -317,7 +317,9 @@ __global__ void __launch_bounds__(1024) k_fed2(const float *__restrict__ Lin, co
                                                float *__restrict__ Lout, int w, int h, size_t lin_bstride,
                                                size_t c_bstride, size_t lout_bstride, FedSteps steps) {
     __shared__ float bufA[FR_H * FR_W], bufB[FR_H * FR_W], sc[FR_H * FR_W];
+    __shared__ float s_hs[FED_SMAX];
     const int S = steps.n;
+    if (threadIdx.x < FED_SMAX) s_hs[threadIdx.x] = 0.5f * steps.tau[threadIdx.x];   // (0.5 * step_size), nonlinear_diffusion.rs:30
     const int tw = FR_W - 2 * S, th = FR_H - 2 * S;          // output tile
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const float *lin = Lin + (size_t)blockIdx.z * lin_bstride;
@@ -360,18 +362,24 @@ __global__ void __launch_bounds__(1024) k_fed2(const float *__restrict__ Lin, co
     }
     float *cur = bufA, *nxt = bufB;
     for (int t = 1; t <= S; t++) {
-        const float hs = 0.5f * steps.tau[t - 1];
+        const float hs = s_hs[t - 1];
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            if (depth[k] >= t) {
-                const float l = cur[li[k]];
-                float v = l;
-                if (hR[k]) v += (hs * cR[k]) * (cur[li[k] + 1] - l);
-                if (hL[k]) v -= (hs * cL[k]) * (l - cur[li[k] - 1]);
-                if (hD[k]) v += (hs * cD[k]) * (cur[li[k] + FR_W] - l);
-                if (hU[k]) v -= (hs * cU[k]) * (l - cur[li[k] - FR_W]);
-                nxt[li[k]] = v;
-            }
+            // every update is a predicated instruction (no divergent branches); a missing neighbour simply
+            // leaves v untouched, exactly like the reference's border-by-omission
+            const bool on = depth[k] >= t;
+            const int i0 = li[k];
+            const float l = cur[i0];
+            const float lr = cur[hR[k] ? i0 + 1 : i0], ll = cur[hL[k] ? i0 - 1 : i0];
+            const float ld = cur[hD[k] ? i0 + FR_W : i0], lu = cur[hU[k] ? i0 - FR_W : i0];
+            float v = l;
+            const float fr = (hs * cR[k]) * (lr - l), fl = (hs * cL[k]) * (l - ll);
+            const float fd = (hs * cD[k]) * (ld - l), fu = (hs * cU[k]) * (l - lu);
+            v = hR[k] ? v + fr : v;
+            v = hL[k] ? v - fl : v;
+            v = hD[k] ? v + fd : v;
+            v = hU[k] ? v - fu : v;
+            if (on) nxt[i0] = v;
         }
         __syncthreads();
         float *tmp = cur; cur = nxt; nxt = tmp;
@@ -544,19 +552,21 @@ __device__ __forceinline__ int find_evolution_by_tile(const EvoTable &T, int til
 
 // Multiscale first derivatives of EVERY evolution in one launch (detector_response.rs:60-65):
 //   Lx = V_off(H_main(Ls)),  Ly = V_main(H_off(Ls)).   grid = (total 32x32 tiles, 1, B)
-__global__ void __launch_bounds__(NT) k_deriv1_all(const float *__restrict__ Ls, float *__restrict__ Lx,
-                                                   float *__restrict__ Ly, size_t bstride, EvoTable T) {
+__global__ void __launch_bounds__(NT) k_deriv1_all(const float *__restrict__ Ls, const float *__restrict__ Lt0,
+                                                   float *__restrict__ Lx, float *__restrict__ Ly, size_t bstride,
+                                                   EvoTable T, int tile_offset) {
     extern __shared__ float sm[];
-    const int e = find_evolution_by_tile(T, blockIdx.x);
+    const int gtile = blockIdx.x + tile_offset;
+    const int e = find_evolution_by_tile(T, gtile);
     const EvoDev ev = T.e[e];
     const int w = ev.w, h = ev.h, sigma = ev.sigma;
-    const int tiles_x = (w + TW - 1) / TW, tile = blockIdx.x - ev.tilebase;
+    const int tiles_x = (w + TW - 1) / TW, tile = gtile - ev.tilebase;
     const int x0 = (tile % tiles_x) * TW, y0 = (tile / tiles_x) * TH;
     const int sw = TW + 2 * sigma, sh = TH + 2 * sigma;
     float *s_in = sm, *s_hm = sm + sh * sw, *s_ho = s_hm + sh * TW;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const size_t base = (size_t)blockIdx.z * bstride + ev.off;
-    const float *src = Ls + base;
+    const float *src = (e == 0 ? Lt0 : Ls) + base;   // evolution 0: Lsmooth IS Lt (lib.rs:201), no copy is made
     for (int ly = ty; ly < sh; ly += 8) {
         const float *row = src + (size_t)clampi(y0 + ly - sigma, 0, h - 1) * w;
         for (int lx = tx; lx < sw; lx += 32) s_in[ly * sw + lx] = row[clampi(x0 + lx - sigma, 0, w - 1)];
@@ -585,12 +595,13 @@ __global__ void __launch_bounds__(NT) k_deriv1_all(const float *__restrict__ Ls,
 // Second derivatives + determinant of Hessian of EVERY evolution in one launch
 // (detector_response.rs:40-47,66-68): Ldet = (Lxx*Lyy - Lxy*Lxy) * sigma^4.
 __global__ void __launch_bounds__(NT) k_deriv2_det_all(const float *__restrict__ Lx, const float *__restrict__ Ly,
-                                                       float *__restrict__ Ldet, size_t bstride, EvoTable T) {
+                                                       float *__restrict__ Ldet, size_t bstride, EvoTable T, int tile_offset) {
     extern __shared__ float sm[];
-    const int e = find_evolution_by_tile(T, blockIdx.x);
+    const int gtile = blockIdx.x + tile_offset;
+    const int e = find_evolution_by_tile(T, gtile);
     const EvoDev ev = T.e[e];
     const int w = ev.w, h = ev.h, sigma = ev.sigma;
-    const int tiles_x = (w + TW - 1) / TW, tile = blockIdx.x - ev.tilebase;
+    const int tiles_x = (w + TW - 1) / TW, tile = gtile - ev.tilebase;
     const int x0 = (tile % tiles_x) * TW, y0 = (tile / tiles_x) * TH;
     const int sw = TW + 2 * sigma, sh = TH + 2 * sigma;
     float *s_x = sm, *s_y = sm + sh * sw, *s_a = s_y + sh * sw, *s_b = s_a + sh * TW, *s_c = s_b + sh * TW;
