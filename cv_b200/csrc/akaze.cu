@@ -120,6 +120,8 @@ struct AkazeWorkspace {
     bool suppress_seq = false;   // CVB_SUPPRESS_SEQ=1: serial reference kernel (debug / A-B check)
     bool suppress_par_only = false;   // CVB_SUPPRESS_GLOBAL=1: force the global-memory parallel kernel
     unsigned *sup_fallback = nullptr;
+    unsigned char *tile_evo = nullptr;   // evolution index of every 32x64 tile (all-evolution launches)
+    bool deriv_v3 = true;                // all derivative sigmas <= 5: column-strip kernels
     OrientTables *ot = nullptr;
     DescTables *dt = nullptr;
     // outputs owned by the workspace for the host-pointer API
@@ -213,7 +215,7 @@ int plan_evolutions(cvb_ctx *ctx, AkazeWorkspace *ws) {
         d.rowbase = rowbase; d.pad = 0;
         d.tilebase = tilebase; d.sigma = (int)e.sigma; d.norm = e.norm; d.middle = e.middle; d.quat = e.quat;
         rowbase += e.h;
-        tilebase += (int)(cdiv((unsigned)e.w, TW) * cdiv((unsigned)e.h, TH));
+        tilebase += (int)(cdiv((unsigned)e.w, SW3) * cdiv((unsigned)e.h, SH3));
     }
     ws->table.n = (int)ws->evo.size();
     ws->table.total_rows = rowbase;
@@ -359,13 +361,26 @@ int ensure_workspace(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, uint32_t batch, uin
     DA(ot, 1); DA(dt, 1);
     DA(kp_out, B * (size_t)cap_out); DA(desc_out, B * (size_t)cap_out * 64); DA(n_out, B);
 #undef DA
+    {
+        std::vector<unsigned char> te((size_t)std::max(ws->table.total_tiles, 1), 0);
+        ws->deriv_v3 = true;
+        for (size_t i = 0; i < ws->evo.size(); i++) {
+            const int t0 = ws->table.e[i].tilebase, t1 = i + 1 < ws->evo.size() ? ws->table.e[i + 1].tilebase : ws->table.total_tiles;
+            for (int t = t0; t < t1; t++) te[(size_t)t] = (unsigned char)i;
+            if (ws->evo[i].sigma > 5) ws->deriv_v3 = false;
+        }
+        rc = dalloc(ctx, ws, &ws->tile_evo, te.size());
+        if (rc) return rc;
+        CVB_CUDA(ctx, cudaMemcpyAsync(ws->tile_evo, te.data(), te.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     CVB_CUDA(ctx, cudaMemsetAsync(ws->overflow, 0, sizeof(unsigned), ctx->stream));
     CVB_CUDA(ctx, cudaMemsetAsync(ws->inv_k, 0, sizeof(float) * B * MAX_EVO, ctx->stream));
     // opt in to large dynamic shared memory where a configuration needs it
     cudaFuncSetAttribute(k_separable, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(k_deriv1_all, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(k_deriv2_det_all, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_deriv1_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_deriv2_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_deriv1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_deriv1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_deriv1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -383,9 +398,9 @@ int launch_separable(cvb_ctx *ctx, const float *in, size_t in_bs, float *out, si
                      const Taps &hk, const Taps &vk) {
     if (hk.ks == vk.ks && (hk.ks == 5 || hk.ks == 9) && memcmp(hk.k, vk.k, sizeof(float) * hk.ks) == 0) {
         CVB_PROF(ctx, "k_blur", 8.0 * w * h * B);
-        dim3 g(cdiv((unsigned)w, BW), cdiv((unsigned)h, BH), B);
-        if (hk.ks == 5) k_blur<5><<<g, NT, 0, ctx->stream>>>(in, out, w, h, in_bs, out_bs, hk);
-        else k_blur<9><<<g, NT, 0, ctx->stream>>>(in, out, w, h, in_bs, out_bs, hk);
+        dim3 g(cdiv((unsigned)w, SW3), cdiv((unsigned)h, SH3), B);
+        if (hk.ks == 5) k_blur_v3<5><<<g, NT, 0, ctx->stream>>>(in, out, w, h, in_bs, out_bs, hk);
+        else k_blur_v3<9><<<g, NT, 0, ctx->stream>>>(in, out, w, h, in_bs, out_bs, hk);
         CVB_LAUNCH_CHECK(ctx);
         return 0;
     }
@@ -462,13 +477,27 @@ int run_extract_eager(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoin
         }
         double px = 0;
         for (int e = e0; e < e1; e++) px += (double)ws->evo[e].w * ws->evo[e].h;
-        dim3 g((unsigned)(t1 - t0), 1, B);
-        { CVB_PROF(ctx, "k_deriv1_all", 12.0 * px * B);
-        k_deriv1_all<<<g, NT, sizeof(float) * (dsh * dsw + 2 * dsh * TW), ds>>>(ws->Lsm, ws->Lt, ws->Lx, ws->Ly, PF, ws->table, t0);
-        CVB_LAUNCH_CHECK(ctx); }
-        { CVB_PROF(ctx, "k_deriv2_det_all", 12.0 * px * B);
-        k_deriv2_det_all<<<g, NT, sizeof(float) * (2 * dsh * dsw + 3 * dsh * TW), ds>>>(ws->Lx, ws->Ly, ws->Ldet, PF, ws->table, t0);
-        CVB_LAUNCH_CHECK(ctx); }
+        if (ws->deriv_v3) {
+            const size_t region = (size_t)(SW3 + 2 * smax) * (SH3 + 2 * smax);
+            dim3 g((unsigned)(t1 - t0), 1, B);
+            { CVB_PROF(ctx, "k_deriv1", 12.0 * px * B);
+            k_deriv1_v3<<<g, NT, sizeof(float) * region, ds>>>(ws->Lsm, ws->Lt, ws->Lx, ws->Ly, PF, ws->table, ws->tile_evo, t0);
+            CVB_LAUNCH_CHECK(ctx); }
+            { CVB_PROF(ctx, "k_deriv2_det", 12.0 * px * B);
+            k_deriv2_v3<<<g, NT, sizeof(float) * 2 * region, ds>>>(ws->Lx, ws->Ly, ws->Ldet, PF, ws->table, ws->tile_evo, t0);
+            CVB_LAUNCH_CHECK(ctx); }
+        } else {   // generic two-pass tiles, one launch pair per evolution (derivative sigma > 5)
+            cudaStream_t keep = ctx->stream;
+            ctx->stream = ds;
+            int rc2 = 0;
+            for (int e = e0; e < e1 && !rc2; e++) {
+                const EvoHost &ev = ws->evo[e];
+                rc2 = launch_deriv1(ctx, ev, (e == 0 ? ws->Lt : ws->Lsm) + ev.off, ws->Lx + ev.off, ws->Ly + ev.off, PF, B);
+                if (!rc2) rc2 = launch_deriv2(ctx, ev, ws->Lx + ev.off, ws->Ly + ev.off, ws->Ldet + ev.off, PF, B);
+            }
+            ctx->stream = keep;
+            if (rc2) return rc2;
+        }
         return 0;
     };
     int octave_first = 0;   // first evolution of the octave being built
@@ -484,7 +513,7 @@ int run_extract_eager(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoin
     rc = launch_separable(ctx, images, P0, ws->tmpA, P0, W, H, B, ws->g1, ws->g1);
     if (rc) return rc;
     { CVB_PROF(ctx, "k_contrast_grad", 4.0 * W * H * B);
-    k_scharr_pm2<1><<<dim3(cdiv((unsigned)W, BW), cdiv((unsigned)H, BH), B), NT, 0, st>>>(ws->tmpA, nullptr, ws->g2, ws->gmax, W, H, P0, P0, nullptr, 0);
+    k_scharr_pm_v3<1><<<dim3(cdiv((unsigned)W, SW3), cdiv((unsigned)H, SH3), B), NT, 0, st>>>(ws->tmpA, nullptr, ws->g2, ws->gmax, W, H, P0, P0, nullptr, 0);
     CVB_LAUNCH_CHECK(ctx); }
     {
         unsigned blocks = std::min<unsigned>(cdiv((unsigned)P0, NT), (unsigned)ctx->num_sms * 8);
@@ -514,7 +543,7 @@ int run_extract_eager(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoin
         if (rc) return rc;
         // Lflow = pm_g2(simple_scharr_x(Lsmooth), simple_scharr_y(Lsmooth), contrast)
         { CVB_PROF(ctx, "k_scharr_pm", 8.0 * e.w * e.h * B);
-        k_scharr_pm2<0><<<dim3(cdiv((unsigned)e.w, BW), cdiv((unsigned)e.h, BH), B), NT, 0, st>>>(ws->Lsm + e.off, ws->Lflow + e.off, nullptr, nullptr, e.w, e.h, PF, PF,
+        k_scharr_pm_v3<0><<<dim3(cdiv((unsigned)e.w, SW3), cdiv((unsigned)e.h, SH3), B), NT, 0, st>>>(ws->Lsm + e.off, ws->Lflow + e.off, nullptr, nullptr, e.w, e.h, PF, PF,
                                                              ws->inv_k + i, MAX_EVO);
         CVB_LAUNCH_CHECK(ctx); }
         // FED steps: nl launches of at most FED_SMAX fused steps (balanced split); the chain ends in Lt_i
