@@ -79,6 +79,7 @@ class ClockSampler(threading.Thread):
 def cpu_reference_step(frames, reps):
     """The reference's CPU path (oracle port): extract both frames, symmetric 2-NN match. Returns seconds/step."""
     from oracle import pyoracle as O
+    O.set_num_threads(os.cpu_count())      # torchrun exports OMP_NUM_THREADS=1; the CPU arm may use every host thread
     t0 = time.perf_counter()
     for r in range(reps):
         pair = frames[r % len(frames)]
@@ -148,7 +149,8 @@ def main():
     # Two independent contexts (each owns a CUDA stream + workspace; the ABI makes distinct contexts independent)
     # alternate steps, so the latency-bound keypoint tail of step i overlaps the image pipeline of step i+1.
     # Timing: CUDA events on the launching stream of context 0, bracketed by full-device synchronisation.
-    NCTX = 2
+    NCTX = int(os.environ.get("CVB_BENCH_CONTEXTS", "6"))          # contexts pipelined in the device-resident measurement
+    NHOST = min(NCTX, int(os.environ.get("CVB_BENCH_HOST_THREADS", "4")))   # host threads (one context each) in the e2e measurement
     ctxs = [cv_b200.Context(local_rank) for _ in range(NCTX)]
     ctx = ctxs[0]
     lib = ctx.lib
@@ -220,7 +222,7 @@ def main():
             self.pairs = torch.empty(cap * 2, dtype=torch.int32).pin_memory()
             self.npairs = C.c_uint32()
             self.h2d = self.d2h = 0
-    houts = [HostOut() for _ in range(NCTX)]
+    houts = [HostOut() for _ in range(NHOST)]
 
     def step_host(i, c):
         cx, o = ctxs[c], houts[c]
@@ -235,17 +237,17 @@ def main():
         return o.npairs.value
 
     def host_worker(c, first, count):
-        for i in range(first + c, first + count, NCTX):
+        for i in range(first + c, first + count, NHOST):
             step_host(i, c)
 
     def run_host(first, count):
-        th = [threading.Thread(target=host_worker, args=(c, first, count)) for c in range(NCTX)]
+        th = [threading.Thread(target=host_worker, args=(c, first, count)) for c in range(NHOST)]
         for t in th:
             t.start()
         for t in th:
             t.join()
 
-    run_host(0, max(Wm, NCTX))
+    run_host(0, max(Wm, NHOST))
     nm = houts[0].npairs.value
     barrier()
     t0 = time.perf_counter()
@@ -300,7 +302,7 @@ def main():
                 "config": {"workload": "configs[1]: AKAZE extract x2 + symmetric Hamming 2-NN, 2 frames 1920x1080 f32, ~5k kp/frame",
                            "frames_per_step_per_gpu": 2, "keypoints_per_frame": n_kp, "matches": int(nm), "maximum_features": MAXF,
                            "detector_threshold": 0.001, "better_by": BETTER_BY,
-                           "pipelining": f"{NCTX} contexts (CUDA streams + workspaces) alternate steps; CUDA graph per context",
+                           "pipelining": f"{NCTX} contexts (CUDA streams + workspaces) alternate steps, CUDA graph per context; e2e: {NHOST} host threads",
                            "l2": f"inputs rotate over a pool of {2 * POOL_PAIRS} distinct frames ({2 * POOL_PAIRS * W * H * 4 / 1e6:.0f} MB > 126 MB L2)"},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "roofline": roofline, "hamming_Gcmp_per_s": gcmp, "cpu_baseline": cpu,

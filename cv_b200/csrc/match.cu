@@ -13,6 +13,7 @@
 // database is split across gridDim.y so that the grid covers all SMs; a second small kernel merges the
 // per-split lists in index order.  The bound is the integer popc pipe, not HBM (working set is L2 resident).
 #include <stdio.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <vector>
 #include "common.cuh"
@@ -128,6 +129,138 @@ __global__ void __launch_bounds__(QT) k_hamming_knn(const uint8_t *__restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Tensor-core formulation (BASELINE north_star: "tensor cores only if the distance matrix is reformulated as
+// a dense int8 contraction").  Each descriptor is unpacked to 512 int8 values in {0,1}; then
+//     hamming(a, b) = |a| + |b| - 2 <a, b>           (exact in s32)
+// and <a, b> for a 16 x 8 block of (query, database) pairs is 16 `mma.sync.m16n8k32.u8.u8.s32` (IMMA.16832)
+// instructions.  A warp keeps its 16 query rows (16 x 512 B) in registers for the whole kernel; database
+// tiles of 64 unpacked descriptors are staged in shared memory with cp.async (double buffered, row stride
+// 576 B so that the 128-bit fragment loads are bank-conflict free).  The (distance, index) key logic and the
+// split / merge structure are shared with the popcount kernel, so results are identical by construction.
+constexpr int IM_WARPS = 4, IM_QT = 16 * IM_WARPS, IM_DT = 64, IM_ROWB = 576;
+constexpr size_t IM_SMEM = 2 * (size_t)IM_DT * IM_ROWB + 2 * IM_DT * sizeof(uint16_t);
+
+// one warp per descriptor: 512 bits -> 512 bytes (0/1) + population count
+__global__ void __launch_bounds__(256) k_unpack_bits(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ n_dev,
+                                                     uint32_t n_host, uint8_t *__restrict__ U, uint16_t *__restrict__ pc) {
+    const uint32_t n = n_dev ? *n_dev : n_host;
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const uint32_t bits = ((const uint16_t *)(desc + (size_t)row * 64))[lane];   // bits 16*lane .. 16*lane+15
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t nib = (bits >> (4 * k)) & 0xfu;
+        w[k] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+    }
+    *(uint4 *)(U + (size_t)row * 512 + 16 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
+    uint32_t c = __popc(bits);
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) pc[row] = (uint16_t)c;
+}
+
+__device__ __forceinline__ void imma_16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+template <int K>
+__global__ void __launch_bounds__(IM_WARPS * 32) k_hamming_imma(const uint8_t *__restrict__ Uq, const uint16_t *__restrict__ pq,
+                                                                const uint32_t *__restrict__ n_dev, uint32_t n_host,
+                                                                const uint8_t *__restrict__ Udb, const uint16_t *__restrict__ pdb,
+                                                                const uint32_t *__restrict__ m_dev, uint32_t m_host, uint32_t chunk,
+                                                                uint32_t *__restrict__ partial) {
+    extern __shared__ __align__(128) uint8_t smraw[];
+    uint8_t *s_db = smraw;                                              // [2][IM_DT][IM_ROWB]
+    uint16_t *s_pb = (uint16_t *)(smraw + 2 * (size_t)IM_DT * IM_ROWB);   // [2][IM_DT]
+    const uint32_t n = n_dev ? *n_dev : n_host, m = m_dev ? *m_dev : m_host;
+    if (blockIdx.x * IM_QT >= n) return;
+    const uint32_t lo = min(blockIdx.y * chunk, m), hi = min(lo + chunk, m), cnt = hi - lo;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const uint32_t q0 = blockIdx.x * IM_QT + wid * 16;
+    const uint32_t rA = min(q0 + g, n - 1), rB = min(q0 + g + 8, n - 1);
+    // A fragments for all 16 k-steps: 8 x 16 B per row
+    uint4 fa[8], fb[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        fa[u] = *(const uint4 *)(Uq + (size_t)rA * 512 + 64 * u + 16 * t);
+        fb[u] = *(const uint4 *)(Uq + (size_t)rB * 512 + 64 * u + 16 * t);
+    }
+    const int pa0 = pq[rA], pa1 = pq[rB];
+    uint32_t best0[K], best1[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) { best0[i] = 0xffffffffu; best1[i] = 0xffffffffu; }
+    const uint32_t ntiles = (cnt + IM_DT - 1) / IM_DT;
+    auto stage = [&](uint32_t tile) {
+        uint8_t *dst = s_db + (size_t)(tile & 1) * IM_DT * IM_ROWB;
+        const uint32_t first = tile * IM_DT;
+        for (int c = threadIdx.x; c < IM_DT * 32; c += IM_WARPS * 32) {    // 32 chunks of 16 B per row
+            const int r = c >> 5, col = c & 31;
+            const uint32_t src_row = lo + min(first + (uint32_t)r, cnt - 1);
+            cp_async16(dst + r * IM_ROWB + col * 16, Udb + (size_t)src_row * 512 + col * 16);
+        }
+        if (threadIdx.x < IM_DT) s_pb[(tile & 1) * IM_DT + threadIdx.x] = pdb[lo + min(first + threadIdx.x, cnt - 1)];
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (ntiles > 0) stage(0);
+    for (uint32_t tile = 0; tile < ntiles; tile++) {
+        if (tile + 1 < ntiles) { stage(tile + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const uint8_t *tb = s_db + (size_t)(tile & 1) * IM_DT * IM_ROWB;
+        const uint16_t *tp = s_pb + (tile & 1) * IM_DT;
+        const uint32_t first = tile * IM_DT;
+#pragma unroll 2
+        for (int j = 0; j < IM_DT / 8; j++) {
+            int c[4] = {0, 0, 0, 0};
+            const uint8_t *brow = tb + (8 * j + g) * IM_ROWB + 16 * t;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint4 b = *(const uint4 *)(brow + 64 * u);
+                imma_16832(c, fa[u].x, fb[u].x, fa[u].y, fb[u].y, b.x, b.y);
+                imma_16832(c, fa[u].z, fb[u].z, fa[u].w, fb[u].w, b.z, b.w);
+            }
+            const uint32_t col = first + 8 * j + 2 * t;       // split-local database index of c[0] / c[2]
+            const int pb0 = tp[8 * j + 2 * t], pb1 = tp[8 * j + 2 * t + 1];
+            if (col < cnt) {
+                insert_key<K>(best0, ((uint32_t)(pa0 + pb0 - 2 * c[0]) << IDX_BITS) | col);
+                insert_key<K>(best1, ((uint32_t)(pa1 + pb0 - 2 * c[2]) << IDX_BITS) | col);
+            }
+            if (col + 1 < cnt) {
+                insert_key<K>(best0, ((uint32_t)(pa0 + pb1 - 2 * c[1]) << IDX_BITS) | (col + 1));
+                insert_key<K>(best1, ((uint32_t)(pa1 + pb1 - 2 * c[3]) << IDX_BITS) | (col + 1));
+            }
+        }
+        __syncthreads();   // buffer (tile & 1) may be overwritten by stage(tile + 2)
+    }
+    // merge the four lanes that share a row
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+        uint32_t o0[K], o1[K];
+#pragma unroll
+        for (int i = 0; i < K; i++) { o0[i] = __shfl_xor_sync(0xffffffffu, best0[i], o); o1[i] = __shfl_xor_sync(0xffffffffu, best1[i], o); }
+#pragma unroll
+        for (int i = 0; i < K; i++) { insert_key<K>(best0, o0[i]); insert_key<K>(best1, o1[i]); }
+    }
+    if (t == 0) {
+        if (q0 + g < n) {
+            uint32_t *out = partial + ((size_t)(q0 + g) * gridDim.y + blockIdx.y) * K;
+#pragma unroll
+            for (int i = 0; i < K; i++) out[i] = best0[i];
+        }
+        if (q0 + g + 8 < n) {
+            uint32_t *out = partial + ((size_t)(q0 + g + 8) * gridDim.y + blockIdx.y) * K;
+#pragma unroll
+            for (int i = 0; i < K; i++) out[i] = best1[i];
+        }
+    }
+}
+
 // merge the per-split lists (split order == index order) into global (idx, dist)
 template <int K>
 __global__ void k_knn_merge(const uint32_t *__restrict__ partial, const uint32_t *__restrict__ n_dev, uint32_t n_host,
@@ -185,12 +318,17 @@ struct MatchWorkspace {
     size_t q_bytes = 0, db_bytes = 0;
     uint32_t *idx = nullptr, *dist = nullptr, *idx2 = nullptr, *dist2 = nullptr, *flag = nullptr;
     size_t idx_elems = 0, dist_elems = 0, idx2_elems = 0, dist2_elems = 0, flag_elems = 0;
+    uint8_t *uq = nullptr, *udb = nullptr;         // unpacked (int8 0/1) descriptors for the tensor-core path
+    uint16_t *pq = nullptr, *pdb = nullptr;
+    size_t uq_bytes = 0, udb_bytes = 0, pq_elems = 0, pdb_elems = 0;
+    int use_imma = -1;                              // CVB_KNN_POPC=1 selects the popcount kernel
 };
 
 void match_workspace_free(MatchWorkspace *ws) {
     if (!ws) return;
     cudaFree(ws->partial); cudaFree(ws->q); cudaFree(ws->db); cudaFree(ws->idx); cudaFree(ws->dist);
     cudaFree(ws->idx2); cudaFree(ws->dist2); cudaFree(ws->flag);
+    cudaFree(ws->uq); cudaFree(ws->udb); cudaFree(ws->pq); cudaFree(ws->pdb);
     delete ws;
 }
 
@@ -219,6 +357,29 @@ int launch_knn(cvb_ctx *ctx, const uint8_t *q, const uint32_t *n_dev, uint32_t n
     return 0;
 }
 
+template <int K>
+int launch_knn_imma(cvb_ctx *ctx, MatchWorkspace *ws, const uint8_t *q, const uint32_t *n_dev, uint32_t n, const uint8_t *db,
+                    const uint32_t *m_dev, uint32_t m, uint32_t splits, uint32_t chunk, uint32_t *idx, uint32_t *dist) {
+    {
+        CVB_PROF(ctx, "k_unpack_bits", 0);
+        k_unpack_bits<<<cdiv(n * 32, 256), 256, 0, ctx->stream>>>(q, n_dev, n, ws->uq, ws->pq);
+        CVB_LAUNCH_CHECK(ctx);
+        k_unpack_bits<<<cdiv(m * 32, 256), 256, 0, ctx->stream>>>(db, m_dev, m, ws->udb, ws->pdb);
+        CVB_LAUNCH_CHECK(ctx);
+    }
+    {
+        static bool attr_set = false;   // per template instance, once per process
+        if (!attr_set) { cudaFuncSetAttribute(k_hamming_imma<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IM_SMEM); attr_set = true; }
+        dim3 grid(cdiv(n, IM_QT), splits);
+        CVB_PROF(ctx, "k_hamming_knn", 64.0 * (double)n * (double)m);
+        k_hamming_imma<K><<<grid, IM_WARPS * 32, IM_SMEM, ctx->stream>>>(ws->uq, ws->pq, n_dev, n, ws->udb, ws->pdb, m_dev, m, chunk, ws->partial);
+        CVB_LAUNCH_CHECK(ctx);
+    }
+    k_knn_merge<K><<<cdiv(n, 128), 128, 0, ctx->stream>>>(ws->partial, n_dev, n, splits, chunk, idx, dist);
+    CVB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 int knn_dev(cvb_ctx *ctx, const uint8_t *q, const uint32_t *n_dev, uint32_t n, const uint8_t *db, const uint32_t *m_dev,
             uint32_t m, uint32_t k, uint32_t *idx, uint32_t *dist) {
     if (k < 1 || k > MAXKNN) return cvb_set_error(ctx, CVB_EINVAL, "k must be 1..%d", MAXKNN);
@@ -226,6 +387,32 @@ int knn_dev(cvb_ctx *ctx, const uint8_t *q, const uint32_t *n_dev, uint32_t n, c
     if (((uintptr_t)q & 15) || ((uintptr_t)db & 15)) return cvb_set_error(ctx, CVB_EINVAL, "descriptor arrays must be 16-byte aligned");
     if (!ctx->match) ctx->match = new MatchWorkspace();
     MatchWorkspace *ws = ctx->match;
+    if (ws->use_imma < 0) { const char *env = getenv("CVB_KNN_POPC"); ws->use_imma = (env && env[0] == '1') ? 0 : 1; }
+    if (ws->use_imma && m > 0) {
+        // tensor-core path: 64-query CTAs, database split so that >= 3 CTAs per SM are in flight
+        uint32_t qblocks = cdiv(n, IM_QT);
+        uint32_t splits = std::max<uint32_t>(1, cdiv((uint32_t)ctx->num_sms * 3u, qblocks));
+        splits = std::min<uint32_t>(splits, std::max<uint32_t>(1, cdiv(m, IM_DT * 2)));
+        uint32_t chunk = cdiv(cdiv(m, splits), IM_DT) * IM_DT;
+        while (chunk > IDX_MASK) { splits *= 2; chunk = cdiv(cdiv(m, splits), IM_DT) * IM_DT; }
+        splits = cdiv(m, chunk);
+        int rc;
+        if ((rc = grow(ctx, &ws->partial, &ws->partial_elems, (size_t)n * splits * k))) return rc;
+        if ((rc = grow(ctx, &ws->uq, &ws->uq_bytes, (size_t)n * 512))) return rc;
+        if ((rc = grow(ctx, &ws->udb, &ws->udb_bytes, (size_t)m * 512))) return rc;
+        if ((rc = grow(ctx, &ws->pq, &ws->pq_elems, (size_t)n))) return rc;
+        if ((rc = grow(ctx, &ws->pdb, &ws->pdb_elems, (size_t)m))) return rc;
+        switch (k) {
+        case 1: return launch_knn_imma<1>(ctx, ws, q, n_dev, n, db, m_dev, m, splits, chunk, idx, dist);
+        case 2: return launch_knn_imma<2>(ctx, ws, q, n_dev, n, db, m_dev, m, splits, chunk, idx, dist);
+        case 3: return launch_knn_imma<3>(ctx, ws, q, n_dev, n, db, m_dev, m, splits, chunk, idx, dist);
+        case 4: return launch_knn_imma<4>(ctx, ws, q, n_dev, n, db, m_dev, m, splits, chunk, idx, dist);
+        case 5: return launch_knn_imma<5>(ctx, ws, q, n_dev, n, db, m_dev, m, splits, chunk, idx, dist);
+        case 6: return launch_knn_imma<6>(ctx, ws, q, n_dev, n, db, m_dev, m, splits, chunk, idx, dist);
+        case 7: return launch_knn_imma<7>(ctx, ws, q, n_dev, n, db, m_dev, m, splits, chunk, idx, dist);
+        default: return launch_knn_imma<8>(ctx, ws, q, n_dev, n, db, m_dev, m, splits, chunk, idx, dist);
+        }
+    }
     // split the database so that the grid covers the machine (>= 2 CTAs per SM) and chunks fit IDX_BITS
     uint32_t qblocks = cdiv(n, QT);
     uint32_t splits = std::max<uint32_t>(1, cdiv((uint32_t)ctx->num_sms * 4u, qblocks));

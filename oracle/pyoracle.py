@@ -92,6 +92,12 @@ def _fp(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
 
+def set_num_threads(n):
+    L = lib()
+    L.ref_set_num_threads.argtypes = [C.c_int]
+    L.ref_set_num_threads(int(n))
+
+
 def default_cfg(**kw):
     c = AkazeCfg()
     lib().ref_akaze_default_cfg(C.byref(c))

@@ -752,6 +752,18 @@ int ref_akaze_stage(const struct ref_akaze *A, int stage, const ref_keypoint **o
 }
 const uint8_t *ref_akaze_descriptors(const struct ref_akaze *A) { return A->desc; }
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* number of OpenMP threads used at the reference's rayon sites (bench.py's CPU arm) */
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* scalar helpers exported so tests can pin the restated libm against the host libm */
 float ref_sinf(float x) { return rl_sinf(x); }
 float ref_cosf(float x) { return rl_cosf(x); }

@@ -49,6 +49,7 @@ void ref_vertical_filter(const float *in, int w, int h, const float *k, int ks, 
 void ref_gaussian_kernel(float r, int ks, float *out);
 void ref_half_size(const float *in, int w, int h, float *out);
 int ref_fed_tau(double T, double tau_max, double *out, int cap);
+void ref_set_num_threads(int n);
 float ref_sinf(float x);
 float ref_cosf(float x);
 float ref_atan2f(float y, float x);
