@@ -121,6 +121,8 @@ struct AkazeWorkspace {
     bool suppress_par_only = false;   // CVB_SUPPRESS_GLOBAL=1: force the global-memory parallel kernel
     unsigned *sup_fallback = nullptr;
     unsigned char *tile_evo = nullptr;   // evolution index of every 32x64 tile (all-evolution launches)
+    MaskLayout mask_layout{};
+    unsigned *extrema_mask = nullptr;
     bool deriv_v3 = true;                // all derivative sigmas <= 5: column-strip kernels
     OrientTables *ot = nullptr;
     DescTables *dt = nullptr;
@@ -371,6 +373,14 @@ int ensure_workspace(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, uint32_t batch, uin
         }
         rc = dalloc(ctx, ws, &ws->tile_evo, te.size());
         if (rc) return rc;
+        int words = 0;
+        for (size_t i = 0; i < ws->evo.size(); i++) {
+            ws->mask_layout.wordbase[i] = words;
+            words += (int)(cdiv((unsigned)ws->evo[i].w, 32) * (unsigned)ws->evo[i].h);
+        }
+        ws->mask_layout.total_words = words;
+        rc = dalloc(ctx, ws, &ws->extrema_mask, (size_t)B * std::max(words, 1));
+        if (rc) return rc;
         CVB_CUDA(ctx, cudaMemcpyAsync(ws->tile_evo, te.data(), te.size(), cudaMemcpyHostToDevice, ctx->stream));
         CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -582,15 +592,17 @@ int run_extract_eager(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoin
     const int R = ws->table.total_rows;
     const float thr = (float)ws->cfg.detector_threshold;
     {
-        dim3 g(cdiv((unsigned)R * 32u, NT), 1, B);
-        { CVB_PROF(ctx, "k_extrema_count", 4.0 * ws->plane_floats * B);
-        k_extrema<false><<<g, NT, 0, st>>>(ws->Ldet, PF, ws->table, thr, ws->rowcount, nullptr, nullptr, 0, ws->overflow);
+        CVB_CUDA(ctx, cudaMemsetAsync(ws->rowcount, 0, sizeof(unsigned) * (size_t)B * R, st));
+        { CVB_PROF(ctx, "k_extrema_mask", 4.0 * ws->plane_floats * B);
+        k_extrema_mask<<<dim3((unsigned)ws->table.total_tiles, 1, B), NT, 0, st>>>(ws->Ldet, PF, ws->table, ws->tile_evo, ws->mask_layout, thr,
+                                                                                    ws->extrema_mask, ws->rowcount);
         CVB_LAUNCH_CHECK(ctx); }
         { CVB_PROF(ctx, "k_scan_rows", 0);
         k_scan_rows<<<B, 1024, 0, st>>>(ws->rowcount, ws->rowoff, ws->ncand, R);
         CVB_LAUNCH_CHECK(ctx); }
-        { CVB_PROF(ctx, "k_extrema_write", 0);
-        k_extrema<true><<<g, NT, 0, st>>>(ws->Ldet, PF, ws->table, thr, nullptr, ws->rowoff, ws->cand, ws->capc, ws->overflow);
+        { CVB_PROF(ctx, "k_extrema_emit", 0);
+        k_extrema_emit<<<dim3(cdiv((unsigned)R * 32u, NT), 1, B), NT, 0, st>>>(ws->Ldet, PF, ws->table, ws->mask_layout, ws->extrema_mask, ws->rowcount,
+                                                                                 ws->rowoff, ws->cand, ws->capc, ws->overflow);
         CVB_LAUNCH_CHECK(ctx); }
     }
     { CVB_PROF(ctx, "k_suppress", 0);

@@ -946,6 +946,86 @@ __global__ void __launch_bounds__(NT) k_extrema(const float *__restrict__ Ldet, 
     if (!WRITE && lane == 0) rowcount[(size_t)blockIdx.z * T.total_rows + warp] = count;
 }
 
+// v3 extrema detection: one pass over Ldet in 32 x 64 column-strip tiles produces a 1-bit-per-pixel mask
+// (strict 3x3 maximum above the threshold on interior pixels, scale_space_extrema.rs:49-59: v > each of the
+// eight neighbours <=> v > their maximum) plus per-row counts; a second, tiny pass turns mask words into the
+// ordered candidate list.  wordbase[e] = first mask word of evolution e; row r of evolution e owns
+// ceil(w/32) consecutive words.
+struct MaskLayout { int wordbase[MAX_EVO]; int total_words; };
+
+__global__ void __launch_bounds__(NT) k_extrema_mask(const float *__restrict__ Ldet, size_t bstride, EvoTable T,
+                                                     const unsigned char *__restrict__ tile_evo, MaskLayout ML, float thr,
+                                                     unsigned *__restrict__ mask, unsigned *__restrict__ rowcount) {
+    constexpr int RW = SW3 + 2;
+    __shared__ float s_in[(SH3 + 2) * RW];
+    const int e = tile_evo[blockIdx.x];
+    const EvoDev ev = T.e[e];
+    int x0, y0;
+    tile_origin_v3(ev, blockIdx.x, x0, y0);
+    stage_region<1, 1>(Ldet + (size_t)blockIdx.z * bstride + ev.off, ev.w, ev.h, x0, y0, s_in);
+    __syncthreads();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int gx = x0 + tx;
+    const bool xin = gx >= 1 && gx < ev.w - 1;
+    const float *col = s_in + (ty * STRIP) * RW + tx;
+    const int wpr = (ev.w + 31) >> 5;
+    unsigned *mrow = mask + (size_t)blockIdx.z * ML.total_words + ML.wordbase[e];
+    unsigned *rc = rowcount + (size_t)blockIdx.z * T.total_rows + ev.rowbase;
+    float m3[STRIP + 2], sd[STRIP + 2], cn[STRIP + 2];
+#pragma unroll
+    for (int r = 0; r < STRIP + 2; r++) {
+        const float l = col[r * RW], c = col[r * RW + 1], rt = col[r * RW + 2];
+        sd[r] = fmaxf(l, rt);
+        m3[r] = fmaxf(sd[r], c);
+        cn[r] = c;
+        if (r >= 2) {
+            const int o = r - 2, gy = y0 + ty * STRIP + o;
+            const float v = cn[o + 1];
+            const float m8 = fmaxf(fmaxf(m3[o], m3[o + 2]), sd[o + 1]);
+            const bool hit = xin && gy >= 1 && gy < ev.h - 1 && v > thr && v > m8;
+            const unsigned bits = __ballot_sync(0xffffffffu, hit);
+            if (tx == 0 && gy < ev.h && x0 < ev.w) {
+                mrow[(size_t)gy * wpr + (x0 >> 5)] = bits;
+                if (bits) atomicAdd(&rc[gy], (unsigned)__popc(bits));
+            }
+        }
+    }
+}
+
+// warp per row: expand the row's mask words into candidates at rowoff[row] (x ascending)
+__global__ void __launch_bounds__(NT) k_extrema_emit(const float *__restrict__ Ldet, size_t bstride, EvoTable T, MaskLayout ML,
+                                                     const unsigned *__restrict__ mask, const unsigned *__restrict__ rowcount,
+                                                     const unsigned *__restrict__ rowoff, Cand *__restrict__ cand, unsigned cap,
+                                                     unsigned *overflow) {
+    const int warp = (blockIdx.x * NT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= T.total_rows) return;
+    const size_t ri = (size_t)blockIdx.z * T.total_rows + warp;
+    if (rowcount[ri] == 0) return;
+    int e = 0;
+    while (e + 1 < T.n && warp >= T.e[e + 1].rowbase) e++;
+    const int y = warp - T.e[e].rowbase, w = T.e[e].w;
+    const int wpr = (w + 31) >> 5;
+    const unsigned *mrow = mask + (size_t)blockIdx.z * ML.total_words + ML.wordbase[e] + (size_t)y * wpr;
+    const float *D = Ldet + (size_t)blockIdx.z * bstride + T.e[e].off + (size_t)y * w;
+    unsigned base = rowoff[ri];
+    for (int wb = 0; wb < wpr; wb += 32) {
+        unsigned word = (wb + lane < wpr) ? mrow[wb + lane] : 0u;
+        const unsigned c = __popc(word);
+        unsigned inc = c;
+        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        unsigned pos = base + inc - c;
+        while (word) {
+            const int b = __ffs(word) - 1;
+            word &= word - 1;
+            const int x = (wb + lane) * 32 + b;
+            if (pos < cap) { Cand cd; cd.x = x; cd.y = y; cd.e = e; cd.v = D[x]; cand[(size_t)blockIdx.z * cap + pos] = cd; }
+            else *overflow = 1u;
+            pos++;
+        }
+        base += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
 // exclusive scan of per-row counts; one CTA of 1024 threads per frame
 __global__ void __launch_bounds__(1024) k_scan_rows(const unsigned *__restrict__ rowcount, unsigned *__restrict__ rowoff,
                                                     unsigned *__restrict__ total, int n) {
