@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(QT) k_hamming_knn(const uint8_t *__restrict__ 
 // tiles of 64 unpacked descriptors are staged in shared memory with cp.async (double buffered, row stride
 // 576 B so that the 128-bit fragment loads are bank-conflict free).  The (distance, index) key logic and the
 // split / merge structure are shared with the popcount kernel, so results are identical by construction.
-constexpr int IM_WARPS = 4, IM_QT = 16 * IM_WARPS, IM_DT = 64, IM_ROWB = 576;
+constexpr int IM_WARPS = 4, IM_QT = 16 * IM_WARPS, IM_DT = 32, IM_ROWB = 576;
 constexpr size_t IM_SMEM = 2 * (size_t)IM_DT * IM_ROWB + 2 * IM_DT * sizeof(uint16_t);
 
 // one warp per descriptor: 512 bits -> 512 bytes (0/1) + population count
@@ -389,9 +389,10 @@ int knn_dev(cvb_ctx *ctx, const uint8_t *q, const uint32_t *n_dev, uint32_t n, c
     MatchWorkspace *ws = ctx->match;
     if (ws->use_imma < 0) { const char *env = getenv("CVB_KNN_POPC"); ws->use_imma = (env && env[0] == '1') ? 0 : 1; }
     if (ws->use_imma && m > 0) {
-        // tensor-core path: 64-query CTAs, database split so that >= 3 CTAs per SM are in flight
+        // tensor-core path: 64-query CTAs; the database is split so that the grid is ONE full wave
+        // (4 CTAs of 128 threads fit per SM: 105 registers, 37 KB shared memory)
         uint32_t qblocks = cdiv(n, IM_QT);
-        uint32_t splits = std::max<uint32_t>(1, cdiv((uint32_t)ctx->num_sms * 3u, qblocks));
+        uint32_t splits = std::max<uint32_t>(1, ((uint32_t)ctx->num_sms * 4u) / qblocks);
         splits = std::min<uint32_t>(splits, std::max<uint32_t>(1, cdiv(m, IM_DT * 2)));
         uint32_t chunk = cdiv(cdiv(m, splits), IM_DT) * IM_DT;
         while (chunk > IDX_MASK) { splits *= 2; chunk = cdiv(cdiv(m, splits), IM_DT) * IM_DT; }

@@ -48,6 +48,13 @@ class LinearKnn:
         return r[0] if r else None
 
 
+def lowe_ratio_matches(ds1, ds2, ratio=0.5, ctx=None):
+    """akaze/tests/estimate_pose.rs:78-97 `match_descriptors`: 2-NN + Lowe ratio in f32, -> [(ix1, ix2), ...]."""
+    idx, dist = hamming_knn(ds1, ds2, 2, ctx)
+    ok = dist[:, 0].astype(np.float32) < dist[:, 1].astype(np.float32) * np.float32(ratio)
+    return [(int(i), int(idx[i, 0])) for i in np.where(ok)[0]]
+
+
 def matching(a, b, better_by=24, strict=False, ctx=None):
     """cv-sfm `matching` (cv-sfm/src/lib.rs:3097-3114: d0 + better_by <= d1); strict=True gives the
     tutorial rule d0 + 24 < d1 (chapter4 main.rs:99).  Returns an int64 array, -1 where None."""

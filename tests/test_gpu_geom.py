@@ -161,3 +161,23 @@ def test_arrsac_vslam_sandbox_configuration():
     assert rot_angle(got[0], R) < 5e-3 and 1.0 - abs(unit(got[1]) @ t) < 1e-3
     res = cv_b200.residuals_camera_to_camera([(got[0], got[1])], a, b)[0]
     assert np.array_equal(np.where(res < 1e-7)[0], got[2])      # model_inliers == { i : residual < threshold }
+
+
+def test_estimate_pose_end_to_end_reference_test():
+    """akaze/tests/estimate_pose.rs:24-76 end to end on the GPU path: extract both KITTI frames, Lowe-ratio match,
+    calibrate, ARRSAC + eight-point: 399 / 343 descriptors, 11 matches, 11 inliers."""
+    from tests.common import kitti_frame
+    ak = cv_b200.Akaze.sparse()
+    kps1, ds1 = ak.extract_from_gray_float_image(kitti_frame("0000000000"))
+    kps2, ds2 = ak.extract_from_gray_float_image(kitti_frame("0000000014"))
+    assert len(ds1) == 399 and len(ds2) == 343
+    pairs = cv_b200.lowe_ratio_matches(ds1, ds2, 0.5)
+    assert len(pairs) == 11
+    K = cv_b200.CameraIntrinsics(focals=(9.842439e2, 9.808141e2), principal_point=(6.9e2, 2.331966e2), skew=0.0)
+    a = K.calibrate_keypoints(kps1[[p[0] for p in pairs]])
+    b = K.calibrate_keypoints(kps2[[p[1] for p in pairs]])
+    assert np.allclose(a[0], O.calibrate(9.842439e2, 9.808141e2, 6.9e2, 2.331966e2, 0.0, float(kps1[pairs[0][0]]["x"]), float(kps1[pairs[0][0]]["y"])), atol=1e-15)
+    out = cv_b200.Arrsac(0.1, cv_b200.Pcg64(bytes([1] * 32))).model_inliers(cv_b200.EightPoint(), a, b)
+    assert out is not None and len(out[2]) == 11
+    px = K.uncalibrate(a)
+    assert np.abs(px[:, 0] - kps1[[p[0] for p in pairs]]["x"]).max() < 1e-6      # cv-pinhole/src/lib.rs:120-133
