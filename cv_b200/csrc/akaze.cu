@@ -388,7 +388,6 @@ int ensure_workspace(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, uint32_t batch, uin
     CVB_CUDA(ctx, cudaMemsetAsync(ws->inv_k, 0, sizeof(float) * B * MAX_EVO, ctx->stream));
     // opt in to large dynamic shared memory where a configuration needs it
     cudaFuncSetAttribute(k_separable, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_deriv1_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_deriv2_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(k_deriv1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -468,7 +467,6 @@ int run_extract_eager(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoin
     const int nbins = (int)ws->cfg.contrast_factor_num_bins;
     int smax = 1;
     for (const EvoHost &e : ws->evo) smax = std::max(smax, (int)e.sigma);
-    const size_t dsh = (size_t)(TH + 2 * smax), dsw = (size_t)(TW + 2 * smax);
     const bool aux_ok = ws->use_aux && !ctx->prof;
     bool forked = false;
     int fork_id = 0;

@@ -139,68 +139,6 @@ __global__ void k_half_size(const float *__restrict__ in, float *__restrict__ ou
     out[(size_t)blockIdx.z * out_bstride + (size_t)y * hw + x] = v;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Simple Scharr (x and y) of Lsmooth fused with pm_g2 -> Lflow.
-// lib.rs:236-248, derivatives.rs:3-11, nonlinear_diffusion.rs:70-83.  Lx/Ly are never written to HBM.
-// Also used (MODE 1) for the contrast-factor gradient: writes g2 = (f64)lx^2 + (f64)ly^2 on interior
-// pixels and a per-frame max (contrast_factor.rs:24-34).
-__device__ __forceinline__ void simple_scharr_at(const float *s, int sw, float &lx, float &ly) {
-    // s points at the centre of a 3x3 neighbourhood inside a shared tile of row stride sw
-    // H pass [-1,0,1] then V pass [3,10,3] for Lx; H [3,10,3] then V [-1,0,1] for Ly.
-    float hm_m = dot2<0, 2>(s[-sw - 1], -1.0f, s[-sw + 1], 1.0f);
-    float hm_0 = dot2<0, 2>(s[-1], -1.0f, s[1], 1.0f);
-    float hm_p = dot2<0, 2>(s[sw - 1], -1.0f, s[sw + 1], 1.0f);
-    lx = dot3<0, 1, 2>(hm_m, 3.0f, hm_0, 10.0f, hm_p, 3.0f);
-    float ho_m = dot3<0, 1, 2>(s[-sw - 1], 3.0f, s[-sw], 10.0f, s[-sw + 1], 3.0f);
-    float ho_p = dot3<0, 1, 2>(s[sw - 1], 3.0f, s[sw], 10.0f, s[sw + 1], 3.0f);
-    ly = dot2<0, 2>(ho_m, -1.0f, ho_p, 1.0f);
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(NT) k_scharr_pm(const float *__restrict__ in, float *__restrict__ out_flow,
-                                                  double *__restrict__ out_g2, unsigned long long *__restrict__ gmax,
-                                                  int w, int h, size_t in_bstride, size_t out_bstride,
-                                                  const float *__restrict__ inv_k, int inv_k_stride) {
-    __shared__ float s_in[(TH + 2) * (TW + 2)];
-    __shared__ unsigned long long s_max;
-    const int sw = TW + 2;
-    const float *src = in + (size_t)blockIdx.z * in_bstride;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    if (MODE == 1 && threadIdx.x == 0) s_max = 0ull;
-    for (int i = threadIdx.x; i < sw * (TH + 2); i += NT) {
-        int ly = i / sw, lx = i - ly * sw;
-        int gx = clampi(x0 + lx - 1, 0, w - 1), gy = clampi(y0 + ly - 1, 0, h - 1);
-        s_in[i] = src[(size_t)gy * w + gx];
-    }
-    __syncthreads();
-    float ik = 0.f;
-    if (MODE == 0) ik = inv_k[(size_t)blockIdx.z * inv_k_stride];
-    unsigned long long lmax = 0ull;
-    for (int i = threadIdx.x; i < TW * TH; i += NT) {
-        int ly = i / TW, lx = i - ly * TW;
-        int gx = x0 + lx, gy = y0 + ly;
-        if (gx >= w || gy >= h) continue;
-        float dx, dy;
-        simple_scharr_at(s_in + (ly + 1) * sw + (lx + 1), sw, dx, dy);
-        if (MODE == 0) {
-            out_flow[(size_t)blockIdx.z * out_bstride + (size_t)gy * w + gx] = 1.0f / (1.0f + ik * (dx * dx + dy * dy));
-        } else {
-            double g2 = -1.0;   // marks non-interior
-            if (gx >= 1 && gx < w - 1 && gy >= 1 && gy < h - 1) {
-                g2 = (double)(dx * dx) + (double)(dy * dy);
-                unsigned long long bits = (unsigned long long)__double_as_longlong(g2);
-                lmax = bits > lmax ? bits : lmax;   // g2 >= 0: bit pattern is order preserving
-            }
-            out_g2[(size_t)blockIdx.z * out_bstride + (size_t)gy * w + gx] = g2;
-        }
-    }
-    if (MODE == 1) {
-        atomicMax(&s_max, lmax);
-        __syncthreads();
-        if (threadIdx.x == 0 && s_max) atomicMax(gmax + blockIdx.z, s_max);
-    }
-}
-
 // contrast_factor.rs:35-48 histogram of floor(nbins * modg/hmax) over interior pixels with modg != 0
 __global__ void __launch_bounds__(NT) k_contrast_hist(const double *__restrict__ g2, const unsigned long long *gmax,
                                                       unsigned *hist, unsigned *npoints, int n, size_t bstride, int nbins) {
@@ -248,64 +186,7 @@ __global__ void k_contrast_final(const unsigned long long *gmax, const unsigned 
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// FED diffusion: `nsteps` explicit steps fused in one launch (temporal blocking, halo = nsteps).
-// nonlinear_diffusion.rs:14-58: flows from the OLD image; L += hf[x]; L -= hf[x-1]; L += vf[y]; L -= vf[y-1]
-// in that order; flow = ((0.5*step)*(ca+cb))*(b-a); image borders by omission.
 struct FedSteps { int n; float tau[FED_SMAX]; };
-
-__global__ void __launch_bounds__(NT) k_fed(const float *__restrict__ Lin, const float *__restrict__ C,
-                                            float *__restrict__ Lout, int w, int h, size_t lin_bstride, size_t c_bstride,
-                                            size_t lout_bstride, FedSteps steps) {
-    extern __shared__ float sm[];
-    const int S = steps.n;
-    const int sw = TW + 2 * S, sh = TH + 2 * S;
-    float *bufA = sm, *bufB = sm + sw * sh, *sc = sm + 2 * sw * sh;
-    const float *lin = Lin + (size_t)blockIdx.z * lin_bstride;
-    const float *cc = C + (size_t)blockIdx.z * c_bstride;
-    const int X0 = blockIdx.x * TW - S, Y0 = blockIdx.y * TH - S;
-    // loaded region clipped to the image
-    const int cx0 = max(X0, 0), cy0 = max(Y0, 0), cx1 = min(X0 + sw, w), cy1 = min(Y0 + sh, h);
-    for (int i = threadIdx.x; i < sw * sh; i += NT) {
-        int ly = i / sw, lx = i - ly * sw;
-        int gx = X0 + lx, gy = Y0 + ly;
-        bool in = gx >= cx0 && gx < cx1 && gy >= cy0 && gy < cy1;
-        size_t g = (size_t)gy * w + gx;
-        bufA[i] = in ? lin[g] : 0.f;
-        sc[i] = in ? cc[g] : 0.f;
-    }
-    __syncthreads();
-    float *cur = bufA, *nxt = bufB;
-    for (int t = 1; t <= S; t++) {
-        const float hs = 0.5f * steps.tau[t - 1];
-        // region whose dependency cone is inside the loaded data (no shrink on true image borders)
-        const int vx0 = cx0 + (cx0 > 0 ? t : 0), vx1 = cx1 - (cx1 < w ? t : 0);
-        const int vy0 = cy0 + (cy0 > 0 ? t : 0), vy1 = cy1 - (cy1 < h ? t : 0);
-        const int vw = vx1 - vx0, vh = vy1 - vy0;
-        if (vw > 0 && vh > 0) {
-            for (int i = threadIdx.x; i < vw * vh; i += NT) {
-                int yy = i / vw, xx = i - yy * vw;
-                int gx = vx0 + xx, gy = vy0 + yy;
-                int li = (gy - Y0) * sw + (gx - X0);
-                float l = cur[li], c0 = sc[li];
-                float v = l;
-                if (gx < w - 1) v += (hs * (c0 + sc[li + 1])) * (cur[li + 1] - l);
-                if (gx > 0) v -= (hs * (sc[li - 1] + c0)) * (l - cur[li - 1]);
-                if (gy < h - 1) v += (hs * (c0 + sc[li + sw])) * (cur[li + sw] - l);
-                if (gy > 0) v -= (hs * (sc[li - sw] + c0)) * (l - cur[li - sw]);
-                nxt[li] = v;
-            }
-        }
-        __syncthreads();
-        float *tmp = cur; cur = nxt; nxt = tmp;
-    }
-    float *dst = Lout + (size_t)blockIdx.z * lout_bstride;
-    for (int i = threadIdx.x; i < TW * TH; i += NT) {
-        int ly = i / TW, lx = i - ly * TW;
-        int gx = blockIdx.x * TW + lx, gy = blockIdx.y * TH + ly;
-        if (gx < w && gy < h) dst[(size_t)gy * w + gx] = cur[(ly + S) * sw + (lx + S)];
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // FED diffusion, v2: 1024-thread CTA owns a 64 x 32 REGION (two cells per thread, no index division);
@@ -476,217 +357,12 @@ __global__ void __launch_bounds__(NT) k_deriv2_det(const float *__restrict__ Lx,
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// v2 tile kernels: compile-time taps, 2-D thread mapping (no index divisions), same arithmetic.
 template <int KS>
 __device__ __forceinline__ float lane_dot_static(const float *w, int stride, const float *k) {
     float l[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < KS; j++) l[j & 3] = w[j * stride] * k[j] + l[j & 3];
     return (l[0] + l[2]) + (l[1] + l[3]);
-}
-
-constexpr int BW = 64, BH = 32;   // output tile of the blur kernels (256 threads as 32 x 8)
-
-// Gaussian blur (image.rs:383-389) with KS = 2*ceil(2*sigma)+1 taps; optional fused half_size of the
-// source (HALF: `in` is the previous octave's image, image.rs:154-199) so the half-sized Lt never
-// makes a round trip through HBM on its own... it is still written (`half_out`) because the FED chain
-// of the new octave starts from it.
-template <int KS>
-__global__ void __launch_bounds__(NT) k_blur(const float *__restrict__ in, float *__restrict__ out, int w, int h,
-                                             size_t in_bstride, size_t out_bstride, Taps tk) {
-    constexpr int R = KS / 2, SW = BW + 2 * R, SH = BH + 2 * R;
-    __shared__ float s_in[SH * SW];
-    __shared__ float s_h[SH * BW];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const float *src = in + (size_t)blockIdx.z * in_bstride;
-    float *dst = out + (size_t)blockIdx.z * out_bstride;
-    const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
-    for (int ly = ty; ly < SH; ly += 8) {
-        const int gy = clampi(y0 + ly - R, 0, h - 1);
-        const float *row = src + (size_t)gy * w;
-        for (int lx = tx; lx < SW; lx += 32) s_in[ly * SW + lx] = row[clampi(x0 + lx - R, 0, w - 1)];
-    }
-    __syncthreads();
-    for (int ly = ty; ly < SH; ly += 8) {
-#pragma unroll
-        for (int k = 0; k < BW / 32; k++) {
-            const int lx = tx + 32 * k;
-            s_h[ly * BW + lx] = lane_dot_static<KS>(s_in + ly * SW + lx, 1, tk.k);
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < BH / 8; r++) {
-        const int ly = ty + 8 * r, gy = y0 + ly;
-#pragma unroll
-        for (int k = 0; k < BW / 32; k++) {
-            const int lx = tx + 32 * k, gx = x0 + lx;
-            if (gx < w && gy < h) dst[(size_t)gy * w + gx] = lane_dot_static<KS>(s_h + ly * BW + lx, BW, tk.k);
-        }
-    }
-}
-
-// runtime-sigma versions of the sparse Scharr sums (lanes chosen by sigma & 3; see scharr_main/off)
-__device__ __forceinline__ float scharr_main_rt(float first, float last, int sm) {
-    const float a = first * -1.0f + 0.f;
-    if ((sm & 1) == 0) { const float l0 = last * 1.0f + a; return (l0 + 0.f) + (0.f + 0.f); }
-    const float l2 = last * 1.0f + 0.f;
-    return (a + l2) + (0.f + 0.f);
-}
-__device__ __forceinline__ float scharr_off_rt(float first, float mid, float last, float norm, float middle, int sm) {
-    const float a = first * norm + 0.f;
-    switch (sm & 3) {
-    case 0: { const float l0 = last * norm + (mid * middle + a); return (l0 + 0.f) + (0.f + 0.f); }
-    case 1: { const float l1 = mid * middle + 0.f, l2 = last * norm + 0.f; return (a + l2) + (l1 + 0.f); }
-    case 2: { const float l0 = last * norm + a, l2 = mid * middle + 0.f; return (l0 + l2) + (0.f + 0.f); }
-    default: { const float l3 = mid * middle + 0.f, l2 = last * norm + 0.f; return (a + l2) + (0.f + l3); }
-    }
-}
-
-__device__ __forceinline__ int find_evolution_by_tile(const EvoTable &T, int tile) {
-    int e = 0;
-    while (e + 1 < T.n && tile >= T.e[e + 1].tilebase) e++;
-    return e;
-}
-
-// Multiscale first derivatives of EVERY evolution in one launch (detector_response.rs:60-65):
-//   Lx = V_off(H_main(Ls)),  Ly = V_main(H_off(Ls)).   grid = (total 32x32 tiles, 1, B)
-__global__ void __launch_bounds__(NT) k_deriv1_all(const float *__restrict__ Ls, const float *__restrict__ Lt0,
-                                                   float *__restrict__ Lx, float *__restrict__ Ly, size_t bstride,
-                                                   EvoTable T, int tile_offset) {
-    extern __shared__ float sm[];
-    const int gtile = blockIdx.x + tile_offset;
-    const int e = find_evolution_by_tile(T, gtile);
-    const EvoDev ev = T.e[e];
-    const int w = ev.w, h = ev.h, sigma = ev.sigma;
-    const int tiles_x = (w + TW - 1) / TW, tile = gtile - ev.tilebase;
-    const int x0 = (tile % tiles_x) * TW, y0 = (tile / tiles_x) * TH;
-    const int sw = TW + 2 * sigma, sh = TH + 2 * sigma;
-    float *s_in = sm, *s_hm = sm + sh * sw, *s_ho = s_hm + sh * TW;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const size_t base = (size_t)blockIdx.z * bstride + ev.off;
-    const float *src = (e == 0 ? Lt0 : Ls) + base;   // evolution 0: Lsmooth IS Lt (lib.rs:201), no copy is made
-    for (int ly = ty; ly < sh; ly += 8) {
-        const float *row = src + (size_t)clampi(y0 + ly - sigma, 0, h - 1) * w;
-        for (int lx = tx; lx < sw; lx += 32) s_in[ly * sw + lx] = row[clampi(x0 + lx - sigma, 0, w - 1)];
-    }
-    __syncthreads();
-    for (int ly = ty; ly < sh; ly += 8) {
-        const float *p = s_in + ly * sw + tx;
-        const float a = p[0], m = p[sigma], z = p[2 * sigma];
-        s_hm[ly * TW + tx] = scharr_main_rt(a, z, sigma);
-        s_ho[ly * TW + tx] = scharr_off_rt(a, m, z, ev.norm, ev.middle, sigma);
-    }
-    __syncthreads();
-    const int gx = x0 + tx;
-#pragma unroll
-    for (int r = 0; r < TH / 8; r++) {
-        const int ly = ty + 8 * r, gy = y0 + ly;
-        if (gx < w && gy < h) {
-            const float *pm = s_hm + ly * TW + tx, *po = s_ho + ly * TW + tx;
-            const size_t g = base + (size_t)gy * w + gx;
-            Lx[g] = scharr_off_rt(pm[0], pm[sigma * TW], pm[2 * sigma * TW], ev.norm, ev.middle, sigma);
-            Ly[g] = scharr_main_rt(po[0], po[2 * sigma * TW], sigma);
-        }
-    }
-}
-
-// Second derivatives + determinant of Hessian of EVERY evolution in one launch
-// (detector_response.rs:40-47,66-68): Ldet = (Lxx*Lyy - Lxy*Lxy) * sigma^4.
-__global__ void __launch_bounds__(NT) k_deriv2_det_all(const float *__restrict__ Lx, const float *__restrict__ Ly,
-                                                       float *__restrict__ Ldet, size_t bstride, EvoTable T, int tile_offset) {
-    extern __shared__ float sm[];
-    const int gtile = blockIdx.x + tile_offset;
-    const int e = find_evolution_by_tile(T, gtile);
-    const EvoDev ev = T.e[e];
-    const int w = ev.w, h = ev.h, sigma = ev.sigma;
-    const int tiles_x = (w + TW - 1) / TW, tile = gtile - ev.tilebase;
-    const int x0 = (tile % tiles_x) * TW, y0 = (tile / tiles_x) * TH;
-    const int sw = TW + 2 * sigma, sh = TH + 2 * sigma;
-    float *s_x = sm, *s_y = sm + sh * sw, *s_a = s_y + sh * sw, *s_b = s_a + sh * TW, *s_c = s_b + sh * TW;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const size_t base = (size_t)blockIdx.z * bstride + ev.off;
-    const float *px = Lx + base, *py = Ly + base;
-    for (int ly = ty; ly < sh; ly += 8) {
-        const size_t ro = (size_t)clampi(y0 + ly - sigma, 0, h - 1) * w;
-        for (int lx = tx; lx < sw; lx += 32) {
-            const size_t g = ro + clampi(x0 + lx - sigma, 0, w - 1);
-            s_x[ly * sw + lx] = px[g];
-            s_y[ly * sw + lx] = py[g];
-        }
-    }
-    __syncthreads();
-    for (int ly = ty; ly < sh; ly += 8) {
-        const float *p = s_x + ly * sw + tx, *q = s_y + ly * sw + tx;
-        const float pa = p[0], pm = p[sigma], pz = p[2 * sigma];
-        s_a[ly * TW + tx] = scharr_main_rt(pa, pz, sigma);
-        s_b[ly * TW + tx] = scharr_off_rt(q[0], q[sigma], q[2 * sigma], ev.norm, ev.middle, sigma);
-        s_c[ly * TW + tx] = scharr_off_rt(pa, pm, pz, ev.norm, ev.middle, sigma);
-    }
-    __syncthreads();
-    const int gx = x0 + tx;
-#pragma unroll
-    for (int r = 0; r < TH / 8; r++) {
-        const int ly = ty + 8 * r, gy = y0 + ly;
-        if (gx < w && gy < h) {
-            const float *pa = s_a + ly * TW + tx, *pb = s_b + ly * TW + tx, *pc = s_c + ly * TW + tx;
-            const float lxx = scharr_off_rt(pa[0], pa[sigma * TW], pa[2 * sigma * TW], ev.norm, ev.middle, sigma);
-            const float lyy = scharr_main_rt(pb[0], pb[2 * sigma * TW], sigma);
-            const float lxy = scharr_main_rt(pc[0], pc[2 * sigma * TW], sigma);
-            Ldet[base + (size_t)gy * w + gx] = (lxx * lyy - lxy * lxy) * ev.quat;
-        }
-    }
-}
-
-// Simple Scharr + pm_g2 (MODE 0) / contrast-factor gradient (MODE 1), 64x32 tile, 2-D mapping.
-template <int MODE>
-__global__ void __launch_bounds__(NT) k_scharr_pm2(const float *__restrict__ in, float *__restrict__ out_flow,
-                                                   double *__restrict__ out_g2, unsigned long long *__restrict__ gmax,
-                                                   int w, int h, size_t in_bstride, size_t out_bstride,
-                                                   const float *__restrict__ inv_k, int inv_k_stride) {
-    constexpr int SW = BW + 2, SH = BH + 2;
-    __shared__ float s_in[SH * SW];
-    __shared__ unsigned long long s_max;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const float *src = in + (size_t)blockIdx.z * in_bstride;
-    const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
-    if (MODE == 1 && threadIdx.x == 0) s_max = 0ull;
-    for (int ly = ty; ly < SH; ly += 8) {
-        const float *row = src + (size_t)clampi(y0 + ly - 1, 0, h - 1) * w;
-        for (int lx = tx; lx < SW; lx += 32) s_in[ly * SW + lx] = row[clampi(x0 + lx - 1, 0, w - 1)];
-    }
-    __syncthreads();
-    float ik = 0.f;
-    if (MODE == 0) ik = inv_k[(size_t)blockIdx.z * inv_k_stride];
-    unsigned long long lmax = 0ull;
-#pragma unroll
-    for (int r = 0; r < BH / 8; r++) {
-        const int ly = ty + 8 * r, gy = y0 + ly;
-#pragma unroll
-        for (int k = 0; k < BW / 32; k++) {
-            const int lx = tx + 32 * k, gx = x0 + lx;
-            if (gx >= w || gy >= h) continue;
-            float dx, dy;
-            simple_scharr_at(s_in + (ly + 1) * SW + (lx + 1), SW, dx, dy);
-            if (MODE == 0) {
-                out_flow[(size_t)blockIdx.z * out_bstride + (size_t)gy * w + gx] = 1.0f / (1.0f + ik * (dx * dx + dy * dy));
-            } else {
-                double g2 = -1.0;
-                if (gx >= 1 && gx < w - 1 && gy >= 1 && gy < h - 1) {
-                    g2 = (double)(dx * dx) + (double)(dy * dy);
-                    unsigned long long bits = (unsigned long long)__double_as_longlong(g2);
-                    lmax = bits > lmax ? bits : lmax;
-                }
-                out_g2[(size_t)blockIdx.z * out_bstride + (size_t)gy * w + gx] = g2;
-            }
-        }
-    }
-    if (MODE == 1) {
-        atomicMax(&s_max, lmax);
-        __syncthreads();
-        if (threadIdx.x == 0 && s_max) atomicMax(gmax + blockIdx.z, s_max);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -906,47 +582,7 @@ __global__ void __launch_bounds__(NT) k_scharr_pm_v3(const float *__restrict__ i
 }
 
 // ---------------------------------------------------------------------------------------------
-// Scale-space extrema candidates (scale_space_extrema.rs:34-60): strict 3x3 maximum above threshold on
-// interior pixels, emitted in the reference's order: evolution ascending, raster within evolution.
-// One warp per image row (all evolutions of a frame form one global row index space).
-__device__ __forceinline__ bool is_extremum(const float *D, int w, int x, int y, float thr) {
-    const float *p = D + (size_t)y * w + x;
-    float v = *p;
-    return v > thr && v > p[-w - 1] && v > p[-w] && v > p[-w + 1] && v > p[-1] && v > p[1] && v > p[w - 1] &&
-           v > p[w] && v > p[w + 1];
-}
-
-template <bool WRITE>
-__global__ void __launch_bounds__(NT) k_extrema(const float *__restrict__ Ldet, size_t bstride, EvoTable T, float thr,
-                                                unsigned *__restrict__ rowcount, const unsigned *__restrict__ rowoff,
-                                                Cand *__restrict__ cand, unsigned cap, unsigned *overflow) {
-    const int warp = (blockIdx.x * NT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= T.total_rows) return;
-    int e = 0;
-    while (e + 1 < T.n && warp >= T.e[e + 1].rowbase) e++;
-    const int y = warp - T.e[e].rowbase, w = T.e[e].w, h = T.e[e].h;
-    const float *D = Ldet + (size_t)blockIdx.z * bstride + T.e[e].off;
-    unsigned count = 0;
-    unsigned base = WRITE ? rowoff[(size_t)blockIdx.z * T.total_rows + warp] : 0;
-    if (y >= 1 && y < h - 1) {
-        for (int xb = 1; xb < w - 1; xb += 32) {
-            int x = xb + lane;
-            bool hit = x < w - 1 && is_extremum(D, w, x, y, thr);
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (WRITE && hit) {
-                unsigned pos = base + count + __popc(m & ((1u << lane) - 1u));
-                if (pos < cap) {
-                    Cand c; c.x = x; c.y = y; c.e = e; c.v = D[(size_t)y * w + x];
-                    cand[(size_t)blockIdx.z * cap + pos] = c;
-                } else *overflow = 1u;
-            }
-            count += __popc(m);
-        }
-    }
-    if (!WRITE && lane == 0) rowcount[(size_t)blockIdx.z * T.total_rows + warp] = count;
-}
-
-// v3 extrema detection: one pass over Ldet in 32 x 64 column-strip tiles produces a 1-bit-per-pixel mask
+// Extrema detection: one pass over Ldet in 32 x 64 column-strip tiles produces a 1-bit-per-pixel mask
 // (strict 3x3 maximum above the threshold on interior pixels, scale_space_extrema.rs:49-59: v > each of the
 // eight neighbours <=> v > their maximum) plus per-row counts; a second, tiny pass turns mask words into the
 // ordered candidate list.  wordbase[e] = first mask word of evolution e; row r of evolution e owns
@@ -1068,7 +704,6 @@ __global__ void __launch_bounds__(1024) k_suppress_seq(const Cand *__restrict__ 
                                                    unsigned *__restrict__ ncache, unsigned capk, unsigned *overflow) {
     __shared__ unsigned s_min[32];
     __shared__ unsigned s_n;
-    __shared__ unsigned s_kmin;
     const int b = blockIdx.x;
     const Cand *cd = cand + (size_t)b * capc;
     cvb_keypoint *kc = cache + (size_t)b * capk;

@@ -1,0 +1,58 @@
+"""Error behaviour of the C ABI on a GPU box: bad arguments return CVB_E* codes with a message, capacity
+overflows are reported (never silently truncated), and nothing aborts the process."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cv_b200
+from cv_b200._lib import CVB_ECAP, CVB_EINVAL, CVB_EUNSUPPORTED, KP_DTYPE
+from tests.common import kitti_frame
+from tests.synth import random_descriptors
+
+pytestmark = pytest.mark.gpu
+
+
+def test_invalid_arguments_are_reported_not_fatal():
+    ctx = cv_b200.Context(0)
+    L = ctx.lib
+    cfg = cv_b200.AkazeConfig().to_c()
+    n = C.c_uint32()
+    img = np.zeros((64, 64), np.float32)
+    kp = np.zeros(16, KP_DTYPE); d = np.zeros((16, 64), np.uint8)
+    assert L.cvb_akaze_extract(ctx.handle, C.byref(cfg), None, 64, 64, kp.ctypes.data, d.ctypes.data, 16, C.byref(n)) == CVB_EINVAL
+    assert L.cvb_akaze_extract(ctx.handle, C.byref(cfg), img.ctypes.data, 0, 64, kp.ctypes.data, d.ctypes.data, 16, C.byref(n)) == CVB_EINVAL
+    assert b"empty" in L.cvb_last_error(ctx.handle)
+    bad = cv_b200.AkazeConfig(descriptor_channels=7).to_c()
+    assert L.cvb_akaze_extract(ctx.handle, C.byref(bad), img.ctypes.data, 64, 64, kp.ctypes.data, d.ctypes.data, 16, C.byref(n)) == CVB_EINVAL
+    bad = cv_b200.AkazeConfig(base_scale_offset=-1.0).to_c()       # the reference asserts sigma > 0 (image.rs:384)
+    assert L.cvb_akaze_extract(ctx.handle, C.byref(bad), img.ctypes.data, 64, 64, kp.ctypes.data, d.ctypes.data, 16, C.byref(n)) == CVB_EINVAL
+    bad = cv_b200.AkazeConfig(descriptor_pattern_size=40).to_c()
+    assert L.cvb_akaze_extract(ctx.handle, C.byref(bad), img.ctypes.data, 64, 64, kp.ctypes.data, d.ctypes.data, 16, C.byref(n)) == CVB_EUNSUPPORTED
+    q = random_descriptors(4, 0)
+    idx = np.zeros((4, 9), np.uint32)
+    assert L.cvb_hamming_knn(ctx.handle, q.ctypes.data, 4, q.ctypes.data, 4, 9, idx.ctypes.data, idx.ctypes.data) == CVB_EINVAL   # k > 8
+    # the context is still usable after errors
+    k, dd = cv_b200.Akaze.sparse(ctx=ctx).extract_from_gray_float_image(kitti_frame("0000000000")[:200, :300].copy())
+    assert len(k) == len(dd)
+
+
+def test_output_capacity_overflow_is_an_error():
+    img = kitti_frame("0000000000")
+    ak = cv_b200.Akaze(0.001, max_keypoints=100)       # 3425 keypoints do not fit 100 slots
+    with pytest.raises(cv_b200.CvbError) as e:
+        ak.extract_from_gray_float_image(img)
+    assert e.value.code == CVB_ECAP
+    ak2 = cv_b200.Akaze(0.001, max_keypoints=100, maximum_features=100)   # Akaze::maximum_features truncation is fine
+    k, d = ak2.extract_from_gray_float_image(img)
+    assert len(d) == 100
+
+
+def test_python_layer_rejects_bad_shapes():
+    with pytest.raises(ValueError):
+        cv_b200.hamming_knn(np.zeros((3, 32), np.uint8), np.zeros((3, 64), np.uint8))
+    with pytest.raises(TypeError):
+        cv_b200.Akaze().extract(np.zeros((8, 8), np.float64))
+    with pytest.raises(ValueError):
+        cv_b200.Akaze().extract_batch(np.zeros((8, 8), np.float32))
+    assert cv_b200.symmetric_matching(random_descriptors(1, 0), random_descriptors(5, 1)).shape == (0, 2)   # < 2 features: no matches
