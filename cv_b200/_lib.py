@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "cvb_akaze_default_cfg", "cvb_akaze_extract", "cvb_akaze_extract_batch", "cvb_akaze_extract_batch_dev",
     "cvb_akaze_debug_num_evolutions", "cvb_akaze_debug_evolution", "cvb_akaze_debug_plane", "cvb_akaze_debug_contrast",
     "cvb_akaze_debug_stage",
-    "cvb_hamming_knn", "cvb_hamming_knn_dev", "cvb_hamming_knn_dev_counts", "cvb_match_symmetric",
+    "cvb_hamming_knn", "cvb_hamming_knn_dev", "cvb_hamming_knn_dev_counts", "cvb_match_symmetric", "cvb_match_symmetric_dev",
     "cvb_arrsac_default_cfg", "cvb_rng_seed_xoshiro256pp", "cvb_rng_seed_pcg64", "cvb_rng_next_u32",
     "cvb_eight_point_batch", "cvb_p3p_batch", "cvb_residuals_camera_to_camera", "cvb_residuals_world_to_camera",
     "cvb_triangulate_linear_eigen", "cvb_arrsac_eight_point", "cvb_arrsac_p3p",
@@ -95,6 +95,7 @@ def load_library():
     L.cvb_hamming_knn_dev.argtypes = [vp, vp, u32, vp, u32, u32, vp, vp]
     L.cvb_hamming_knn_dev_counts.argtypes = [vp, vp, vp, u32, vp, vp, u32, u32, vp, vp]
     L.cvb_match_symmetric.argtypes = [vp, vp, u32, vp, u32, u32, vp, u32, C.POINTER(u32)]
+    L.cvb_match_symmetric_dev.argtypes = [vp, vp, u32, vp, u32, u32, vp]
     _LIB = L
     return L
 

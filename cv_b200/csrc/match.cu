@@ -481,6 +481,30 @@ int cvb_hamming_knn(cvb_ctx *ctx, const uint8_t *q, uint32_t n, const uint8_t *d
     return 0;
 }
 
+int cvb_match_symmetric_dev(cvb_ctx *ctx, const uint8_t *a_dev, uint32_t n, const uint8_t *b_dev, uint32_t m, uint32_t better_by,
+                            uint32_t *match_out_dev) {
+    if (!ctx) return CVB_EINVAL;
+    if (n == 0) return 0;
+    if (!a_dev || !match_out_dev || (m && !b_dev)) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->match) ctx->match = new MatchWorkspace();
+    MatchWorkspace *ws = ctx->match;
+    if (n < 2 || m < 2) {   // cv-sfm/src/lib.rs:3099-3101: no matches at all
+        CVB_CUDA(ctx, cudaMemsetAsync(match_out_dev, 0xff, sizeof(uint32_t) * n, ctx->stream));
+        return 0;
+    }
+    int rc;
+    if ((rc = grow(ctx, &ws->idx, &ws->idx_elems, (size_t)n * 2))) return rc;
+    if ((rc = grow(ctx, &ws->dist, &ws->dist_elems, (size_t)n * 2))) return rc;
+    if ((rc = grow(ctx, &ws->idx2, &ws->idx2_elems, (size_t)m * 2))) return rc;
+    if ((rc = grow(ctx, &ws->dist2, &ws->dist2_elems, (size_t)m * 2))) return rc;
+    if ((rc = knn_dev(ctx, a_dev, nullptr, n, b_dev, nullptr, m, 2, ws->idx, ws->dist))) return rc;
+    if ((rc = knn_dev(ctx, b_dev, nullptr, m, a_dev, nullptr, n, 2, ws->idx2, ws->dist2))) return rc;
+    k_symmetric<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ws->idx, ws->dist, ws->idx2, ws->dist2, n, m, better_by, match_out_dev);
+    CVB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
 int cvb_match_symmetric(cvb_ctx *ctx, const uint8_t *a, uint32_t n, const uint8_t *b, uint32_t m, uint32_t better_by,
                         uint32_t *pairs_out, uint32_t cap, uint32_t *n_out) {
     if (!ctx) return CVB_EINVAL;

@@ -142,6 +142,11 @@ int cvb_hamming_knn_dev_counts(cvb_ctx *ctx, const uint8_t *queries_dev, const u
 int cvb_match_symmetric(cvb_ctx *ctx, const uint8_t *desc_a, uint32_t n, const uint8_t *desc_b, uint32_t m,
                         uint32_t better_by, uint32_t *pairs_out, uint32_t cap, uint32_t *n_out);
 
+/* Device-resident variant: a_dev / b_dev are device descriptor arrays; match_out_dev[n] receives, for every a, the
+ * index of its symmetric match in b or 0xffffffff.  Asynchronous on the context stream. */
+int cvb_match_symmetric_dev(cvb_ctx *ctx, const uint8_t *a_dev, uint32_t n, const uint8_t *b_dev, uint32_t m,
+                            uint32_t better_by, uint32_t *match_out_dev);
+
 /* ---- geometric verification ------------------------------------------------------------------
  * sample_consensus::{Estimator, Model, Consensus} surfaces (external crate sample-consensus 1.0.2, re-exported at
  * cv-core/src/lib.rs:82) with the solvers and residuals of the reference:
