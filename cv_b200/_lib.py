@@ -47,7 +47,7 @@ ABI_SYMBOLS = [
     "cvb_akaze_debug_stage",
     "cvb_hamming_knn", "cvb_hamming_knn_dev", "cvb_hamming_knn_dev_counts", "cvb_match_symmetric", "cvb_match_symmetric_dev",
     "cvb_arrsac_default_cfg", "cvb_rng_seed_xoshiro256pp", "cvb_rng_seed_pcg64", "cvb_rng_next_u32",
-    "cvb_eight_point_batch", "cvb_p3p_batch", "cvb_residuals_camera_to_camera", "cvb_residuals_world_to_camera",
+    "cvb_eight_point_batch", "cvb_p3p_batch", "cvb_five_point_batch", "cvb_arrsac_five_point", "cvb_residuals_camera_to_camera", "cvb_residuals_world_to_camera",
     "cvb_triangulate_linear_eigen", "cvb_arrsac_eight_point", "cvb_arrsac_p3p",
 ]
 

@@ -80,7 +80,7 @@ __device__ __forceinline__ double det3(const double *m) {
 
 // sorted SVD of a 3x3 matrix through the eigen-decomposition of MtM; u3 = u1 x u2 (its sign is normalised by
 // the det(U) > 0 rule of essential.rs:139-143 anyway)
-__device__ bool svd3(const double *M, double eps, int iters, double *U, double *Vt) {
+__device__ __noinline__ bool svd3(const double *M, double eps, int iters, double *U, double *Vt) {
     double MtM[9], d[3], V[9];
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) MtM[i * 3 + j] = M[i] * M[j] + M[3 + i] * M[3 + j] + M[6 + i] * M[6 + j];
@@ -384,13 +384,315 @@ __device__ int p3p(const double *bearings, const double *world, const uint32_t *
     return nl;
 }
 
+// ---- five-point (nister-stewenius/src/lib.rs:50-330).  nalgebra's full_piv_lu / complex_eigenvalues / try_svd are
+// implemented as complete-pivoting elimination, Hessenberg + Francis double-shift QR, and one-sided Jacobi.
+// `row0`: first eigenvector row used as (x, y, z, 1).  The reference takes rows 5..8 (`fixed_rows::<4>(5)`, lib.rs:229)
+// although the monomial basis puts (x, y, z, 1) in rows 6..9, so its essentials violate the cubic constraints; row0 = 5
+// reproduces the reference, row0 = 6 is the mathematically correct solver.
+constexpr int FPN = 10;
+// __noinline__: with every helper inlined into one five-point frame, nvcc 12.9 -O3 produced a wrong complete-pivoting
+// elimination on sm_100a (the same text is right stand-alone and on the host); separate frames are bit-identical to the CPU.
+__device__ __noinline__ bool lu_full_pivot_solve(const double *Ain, const double *Bin, double *X) {
+    double A[FPN][FPN], B[FPN][FPN];
+    int colperm[FPN];
+    for (int i = 0; i < FPN; i++) for (int j = 0; j < FPN; j++) { A[i][j] = Ain[i * FPN + j]; B[i][j] = Bin[i * FPN + j]; }
+    for (int i = 0; i < FPN; i++) colperm[i] = i;
+    for (int k = 0; k < FPN; k++) {
+        int pr = k, pc = k; double best = -1.0;
+        for (int i = k; i < FPN; i++) for (int j = k; j < FPN; j++) if (fabs(A[i][j]) > best) { best = fabs(A[i][j]); pr = i; pc = j; }
+        if (best == 0.0) return false;
+        if (pr != k) for (int j = 0; j < FPN; j++) { double t = A[k][j]; A[k][j] = A[pr][j]; A[pr][j] = t; t = B[k][j]; B[k][j] = B[pr][j]; B[pr][j] = t; }
+        if (pc != k) { for (int i = 0; i < FPN; i++) { double t = A[i][k]; A[i][k] = A[i][pc]; A[i][pc] = t; } int t = colperm[k]; colperm[k] = colperm[pc]; colperm[pc] = t; }
+        for (int i = k + 1; i < FPN; i++) {
+            const double f = A[i][k] / A[k][k];
+            if (f == 0.0) continue;
+            for (int j = k; j < FPN; j++) A[i][j] -= f * A[k][j];
+            for (int j = 0; j < FPN; j++) B[i][j] -= f * B[k][j];
+        }
+    }
+    double Y[FPN][FPN];
+    for (int c = 0; c < FPN; c++)
+        for (int i = FPN - 1; i >= 0; i--) {
+            double v = B[i][c];
+            for (int j = i + 1; j < FPN; j++) v -= A[i][j] * Y[j][c];
+            Y[i][c] = v / A[i][i];
+        }
+    for (int i = 0; i < FPN; i++) for (int c = 0; c < FPN; c++) X[colperm[i] * FPN + c] = Y[i][c];
+    return true;
+}
+
+__device__ __forceinline__ double fp_sign(double a, double b) { return b >= 0.0 ? fabs(a) : -fabs(a); }
+__device__ __noinline__ bool real_eigenvalues10(const double *Ain, double *wr, double *wi) {
+    const int n = FPN;
+    double a[FPN][FPN];
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) a[i][j] = Ain[i * n + j];
+    for (int m = 1; m < n - 1; m++) {
+        double x = 0.0; int i = m;
+        for (int j = m; j < n; j++) if (fabs(a[j][m - 1]) > fabs(x)) { x = a[j][m - 1]; i = j; }
+        if (i != m) {
+            for (int j = m - 1; j < n; j++) { double t = a[i][j]; a[i][j] = a[m][j]; a[m][j] = t; }
+            for (int j = 0; j < n; j++) { double t = a[j][i]; a[j][i] = a[j][m]; a[j][m] = t; }
+        }
+        if (x != 0.0)
+            for (i = m + 1; i < n; i++) {
+                double y = a[i][m - 1];
+                if (y != 0.0) {
+                    y /= x; a[i][m - 1] = y;
+                    for (int j = m; j < n; j++) a[i][j] -= y * a[m][j];
+                    for (int j = 0; j < n; j++) a[j][m] += y * a[j][i];
+                }
+            }
+    }
+    for (int i = 2; i < n; i++) for (int j = 0; j < i - 1; j++) a[i][j] = 0.0;
+    int nn = n - 1, l, its;
+    double p = 0, q = 0, r = 0, s, t = 0.0, u, v, w, x, y, z, anorm = 0.0;
+    for (int i = 0; i < n; i++) for (int j = (i > 0 ? i - 1 : 0); j < n; j++) anorm += fabs(a[i][j]);
+    while (nn >= 0) {
+        its = 0;
+        do {
+            for (l = nn; l >= 1; l--) {
+                s = fabs(a[l - 1][l - 1]) + fabs(a[l][l]);
+                if (s == 0.0) s = anorm;
+                if (fabs(a[l][l - 1]) + s == s) { a[l][l - 1] = 0.0; break; }
+            }
+            x = a[nn][nn];
+            if (l == nn) { wr[nn] = x + t; wi[nn--] = 0.0; }
+            else {
+                y = a[nn - 1][nn - 1]; w = a[nn][nn - 1] * a[nn - 1][nn];
+                if (l == nn - 1) {
+                    p = 0.5 * (y - x); q = p * p + w; z = sqrt(fabs(q)); x += t;
+                    if (q >= 0.0) {
+                        z = p + fp_sign(z, p);
+                        wr[nn - 1] = wr[nn] = x + z;
+                        if (z != 0.0) wr[nn] = x - w / z;
+                        wi[nn - 1] = wi[nn] = 0.0;
+                    } else { wr[nn - 1] = wr[nn] = x + p; wi[nn] = z; wi[nn - 1] = -z; }
+                    nn -= 2;
+                } else {
+                    if (its == 60) return false;
+                    if (its == 10 || its == 20) {
+                        t += x;
+                        for (int i = 0; i <= nn; i++) a[i][i] -= x;
+                        s = fabs(a[nn][nn - 1]) + fabs(a[nn - 1][nn - 2]);
+                        y = x = 0.75 * s; w = -0.4375 * s * s;
+                    }
+                    ++its;
+                    int m;
+                    for (m = nn - 2; m >= l; m--) {
+                        z = a[m][m]; r = x - z; s = y - z;
+                        p = (r * s - w) / a[m + 1][m] + a[m][m + 1];
+                        q = a[m + 1][m + 1] - z - r - s;
+                        r = a[m + 2][m + 1];
+                        s = fabs(p) + fabs(q) + fabs(r);
+                        p /= s; q /= s; r /= s;
+                        if (m == l) break;
+                        u = fabs(a[m][m - 1]) * (fabs(q) + fabs(r));
+                        v = fabs(p) * (fabs(a[m - 1][m - 1]) + fabs(z) + fabs(a[m + 1][m + 1]));
+                        if (u + v == v) break;
+                    }
+                    for (int i = m + 2; i <= nn; i++) { a[i][i - 2] = 0.0; if (i != m + 2) a[i][i - 3] = 0.0; }
+                    for (int k = m; k <= nn - 1; k++) {
+                        if (k != m) {
+                            p = a[k][k - 1]; q = a[k + 1][k - 1]; r = 0.0;
+                            if (k != nn - 1) r = a[k + 2][k - 1];
+                            if ((x = fabs(p) + fabs(q) + fabs(r)) != 0.0) { p /= x; q /= x; r /= x; }
+                        }
+                        if ((s = fp_sign(sqrt(p * p + q * q + r * r), p)) != 0.0) {
+                            if (k == m) { if (l != m) a[k][k - 1] = -a[k][k - 1]; }
+                            else a[k][k - 1] = -s * x;
+                            p += s; x = p / s; y = q / s; z = r / s; q /= p; r /= p;
+                            for (int j = k; j <= nn; j++) {
+                                p = a[k][j] + q * a[k + 1][j];
+                                if (k != nn - 1) { p += r * a[k + 2][j]; a[k + 2][j] -= p * z; }
+                                a[k + 1][j] -= p * y; a[k][j] -= p * x;
+                            }
+                            const int mmin = nn < k + 3 ? nn : k + 3;
+                            for (int i = l; i <= mmin; i++) {
+                                p = x * a[i][k] + y * a[i][k + 1];
+                                if (k != nn - 1) { p += z * a[i][k + 2]; a[i][k + 2] -= p * r; }
+                                a[i][k + 1] -= p * q; a[i][k] -= p;
+                            }
+                        }
+                    }
+                }
+            }
+        } while (l < nn - 1);
+    }
+    return true;
+}
+
+__device__ __noinline__ bool min_right_singular_vector10(const double *Min, double eps, int max_sweeps, double *vec, double *smin) {
+    double U[FPN][FPN], V[FPN][FPN];
+    for (int i = 0; i < FPN; i++) for (int j = 0; j < FPN; j++) { U[i][j] = Min[i * FPN + j]; V[i][j] = i == j ? 1.0 : 0.0; }
+    bool converged = false;
+    for (int sweep = 0; sweep < max_sweeps && !converged; sweep++) {
+        converged = true;
+        for (int p = 0; p < FPN - 1; p++)
+            for (int q = p + 1; q < FPN; q++) {
+                double alpha = 0, beta = 0, gamma = 0;
+                for (int i = 0; i < FPN; i++) { alpha += U[i][p] * U[i][p]; beta += U[i][q] * U[i][q]; gamma += U[i][p] * U[i][q]; }
+                if (gamma == 0.0 || fabs(gamma) <= eps * sqrt(alpha * beta)) continue;
+                converged = false;
+                const double zeta = (beta - alpha) / (2.0 * gamma);
+                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                for (int i = 0; i < FPN; i++) {
+                    const double up = U[i][p], uq = U[i][q];
+                    U[i][p] = c * up - s * uq; U[i][q] = s * up + c * uq;
+                    const double vp = V[i][p], vq = V[i][q];
+                    V[i][p] = c * vp - s * vq; V[i][q] = s * vp + c * vq;
+                }
+            }
+    }
+    if (!converged) return false;
+    int best = 0; double bn = -1.0;
+    for (int j = 0; j < FPN; j++) {
+        double nn = 0; for (int i = 0; i < FPN; i++) nn += U[i][j] * U[i][j];
+        if (bn < 0.0 || nn < bn) { bn = nn; best = j; }
+    }
+    *smin = sqrt(bn);
+    for (int i = 0; i < FPN; i++) vec[i] = V[i][best];
+    return true;
+}
+
+enum { BXXX = 0, BXXY, BXYY, BYYY, BXXZ, BXYZ, BYYZ, BXZZ, BYZZ, BZZZ, BXX, BXY, BYY, BXZ, BYZ, BZZ, BX, BY, BZ, B1 };
+__device__ void fp_o1(const double *a, const double *b, double *r) {
+    for (int i = 0; i < 20; i++) r[i] = 0.0;
+    r[BXX] = a[0] * b[0]; r[BXY] = a[0] * b[1] + a[1] * b[0]; r[BXZ] = a[0] * b[2] + a[2] * b[0];
+    r[BYY] = a[1] * b[1]; r[BYZ] = a[1] * b[2] + a[2] * b[1]; r[BZZ] = a[2] * b[2];
+    r[BX] = a[0] * b[3] + a[3] * b[0]; r[BY] = a[1] * b[3] + a[3] * b[1]; r[BZ] = a[2] * b[3] + a[3] * b[2]; r[B1] = a[3] * b[3];
+}
+__device__ void fp_o2(const double *a, const double *b, double *r) {
+    r[BXXX] = a[BXX] * b[0];
+    r[BXXY] = a[BXX] * b[1] + a[BXY] * b[0];
+    r[BXXZ] = a[BXX] * b[2] + a[BXZ] * b[0];
+    r[BXYY] = a[BXY] * b[1] + a[BYY] * b[0];
+    r[BXYZ] = a[BXY] * b[2] + a[BYZ] * b[0] + a[BXZ] * b[1];
+    r[BXZZ] = a[BXZ] * b[2] + a[BZZ] * b[0];
+    r[BYYY] = a[BYY] * b[1];
+    r[BYYZ] = a[BYY] * b[2] + a[BYZ] * b[1];
+    r[BYZZ] = a[BYZ] * b[2] + a[BZZ] * b[1];
+    r[BZZZ] = a[BZZ] * b[2];
+    r[BXX] = a[BXX] * b[3] + a[BX] * b[0];
+    r[BXY] = a[BXY] * b[3] + a[BX] * b[1] + a[BY] * b[0];
+    r[BXZ] = a[BXZ] * b[3] + a[BX] * b[2] + a[BZ] * b[0];
+    r[BYY] = a[BYY] * b[3] + a[BY] * b[1];
+    r[BYZ] = a[BYZ] * b[3] + a[BY] * b[2] + a[BZ] * b[1];
+    r[BZZ] = a[BZZ] * b[3] + a[BZ] * b[2];
+    r[BX] = a[BX] * b[3] + a[B1] * b[0];
+    r[BY] = a[BY] * b[3] + a[B1] * b[1];
+    r[BZ] = a[BZ] * b[3] + a[B1] * b[2];
+    r[B1] = a[B1] * b[3];
+}
+
+// essential matrix -> the four candidate poses (cv-pinhole/src/essential.rs:114-162,217-231)
+__device__ __noinline__ int essential_poses(const double *E, cvb_pose *out) {
+    double U[9], Vt[9];
+    if (!svd3(E, 1e-12, 1000, U, Vt)) return 0;
+    if (det3(U) < 0.0) for (int r = 0; r < 3; r++) U[r * 3 + 2] *= -1.0;
+    if (det3(Vt) < 0.0) for (int c = 0; c < 3; c++) Vt[6 + c] *= -1.0;
+    const double W[9] = {0, -1, 0, 1, 0, 0, 0, 0, 1}, Wt[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1};
+    double UW[9], Ra[9], Rb[9];
+    mat3_mul(U, W, UW); mat3_mul(UW, Vt, Ra);
+    mat3_mul(U, Wt, UW); mat3_mul(UW, Vt, Rb);
+    const double t[3] = {U[2], U[5], U[8]};
+    for (int k = 0; k < 4; k++) {
+        for (int i = 0; i < 9; i++) out[k].r[i] = (k & 1) ? Rb[i] : Ra[i];
+        for (int r = 0; r < 3; r++) out[k].t[r] = (k & 2) ? -t[r] : t[r];
+    }
+    return 4;
+}
+
+__device__ int five_point(const double *a, const double *b, const uint32_t *idx, int row0, cvb_pose *out) {
+    double A[5][9], EE[81], d[9], V[81];
+    for (int i = 0; i < 5; i++) {
+        const double *pa = a + 3 * (size_t)idx[i], *pb = b + 3 * (size_t)idx[i];
+        for (int j = 0; j < 3; j++)
+            for (int k = 0; k < 3; k++) A[i][3 * j + k] = pa[j] * pb[k];
+    }
+    for (int r = 0; r < 9; r++)
+        for (int c = 0; c < 9; c++) { double s = 0; for (int i = 0; i < 5; i++) s += A[i][r] * A[i][c]; EE[r * 9 + c] = s; }
+    if (!sym_eigen<9>(EE, 1e-12, 1000, d, V)) return 0;
+    int src[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
+    for (int i = 1; i < 9; i++) { int x = src[i], j = i; while (j > 0 && d[src[j - 1]] > d[x]) { src[j] = src[j - 1]; j--; } src[j] = x; }
+    int nullity = -1;
+    for (int i = 0; i < 9; i++) if (d[src[i]] > 1e-12) { nullity = i; break; }
+    if (nullity != 4) return 0;
+    double eb[9][4];
+    for (int c = 0; c < 4; c++) for (int r = 0; r < 9; r++) eb[r][c] = V[r * 9 + src[c]];
+    double ep[3][3][4];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 4; k++) ep[i][j][k] = eb[3 * i + j][k];
+    double M[10][20], t1[20], t2[20], t3[20], acc[20];
+    {
+        const int ia[3][2] = {{1, 2}, {2, 0}, {0, 1}};
+        for (int k = 0; k < 20; k++) acc[k] = 0.0;
+        for (int c = 0; c < 3; c++) {
+            const int p = ia[c][0], q = ia[c][1];
+            fp_o1(ep[0][p], ep[1][q], t1); fp_o1(ep[0][q], ep[1][p], t2);
+            for (int k = 0; k < 20; k++) t1[k] -= t2[k];
+            fp_o2(t1, ep[2][c], t3);
+            for (int k = 0; k < 20; k++) acc[k] += t3[k];
+        }
+        for (int k = 0; k < 20; k++) M[0][k] = acc[k];
+    }
+    double eet[3][3][20], L[3][3][20];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            if (i <= j) {
+                fp_o1(ep[i][0], ep[j][0], t1); fp_o1(ep[i][1], ep[j][1], t2); fp_o1(ep[i][2], ep[j][2], t3);
+                for (int k = 0; k < 20; k++) eet[i][j][k] = t1[k] + t2[k] + t3[k];
+            } else for (int k = 0; k < 20; k++) eet[i][j][k] = eet[j][i][k];
+        }
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 20; k++) L[i][j][k] = eet[i][j][k];
+    for (int k = 0; k < 20; k++) {
+        const double tr = 0.5 * (eet[0][0][k] + eet[1][1][k] + eet[2][2][k]);
+        for (int i = 0; i < 3; i++) L[i][i][k] -= tr;
+    }
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            fp_o2(L[i][0], ep[0][j], t1); fp_o2(L[i][1], ep[1][j], t2); fp_o2(L[i][2], ep[2][j], t3);
+            for (int k = 0; k < 20; k++) M[1 + i * 3 + j][k] = t1[k] + t2[k] + t3[k];
+        }
+    double Cl[100], Cr[100], X[100];
+    for (int i = 0; i < 10; i++) for (int j = 0; j < 10; j++) { Cl[i * 10 + j] = M[i][j]; Cr[i * 10 + j] = M[i][10 + j]; }
+    if (!lu_full_pivot_solve(Cl, Cr, X)) return 0;
+    double At[100];
+    for (int i = 0; i < 100; i++) At[i] = 0.0;
+    for (int j = 0; j < 10; j++) {
+        At[0 * 10 + j] = X[0 * 10 + j]; At[1 * 10 + j] = X[1 * 10 + j]; At[2 * 10 + j] = X[2 * 10 + j];
+        At[3 * 10 + j] = X[4 * 10 + j]; At[4 * 10 + j] = X[5 * 10 + j]; At[5 * 10 + j] = X[7 * 10 + j];
+    }
+    At[6 * 10 + 0] = -1.0; At[7 * 10 + 1] = -1.0; At[8 * 10 + 3] = -1.0; At[9 * 10 + 6] = -1.0;
+    double wr[10], wi[10];
+    if (!real_eigenvalues10(At, wr, wi)) return 0;
+    int n = 0;
+    for (int i = 0; i < 10; i++) {
+        if (wi[i] != 0.0) continue;
+        double *Mx = Cl;   // reuse
+        double vec[10], smin;
+        for (int k = 0; k < 100; k++) Mx[k] = At[k];
+        for (int k = 0; k < 10; k++) Mx[k * 10 + k] -= wr[i];
+        if (!min_right_singular_vector10(Mx, 1e-15, 1000, vec, &smin)) continue;
+        if (!(smin < 1e-12)) continue;
+        double ev[9], E[9];
+        for (int r = 0; r < 9; r++) ev[r] = eb[r][0] * vec[row0] + eb[r][1] * vec[row0 + 1] + eb[r][2] * vec[row0 + 2] + eb[r][3] * vec[row0 + 3];
+        for (int k = 0; k < 9; k++) E[(k % 3) * 3 + (k / 3)] = ev[k];
+        n += essential_poses(E, out + n);
+    }
+    return n;
+}
+
 // ------------------------------------------------------------------------------------------ kernels
 template <int KIND>
 __global__ void __launch_bounds__(128) k_estimate(const double *__restrict__ a, const double *__restrict__ b,
                                                   const uint32_t *__restrict__ samples, uint32_t H, cvb_pose *poses,
-                                                  uint8_t *nposes) {
+                                                  uint8_t *nposes, int row0) {
     const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= H) return;
+    if (KIND == 2) {   // five-point: up to 40 poses per sample, written straight to global memory
+        nposes[h] = (uint8_t)five_point(a, b, samples + (size_t)h * 5, row0, poses + (size_t)h * 40);
+        return;
+    }
     cvb_pose out[4];
     int n;
     if (KIND == 0) n = eight_point(a, b, samples + (size_t)h * 8, out);
@@ -482,6 +784,11 @@ void geom_workspace_free(GeomWorkspace *g) {
 
 namespace {
 
+// estimator kinds: 0 EightPoint, 1 LambdaTwist (P3P), 2 NisterStewenius (five-point)
+inline uint32_t kind_K(int kind) { return kind == 0 ? 8u : (kind == 1 ? 3u : 5u); }      // Estimator::MIN_SAMPLES
+inline uint32_t kind_M(int kind) { return kind == 2 ? 40u : 4u; }                         // ModelIter capacity
+inline int kind_res(int kind) { return kind == 1 ? 1 : 0; }                               // residual: 0 CameraToCamera, 1 WorldToCamera
+
 GeomWorkspace *gws(cvb_ctx *ctx) {
     if (!ctx->geom) ctx->geom = new GeomWorkspace();
     return ctx->geom;
@@ -499,25 +806,25 @@ int upload_data(cvb_ctx *ctx, int kind, const double *a, const double *b, uint32
     GeomWorkspace *g = gws(ctx);
     int rc = upload(ctx, g->a, a, sizeof(double) * 3 * (size_t)n);
     if (rc) return rc;
-    return upload(ctx, g->b, b, sizeof(double) * (kind == 0 ? 3 : 4) * (size_t)n);
+    return upload(ctx, g->b, b, sizeof(double) * (kind_res(kind) == 0 ? 3 : 4) * (size_t)n);
 }
 
 // estimate H minimal samples (host index lists) -> device poses (H x 4) + host counts
-int estimate_dev(cvb_ctx *ctx, int kind, const uint32_t *samples, uint32_t H, std::vector<uint8_t> &nposes) {
+int estimate_dev(cvb_ctx *ctx, int kind, const uint32_t *samples, uint32_t H, std::vector<uint8_t> &nposes, int row0 = 5) {
     GeomWorkspace *g = gws(ctx);
-    const uint32_t K = kind == 0 ? 8 : 3;
+    const uint32_t K = kind_K(kind), M = kind_M(kind);
     int rc = upload(ctx, g->samples, samples, sizeof(uint32_t) * K * (size_t)H);
     if (rc) return rc;
-    if ((rc = g->poses.ensure(ctx, sizeof(cvb_pose) * 4 * (size_t)H))) return rc;
+    if ((rc = g->poses.ensure(ctx, sizeof(cvb_pose) * M * (size_t)H))) return rc;
     if ((rc = g->nposes.ensure(ctx, H))) return rc;
+    CVB_CUDA(ctx, cudaMemsetAsync(g->poses.p, 0, sizeof(cvb_pose) * M * (size_t)H, ctx->stream));
     {
-        CVB_PROF(ctx, kind == 0 ? "k_estimate_eight_point" : "k_estimate_p3p", 0);
-        if (kind == 0)
-            k_estimate<0><<<cdiv(H, 128), 128, 0, ctx->stream>>>((const double *)g->a.p, (const double *)g->b.p, (const uint32_t *)g->samples.p, H,
-                                                                 (cvb_pose *)g->poses.p, (uint8_t *)g->nposes.p);
-        else
-            k_estimate<1><<<cdiv(H, 128), 128, 0, ctx->stream>>>((const double *)g->a.p, (const double *)g->b.p, (const uint32_t *)g->samples.p, H,
-                                                                 (cvb_pose *)g->poses.p, (uint8_t *)g->nposes.p);
+        CVB_PROF(ctx, kind == 0 ? "k_estimate_eight_point" : (kind == 1 ? "k_estimate_p3p" : "k_estimate_five_point"), 0);
+        const double *a = (const double *)g->a.p, *b = (const double *)g->b.p;
+        const uint32_t *sp = (const uint32_t *)g->samples.p;
+        if (kind == 0) k_estimate<0><<<cdiv(H, 128), 128, 0, ctx->stream>>>(a, b, sp, H, (cvb_pose *)g->poses.p, (uint8_t *)g->nposes.p, row0);
+        else if (kind == 1) k_estimate<1><<<cdiv(H, 128), 128, 0, ctx->stream>>>(a, b, sp, H, (cvb_pose *)g->poses.p, (uint8_t *)g->nposes.p, row0);
+        else k_estimate<2><<<cdiv(H, 128), 128, 0, ctx->stream>>>(a, b, sp, H, (cvb_pose *)g->poses.p, (uint8_t *)g->nposes.p, row0);
         CVB_LAUNCH_CHECK(ctx);
     }
     nposes.resize(H);
@@ -539,8 +846,8 @@ int masks_dev(cvb_ctx *ctx, int kind, const cvb_pose *poses_dev, uint32_t m, uin
     for (uint32_t p0 = 0; p0 < m; p0 += 65535) {   // gridDim.y limit
         const uint32_t pm = std::min<uint32_t>(65535, m - p0);
         dim3 grid(cdiv(cnt, 256), pm);
-        CVB_PROF(ctx, kind == 0 ? "k_residuals_c2c" : "k_residuals_w2c", (kind == 0 ? 48.0 : 56.0) * pm * cnt);
-        if (kind == 0)
+        CVB_PROF(ctx, kind_res(kind) == 0 ? "k_residuals_c2c" : "k_residuals_w2c", (kind_res(kind) == 0 ? 48.0 : 56.0) * pm * cnt);
+        if (kind_res(kind) == 0)
             k_residuals<0, 1><<<grid, 256, 0, ctx->stream>>>(poses_dev + p0, pm, (const double *)g->a.p, (const double *)g->b.p, i0, i1, thr, nullptr, 0,
                                                              (uint32_t *)g->masks.p + (size_t)p0 * words, words);
         else
@@ -580,8 +887,8 @@ void populate_samples(cvb_rng *rng, uint32_t k, uint32_t len, uint32_t *out) {
 // initialisation with an adaptive SPRT over the first blocks, then block-wise scoring / halving / re-estimation
 // from the inliers of the current best.  All residuals come from the GPU as bit masks.
 int arrsac_run(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const double *a, const double *b, uint32_t n, cvb_rng *rng,
-               cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers, int32_t *found) {
-    const uint32_t K = kind == 0 ? 8 : 3;
+               cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers, int32_t *found, int row0 = 5) {
+    const uint32_t K = kind_K(kind), MM = kind_M(kind);
     *found = 0;
     if (n_inliers) *n_inliers = 0;
     if (n < K) return 0;
@@ -598,21 +905,21 @@ int arrsac_run(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const double *
     std::vector<uint32_t> samples((size_t)H0 * K);
     for (uint32_t h = 0; h < H0; h++) populate_samples(rng, K, n, samples.data() + (size_t)h * K);
     std::vector<uint8_t> nposes;
-    if ((rc = estimate_dev(ctx, kind, samples.data(), H0, nposes))) return rc;
+    if ((rc = estimate_dev(ctx, kind, samples.data(), H0, nposes, row0))) return rc;
     // inlier masks of every candidate model over the initialisation blocks only (what the SPRT looks at)
     const uint32_t init_n = std::min<uint32_t>(cfg->block_size * cfg->initialization_blocks, n);
     std::vector<uint32_t> masks;
     uint32_t words = 0;
-    if ((rc = masks_dev(ctx, kind, (const cvb_pose *)g->poses.p, H0 * 4, 0, init_n, thr, masks, &words))) return rc;
-    std::vector<cvb_pose> poses_host((size_t)H0 * 4);
-    CVB_CUDA(ctx, cudaMemcpy(poses_host.data(), g->poses.p, sizeof(cvb_pose) * 4 * (size_t)H0, cudaMemcpyDeviceToHost));
+    if ((rc = masks_dev(ctx, kind, (const cvb_pose *)g->poses.p, H0 * MM, 0, init_n, thr, masks, &words))) return rc;
+    std::vector<cvb_pose> poses_host((size_t)H0 * MM);
+    CVB_CUDA(ctx, cudaMemcpy(poses_host.data(), g->poses.p, sizeof(cvb_pose) * MM * (size_t)H0, cudaMemcpyDeviceToHost));
     float epsilon = cfg->initial_epsilon, delta = cfg->initial_delta;
     uint32_t best_inliers = 0;
     uint64_t rej_inliers = 0, rej_tested = 0;
     std::vector<Hyp> H;
     for (uint32_t h = 0; h < H0; h++)
         for (uint32_t mi = 0; mi < nposes[h]; mi++) {
-            const uint32_t *row = masks.data() + ((size_t)h * 4 + mi) * words;
+            const uint32_t *row = masks.data() + ((size_t)h * MM + mi) * words;
             const float pos = delta / epsilon, neg = (1.0f - delta) / (1.0f - epsilon);
             float ratio = 1.0f;
             uint32_t inl = 0, tested = 0;
@@ -624,7 +931,7 @@ int arrsac_run(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const double *
                 if (ratio > cfg->likelihood_ratio_threshold) { pass = false; break; }
             }
             if (pass) {
-                Hyp hy; hy.m = poses_host[(size_t)h * 4 + mi]; hy.inliers = inl; hy.mask.assign(nwords, 0u);
+                Hyp hy; hy.m = poses_host[(size_t)h * MM + mi]; hy.inliers = inl; hy.mask.assign(nwords, 0u);
                 for (uint32_t w = 0; w < words; w++) hy.mask[w] = row[w];
                 H.push_back(std::move(hy));
                 if (inl > best_inliers) {
@@ -669,19 +976,19 @@ int arrsac_run(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const double *
             const uint32_t G = cfg->estimations_per_block;
             for (uint32_t gi = 0; gi < G; gi++) {
                 uint32_t loc[8];
-                populate_samples(rng, K, (uint32_t)pool.size(), loc);
+                populate_samples(rng, K, (uint32_t)pool.size(), loc);   // K <= 8
                 for (uint32_t k = 0; k < K; k++) idx[(size_t)gi * K + k] = pool[loc[k]];
             }
-            if ((rc = estimate_dev(ctx, kind, idx.data(), G, nposes))) return rc;
-            if ((rc = masks_dev(ctx, kind, (const cvb_pose *)g->poses.p, G * 4, 0, n, thr, masks, &words))) return rc;
-            poses_host.resize((size_t)G * 4);
-            CVB_CUDA(ctx, cudaMemcpy(poses_host.data(), g->poses.p, sizeof(cvb_pose) * 4 * (size_t)G, cudaMemcpyDeviceToHost));
+            if ((rc = estimate_dev(ctx, kind, idx.data(), G, nposes, row0))) return rc;
+            if ((rc = masks_dev(ctx, kind, (const cvb_pose *)g->poses.p, G * MM, 0, n, thr, masks, &words))) return rc;
+            poses_host.resize((size_t)G * MM);
+            CVB_CUDA(ctx, cudaMemcpy(poses_host.data(), g->poses.p, sizeof(cvb_pose) * MM * (size_t)G, cudaMemcpyDeviceToHost));
             for (uint32_t gi = 0; gi < G; gi++)
                 for (uint32_t mi = 0; mi < nposes[gi]; mi++) {
-                    const uint32_t *row = masks.data() + ((size_t)gi * 4 + mi) * words;
+                    const uint32_t *row = masks.data() + ((size_t)gi * MM + mi) * words;
                     const uint32_t inl = popc_range(row, 0, end);
                     if (inl > worst) {
-                        Hyp hy; hy.m = poses_host[(size_t)gi * 4 + mi]; hy.inliers = inl; hy.mask.assign(row, row + words);
+                        Hyp hy; hy.m = poses_host[(size_t)gi * MM + mi]; hy.inliers = inl; hy.mask.assign(row, row + words);
                         H.push_back(std::move(hy));
                     }
                 }
@@ -730,20 +1037,20 @@ int residuals_host(cvb_ctx *ctx, int kind, const cvb_pose *poses, uint32_t m, co
 }
 
 int estimate_host(cvb_ctx *ctx, int kind, const double *a, const double *b, uint32_t n, const uint32_t *samples, uint32_t H,
-                  cvb_pose *poses_out, uint8_t *nposes_out) {
+                  cvb_pose *poses_out, uint8_t *nposes_out, int row0 = 5) {
     if (!ctx) return CVB_EINVAL;
     if (!a || !b || (H && (!samples || !poses_out || !nposes_out))) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
     if (H == 0) return 0;
-    const uint32_t K = kind == 0 ? 8 : 3;
+    const uint32_t K = kind_K(kind);
     for (size_t i = 0; i < (size_t)H * K; i++)
         if (samples[i] >= n) return cvb_set_error(ctx, CVB_EINVAL, "sample index %u out of range (n = %u)", samples[i], n);
     CVB_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = upload_data(ctx, kind, a, b, n);
     if (rc) return rc;
     std::vector<uint8_t> np;
-    if ((rc = estimate_dev(ctx, kind, samples, H, np))) return rc;
+    if ((rc = estimate_dev(ctx, kind, samples, H, np, row0))) return rc;
     memcpy(nposes_out, np.data(), H);
-    CVB_CUDA(ctx, cudaMemcpy(poses_out, gws(ctx)->poses.p, sizeof(cvb_pose) * 4 * (size_t)H, cudaMemcpyDeviceToHost));
+    CVB_CUDA(ctx, cudaMemcpy(poses_out, gws(ctx)->poses.p, sizeof(cvb_pose) * kind_M(kind) * (size_t)H, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -811,6 +1118,11 @@ int cvb_p3p_batch(cvb_ctx *ctx, const double *bearings, const double *world, uin
                   cvb_pose *poses_out, uint8_t *nposes_out) {
     return estimate_host(ctx, 1, bearings, world, n, samples, H, poses_out, nposes_out);
 }
+int cvb_five_point_batch(cvb_ctx *ctx, const double *a, const double *b, uint32_t n, const uint32_t *samples, uint32_t H,
+                         int32_t eigenvector_row0, cvb_pose *poses_out, uint8_t *nposes_out) {
+    if (ctx && eigenvector_row0 != 5 && eigenvector_row0 != 6) return cvb_set_error(ctx, CVB_EINVAL, "eigenvector_row0 must be 5 (reference) or 6 (corrected)");
+    return estimate_host(ctx, 2, a, b, n, samples, H, poses_out, nposes_out, eigenvector_row0);
+}
 int cvb_residuals_camera_to_camera(cvb_ctx *ctx, const cvb_pose *poses, uint32_t m, const double *a, const double *b, uint32_t n, double *out) {
     return residuals_host(ctx, 0, poses, m, a, b, n, out);
 }
@@ -852,6 +1164,14 @@ int cvb_arrsac_eight_point(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double
     if (!ctx) return CVB_EINVAL;
     if (!cfg || !rng || !model_out || !found || (n && (!a || !b))) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
     return arrsac_run(ctx, cfg, 0, a, b, n, rng, model_out, inliers_out, cap, n_inliers, found);
+}
+int cvb_arrsac_five_point(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *a, const double *b, uint32_t n, cvb_rng *rng,
+                          int32_t eigenvector_row0, cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers,
+                          int32_t *found) {
+    if (!ctx) return CVB_EINVAL;
+    if (!cfg || !rng || !model_out || !found || (n && (!a || !b))) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    if (eigenvector_row0 != 5 && eigenvector_row0 != 6) return cvb_set_error(ctx, CVB_EINVAL, "eigenvector_row0 must be 5 (reference) or 6 (corrected)");
+    return arrsac_run(ctx, cfg, 2, a, b, n, rng, model_out, inliers_out, cap, n_inliers, found, eigenvector_row0);
 }
 int cvb_arrsac_p3p(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *bearings, const double *world, uint32_t n, cvb_rng *rng,
                    cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers, int32_t *found) {

@@ -67,6 +67,9 @@ def _lib(ctx):
         L.cvb_rng_next_u32.restype = u32
         L.cvb_eight_point_batch.argtypes = [vp, vp, vp, u32, vp, u32, vp, vp]
         L.cvb_p3p_batch.argtypes = [vp, vp, vp, u32, vp, u32, vp, vp]
+        L.cvb_five_point_batch.argtypes = [vp, vp, vp, u32, vp, u32, C.c_int32, vp, vp]
+        L.cvb_arrsac_five_point.argtypes = [vp, C.POINTER(ArrsacCfg), vp, vp, u32, C.POINTER(Rng), C.c_int32, C.POINTER(Pose), vp, u32,
+                                            C.POINTER(u32), C.POINTER(C.c_int32)]
         L.cvb_residuals_camera_to_camera.argtypes = [vp, vp, u32, vp, vp, u32, vp]
         L.cvb_residuals_world_to_camera.argtypes = [vp, vp, u32, vp, vp, u32, vp]
         L.cvb_triangulate_linear_eigen.argtypes = [vp, vp, vp, vp, u32, vp, vp]
@@ -117,6 +120,30 @@ class EightPoint:
     def estimate(self, a, b, ctx=None):
         """Estimator::estimate on exactly the first 8 matches."""
         poses, cnt = self.estimate_batch(a, b, np.arange(8, dtype=np.uint32)[None], ctx)
+        return [(poses[0, k]["r"].reshape(3, 3).copy(), poses[0, k]["t"].copy()) for k in range(cnt[0])]
+
+
+class NisterStewenius:
+    """nister_stewenius::NisterStewenius: MIN_SAMPLES = 5, up to 40 CameraToCamera poses per sample
+    (nister-stewenius/src/lib.rs:303-330).  `corrected=False` reproduces the reference bit for bit in structure,
+    including its off-by-one eigenvector rows (lib.rs:229); `corrected=True` reads (x, y, z, 1) from rows 6..9."""
+    MIN_SAMPLES = 5
+
+    def __init__(self, corrected=False):
+        self.row0 = 6 if corrected else 5
+
+    def estimate_batch(self, a, b, samples, ctx=None):
+        ctx, L = _lib(ctx)
+        a, b = _f64(a, 3), _f64(b, 3)
+        s = np.ascontiguousarray(samples, np.uint32).reshape(-1, 5)
+        poses = np.zeros((len(s), 40), POSE_DTYPE)
+        cnt = np.zeros(len(s), np.uint8)
+        ctx.check(L.cvb_five_point_batch(ctx.handle, a.ctypes.data, b.ctypes.data, len(a), s.ctypes.data, len(s), self.row0,
+                                         poses.ctypes.data, cnt.ctypes.data))
+        return poses, cnt
+
+    def estimate(self, a, b, ctx=None):
+        poses, cnt = self.estimate_batch(a, b, np.arange(5, dtype=np.uint32)[None], ctx)
         return [(poses[0, k]["r"].reshape(3, 3).copy(), poses[0, k]["t"].copy()) for k in range(cnt[0])]
 
 
@@ -202,13 +229,18 @@ class Arrsac:
     def model_inliers(self, estimator, a, b):
         """Consensus::model_inliers: (R, t, inlier indices) or None.  estimator: EightPoint (a, b bearings) or
         LambdaTwist (a bearings, b homogeneous world points)."""
-        two_view = isinstance(estimator, EightPoint)
+        two_view = isinstance(estimator, (EightPoint, NisterStewenius))
         a = _f64(a, 3); b = _f64(b, 3 if two_view else 4)
         n = len(a)
         model = Pose(); inl = np.zeros(max(n, 1), np.uint32); cnt = C.c_uint32(); found = C.c_int32()
-        fn = self._L.cvb_arrsac_eight_point if two_view else self._L.cvb_arrsac_p3p
-        self.ctx.check(fn(self.ctx.handle, C.byref(self.cfg), a.ctypes.data, b.ctypes.data, n, C.byref(self.rng.state), C.byref(model),
-                          inl.ctypes.data, n, C.byref(cnt), C.byref(found)))
+        if isinstance(estimator, NisterStewenius):
+            self.ctx.check(self._L.cvb_arrsac_five_point(self.ctx.handle, C.byref(self.cfg), a.ctypes.data, b.ctypes.data, n,
+                                                         C.byref(self.rng.state), estimator.row0, C.byref(model), inl.ctypes.data, n,
+                                                         C.byref(cnt), C.byref(found)))
+        else:
+            fn = self._L.cvb_arrsac_eight_point if two_view else self._L.cvb_arrsac_p3p
+            self.ctx.check(fn(self.ctx.handle, C.byref(self.cfg), a.ctypes.data, b.ctypes.data, n, C.byref(self.rng.state), C.byref(model),
+                              inl.ctypes.data, n, C.byref(cnt), C.byref(found)))
         if not found.value:
             return None
         return np.array(model.r).reshape(3, 3), np.array(model.t), inl[:cnt.value].copy()

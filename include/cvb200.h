@@ -180,6 +180,12 @@ int cvb_eight_point_batch(cvb_ctx *ctx, const double *a, const double *b, uint32
                           cvb_pose *poses_out, uint8_t *nposes_out);
 int cvb_p3p_batch(cvb_ctx *ctx, const double *bearings, const double *world, uint32_t n, const uint32_t *samples, uint32_t H,
                   cvb_pose *poses_out, uint8_t *nposes_out);
+/* NisterStewenius::estimate (nister-stewenius/src/lib.rs:303-330): samples[h*5..], up to 40 poses per sample
+ * (poses_out: H*40).  eigenvector_row0 = 5 reproduces the reference, whose `fixed_rows::<4>(5)` (lib.rs:229) reads
+ * the (x, y, z, 1) solution one row too early (the monomial basis has them in rows 6..9), so its essential matrices
+ * violate the cubic constraints; eigenvector_row0 = 6 is the corrected solver. */
+int cvb_five_point_batch(cvb_ctx *ctx, const double *a, const double *b, uint32_t n, const uint32_t *samples, uint32_t H,
+                         int32_t eigenvector_row0, cvb_pose *poses_out, uint8_t *nposes_out);
 /* out[m*n]: residual of pose p for datum i at out[p*n + i] */
 int cvb_residuals_camera_to_camera(cvb_ctx *ctx, const cvb_pose *poses, uint32_t m, const double *a, const double *b,
                                    uint32_t n, double *out);
@@ -191,6 +197,9 @@ int cvb_triangulate_linear_eigen(cvb_ctx *ctx, const cvb_pose *poses, const doub
 /* Consensus::model_inliers.  *found = 0 -> None.  inliers_out: ascending datum indices (at most cap written). */
 int cvb_arrsac_eight_point(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *a, const double *b, uint32_t n, cvb_rng *rng,
                            cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers, int32_t *found);
+int cvb_arrsac_five_point(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *a, const double *b, uint32_t n, cvb_rng *rng,
+                          int32_t eigenvector_row0, cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap,
+                          uint32_t *n_inliers, int32_t *found);
 int cvb_arrsac_p3p(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *bearings, const double *world, uint32_t n,
                    cvb_rng *rng, cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers, int32_t *found);
 

@@ -238,6 +238,10 @@ def _geom():
         L.ref_residual_w2c.restype = C.c_double
         L.ref_residual_w2c.argtypes = [C.POINTER(Pose), dp, dp]
         L.ref_p3p.argtypes = [dp, dp, C.POINTER(Pose)]
+        L.ref_real_eigenvalues10.argtypes = [dp, dp, dp]
+        L.ref_five_point_essentials.argtypes = [dp, dp, dp]
+        L.ref_five_point.argtypes = [dp, dp, C.POINTER(Pose)]
+        L.ref_five_point_set_row0.argtypes = [C.c_int]
         L.ref_triangulate_linear_eigen.argtypes = [C.POINTER(Pose), dp, C.c_int, dp]
         L.ref_calibrate.argtypes = [C.c_double] * 7 + [dp]
         L.ref_rng_seed_xoshiro.argtypes = [C.POINTER(Rng), C.c_uint64]
@@ -309,6 +313,31 @@ def p3p(bearings, world):
     a = np.ascontiguousarray(bearings, np.float64); b = np.ascontiguousarray(world, np.float64)
     out = (Pose * 4)()
     n = _geom().ref_p3p(_dp(a), _dp(b), out)
+    return [out[i].numpy() for i in range(n)]
+
+
+def real_eigenvalues10(A):
+    A = np.ascontiguousarray(A, np.float64); wr = np.zeros(10); wi = np.zeros(10)
+    ok = _geom().ref_real_eigenvalues10(_dp(A), _dp(wr), _dp(wi))
+    return ok, wr + 1j * wi
+
+
+def five_point_set_row0(r0):
+    """5 = the reference's eigenvector rows (nister-stewenius/src/lib.rs:229), 6 = mathematically correct rows."""
+    _geom().ref_five_point_set_row0(r0)
+
+
+def five_point_essentials(a, b):
+    a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+    Es = np.zeros(90)
+    n = _geom().ref_five_point_essentials(_dp(a), _dp(b), _dp(Es))
+    return Es[:9 * n].reshape(n, 3, 3).copy()
+
+
+def five_point(a, b):
+    a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+    out = (Pose * 40)()
+    n = _geom().ref_five_point(_dp(a), _dp(b), out)
     return [out[i].numpy() for i in range(n)]
 
 

@@ -181,6 +181,320 @@ double ref_essential_residual(const double *E, const double *a, const double *b)
     return fabs(dot3(nb, Ea));
 }
 
+/* ------------------------------------------------------------------ five-point (nister-stewenius/src/lib.rs) */
+/* nalgebra pieces used by the reference and restated here: full_piv_lu().solve (Gaussian elimination with
+ * complete pivoting), complex_eigenvalues() (Hessenberg reduction + Francis double-shift QR, EISPACK hqr),
+ * try_svd(false, true, ..) (one-sided Jacobi: accurate small singular values + right singular vectors). */
+#define FP_N 10
+static int lu_full_pivot_solve(const double *Ain, const double *Bin, double *X) { /* A X = B, all 10x10 row-major */
+    double A[FP_N][FP_N], B[FP_N][FP_N];
+    int colperm[FP_N];
+    memcpy(A, Ain, sizeof(A)); memcpy(B, Bin, sizeof(B));
+    for (int i = 0; i < FP_N; i++) colperm[i] = i;
+    for (int k = 0; k < FP_N; k++) {
+        int pr = k, pc = k; double best = -1.0;
+        for (int i = k; i < FP_N; i++) for (int j = k; j < FP_N; j++) if (fabs(A[i][j]) > best) { best = fabs(A[i][j]); pr = i; pc = j; }
+        if (best == 0.0) return 0; /* singular: nalgebra's solve returns None */
+        if (pr != k) for (int j = 0; j < FP_N; j++) { double t = A[k][j]; A[k][j] = A[pr][j]; A[pr][j] = t; t = B[k][j]; B[k][j] = B[pr][j]; B[pr][j] = t; }
+        if (pc != k) { for (int i = 0; i < FP_N; i++) { double t = A[i][k]; A[i][k] = A[i][pc]; A[i][pc] = t; } int t = colperm[k]; colperm[k] = colperm[pc]; colperm[pc] = t; }
+        for (int i = k + 1; i < FP_N; i++) {
+            double f = A[i][k] / A[k][k];
+            if (f == 0.0) continue;
+            for (int j = k; j < FP_N; j++) A[i][j] -= f * A[k][j];
+            for (int j = 0; j < FP_N; j++) B[i][j] -= f * B[k][j];
+        }
+    }
+    double Y[FP_N][FP_N];
+    for (int c = 0; c < FP_N; c++)
+        for (int i = FP_N - 1; i >= 0; i--) {
+            double v = B[i][c];
+            for (int j = i + 1; j < FP_N; j++) v -= A[i][j] * Y[j][c];
+            Y[i][c] = v / A[i][i];
+        }
+    for (int i = 0; i < FP_N; i++) for (int c = 0; c < FP_N; c++) X[colperm[i] * FP_N + c] = Y[i][c];
+    return 1;
+}
+
+#define FP_SIGN(a, b) ((b) >= 0.0 ? fabs(a) : -fabs(a))
+/* eigenvalues of a real 10x10 matrix: wr + i wi (wi == 0 exactly for real eigenvalues). returns 0 on non-convergence */
+int ref_real_eigenvalues10(const double *Ain, double *wr, double *wi) {
+    const int n = FP_N;
+    double a[FP_N][FP_N];
+    memcpy(a, Ain, sizeof(a));
+    /* reduction to upper Hessenberg form by stabilised elementary similarity transformations */
+    for (int m = 1; m < n - 1; m++) {
+        double x = 0.0; int i = m;
+        for (int j = m; j < n; j++) if (fabs(a[j][m - 1]) > fabs(x)) { x = a[j][m - 1]; i = j; }
+        if (i != m) {
+            for (int j = m - 1; j < n; j++) { double t = a[i][j]; a[i][j] = a[m][j]; a[m][j] = t; }
+            for (int j = 0; j < n; j++) { double t = a[j][i]; a[j][i] = a[j][m]; a[j][m] = t; }
+        }
+        if (x != 0.0)
+            for (i = m + 1; i < n; i++) {
+                double y = a[i][m - 1];
+                if (y != 0.0) {
+                    y /= x; a[i][m - 1] = y;
+                    for (int j = m; j < n; j++) a[i][j] -= y * a[m][j];
+                    for (int j = 0; j < n; j++) a[j][m] += y * a[j][i];
+                }
+            }
+    }
+    for (int i = 2; i < n; i++) for (int j = 0; j < i - 1; j++) a[i][j] = 0.0;
+    /* Francis double-shift QR on the Hessenberg matrix */
+    int nn = n - 1, l, its;
+    double p = 0, q = 0, r = 0, s, t = 0.0, u, v, w, x, y, z, anorm = 0.0;
+    for (int i = 0; i < n; i++) for (int j = (i > 0 ? i - 1 : 0); j < n; j++) anorm += fabs(a[i][j]);
+    while (nn >= 0) {
+        its = 0;
+        do {
+            for (l = nn; l >= 1; l--) {
+                s = fabs(a[l - 1][l - 1]) + fabs(a[l][l]);
+                if (s == 0.0) s = anorm;
+                if (fabs(a[l][l - 1]) + s == s) { a[l][l - 1] = 0.0; break; }
+            }
+            x = a[nn][nn];
+            if (l == nn) { wr[nn] = x + t; wi[nn--] = 0.0; }
+            else {
+                y = a[nn - 1][nn - 1]; w = a[nn][nn - 1] * a[nn - 1][nn];
+                if (l == nn - 1) {
+                    p = 0.5 * (y - x); q = p * p + w; z = sqrt(fabs(q)); x += t;
+                    if (q >= 0.0) {
+                        z = p + FP_SIGN(z, p);
+                        wr[nn - 1] = wr[nn] = x + z;
+                        if (z != 0.0) wr[nn] = x - w / z;
+                        wi[nn - 1] = wi[nn] = 0.0;
+                    } else { wr[nn - 1] = wr[nn] = x + p; wi[nn] = z; wi[nn - 1] = -z; }
+                    nn -= 2;
+                } else {
+                    if (its == 60) return 0;
+                    if (its == 10 || its == 20) {
+                        t += x;
+                        for (int i = 0; i <= nn; i++) a[i][i] -= x;
+                        s = fabs(a[nn][nn - 1]) + fabs(a[nn - 1][nn - 2]);
+                        y = x = 0.75 * s; w = -0.4375 * s * s;
+                    }
+                    ++its;
+                    int m;
+                    for (m = nn - 2; m >= l; m--) {
+                        z = a[m][m]; r = x - z; s = y - z;
+                        p = (r * s - w) / a[m + 1][m] + a[m][m + 1];
+                        q = a[m + 1][m + 1] - z - r - s;
+                        r = a[m + 2][m + 1];
+                        s = fabs(p) + fabs(q) + fabs(r);
+                        p /= s; q /= s; r /= s;
+                        if (m == l) break;
+                        u = fabs(a[m][m - 1]) * (fabs(q) + fabs(r));
+                        v = fabs(p) * (fabs(a[m - 1][m - 1]) + fabs(z) + fabs(a[m + 1][m + 1]));
+                        if (u + v == v) break;
+                    }
+                    for (int i = m + 2; i <= nn; i++) { a[i][i - 2] = 0.0; if (i != m + 2) a[i][i - 3] = 0.0; }
+                    for (int k = m; k <= nn - 1; k++) {
+                        if (k != m) {
+                            p = a[k][k - 1]; q = a[k + 1][k - 1]; r = 0.0;
+                            if (k != nn - 1) r = a[k + 2][k - 1];
+                            if ((x = fabs(p) + fabs(q) + fabs(r)) != 0.0) { p /= x; q /= x; r /= x; }
+                        }
+                        if ((s = FP_SIGN(sqrt(p * p + q * q + r * r), p)) != 0.0) {
+                            if (k == m) { if (l != m) a[k][k - 1] = -a[k][k - 1]; }
+                            else a[k][k - 1] = -s * x;
+                            p += s; x = p / s; y = q / s; z = r / s; q /= p; r /= p;
+                            for (int j = k; j <= nn; j++) {
+                                p = a[k][j] + q * a[k + 1][j];
+                                if (k != nn - 1) { p += r * a[k + 2][j]; a[k + 2][j] -= p * z; }
+                                a[k + 1][j] -= p * y; a[k][j] -= p * x;
+                            }
+                            int mmin = nn < k + 3 ? nn : k + 3;
+                            for (int i = l; i <= mmin; i++) {
+                                p = x * a[i][k] + y * a[i][k + 1];
+                                if (k != nn - 1) { p += z * a[i][k + 2]; a[i][k + 2] -= p * r; }
+                                a[i][k + 1] -= p * q; a[i][k] -= p;
+                            }
+                        }
+                    }
+                }
+            }
+        } while (l < nn - 1);
+    }
+    return 1;
+}
+
+/* right singular vector of the smallest singular value of a 10x10 matrix (one-sided Jacobi on the columns);
+ * *smin receives that singular value. returns 0 on non-convergence */
+static int min_right_singular_vector10(const double *Min, double eps, int max_sweeps, double *vec, double *smin) {
+    double U[FP_N][FP_N], V[FP_N][FP_N];
+    memcpy(U, Min, sizeof(U));
+    for (int i = 0; i < FP_N; i++) for (int j = 0; j < FP_N; j++) V[i][j] = i == j ? 1.0 : 0.0;
+    int converged = 0;
+    for (int sweep = 0; sweep < max_sweeps && !converged; sweep++) {
+        converged = 1;
+        for (int p = 0; p < FP_N - 1; p++)
+            for (int q = p + 1; q < FP_N; q++) {
+                double alpha = 0, beta = 0, gamma = 0;
+                for (int i = 0; i < FP_N; i++) { alpha += U[i][p] * U[i][p]; beta += U[i][q] * U[i][q]; gamma += U[i][p] * U[i][q]; }
+                if (gamma == 0.0 || fabs(gamma) <= eps * sqrt(alpha * beta)) continue;
+                converged = 0;
+                double zeta = (beta - alpha) / (2.0 * gamma);
+                double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                for (int i = 0; i < FP_N; i++) {
+                    double up = U[i][p], uq = U[i][q];
+                    U[i][p] = c * up - s * uq; U[i][q] = s * up + c * uq;
+                    double vp = V[i][p], vq = V[i][q];
+                    V[i][p] = c * vp - s * vq; V[i][q] = s * vp + c * vq;
+                }
+            }
+    }
+    if (!converged) return 0;
+    int best = 0; double bn = -1.0;
+    for (int j = 0; j < FP_N; j++) {
+        double nn = 0; for (int i = 0; i < FP_N; i++) nn += U[i][j] * U[i][j];
+        if (bn < 0.0 || nn < bn) { bn = nn; best = j; }
+    }
+    *smin = sqrt(bn);
+    for (int i = 0; i < FP_N; i++) vec[i] = V[i][best];
+    return 1;
+}
+
+#ifndef REF_FIVE_POINT_ROW0
+#define REF_FIVE_POINT_ROW0 5
+#endif
+static int ref_five_point_row0 = REF_FIVE_POINT_ROW0;
+double ref_fp_dbg[30];   /* last call: (wr, wi, smin) per eigenvalue, for tests */
+void ref_five_point_set_row0(int r0) { ref_five_point_row0 = r0; }   /* 5 = reference behaviour, 6 = corrected */
+
+enum { BXXX = 0, BXXY, BXYY, BYYY, BXXZ, BXYZ, BYYZ, BXZZ, BYZZ, BZZZ, BXX, BXY, BYY, BXZ, BYZ, BZZ, BX, BY, BZ, B1 };
+static void fp_o1(const double *a, const double *b, double *r) { /* lib.rs:98-111 */
+    for (int i = 0; i < 20; i++) r[i] = 0.0;
+    r[BXX] = a[0] * b[0]; r[BXY] = a[0] * b[1] + a[1] * b[0]; r[BXZ] = a[0] * b[2] + a[2] * b[0];
+    r[BYY] = a[1] * b[1]; r[BYZ] = a[1] * b[2] + a[2] * b[1]; r[BZZ] = a[2] * b[2];
+    r[BX] = a[0] * b[3] + a[3] * b[0]; r[BY] = a[1] * b[3] + a[3] * b[1]; r[BZ] = a[2] * b[3] + a[3] * b[2]; r[B1] = a[3] * b[3];
+}
+static void fp_o2(const double *a, const double *b, double *r) { /* lib.rs:113-136 */
+    r[BXXX] = a[BXX] * b[0];
+    r[BXXY] = a[BXX] * b[1] + a[BXY] * b[0];
+    r[BXXZ] = a[BXX] * b[2] + a[BXZ] * b[0];
+    r[BXYY] = a[BXY] * b[1] + a[BYY] * b[0];
+    r[BXYZ] = a[BXY] * b[2] + a[BYZ] * b[0] + a[BXZ] * b[1];
+    r[BXZZ] = a[BXZ] * b[2] + a[BZZ] * b[0];
+    r[BYYY] = a[BYY] * b[1];
+    r[BYYZ] = a[BYY] * b[2] + a[BYZ] * b[1];
+    r[BYZZ] = a[BYZ] * b[2] + a[BZZ] * b[1];
+    r[BZZZ] = a[BZZ] * b[2];
+    r[BXX] = a[BXX] * b[3] + a[BX] * b[0];
+    r[BXY] = a[BXY] * b[3] + a[BX] * b[1] + a[BY] * b[0];
+    r[BXZ] = a[BXZ] * b[3] + a[BX] * b[2] + a[BZ] * b[0];
+    r[BYY] = a[BYY] * b[3] + a[BY] * b[1];
+    r[BYZ] = a[BYZ] * b[3] + a[BY] * b[2] + a[BZ] * b[1];
+    r[BZZ] = a[BZZ] * b[3] + a[BZ] * b[2];
+    r[BX] = a[BX] * b[3] + a[B1] * b[0];
+    r[BY] = a[BY] * b[3] + a[B1] * b[1];
+    r[BZ] = a[BZ] * b[3] + a[B1] * b[2];
+    r[B1] = a[B1] * b[3];
+}
+
+/* nister-stewenius/src/lib.rs:50-96,138-330: five matches (a, b: 5 x 3 unit bearings) -> up to 10 essential matrices
+ * (row-major) ; returns the count */
+int ref_five_point_essentials(const double *a, const double *b, double *Es) {
+    /* step 1: null space of the 5x9 epipolar constraint (lib.rs:50-96) */
+    double A[5][9], EE[81], d[9], V[81];
+    for (int i = 0; i < 5; i++)
+        for (int j = 0; j < 3; j++)
+            for (int k = 0; k < 3; k++) A[i][3 * j + k] = a[3 * i + j] * b[3 * i + k];
+    for (int r = 0; r < 9; r++)
+        for (int c = 0; c < 9; c++) { double s = 0; for (int i = 0; i < 5; i++) s += A[i][r] * A[i][c]; EE[r * 9 + c] = s; }
+    if (!ref_sym_eigen(9, EE, 1e-12, 1000, d, V)) return 0;
+    int src[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
+    for (int i = 1; i < 9; i++) { int x = src[i], j = i; while (j > 0 && d[src[j - 1]] > d[x]) { src[j] = src[j - 1]; j--; } src[j] = x; }
+    int nullity = -1;
+    for (int i = 0; i < 9; i++) if (d[src[i]] > 1e-12) { nullity = i; break; }
+    if (nullity != 4) return 0;
+    double eb[9][4];
+    for (int c = 0; c < 4; c++) for (int r = 0; r < 9; r++) eb[r][c] = V[r * 9 + src[c]];
+    /* step 2: polynomial constraints (lib.rs:138-204) */
+    double ep[3][3][4];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 4; k++) ep[i][j][k] = eb[3 * i + j][k];
+    double M[10][20], t1[20], t2[20], t3[20], acc[20];
+    {
+        const int ia[3][2] = {{1, 2}, {2, 0}, {0, 1}};
+        for (int k = 0; k < 20; k++) acc[k] = 0.0;
+        for (int c = 0; c < 3; c++) {   /* det(E): sum_c (e0[p] e1[q] - e0[q] e1[p]) e2[c] with (p, q) = cyclic */
+            int p = ia[c][0], q = ia[c][1];
+            fp_o1(ep[0][p], ep[1][q], t1); fp_o1(ep[0][q], ep[1][p], t2);
+            for (int k = 0; k < 20; k++) t1[k] -= t2[k];
+            fp_o2(t1, ep[2][c], t3);
+            for (int k = 0; k < 20; k++) acc[k] += t3[k];
+        }
+        memcpy(M[0], acc, sizeof(acc));
+    }
+    double eet[3][3][20], L[3][3][20];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            if (i <= j) {
+                fp_o1(ep[i][0], ep[j][0], t1); fp_o1(ep[i][1], ep[j][1], t2); fp_o1(ep[i][2], ep[j][2], t3);
+                for (int k = 0; k < 20; k++) eet[i][j][k] = t1[k] + t2[k] + t3[k];
+            } else memcpy(eet[i][j], eet[j][i], sizeof(t1));
+        }
+    memcpy(L, eet, sizeof(L));
+    for (int k = 0; k < 20; k++) {
+        double tr = 0.5 * (eet[0][0][k] + eet[1][1][k] + eet[2][2][k]);
+        for (int i = 0; i < 3; i++) L[i][i][k] -= tr;
+    }
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            fp_o2(L[i][0], ep[0][j], t1); fp_o2(L[i][1], ep[1][j], t2); fp_o2(L[i][2], ep[2][j], t3);
+            for (int k = 0; k < 20; k++) M[1 + i * 3 + j][k] = t1[k] + t2[k] + t3[k];
+        }
+    /* step 3: Gauss-Jordan through a fully pivoted LU (lib.rs:255-262) */
+    double Cl[100], Cr[100], X[100];
+    for (int i = 0; i < 10; i++) for (int j = 0; j < 10; j++) { Cl[i * 10 + j] = M[i][j]; Cr[i * 10 + j] = M[i][10 + j]; }
+    if (!lu_full_pivot_solve(Cl, Cr, X)) return 0;
+    /* action matrix (lib.rs:266-278) */
+    double At[100];
+    memset(At, 0, sizeof(At));
+    for (int j = 0; j < 10; j++) {
+        At[0 * 10 + j] = X[0 * 10 + j]; At[1 * 10 + j] = X[1 * 10 + j]; At[2 * 10 + j] = X[2 * 10 + j];
+        At[3 * 10 + j] = X[4 * 10 + j]; At[4 * 10 + j] = X[5 * 10 + j]; At[5 * 10 + j] = X[7 * 10 + j];
+    }
+    At[6 * 10 + 0] = -1.0; At[7 * 10 + 1] = -1.0; At[8 * 10 + 3] = -1.0; At[9 * 10 + 6] = -1.0;
+    /* eigenvalues; for the real ones the eigenvector via the smallest right singular vector (lib.rs:206-237) */
+    double wr[10], wi[10];
+    if (!ref_real_eigenvalues10(At, wr, wi)) return 0;
+    int ne = 0;
+    for (int i = 0; i < 10; i++) {
+        ref_fp_dbg[i * 3] = wr[i]; ref_fp_dbg[i * 3 + 1] = wi[i]; ref_fp_dbg[i * 3 + 2] = -1.0;
+        if (wi[i] != 0.0) continue;
+        double Mx[100], vec[10], smin;
+        memcpy(Mx, At, sizeof(Mx));
+        for (int k = 0; k < 10; k++) Mx[k * 10 + k] -= wr[i];
+        if (!min_right_singular_vector10(Mx, 1e-15, 1000, vec, &smin)) continue;
+        ref_fp_dbg[i * 3 + 2] = smin;
+        if (!(smin < 1e-12)) continue;
+        double ev[9];
+        /* `v.fixed_rows::<4>(5)` (lib.rs:229): rows 5..8 of the eigenvector.  The monomial basis is
+         * [xx xy yy xz yz zz x y z 1], so (x, y, z, 1) are rows 6..9 (OpenMVG, from which this solver derives, takes
+         * tail<4>()): the reference is off by one and its essentials do not satisfy the cubic constraints -- which is
+         * presumably why nister-stewenius/tests/manual.rs is commented out upstream.  The restatement reproduces the
+         * reference (REF_FIVE_POINT_ROW0 = 5); building with -DREF_FIVE_POINT_ROW0=6 gives the mathematically correct
+         * solver and is used by tests/test_oracle_geom.py to validate every other step of the restatement. */
+        const int r0 = ref_five_point_row0;
+        for (int r = 0; r < 9; r++) ev[r] = eb[r][0] * vec[r0] + eb[r][1] * vec[r0 + 1] + eb[r][2] * vec[r0 + 2] + eb[r][3] * vec[r0 + 3];
+        for (int k = 0; k < 9; k++) Es[ne * 9 + (k % 3) * 3 + (k / 3)] = ev[k]; /* Matrix3::from_iterator: column-major */
+        ne++;
+    }
+    return ne;
+}
+
+/* Estimator::estimate (lib.rs:310-329): up to 40 CameraToCamera poses */
+int ref_five_point(const double *a, const double *b, ref_pose *out) {
+    double Es[90];
+    int ne = ref_five_point_essentials(a, b, Es), n = 0;
+    for (int i = 0; i < ne; i++) {
+        ref_pose p4[4];
+        if (ref_essential_poses(Es + 9 * i, 1e-12, 1000, p4) == 4) { memcpy(out + n, p4, sizeof(p4)); n += 4; }
+    }
+    return n;
+}
+
 /* ------------------------------------------------------------------ residuals */
 /* point.rs:20-25 Projective::from_homogeneous */
 static void from_homogeneous(double *p) {
@@ -515,11 +829,17 @@ static void hv_sort(hyp_vec *h) {
     }
 }
 
-/* kind: 0 = EightPoint over FeatureMatch (a, b: n x 3 each), 1 = LambdaTwist over FeatureWorldMatch (a = bearings n x 3, b = world n x 4) */
+/* kind: 0 = EightPoint over FeatureMatch (a, b: n x 3 each), 1 = LambdaTwist over FeatureWorldMatch (a = bearings n x 3,
+ * b = world n x 4), 2 = NisterStewenius over FeatureMatch */
 static double model_residual(int kind, const ref_pose *m, const double *a, const double *b, uint32_t i) {
-    return kind == 0 ? ref_residual_c2c(m, a + 3 * (size_t)i, b + 3 * (size_t)i) : ref_residual_w2c(m, a + 3 * (size_t)i, b + 4 * (size_t)i);
+    return kind != 1 ? ref_residual_c2c(m, a + 3 * (size_t)i, b + 3 * (size_t)i) : ref_residual_w2c(m, a + 3 * (size_t)i, b + 4 * (size_t)i);
 }
-static int model_estimate(int kind, const double *a, const double *b, const uint32_t *idx, ref_pose out[4]) {
+static int model_estimate(int kind, const double *a, const double *b, const uint32_t *idx, ref_pose *out) {
+    if (kind == 2) { /* NisterStewenius over FeatureMatch: 5 samples, up to 40 poses */
+        double sa[15], sb[15];
+        for (int k = 0; k < 5; k++) { memcpy(sa + 3 * k, a + 3 * (size_t)idx[k], 24); memcpy(sb + 3 * k, b + 3 * (size_t)idx[k], 24); }
+        return ref_five_point(sa, sb, out);
+    }
     if (kind == 0) {
         double sa[24], sb[24];
         for (int k = 0; k < 8; k++) { memcpy(sa + 3 * k, a + 3 * (size_t)idx[k], 24); memcpy(sb + 3 * k, b + 3 * (size_t)idx[k], 24); }
@@ -541,7 +861,7 @@ static void populate_samples(ref_rng *rng, uint32_t k, uint32_t len, uint32_t *o
 
 int ref_arrsac(const ref_arrsac_cfg *cfg, int kind, const double *a, const double *b, uint32_t n, ref_rng *rng,
                ref_pose *model_out, uint32_t *inliers_out, uint32_t *n_inliers) {
-    const uint32_t K = kind == 0 ? 8 : 3;
+    const uint32_t K = kind == 0 ? 8 : (kind == 1 ? 3 : 5);
     *n_inliers = 0;
     if (n < K) return 0;
     const double thr = cfg->inlier_threshold;
@@ -552,7 +872,7 @@ int ref_arrsac(const ref_arrsac_cfg *cfg, int kind, const double *a, const doubl
     uint32_t best_inliers = 0;
     uint64_t rej_inliers = 0, rej_tested = 0;
     uint32_t idx[8];
-    ref_pose models[4];
+    ref_pose models[40];
     for (uint32_t h = 0; h < cfg->initialization_hypotheses; h++) {
         populate_samples(rng, K, n, idx);
         int nm = model_estimate(kind, a, b, idx, models);

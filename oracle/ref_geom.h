@@ -19,6 +19,10 @@ int ref_svd3(const double *M, double eps, int max_iter, double *U, double *s, do
 int ref_eight_point_essential(const double *a, const double *b, double eps, int iters, double *E);
 int ref_essential_poses(const double *E, double eps, int iters, ref_pose out[4]);
 int ref_eight_point(const double *a, const double *b, ref_pose out[4]);
+int ref_real_eigenvalues10(const double *A, double *wr, double *wi);
+int ref_five_point_essentials(const double *a, const double *b, double *Es);
+int ref_five_point(const double *a, const double *b, ref_pose *out);
+void ref_five_point_set_row0(int r0);
 double ref_essential_residual(const double *E, const double *a, const double *b);
 double ref_residual_c2c(const ref_pose *P, const double *a, const double *b);
 double ref_residual_w2c(const ref_pose *P, const double *bearing, const double *world);

@@ -181,3 +181,39 @@ def test_estimate_pose_end_to_end_reference_test():
     assert out is not None and len(out[2]) == 11
     px = K.uncalibrate(a)
     assert np.abs(px[:, 0] - kps1[[p[0] for p in pairs]]["x"]).max() < 1e-6      # cv-pinhole/src/lib.rs:120-133
+
+
+@pytest.mark.parametrize("corrected", [False, True])
+def test_five_point_batch_matches_oracle(corrected):
+    rng = np.random.default_rng(31)
+    R, t, a, b, _ = two_view_scene(rng, 120, noise=0.0)
+    samples = np.stack([rng.choice(120, 5, replace=False) for _ in range(200)]).astype(np.uint32)
+    poses, cnt = cv_b200.NisterStewenius(corrected=corrected).estimate_batch(a, b, samples)
+    O.five_point_set_row0(6 if corrected else 5)
+    try:
+        hit = 0
+        for h in range(len(samples)):
+            want = O.five_point(a[samples[h]], b[samples[h]])
+            assert cnt[h] == len(want), h
+            for k, (Rw, tw) in enumerate(want):
+                assert np.allclose(poses[h, k]["r"].reshape(3, 3), Rw, atol=1e-7) and np.allclose(poses[h, k]["t"], tw, atol=1e-7)
+            hit += any(np.allclose(poses[h, k]["r"].reshape(3, 3), R, atol=1e-6) and 1 - poses[h, k]["t"] @ t < 1e-9 for k in range(cnt[h]))
+        assert (hit > 180) if corrected else (hit == 0)      # the reference's off-by-one rows never recover the pose
+    finally:
+        O.five_point_set_row0(5)
+
+
+def test_arrsac_five_point_corrected_matches_oracle():
+    rng = np.random.default_rng(41)
+    R, t, a, b, good = two_view_scene(rng, 400, outlier_frac=0.3, noise=1e-4)
+    thr = 1e-6
+    got = cv_b200.Arrsac(thr, cv_b200.Xoshiro256PlusPlus(3)).model_inliers(cv_b200.NisterStewenius(corrected=True), a, b)
+    O.five_point_set_row0(6)
+    try:
+        want = O.arrsac(O.arrsac_cfg(thr), 2, a, b, O.rng_xoshiro(3))
+    finally:
+        O.five_point_set_row0(5)
+    assert got is not None and want is not None
+    assert np.array_equal(got[2], want[2])
+    assert np.allclose(got[0], want[0], atol=1e-7) and np.allclose(got[1], want[1], atol=1e-7)
+    assert good[got[2]].mean() > 0.95 and len(got[2]) > 100

@@ -147,3 +147,36 @@ def test_kitti_estimate_pose_reference_test():
     b = np.array([O.calibrate(fx, fy, cx, cy, 0.0, float(g["kps14"][idx[i, 0]]["x"]), float(g["kps14"][idx[i, 0]]["y"])) for i in sel])
     out = O.arrsac(O.arrsac_cfg(0.1), 0, a, b, O.rng_pcg64(bytes([1] * 32)))
     assert out is not None and len(out[2]) == 11
+
+
+def test_five_point_restatement_and_reference_quirk():
+    """nister-stewenius has no end-to-end test upstream (tests/manual.rs is commented out).  Every step of the
+    restatement is validated here with the mathematically correct eigenvector rows (6..9): the true essential matrix
+    is among the solutions.  With the reference's rows 5..8 (lib.rs:229) it never is -- the quirk is reproduced."""
+    rng = np.random.default_rng(7)
+    for _ in range(50):
+        A = rng.standard_normal((10, 10))
+        ok, ev = O.real_eigenvalues10(A)
+        assert ok and np.allclose(np.sort_complex(ev), np.sort_complex(np.linalg.eigvals(A)), atol=1e-9)
+    scenes = [two_view_scene(rng, 5) for _ in range(100)]
+
+    def hits():
+        h = 0
+        for R, t, a, b, _ in scenes:
+            Et = skew(t) @ R
+            Et /= np.linalg.norm(Et)
+            Es = O.five_point_essentials(a, b)
+            assert len(Es) <= 10
+            for E in Es:                                   # every solution lies in the epipolar null space
+                assert max(abs(b[k] @ E @ a[k]) for k in range(5)) < 1e-9 * np.linalg.norm(E)
+            h += any(min(np.abs(E / np.linalg.norm(E) - Et).max(), np.abs(E / np.linalg.norm(E) + Et).max()) < 1e-6 for E in Es)
+        return h
+    try:
+        O.five_point_set_row0(6)
+        assert hits() >= 95
+        R, t, a, b, _ = scenes[0]
+        assert any(rot_angle(Rp, R) < 1e-6 and 1 - unit(tp) @ t < 1e-9 for Rp, tp in O.five_point(a, b))
+        O.five_point_set_row0(5)
+        assert hits() == 0
+    finally:
+        O.five_point_set_row0(5)
