@@ -156,6 +156,13 @@ void akaze_workspace_free(AkazeWorkspace *ws) {
 
 namespace {
 
+// fused FED steps per launch (halo grows with it); CVB_FED_FUSE=1..FED_SMAX overrides for experiments
+int fed_fuse_steps() {
+    static int v = 0;
+    if (!v) { const char *env = getenv("CVB_FED_FUSE"); v = env ? std::min(std::max(atoi(env), 1), FED_SMAX) : FED_FUSE_DEFAULT; }
+    return v;
+}
+
 template <typename T>
 int dalloc(cvb_ctx *ctx, AkazeWorkspace *ws, T **p, size_t n) {
     void *q = nullptr;
@@ -556,7 +563,8 @@ int run_extract_eager(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoin
         CVB_LAUNCH_CHECK(ctx); }
         // FED steps: nl launches of at most FED_SMAX fused steps (balanced split); the chain ends in Lt_i
         const int n = (int)e.tau.size();
-        const int nl = (n + FED_SMAX - 1) / FED_SMAX;
+        const int fed_fuse = fed_fuse_steps();
+        const int nl = (n + fed_fuse - 1) / fed_fuse;
         if (nl == 0) {
             CVB_CUDA(ctx, cudaMemcpy2DAsync(ws->Lt + e.off, PF * sizeof(float), src, src_bs * sizeof(float),
                                             (size_t)e.w * e.h * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
@@ -574,8 +582,9 @@ int run_extract_eager(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoin
             else if (((nl - 1 - l) & 1) == 1) { dst = ws->tmpA; dst_bs = P0; }
             else { dst = ws->tmpB; dst_bs = P0; }
             { CVB_PROF(ctx, "k_fed", 12.0 * fs.n * e.w * e.h * B);
-            dim3 grd(cdiv((unsigned)e.w, (unsigned)(FR_W - 2 * fs.n)), cdiv((unsigned)e.h, (unsigned)(FR_H - 2 * fs.n)), B);
-            k_fed2<<<grd, 1024, 0, st>>>(cur, ws->Lflow + e.off, dst, e.w, e.h, cur_bs, PF, dst_bs, fs);
+            const int hx = (fs.n + 3) & ~3;
+            dim3 grd(cdiv((unsigned)e.w, (unsigned)(F3_W - 2 * hx)), cdiv((unsigned)e.h, (unsigned)(F3_H - 2 * fs.n)), B);
+            k_fed3<<<grd, F3_H * 16, 0, st>>>(cur, ws->Lflow + e.off, dst, e.w, e.h, cur_bs, PF, dst_bs, fs);
             CVB_LAUNCH_CHECK(ctx); }
             cur = dst; cur_bs = dst_bs;
         }
