@@ -16,5 +16,8 @@ from .knn import LinearKnn, hamming_knn, lowe_ratio_matches, matching, symmetric
 from .pinhole import CameraIntrinsics  # noqa: F401
 from .geom import (Arrsac, EightPoint, LambdaTwist, LinearEigenTriangulator, NisterStewenius, Pcg64, Xoshiro256PlusPlus,  # noqa: F401
                    residuals_camera_to_camera, residuals_world_to_camera)
+from .optimize import (observation_losses, single_view_simple_optimize_l2, single_view_simple_optimize_l2_batch,  # noqa: F401
+                       three_view_adaptive_optimize_l2, three_view_optimize_l2_batch, three_view_simple_optimize_l2,
+                       tri_landmarks_robust)
 
 __version__ = "0.1.0"

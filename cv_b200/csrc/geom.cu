@@ -723,36 +723,351 @@ __global__ void __launch_bounds__(256) k_residuals(const cvb_pose *__restrict__ 
     }
 }
 
-// cv-geom/src/triangulation.rs:82-130, one thread per landmark
+// cv-geom/src/triangulation.rs:82-130: n >= 2 observations (WorldToCamera pose, bearing) -> homogeneous world point
+__device__ bool triangulate_linear_eigen(const cvb_pose *poses, const double *bearings, uint32_t n, double *p) {
+    if (n < 2) return false;
+    double A[16], d[4], V[16];
+    for (int i = 0; i < 16; i++) A[i] = 0.0;
+    for (uint32_t i = 0; i < n; i++) design_add(poses[i].r, poses[i].t, bearings + 3 * (size_t)i, A);
+    if (!sym_eigen<4>(A, 1e-12, 1000, d, V)) return false;
+    int best = 0;
+    for (int i = 1; i < 4; i++)
+        if (d[i] < d[best]) best = i;
+    p[0] = V[best]; p[1] = V[4 + best]; p[2] = V[8 + best]; p[3] = V[12 + best];
+    from_homogeneous(p);
+    if (!(isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]) && isfinite(p[3]))) return false;
+    for (uint32_t i = 0; i < n; i++) {
+        const double *bb = bearings + 3 * (size_t)i, *R = poses[i].r;
+        const double wb[3] = {R[0] * bb[0] + R[3] * bb[1] + R[6] * bb[2], R[1] * bb[0] + R[4] * bb[1] + R[7] * bb[2],
+                              R[2] * bb[0] + R[5] * bb[1] + R[8] * bb[2]};
+        if (signbit(dot3(wb, p))) return false;
+    }
+    return true;
+}
+// one thread per landmark
 __global__ void __launch_bounds__(128) k_triangulate(const cvb_pose *__restrict__ poses, const double *__restrict__ bearings,
                                                      const uint32_t *__restrict__ offsets, uint32_t L, double *__restrict__ xyzw,
                                                      uint8_t *__restrict__ ok) {
     const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= L) return;
     const uint32_t o0 = offsets[l], o1 = offsets[l + 1];
-    uint8_t good = 0;
     double p[4] = {0, 0, 0, 0};
-    if (o1 - o0 >= 2) {
-        double A[16], d[4], V[16];
-        for (int i = 0; i < 16; i++) A[i] = 0.0;
-        for (uint32_t i = o0; i < o1; i++) design_add(poses[i].r, poses[i].t, bearings + 3 * (size_t)i, A);
-        if (sym_eigen<4>(A, 1e-12, 1000, d, V)) {
-            int best = 0;
-            for (int i = 1; i < 4; i++)
-                if (d[i] < d[best]) best = i;
-            p[0] = V[best]; p[1] = V[4 + best]; p[2] = V[8 + best]; p[3] = V[12 + best];
-            from_homogeneous(p);
-            good = isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]) && isfinite(p[3]);
-            for (uint32_t i = o0; i < o1 && good; i++) {
-                const double *bb = bearings + 3 * (size_t)i, *R = poses[i].r;
-                const double wb[3] = {R[0] * bb[0] + R[3] * bb[1] + R[6] * bb[2], R[1] * bb[0] + R[4] * bb[1] + R[7] * bb[2],
-                                      R[2] * bb[0] + R[5] * bb[1] + R[8] * bb[2]};
-                if (signbit(dot3(wb, p))) good = 0;
-            }
-        }
-    }
-    ok[l] = good;
+    const bool good = triangulate_linear_eigen(poses + o0, bearings + 3 * (size_t)o0, o1 - o0, p);
+    ok[l] = good ? 1 : 0;
     for (int i = 0; i < 4; i++) xyzw[(size_t)l * 4 + i] = good ? p[i] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------ post-consensus refinement
+// cv-optimize single_view_simple_optimize_l2 / three_view_{simple,adaptive}_optimize_l2 with cv-geom's epipolar gradients,
+// and cv-sfm's robustness checks.  One CTA per problem iterates to completion on the device: every iteration the threads
+// evaluate the per-landmark tangents, a fixed-shape reduction tree adds them (warp shuffles, then the warps in order; the
+// reference adds them in landmark order, so sums agree to rounding, not bit for bit), thread 0 replays the reference's
+// bookkeeping (patience counter, pose update) and publishes the pose for the next iteration.
+__device__ __forceinline__ void rotv(const double *R, const double *v, double *o) { for (int r = 0; r < 3; r++) o[r] = dot3(R + 3 * r, v); }
+__device__ __forceinline__ bool any_nan3(const double *v) { return isnan(v[0]) || isnan(v[1]) || isnan(v[2]); }
+__device__ __forceinline__ void normalize3(const double *v, double *o) { const double n = norm3(v); o[0] = v[0] / n; o[1] = v[1] / n; o[2] = v[2] / n; }
+// Se3TangentSpace::new (cv-core/src/so3.rs:23-34)
+__device__ __forceinline__ void tangent_new(double *t, double *r) {
+    if (any_nan3(t)) t[0] = t[1] = t[2] = 0.0;
+    if (any_nan3(r)) r[0] = r[1] = r[2] = 0.0;
+}
+// nalgebra Rotation3::from_scaled_axis
+__device__ void rot_from_scaled_axis(const double *v, double *R) {
+    const double angle = norm3(v);
+    if (angle == 0.0) { for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0) ? 1.0 : 0.0; return; }
+    const double ux = v[0] / angle, uy = v[1] / angle, uz = v[2] / angle;
+    const double sqx = ux * ux, sqy = uy * uy, sqz = uz * uz, sn = sin(angle), c = cos(angle), omc = 1.0 - c;
+    R[0] = sqx + (1.0 - sqx) * c; R[1] = ux * uy * omc - uz * sn; R[2] = ux * uz * omc + uy * sn;
+    R[3] = ux * uy * omc + uz * sn; R[4] = sqy + (1.0 - sqy) * c; R[5] = uy * uz * omc - ux * sn;
+    R[6] = ux * uz * omc - uy * sn; R[7] = uy * uz * omc + ux * sn; R[8] = sqz + (1.0 - sqz) * c;
+}
+// pose <- Se3TangentSpace{trans, rot}.isometry() * pose (so3.rs:57-60)
+__device__ void apply_delta(const double *trans, const double *rot, cvb_pose *P) {
+    double Rd[9], td[3], Rn[9], tn[3];
+    rot_from_scaled_axis(rot, Rd);
+    rotv(Rd, trans, td);
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) Rn[3 * r + c] = Rd[3 * r] * P->r[c] + Rd[3 * r + 1] * P->r[3 + c] + Rd[3 * r + 2] * P->r[6 + c];
+    rotv(Rd, P->t, tn);
+    for (int r = 0; r < 3; r++) tn[r] = td[r] + tn[r];
+    for (int i = 0; i < 9; i++) P->r[i] = Rn[i];
+    for (int i = 0; i < 3; i++) P->t[i] = tn[i];
+}
+__device__ void pose_inverse(const cvb_pose &P, cvb_pose *o) {
+    const double nt[3] = {-P.t[0], -P.t[1], -P.t[2]};
+    double R[9];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[3 * r + c] = P.r[3 * c + r];
+    rotv(R, nt, o->t);
+    for (int i = 0; i < 9; i++) o->r[i] = R[i];
+}
+// cv-geom/src/epipolar.rs:193-198
+__device__ void world_pose_gradient(const double *translation, const double *b, double *tg, double *rg) {
+    const double d = dot3(translation, b);
+    double nt[3];
+    for (int i = 0; i < 3; i++) tg[i] = d * b[i] - translation[i];
+    normalize3(translation, nt);
+    cross3(nt, b, rg);
+    tangent_new(tg, rg);
+}
+// cv-optimize/src/single_view_optimizer.rs:4-14
+__device__ bool landmark_delta(const cvb_pose &P, const double *bearing, const double *world, double *tg, double *rg) {
+    double q[4];
+    pose_apply(P, world, q);
+    from_homogeneous(q);
+    if (q[3] == 0.0) return false;
+    const double p[3] = {q[0] / q[3], q[1] / q[3], q[2] / q[3]};
+    world_pose_gradient(p, bearing, tg, rg);
+    return true;
+}
+// epipolar.rs:8-50
+__device__ bool sine_l1_point(const double *t, const double *a_in, const double *b_in, double *p) {
+    double ca[3], cb[3], na[3], nb[3], a[3], b[3];
+    cross3(a_in, t, ca); const double can = norm3(ca); for (int i = 0; i < 3; i++) na[i] = ca[i] / can;
+    cross3(b_in, t, cb); const double cbn = norm3(cb); for (int i = 0; i < 3; i++) nb[i] = cb[i] / cbn;
+    for (int i = 0; i < 3; i++) { a[i] = a_in[i]; b[i] = b_in[i]; }
+    if (can < cbn) { const double d = dot3(a_in, nb); double v[3]; for (int i = 0; i < 3; i++) v[i] = a_in[i] - d * nb[i]; normalize3(v, a); }
+    else { const double d = dot3(b_in, na); double v[3]; for (int i = 0; i < 3; i++) v[i] = b_in[i] - d * na[i]; normalize3(v, b); }
+    double z[3], tb[3];
+    cross3(a, b, z); cross3(t, b, tb);
+    double q[4] = {a[0], a[1], a[2], dot3(z, z) / dot3(z, tb)};
+    from_homogeneous(q);
+    for (int i = 0; i < 4; i++) if (!isfinite(q[i])) return false;
+    if (signbit(dot3(q, a)) || signbit(dot3(q, b))) return false;
+    if (q[3] == 0.0) return false;
+    for (int i = 0; i < 3; i++) p[i] = q[i] / q[3];
+    return true;
+}
+// epipolar.rs:53-71
+__device__ void rotation_gradient(const double *t, const double *a, const double *b, double *o) {
+    double ca[3], cb[3], na[3], nb[3];
+    cross3(a, t, ca); cross3(b, t, cb);
+    normalize3(ca, na); normalize3(cb, nb);
+    cross3(nb, na, o);
+}
+// epipolar.rs:85-176: out = [first.t, first.r, second.t, second.r]
+__device__ void three_view_gradients(const double *c, const double *f, const double *ftoc, const double *s, const double *stoc, double *out) {
+    double stof[3], rcf[3], rcs[3], rfs[3], p[3], q[3], tf[3] = {0, 0, 0}, ts[3] = {0, 0, 0}, tc[3] = {0, 0, 0}, neg[3];
+    for (int i = 0; i < 3; i++) stof[i] = stoc[i] - ftoc[i];
+    rotation_gradient(ftoc, c, f, rcf); rotation_gradient(stoc, c, s, rcs); rotation_gradient(stof, f, s, rfs);
+    double *ft = out, *fr = out + 3, *st = out + 6, *sr = out + 9;
+    for (int i = 0; i < 3; i++) {
+        fr[i] = rcf[i] * (2.0 / 3.0) + (-rfs[i]) * (1.0 / 3.0);
+        sr[i] = rcs[i] * (2.0 / 3.0) + rfs[i] * (1.0 / 3.0);
+    }
+    for (int i = 0; i < 3; i++) neg[i] = -stoc[i];
+    if (sine_l1_point(neg, c, s, p)) { for (int i = 0; i < 3; i++) q[i] = p[i] - ftoc[i]; const double d = dot3(q, f); for (int i = 0; i < 3; i++) tf[i] = q[i] - d * f[i]; }
+    for (int i = 0; i < 3; i++) neg[i] = -ftoc[i];
+    if (sine_l1_point(neg, c, f, p)) { for (int i = 0; i < 3; i++) q[i] = p[i] - stoc[i]; const double d = dot3(q, s); for (int i = 0; i < 3; i++) ts[i] = q[i] - d * s[i]; }
+    for (int i = 0; i < 3; i++) neg[i] = -stof[i];
+    if (sine_l1_point(neg, f, s, p)) { for (int i = 0; i < 3; i++) q[i] = p[i] + ftoc[i]; const double d = dot3(q, c); for (int i = 0; i < 3; i++) tc[i] = d * c[i] - q[i]; }
+    for (int i = 0; i < 3; i++) {
+        ft[i] = tf[i] * (2.0 / 3.0) + tc[i] * (1.0 / 3.0);
+        st[i] = ts[i] * (2.0 / 3.0) + tc[i] * (1.0 / 3.0);
+    }
+    tangent_new(ft, fr); tangent_new(st, sr);
+}
+// epipolar.rs:200-232
+__device__ double epipolar_loss(const double *t, const double *a, const double *b) {
+    double ca[3], cb[3];
+    cross3(a, t, ca); cross3(b, t, cb);
+    const double na2 = dot3(ca, ca), nb2 = dot3(cb, cb);
+    double res;
+    if (na2 < nb2) { const double sc = 1.0 / sqrt(nb2); const double v[3] = {cb[0] * sc, cb[1] * sc, cb[2] * sc}; res = fabs(dot3(a, v)); }
+    else { const double sc = 1.0 / sqrt(na2); const double v[3] = {ca[0] * sc, ca[1] * sc, ca[2] * sc}; res = fabs(dot3(b, v)); }
+    if (isnan(res) || signbit(dot3(a, b))) return 1.0;
+    return res;
+}
+
+constexpr int OPT_NT = 512, OPT_WARPS = OPT_NT / 32;
+// sums acc[0..NV) over the CTA into s_out[0..NV) (valid for thread 0 after the call); fixed tree -> run-to-run reproducible
+template <int NV>
+__device__ __forceinline__ void block_sum(double *acc, double *s_red) {
+#pragma unroll
+    for (int k = 0; k < NV; k++)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < NV; k++) s_red[w * NV + k] = acc[k];
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int k = 0; k < NV; k++) {
+            double s = s_red[k];
+            for (int ww = 1; ww < OPT_WARPS; ww++) s += s_red[ww * NV + k];
+            acc[k] = s;
+        }
+}
+
+// single_view_optimizer.rs:80-135, one CTA per (pose, landmark list)
+__global__ void __launch_bounds__(OPT_NT) k_single_view_opt(const cvb_pose *__restrict__ poses_in, const double *__restrict__ bearings,
+                                                            const double *__restrict__ world, const uint32_t *__restrict__ offsets,
+                                                            double rate, uint32_t iterations, cvb_pose *__restrict__ poses_out,
+                                                            uint32_t *__restrict__ updates_out) {
+    __shared__ cvb_pose P;
+    __shared__ double s_red[OPT_WARPS * 6];
+    __shared__ int s_stop;
+    const uint32_t b = blockIdx.x, o0 = offsets[b], n = offsets[b + 1] - o0;
+    if (threadIdx.x == 0) { P = poses_in[b]; s_stop = 0; }
+    __syncthreads();
+    double best_t = INFINITY, best_r = INFINITY;
+    uint32_t no_improve = 0, updates = 0;
+    const double inv_len = 1.0 / (double)n;
+    if (n > 0)
+        for (uint32_t it = 0; it < iterations; it++) {
+            double acc[6] = {0, 0, 0, 0, 0, 0}, tg[3], rg[3];
+            const cvb_pose Pl = P;
+            for (uint32_t i = threadIdx.x; i < n; i += OPT_NT)
+                if (landmark_delta(Pl, bearings + 3 * (size_t)(o0 + i), world + 4 * (size_t)(o0 + i), tg, rg))
+                    for (int k = 0; k < 3; k++) { acc[k] += tg[k]; acc[3 + k] += rg[k]; }
+            block_sum<6>(acc, s_red);
+            if (threadIdx.x == 0) {
+                double dt[3], dr[3];
+                for (int k = 0; k < 3; k++) { dt[k] = (acc[k] * inv_len) * rate; dr[k] = (acc[3 + k] * inv_len) * rate; }
+                no_improve++;
+                const double t = norm3(acc), r = norm3(acc + 3);
+                if (best_t > t) { best_t = t; no_improve = 0; }
+                if (best_r > r) { best_r = r; no_improve = 0; }
+                if (no_improve >= 50) s_stop = 1;
+                else {
+                    apply_delta(dt, dr, &P); updates++;
+                    if (it == iterations - 1) s_stop = 1;
+                }
+            }
+            __syncthreads();
+            if (s_stop) break;
+        }
+    if (threadIdx.x == 0) { poses_out[b] = P; updates_out[b] = updates; }
+}
+
+// three_view_optimizer.rs:126-272, one CTA per (pose pair, observation triples); obs = [centre, first, second] bearings
+__global__ void __launch_bounds__(OPT_NT) k_three_view_opt(const cvb_pose *__restrict__ poses_in, const double *__restrict__ obs,
+                                                           const uint32_t *__restrict__ offsets, int adaptive, double rate,
+                                                           uint32_t iterations, cvb_pose *__restrict__ poses_out,
+                                                           uint32_t *__restrict__ updates_out) {
+    __shared__ cvb_pose P[2];
+    __shared__ double s_red[OPT_WARPS * 16];
+    __shared__ int s_stop;
+    const uint32_t b = blockIdx.x, o0 = offsets[b], n = offsets[b + 1] - o0;
+    if (threadIdx.x == 0) {
+        if (n > 0) { pose_inverse(poses_in[2 * b], &P[0]); pose_inverse(poses_in[2 * b + 1], &P[1]); }
+        s_stop = 0;
+    }
+    __syncthreads();
+    double best[2][2] = {{INFINITY, INFINITY}, {INFINITY, INFINITY}};
+    uint32_t no_improve = 0, updates = 0;
+    const double inv_len = 1.0 / (double)n;
+    if (n > 0)
+        for (uint32_t it = 0; it < iterations; it++) {
+            double acc[16], g[12];
+            for (int k = 0; k < 16; k++) acc[k] = 0.0;
+            const cvb_pose P0 = P[0], P1 = P[1];
+            for (uint32_t i = threadIdx.x; i < n; i += OPT_NT) {
+                const double *o = obs + 9 * (size_t)(o0 + i);
+                double f[3], s[3];
+                rotv(P0.r, o + 3, f); rotv(P1.r, o + 6, s);
+                three_view_gradients(o, f, P0.t, s, P1.t, g);
+                for (int k = 0; k < 12; k++) acc[k] += g[k];
+                if (adaptive) { acc[12] += norm3(g); acc[13] += norm3(g + 3); acc[14] += norm3(g + 6); acc[15] += norm3(g + 9); }
+            }
+            block_sum<16>(acc, s_red);
+            if (threadIdx.x == 0) {
+                double d[12];
+                bool stop = false;
+                if (!adaptive) {
+                    const double sc = inv_len * rate;
+                    for (int k = 0; k < 12; k++) d[k] = acc[k] * sc;
+                    no_improve++;
+                    for (int v = 0; v < 2; v++) {
+                        const double t = norm3(acc + 6 * v), r = norm3(acc + 6 * v + 3);
+                        if (best[v][0] > t) { best[v][0] = t; no_improve = 0; }
+                        if (best[v][1] > r) { best[v][1] = r; no_improve = 0; }
+                    }
+                    stop = no_improve >= 50;
+                } else {
+                    for (int v = 0; v < 2; v++) {
+                        double l2[6];
+                        for (int k = 0; k < 6; k++) l2[k] = acc[6 * v + k] * inv_len;
+                        const double tstd = acc[12 + 2 * v] * inv_len, rstd = acc[13 + 2 * v] * inv_len;
+                        double trate = norm3(l2) / tstd, rrate = norm3(l2 + 3) / rstd;
+                        if (!isfinite(trate)) trate = 0.0;
+                        if (!isfinite(rrate)) rrate = 0.0;
+                        for (int k = 0; k < 3; k++) { d[6 * v + k] = l2[k] * trate; d[6 * v + 3 + k] = l2[3 + k] * rrate; }
+                    }
+                }
+                if (stop) s_stop = 1;
+                else {
+                    apply_delta(d, d + 3, &P[0]); apply_delta(d + 6, d + 9, &P[1]); updates++;
+                    if (it == iterations - 1) s_stop = 1;
+                }
+            }
+            __syncthreads();
+            if (s_stop) break;
+        }
+    if (threadIdx.x == 0) {
+        if (n > 0) { pose_inverse(P[0], &poses_out[2 * b]); pose_inverse(P[1], &poses_out[2 * b + 1]); }
+        else { poses_out[2 * b] = poses_in[2 * b]; poses_out[2 * b + 1] = poses_in[2 * b + 1]; }
+        updates_out[b] = updates;
+    }
+}
+
+__device__ void pose_mul(const cvb_pose &A, const cvb_pose &B, cvb_pose *o) {
+    for (int i = 0; i < 3; i++)
+        for (int c = 0; c < 3; c++) o->r[3 * i + c] = A.r[3 * i] * B.r[c] + A.r[3 * i + 1] * B.r[3 + c] + A.r[3 * i + 2] * B.r[6 + c];
+    double sh[3];
+    rotv(A.r, B.t, sh);
+    for (int i = 0; i < 3; i++) o->t[i] = A.t[i] + sh[i];
+}
+__device__ double transformed_cosine_distance(const cvb_pose &P, const double *point_h, const double *bearing) {
+    double q[4];
+    pose_apply(P, point_h, q);
+    from_homogeneous(q);
+    return 1.0 - dot3(q, bearing);
+}
+// cv-sfm/src/lib.rs:2570-2620 observation_loss of every observation; one thread per landmark
+__global__ void __launch_bounds__(128) k_observation_losses(const cvb_pose *__restrict__ poses, const double *__restrict__ bearings,
+                                                            const uint32_t *__restrict__ offsets, uint32_t L, double *__restrict__ loss) {
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const uint32_t o0 = offsets[l], n = offsets[l + 1] - o0;
+    const cvb_pose *P = poses + o0;
+    const double *B = bearings + 3 * (size_t)o0;
+    if (n == 0) return;
+    if (n == 1) { loss[o0] = 2.0; return; }
+    if (n == 2) {
+        cvb_pose inv, tot;
+        double fb[3];
+        pose_inverse(P[0], &inv); pose_mul(P[1], inv, &tot);
+        rotv(tot.r, B, fb);
+        const double v = 1.0 - cos(asin(epipolar_loss(tot.t, fb, B + 3)));
+        loss[o0] = v; loss[o0 + 1] = v;
+        return;
+    }
+    double p[4];
+    const bool ok = triangulate_linear_eigen(P, B, n, p);
+    for (uint32_t i = 0; i < n; i++) loss[o0 + i] = ok ? transformed_cosine_distance(P[i], p, B + 3 * (size_t)i) : 2.0;
+}
+// cv-sfm/src/lib.rs:1320-1360 is_tri_landmark_robust; one thread per (centre, first, second) observation triple of one pose pair
+__global__ void __launch_bounds__(128) k_tri_landmark_robust(cvb_pose first, cvb_pose second, const double *__restrict__ obs, uint32_t n,
+                                                             double max_cos, double inc_min_cos, uint8_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *c = obs + 9 * (size_t)i, *f = c + 3, *s = c + 6;
+    cvb_pose P[3];
+    for (int k = 0; k < 9; k++) P[0].r[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    P[0].t[0] = P[0].t[1] = P[0].t[2] = 0.0;
+    P[1] = first; P[2] = second;
+    double p[4];
+    if (!triangulate_linear_eigen(P, c, 3, p)) { out[i] = 0; return; }
+    from_homogeneous(p);   // CameraPoint::from_homogeneous(p.0)
+    double fc[3], sc[3];
+    for (int k = 0; k < 3; k++) {
+        fc[k] = first.r[k] * f[0] + first.r[3 + k] * f[1] + first.r[6 + k] * f[2];
+        sc[k] = second.r[k] * s[0] + second.r[3 + k] * s[1] + second.r[6 + k] * s[2];
+    }
+    const bool cosine_ok = 1.0 - dot3(p, c) < max_cos && transformed_cosine_distance(first, p, f) < max_cos
+        && transformed_cosine_distance(second, p, s) < max_cos;
+    const bool incidence_ok = 1.0 - dot3(c, fc) > inc_min_cos || 1.0 - dot3(c, sc) > inc_min_cos || 1.0 - dot3(fc, sc) > inc_min_cos;
+    out[i] = cosine_ok && incidence_ok;
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -1178,6 +1493,120 @@ int cvb_arrsac_p3p(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *bearin
     if (!ctx) return CVB_EINVAL;
     if (!cfg || !rng || !model_out || !found || (n && (!bearings || !world))) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
     return arrsac_run(ctx, cfg, 1, bearings, world, n, rng, model_out, inliers_out, cap, n_inliers, found);
+}
+
+int cvb_single_view_optimize_l2(cvb_ctx *ctx, const cvb_pose *poses, uint32_t B, double optimization_rate, uint32_t iterations,
+                                const double *bearings, const double *world, const uint32_t *offsets, cvb_pose *poses_out,
+                                uint32_t *updates_out) {
+    if (!ctx) return CVB_EINVAL;
+    if (B == 0) return 0;
+    if (!poses || !offsets || !poses_out) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    for (uint32_t b = 0; b < B; b++)
+        if (offsets[b + 1] < offsets[b]) return cvb_set_error(ctx, CVB_EINVAL, "offsets must be non-decreasing");
+    const uint32_t n = offsets[B];
+    if (n && (!bearings || !world)) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    GeomWorkspace *g = gws(ctx);
+    int rc;
+    if ((rc = upload(ctx, g->poses, poses, sizeof(cvb_pose) * (size_t)B))) return rc;
+    if ((rc = upload(ctx, g->a, bearings, sizeof(double) * 3 * (size_t)n))) return rc;
+    if ((rc = upload(ctx, g->b, world, sizeof(double) * 4 * (size_t)n))) return rc;
+    if ((rc = upload(ctx, g->offsets, offsets, sizeof(uint32_t) * ((size_t)B + 1)))) return rc;
+    if ((rc = g->out.ensure(ctx, sizeof(cvb_pose) * (size_t)B))) return rc;
+    if ((rc = g->ok.ensure(ctx, sizeof(uint32_t) * (size_t)B))) return rc;
+    {
+        CVB_PROF(ctx, "k_single_view_opt", 0.0);
+        k_single_view_opt<<<B, OPT_NT, 0, ctx->stream>>>((const cvb_pose *)g->poses.p, (const double *)g->a.p, (const double *)g->b.p,
+                                                         (const uint32_t *)g->offsets.p, optimization_rate, iterations, (cvb_pose *)g->out.p,
+                                                         (uint32_t *)g->ok.p);
+        CVB_LAUNCH_CHECK(ctx);
+    }
+    CVB_CUDA(ctx, cudaMemcpyAsync(poses_out, g->out.p, sizeof(cvb_pose) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint32_t> upd(B);
+    CVB_CUDA(ctx, cudaMemcpyAsync(upd.data(), g->ok.p, sizeof(uint32_t) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (updates_out) memcpy(updates_out, upd.data(), sizeof(uint32_t) * (size_t)B);
+    return 0;
+}
+
+int cvb_three_view_optimize_l2(cvb_ctx *ctx, const cvb_pose *poses, uint32_t B, int32_t adaptive, double optimization_rate,
+                               uint32_t iterations, const double *observations, const uint32_t *offsets, cvb_pose *poses_out,
+                               uint32_t *updates_out) {
+    if (!ctx) return CVB_EINVAL;
+    if (B == 0) return 0;
+    if (!poses || !offsets || !poses_out) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    for (uint32_t b = 0; b < B; b++)
+        if (offsets[b + 1] < offsets[b]) return cvb_set_error(ctx, CVB_EINVAL, "offsets must be non-decreasing");
+    const uint32_t n = offsets[B];
+    if (n && !observations) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    GeomWorkspace *g = gws(ctx);
+    int rc;
+    if ((rc = upload(ctx, g->poses, poses, sizeof(cvb_pose) * 2 * (size_t)B))) return rc;
+    if ((rc = upload(ctx, g->a, observations, sizeof(double) * 9 * (size_t)n))) return rc;
+    if ((rc = upload(ctx, g->offsets, offsets, sizeof(uint32_t) * ((size_t)B + 1)))) return rc;
+    if ((rc = g->out.ensure(ctx, sizeof(cvb_pose) * 2 * (size_t)B))) return rc;
+    if ((rc = g->ok.ensure(ctx, sizeof(uint32_t) * (size_t)B))) return rc;
+    {
+        CVB_PROF(ctx, "k_three_view_opt", 0.0);
+        k_three_view_opt<<<B, OPT_NT, 0, ctx->stream>>>((const cvb_pose *)g->poses.p, (const double *)g->a.p, (const uint32_t *)g->offsets.p,
+                                                        adaptive ? 1 : 0, optimization_rate, iterations, (cvb_pose *)g->out.p, (uint32_t *)g->ok.p);
+        CVB_LAUNCH_CHECK(ctx);
+    }
+    CVB_CUDA(ctx, cudaMemcpyAsync(poses_out, g->out.p, sizeof(cvb_pose) * 2 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint32_t> upd(B);
+    CVB_CUDA(ctx, cudaMemcpyAsync(upd.data(), g->ok.p, sizeof(uint32_t) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (updates_out) memcpy(updates_out, upd.data(), sizeof(uint32_t) * (size_t)B);
+    return 0;
+}
+
+int cvb_observation_losses(cvb_ctx *ctx, const cvb_pose *poses, const double *bearings, const uint32_t *offsets, uint32_t L,
+                           double *loss_out) {
+    if (!ctx) return CVB_EINVAL;
+    if (L == 0) return 0;
+    if (!poses || !bearings || !offsets || !loss_out) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    for (uint32_t l = 0; l < L; l++)
+        if (offsets[l + 1] < offsets[l]) return cvb_set_error(ctx, CVB_EINVAL, "offsets must be non-decreasing");
+    const uint32_t nobs = offsets[L];
+    if (nobs == 0) return 0;
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    GeomWorkspace *g = gws(ctx);
+    int rc;
+    if ((rc = upload(ctx, g->poses, poses, sizeof(cvb_pose) * (size_t)nobs))) return rc;
+    if ((rc = upload(ctx, g->a, bearings, sizeof(double) * 3 * (size_t)nobs))) return rc;
+    if ((rc = upload(ctx, g->offsets, offsets, sizeof(uint32_t) * ((size_t)L + 1)))) return rc;
+    if ((rc = g->out.ensure(ctx, sizeof(double) * (size_t)nobs))) return rc;
+    {
+        CVB_PROF(ctx, "k_observation_losses", 128.0 * nobs);
+        k_observation_losses<<<cdiv(L, 128), 128, 0, ctx->stream>>>((const cvb_pose *)g->poses.p, (const double *)g->a.p,
+                                                                    (const uint32_t *)g->offsets.p, L, (double *)g->out.p);
+        CVB_LAUNCH_CHECK(ctx);
+    }
+    CVB_CUDA(ctx, cudaMemcpyAsync(loss_out, g->out.p, sizeof(double) * (size_t)nobs, cudaMemcpyDeviceToHost, ctx->stream));
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int cvb_tri_landmarks_robust(cvb_ctx *ctx, const cvb_pose *first_pose, const cvb_pose *second_pose, const double *observations, uint32_t n,
+                             double maximum_cosine_distance, double incidence_minimum_cosine_distance, uint8_t *robust_out) {
+    if (!ctx) return CVB_EINVAL;
+    if (n == 0) return 0;
+    if (!first_pose || !second_pose || !observations || !robust_out) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    GeomWorkspace *g = gws(ctx);
+    int rc;
+    if ((rc = upload(ctx, g->a, observations, sizeof(double) * 9 * (size_t)n))) return rc;
+    if ((rc = g->ok.ensure(ctx, n))) return rc;
+    {
+        CVB_PROF(ctx, "k_tri_landmark_robust", 72.0 * n);
+        k_tri_landmark_robust<<<cdiv(n, 128), 128, 0, ctx->stream>>>(*first_pose, *second_pose, (const double *)g->a.p, n, maximum_cosine_distance,
+                                                                     incidence_minimum_cosine_distance, (uint8_t *)g->ok.p);
+        CVB_LAUNCH_CHECK(ctx);
+    }
+    CVB_CUDA(ctx, cudaMemcpyAsync(robust_out, g->ok.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 }  // extern "C"

@@ -203,6 +203,33 @@ int cvb_arrsac_five_point(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double 
 int cvb_arrsac_p3p(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *bearings, const double *world, uint32_t n,
                    cvb_rng *rng, cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers, int32_t *found);
 
+/* ---- post-consensus refinement and robustness checks ------------------------------
+ *   cvb_single_view_optimize_l2 <- cv_optimize::single_view_simple_optimize_l2   cv-optimize/src/single_view_optimizer.rs:80-135
+ *                                  (call sites cv-sfm/src/lib.rs:1655,1706; gradient cv-geom/src/epipolar.rs:193-198)
+ *   cvb_three_view_optimize_l2  <- three_view_simple_optimize_l2 (adaptive = 0), three_view_adaptive_optimize_l2 (adaptive = 1,
+ *                                  optimization_rate unused)                       cv-optimize/src/three_view_optimizer.rs:126-272
+ *                                  (call sites cv-sfm/src/lib.rs:1131,1180,2039; gradients cv-geom/src/epipolar.rs:85-176)
+ *   cvb_observation_losses      <- VSlam::observation_loss for every observation   cv-sfm/src/lib.rs:2570-2620
+ *   cvb_tri_landmarks_robust    <- VSlam::is_tri_landmark_robust                   cv-sfm/src/lib.rs:1320-1360
+ * B independent problems per call, problem b owns data offsets[b]..offsets[b+1]; each problem iterates to completion inside one
+ * CTA (per-iteration tangent sums by a fixed reduction tree; the reference adds in landmark order, so results agree to rounding).
+ * updates_out[b] = pose updates applied before the reference's patience rule or the iteration cap stopped the loop (may be NULL). */
+int cvb_single_view_optimize_l2(cvb_ctx *ctx, const cvb_pose *poses, uint32_t B, double optimization_rate, uint32_t iterations,
+                                const double *bearings, const double *world, const uint32_t *offsets, cvb_pose *poses_out,
+                                uint32_t *updates_out);
+/* poses[2*b], poses[2*b+1]: CameraToCamera centre->first, centre->second; observations[i*9..]: centre, first, second bearings */
+int cvb_three_view_optimize_l2(cvb_ctx *ctx, const cvb_pose *poses, uint32_t B, int32_t adaptive, double optimization_rate,
+                               uint32_t iterations, const double *observations, const uint32_t *offsets, cvb_pose *poses_out,
+                               uint32_t *updates_out);
+/* L landmarks with (WorldToCamera pose, bearing) observation lists as in cvb_triangulate_linear_eigen; loss_out[i] per observation:
+ * 2.0 for a single observation or a failed triangulation, the epipolar loss as a cosine distance for two, else 1 - cos to the
+ * triangulated point */
+int cvb_observation_losses(cvb_ctx *ctx, const cvb_pose *poses, const double *bearings, const uint32_t *offsets, uint32_t L,
+                           double *loss_out);
+int cvb_tri_landmarks_robust(cvb_ctx *ctx, const cvb_pose *first_pose, const cvb_pose *second_pose, const double *observations,
+                             uint32_t n, double maximum_cosine_distance, double incidence_minimum_cosine_distance,
+                             uint8_t *robust_out);
+
 #ifdef __cplusplus
 }
 #endif

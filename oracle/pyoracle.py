@@ -385,3 +385,70 @@ def arrsac(cfg, kind, a, b, rng):
         return None
     R, t = model.numpy()
     return R, t, inl[:cnt.value].copy()
+
+
+# ---------------------------------------------------------------------------------------------
+# post-consensus refinement and robustness checks (oracle/ref_optimize.c)
+_opt_ready = False
+
+
+def _opt():
+    global _opt_ready
+    L = _geom()
+    if not _opt_ready:
+        dp = C.POINTER(C.c_double)
+        L.ref_world_pose_gradient.argtypes = [dp, dp, dp, dp]
+        L.ref_single_view_optimize_l2.restype = C.c_uint32
+        L.ref_single_view_optimize_l2.argtypes = [C.POINTER(Pose), C.c_double, C.c_uint32, dp, dp, C.c_uint32]
+        L.ref_three_view_gradients.argtypes = [dp] * 6
+        L.ref_three_view_optimize_l2.restype = C.c_uint32
+        L.ref_three_view_optimize_l2.argtypes = [C.POINTER(Pose), C.c_int, C.c_double, C.c_uint32, dp, C.c_uint32]
+        L.ref_epipolar_loss.restype = C.c_double
+        L.ref_epipolar_loss.argtypes = [dp, dp, dp]
+        L.ref_observation_losses.argtypes = [C.POINTER(Pose), dp, C.c_uint32, dp]
+        L.ref_is_tri_landmark_robust.argtypes = [C.POINTER(Pose), C.POINTER(Pose), dp, dp, dp, C.c_double, C.c_double]
+        _opt_ready = True
+    return L
+
+
+def single_view_optimize_l2(pose, rate, iterations, bearings, world):
+    """single_view_simple_optimize_l2 -> (R, t, pose updates applied)"""
+    p = make_pose(*pose)
+    b = np.ascontiguousarray(bearings, np.float64); w = np.ascontiguousarray(world, np.float64)
+    it = _opt().ref_single_view_optimize_l2(C.byref(p), rate, iterations, _dp(b), _dp(w), len(b))
+    R, t = p.numpy()
+    return R, t, it
+
+
+def three_view_gradients(c, f, ftoc, s, stoc):
+    out = np.zeros(12)
+    a = [np.ascontiguousarray(x, np.float64) for x in (c, f, ftoc, s, stoc)]
+    _opt().ref_three_view_gradients(*[_dp(x) for x in a], _dp(out))
+    return out
+
+
+def three_view_optimize_l2(poses, rate, iterations, obs, adaptive=False):
+    """three_view_simple_optimize_l2 / three_view_adaptive_optimize_l2; obs[n, 3, 3] = (centre, first, second) bearings"""
+    arr = (Pose * 2)(make_pose(*poses[0]), make_pose(*poses[1]))
+    o = np.ascontiguousarray(obs, np.float64).reshape(-1, 9)
+    it = _opt().ref_three_view_optimize_l2(arr, int(adaptive), rate, iterations, _dp(o), len(o))
+    return [arr[0].numpy(), arr[1].numpy()], it
+
+
+def epipolar_loss(t, a, b):
+    t, a, b = [np.ascontiguousarray(x, np.float64) for x in (t, a, b)]
+    return _opt().ref_epipolar_loss(_dp(t), _dp(a), _dp(b))
+
+
+def observation_losses(poses, bearings):
+    arr = (Pose * len(poses))(*[make_pose(R, t) for R, t in poses])
+    b = np.ascontiguousarray(bearings, np.float64)
+    out = np.zeros(len(poses))
+    _opt().ref_observation_losses(arr, _dp(b), len(poses), _dp(out))
+    return out
+
+
+def is_tri_landmark_robust(first, second, c, f, s, max_cos, inc_min_cos):
+    c, f, s = [np.ascontiguousarray(x, np.float64) for x in (c, f, s)]
+    return bool(_opt().ref_is_tri_landmark_robust(C.byref(make_pose(*first)), C.byref(make_pose(*second)), _dp(c), _dp(f), _dp(s),
+                                                  max_cos, inc_min_cos))

@@ -35,6 +35,15 @@ uint32_t ref_rng_next_u32(ref_rng *r);
 void ref_arrsac_default_cfg(ref_arrsac_cfg *c, double inlier_threshold);
 int ref_arrsac(const ref_arrsac_cfg *cfg, int kind, const double *a, const double *b, uint32_t n, ref_rng *rng,
                ref_pose *model_out, uint32_t *inliers_out, uint32_t *n_inliers);
+/* ref_optimize.c: post-consensus refinement and robustness checks */
+void ref_world_pose_gradient(const double *translation, const double *b, double *tg, double *rg);
+uint32_t ref_single_view_optimize_l2(ref_pose *pose, double rate, uint32_t iterations, const double *bearings, const double *world, uint32_t n);
+void ref_three_view_gradients(const double *c, const double *f, const double *ftoc, const double *s, const double *stoc, double *out);
+uint32_t ref_three_view_optimize_l2(ref_pose poses[2], int adaptive, double rate, uint32_t iterations, const double *obs, uint32_t n);
+double ref_epipolar_loss(const double *t, const double *a, const double *b);
+void ref_observation_losses(const ref_pose *poses, const double *bearings, uint32_t n, double *loss);
+int ref_is_tri_landmark_robust(const ref_pose *first, const ref_pose *second, const double *c, const double *f, const double *s,
+                               double maximum_cosine_distance, double incidence_minimum_cosine_distance);
 #ifdef __cplusplus
 }
 #endif

@@ -78,3 +78,22 @@ def pnp_scene(rng, n, outlier_frac=0.0, noise=0.0):
         good[idx] = False
     perm = rng.permutation(n)
     return R, t, bearing[perm], world_homog(Wp)[perm], good[perm]
+
+
+def three_view_scene(rng, n, noise=0.0):
+    """Centre camera = identity; returns [(R1, t1), (R2, t2)] CameraToCamera (centre -> first / second) and obs[n, 3, 3]."""
+    poses = []
+    for sgn in (1.0, -1.0):
+        R = rot_from_scaled_axis(rng.uniform(-1, 1, 3) * 0.15)
+        t = np.array([sgn * rng.uniform(0.4, 0.8), rng.uniform(-0.2, 0.2), rng.uniform(-0.1, 0.1)])
+        poses.append((R, t))
+    X = np.stack([rng.uniform(-2, 2, n), rng.uniform(-2, 2, n), rng.uniform(3, 8, n)], 1)
+    obs = np.stack([unit(X), unit(X @ poses[0][0].T + poses[0][1]), unit(X @ poses[1][0].T + poses[1][1])], 1)
+    if noise:
+        obs = unit(obs + rng.normal(0, noise, obs.shape))
+    return poses, obs
+
+
+def perturb_pose(rng, pose, rot=0.01, trans=0.02):
+    R, t = pose
+    return rot_from_scaled_axis(rng.normal(0, 1, 3) * rot) @ R, t + rng.normal(0, 1, 3) * trans
