@@ -19,5 +19,6 @@ from .geom import (Arrsac, EightPoint, LambdaTwist, LinearEigenTriangulator, Nis
 from .optimize import (observation_losses, single_view_simple_optimize_l2, single_view_simple_optimize_l2_batch,  # noqa: F401
                        three_view_adaptive_optimize_l2, three_view_optimize_l2_batch, three_view_simple_optimize_l2,
                        tri_landmarks_robust)
+from .sfm_match import landmark_matches  # noqa: F401
 
 __version__ = "0.1.0"

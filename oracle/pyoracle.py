@@ -452,3 +452,35 @@ def is_tri_landmark_robust(first, second, c, f, s, max_cos, inc_min_cos):
     c, f, s = [np.ascontiguousarray(x, np.float64) for x in (c, f, s)]
     return bool(_opt().ref_is_tri_landmark_robust(C.byref(make_pose(*first)), C.byref(make_pose(*second)), _dp(c), _dp(f), _dp(s),
                                                   max_cos, inc_min_cos))
+
+
+def landmark_matches_ref(new_descriptors, views, better_by=24, landmark_views=None, landmark_observations=None):
+    """Loop-for-loop restatement of cv-sfm/src/lib.rs:1468-1576 (matching part of register_frame_subset) over the exact
+    LinearKnn; ties among equal distances broken by landmark id (the reference's HashMap order is unspecified).  Small cases only."""
+    original = []
+    for f in range(len(new_descriptors)):
+        raw = []
+        for desc, landmarks in views:
+            idx, dist = hamming_knn(new_descriptors[f:f + 1], desc, 3)
+            raw += [(int(landmarks[i]), int(d)) for i, d in zip(idx[0], dist[0]) if i != 0xFFFFFFFF]
+        best_of = {}
+        for l, d in raw:
+            if l not in best_of or best_of[l] > d:
+                best_of[l] = d
+        items = sorted(best_of.items(), key=lambda ld: (ld[1], ld[0]))
+        best = items[:3]
+        assert len(best) == 3
+        if best[0][1] + better_by <= best[1][1]:
+            original.append(((best[0][0],), f))
+        elif best[1][1] + better_by <= best[2][1]:
+            a, b = best[0][0], best[1][0]
+            if landmark_views is None or not (set(landmark_views[a]) & set(landmark_views[b])):
+                original.append(((a, b), f))
+    counts = {}
+    for ls, _ in original:
+        for l in ls:
+            counts[l] = counts.get(l, 0) + 1
+    kept = [m for m in original if all(counts[l] == 1 for l in m[0])]
+    if landmark_observations is not None:
+        kept = sorted(kept, key=lambda m: -sum(landmark_observations[l] for l in m[0]))
+    return kept

@@ -65,3 +65,34 @@ def test_large_problem_properties():
     assert (dist[:, 1] >= dist[:, 0]).all()
     x = np.unpackbits(d[:5000] ^ d[idx[:, 1]], axis=1).sum(1)
     assert np.array_equal(x.astype(np.uint32), dist[:, 1])
+
+
+def test_landmark_matches_against_loop_restatement():
+    """cv-sfm register_frame_subset's matching stage (cv-sfm/src/lib.rs:1468-1576) over three views."""
+    rng = np.random.default_rng(11)
+    n_land = 400
+    proto = rng.integers(0, 256, (n_land, 64), dtype=np.uint8)
+    proto[:, 60] &= 0x3F; proto[:, 61:] = 0                        # 486-bit descriptors
+
+    def noisy(d, flips):
+        d = d.copy()
+        for r in range(len(d)):
+            for bit in rng.choice(486, flips, replace=False):
+                d[r, bit >> 3] ^= 1 << (bit & 7)
+        return d
+    views, landmark_views, obs_count = [], {l: set() for l in range(n_land + 40)}, {l: 0 for l in range(n_land + 40)}
+    for v in range(3):
+        ids = rng.choice(n_land, 250, replace=False)
+        desc = noisy(proto[ids], 12)
+        ids = ids.copy()
+        if v > 0:
+            ids[:20] = n_land + np.arange(20) + 20 * (v - 1)       # the same points tracked as separate landmarks: merge candidates
+        views.append((desc, ids))
+        for l in ids:
+            landmark_views[int(l)].add(v); obs_count[int(l)] += 1
+    new = noisy(proto[rng.choice(n_land, 300, replace=False)], 10)
+    got = cv_b200.landmark_matches(new, views, 24, landmark_views, obs_count)
+    want = O.landmark_matches_ref(new, views, 24, landmark_views, obs_count)
+    assert got == want
+    assert sum(len(m[0]) == 1 for m in got) > 100 and sum(len(m[0]) == 2 for m in got) > 3
+    assert cv_b200.landmark_matches(new, views, 24) == O.landmark_matches_ref(new, views, 24)
