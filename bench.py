@@ -281,8 +281,15 @@ def main():
     hb = {k: v for k, v in rep.items() if v["bytes"] > 0}
     dom = max(hb.items(), key=lambda kv: kv[1]["ms"])
     achieved = dom[1]["bytes"] / (dom[1]["ms"] * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:      # DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), not measured live
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom[0])
+        if tj:
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "launch_ms": dom[1]["ms"] / dom[1]["launches"], "bytes_per_launch": dom[1]["bytes"] / dom[1]["launches"],
                 "timing": "per-kernel CUDA events on the launching stream, separate instrumented pass of the same steps",
                 "pipeline_alg_GBps": value / world * ALG_BYTES_PER_FRAME / 1e9, "pipeline_frac": value / world * ALG_BYTES_PER_FRAME / 1e9 / hbm_peak,
