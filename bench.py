@@ -149,7 +149,7 @@ def main():
     # Two independent contexts (each owns a CUDA stream + workspace; the ABI makes distinct contexts independent)
     # alternate steps, so the latency-bound keypoint tail of step i overlaps the image pipeline of step i+1.
     # Timing: CUDA events on the launching stream of context 0, bracketed by full-device synchronisation.
-    NCTX = int(os.environ.get("CVB_BENCH_CONTEXTS", "6"))          # contexts pipelined in the device-resident measurement
+    NCTX = int(os.environ.get("CVB_BENCH_CONTEXTS", "8"))          # contexts pipelined in the device-resident measurement
     NHOST = min(NCTX, int(os.environ.get("CVB_BENCH_HOST_THREADS", "4")))   # host threads (one context each) in the e2e measurement
     ctxs = [cv_b200.Context(local_rank) for _ in range(NCTX)]
     ctx = ctxs[0]

@@ -60,27 +60,31 @@ __device__ __forceinline__ float lane_dot(const float *w, int stride, const floa
 }
 
 // Sparse 2-/3-tap versions of the same sum for the Scharr kernels (derivatives.rs:3-11, 54-79).
-// Zero taps contribute (w*0)+acc == acc (acc is never -0), so only the non-zero taps are evaluated,
-// each in its own lane JA/JB/JC = tap index & 3, in increasing tap order.
+// Only the non-zero taps are evaluated.  The reference adds every product to a lane that starts at +0 and reduces
+// (l0+l2)+(l1+l3) with the empty lanes still +0; adding +0 changes a value only when it is -0 (-> +0), and a sum of
+// values none of which is -0 is never -0.  So the reference's result equals the sum of the products ASSOCIATED the same
+// way (products sharing a lane first, then lanes of the same pair {0,2} / {1,3}, two-term adds commute exactly), with one
+// final "+ 0.0f" that maps a -0 result to the reference's +0: 3-4 flops less per dot, bit-identical.
 template <int JA, int JB>
 __device__ __forceinline__ float dot2(float a, float ka, float b, float kb) {
-    float l[4] = {0.f, 0.f, 0.f, 0.f};
-    l[JA] = a * ka + l[JA];
-    l[JB] = b * kb + l[JB];
-    return (l[0] + l[2]) + (l[1] + l[3]);
+    return (a * ka + b * kb) + 0.f;
 }
 template <int JA, int JB, int JC>
 __device__ __forceinline__ float dot3(float a, float ka, float b, float kb, float c, float kc) {
-    float l[4] = {0.f, 0.f, 0.f, 0.f};
-    l[JA] = a * ka + l[JA];
-    l[JB] = b * kb + l[JB];
-    l[JC] = c * kc + l[JC];
-    return (l[0] + l[2]) + (l[1] + l[3]);
+    const float pa = a * ka, pb = b * kb, pc = c * kc;
+    float r;
+    if (JA == JB) r = (JC == JA) ? pc + (pb + pa) : (pb + pa) + pc;      // lane JA holds pb + pa (then pc + it)
+    else if (JA == JC) r = (pc + pa) + pb;
+    else if (JB == JC) r = (pc + pb) + pa;
+    else if ((JA ^ JB) == 2) r = (pa + pb) + pc;                          // distinct lanes: the same-pair two are added first
+    else if ((JA ^ JC) == 2) r = (pa + pc) + pb;
+    else r = (pb + pc) + pa;
+    return r + 0.f;
 }
 // Scharr "main" kernel [-1, 0.., 1] of size 2s+1: taps 0 and 2s.  SM = s & 3.
 template <int SM>
 __device__ __forceinline__ float scharr_main(float first, float last) {
-    return dot2<0, (2 * SM) & 3>(first, -1.0f, last, 1.0f);
+    return (last - first) + 0.f;   // (-1*first) + (1*last): both products exact, see dot2
 }
 // Scharr "off" kernel [norm, 0.., middle, 0.., norm]: taps 0, s, 2s.
 template <int SM>
@@ -414,10 +418,32 @@ __global__ void __launch_bounds__(NT) k_deriv2_det(const float *__restrict__ Lx,
 
 template <int KS>
 __device__ __forceinline__ float lane_dot_static(const float *w, int stride, const float *k) {
-    float l[4] = {0.f, 0.f, 0.f, 0.f};
+    // same sum as lane_dot without the additions of +0 (first touch of a lane, empty lanes); the trailing + 0.0f restores
+    // the reference's +0 where every product is -0 (see dot2 / dot3)
+    float l[4];
 #pragma unroll
-    for (int j = 0; j < KS; j++) l[j & 3] = w[j * stride] * k[j] + l[j & 3];
-    return (l[0] + l[2]) + (l[1] + l[3]);
+    for (int j = 0; j < KS; j++) {
+        const float p = w[j * stride] * k[j];
+        l[j & 3] = j < 4 ? p : p + l[j & 3];
+    }
+    if (KS == 1) return l[0] + 0.f;
+    if (KS == 2) return (l[0] + l[1]) + 0.f;
+    if (KS == 3) return ((l[0] + l[2]) + l[1]) + 0.f;
+    return ((l[0] + l[2]) + (l[1] + l[3])) + 0.f;
+}
+// the same for KS values already in registers (vertical passes of the column-strip kernels)
+template <int KS>
+__device__ __forceinline__ float lane_dot_regs(const float *v, const float *k) {
+    float l[4];
+#pragma unroll
+    for (int j = 0; j < KS; j++) {
+        const float p = v[j] * k[j];
+        l[j & 3] = j < 4 ? p : p + l[j & 3];
+    }
+    if (KS == 1) return l[0] + 0.f;
+    if (KS == 2) return (l[0] + l[1]) + 0.f;
+    if (KS == 3) return ((l[0] + l[2]) + l[1]) + 0.f;
+    return ((l[0] + l[2]) + (l[1] + l[3])) + 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -596,10 +622,7 @@ __global__ void __launch_bounds__(NT) k_blur_v3(const float *__restrict__ in, fl
         hv[r] = lane_dot_static<KS>(col + r * RW, 1, tk.k);            // horizontal pass of input row (y - R + r)
         if (r >= 2 * R) {
             const int o = r - 2 * R, gy = y0 + ty * STRIP + o;
-            float l[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int j = 0; j < KS; j++) l[j & 3] = hv[o + j] * tk.k[j] + l[j & 3];   // vertical pass, same lane order
-            if (gy < h) dst[(size_t)gy * w + gx] = (l[0] + l[2]) + (l[1] + l[3]);
+            if (gy < h) dst[(size_t)gy * w + gx] = lane_dot_regs<KS>(hv + o, tk.k);   // vertical pass, same lane order
         }
     }
 }
