@@ -150,7 +150,7 @@ def main():
     # alternate steps, so the latency-bound keypoint tail of step i overlaps the image pipeline of step i+1.
     # Timing: CUDA events on the launching stream of context 0, bracketed by full-device synchronisation.
     NCTX = int(os.environ.get("CVB_BENCH_CONTEXTS", "8"))          # contexts pipelined in the device-resident measurement
-    NHOST = min(NCTX, int(os.environ.get("CVB_BENCH_HOST_THREADS", "4")))   # host threads (one context each) in the e2e measurement
+    NHOST = min(NCTX, int(os.environ.get("CVB_BENCH_HOST_THREADS", "8")))   # host threads (one context each) in the e2e measurement
     ctxs = [cv_b200.Context(local_rank) for _ in range(NCTX)]
     ctx = ctxs[0]
     lib = ctx.lib
@@ -236,18 +236,30 @@ def main():
         o.d2h = 8 + 4 + (na + nb) * (KP_DTYPE.itemsize + 64) + na * 4
         return o.npairs.value
 
-    def host_worker(c, first, count):
-        for i in range(first + c, first + count, NHOST):
+    def host_worker(c, take):
+        while True:              # steps are handed out dynamically: a thread that finishes early takes the next one
+            i = take()
+            if i is None:
+                return
             step_host(i, c)
 
     def run_host(first, count):
-        th = [threading.Thread(target=host_worker, args=(c, first, count)) for c in range(NHOST)]
+        lock, nxt = threading.Lock(), [first]
+
+        def take():
+            with lock:
+                i = nxt[0]
+                if i >= first + count:
+                    return None
+                nxt[0] = i + 1
+                return i
+        th = [threading.Thread(target=host_worker, args=(c, take)) for c in range(NHOST)]
         for t in th:
             t.start()
         for t in th:
             t.join()
 
-    run_host(0, max(Wm, NHOST))
+    run_host(0, max(Wm, 3 * NHOST))          # every host thread / context has run a few steps before the timed region
     nm = houts[0].npairs.value
     barrier()
     t0 = time.perf_counter()

@@ -1492,21 +1492,46 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_descriptors(const cvb_keypo
         const float xf = kp.x / ratio, yf = kp.y / ratio;
         const float co = dlm::cosf_glibc(kp.angle), si = dlm::sinf_glibc(kp.angle);
         bool oob = false;
-        for (int p = lane; p < nl * nl; p += 32) {
-            const int ki = p / nl, lj = p - ki * nl;
-            const float kf = (float)(ki - pattern), lf = (float)(lj - pattern);
-            const float sample_y = yf + (lf * co * scale + kf * si * scale);
-            const float sample_x = xf + (-lf * si * scale + kf * co * scale);
-            const float ry_ = roundf(sample_y), rx_ = roundf(sample_x);
-            if (!(rx_ >= 0.f && rx_ < (float)W) || !(ry_ >= 0.f && ry_ < (float)H)) { oob = true; continue; }
-            const size_t g = (size_t)(int)ry_ * W + (int)rx_;
-            s_lat[wid][0][p] = PT[g];
-            if (nch > 1) {
-                const float rx = PX[g], ry = PY[g];
-                if (nch == 2) s_lat[wid][1][p] = sqrtf(rx * rx + ry * ry);
-                else {
-                    s_lat[wid][2][p] = rx * co + ry * si;      // rry
-                    s_lat[wid][1][p] = -rx * si + ry * co;     // rrx
+        // lattice gathers in batches: all addresses, then all loads, then the arithmetic (a rolled loop would pay one L2
+        // round trip per iteration)
+        constexpr int GB = 7;
+        for (int p0 = lane; p0 < nl * nl; p0 += 32 * GB) {
+            size_t g[GB];
+            float vt[GB], vx[GB], vy[GB];
+#pragma unroll
+            for (int u = 0; u < GB; u++) {
+                const int p = p0 + 32 * u;
+                g[u] = (size_t)-1;
+                if (p < nl * nl) {
+                    const int ki = p / nl, lj = p - ki * nl;
+                    const float kf = (float)(ki - pattern), lf = (float)(lj - pattern);
+                    const float sample_y = yf + (lf * co * scale + kf * si * scale);
+                    const float sample_x = xf + (-lf * si * scale + kf * co * scale);
+                    const float ry_ = roundf(sample_y), rx_ = roundf(sample_x);
+                    if (!(rx_ >= 0.f && rx_ < (float)W) || !(ry_ >= 0.f && ry_ < (float)H)) oob = true;
+                    else g[u] = (size_t)(int)ry_ * W + (int)rx_;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < GB; u++) {
+                vt[u] = vx[u] = vy[u] = 0.f;
+                if (g[u] != (size_t)-1) {
+                    vt[u] = PT[g[u]];
+                    if (nch > 1) { vx[u] = PX[g[u]]; vy[u] = PY[g[u]]; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < GB; u++) {
+                const int p = p0 + 32 * u;
+                if (g[u] == (size_t)-1) continue;
+                s_lat[wid][0][p] = vt[u];
+                if (nch > 1) {
+                    const float rx = vx[u], ry = vy[u];
+                    if (nch == 2) s_lat[wid][1][p] = sqrtf(rx * rx + ry * ry);
+                    else {
+                        s_lat[wid][2][p] = rx * co + ry * si;      // rry
+                        s_lat[wid][1][p] = -rx * si + ry * co;     // rrx
+                    }
                 }
             }
         }
