@@ -20,6 +20,10 @@ import argparse
 import ctypes as C
 import json
 import os
+
+# many contexts (streams) are pipelined: give every stream its own hardware queue (default 8 would alias unrelated contexts
+# onto one queue and serialise them); must be set before the CUDA context exists
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import subprocess
 import sys
 import threading
@@ -51,12 +55,29 @@ class ClockSampler(threading.Thread):
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, pci=None):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.pci, self.samples, self.stop_flag = index, pci, [], False
 
     def run(self):
-        while not self.stop_flag:
+        # NVML in-process (the library nvidia-smi itself reads): spawning nvidia-smi ten times a second inside the timed
+        # region takes driver locks for tens of ms and throttles the launching threads
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByPciBusId(self.pci.encode()) if self.pci else N.nvmlDeviceGetHandleByIndex(self.index)
+            reasons_fn = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")]
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                r = reasons_fn(h)
+                self.samples.append([str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx)] +
+                                    ["Active" if r & b else "Not Active" for b, _ in bits])
+                time.sleep(0.02)
+            return
+        except Exception:
+            pass
+        while not self.stop_flag:          # fallback: the nvidia-smi query line of the profiling recipe
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -64,7 +85,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.25)
 
     def summary(self):
         if not self.samples:
@@ -118,6 +139,22 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(props):
+    """Run this process (and the pinned buffers it first-touches) on the CPUs local to the GPU's PCIe root, like a deployed
+    service would; silently skipped when sysfs does not expose the topology."""
+    try:
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        cpus = set()
+        for part in open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -139,6 +176,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    if os.environ.get("CVB_BENCH_NUMA_BIND", "1") == "1":
+        bind_to_gpu_numa_node(torch.cuda.get_device_properties(local_rank))
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -149,8 +188,8 @@ def main():
     # Two independent contexts (each owns a CUDA stream + workspace; the ABI makes distinct contexts independent)
     # alternate steps, so the latency-bound keypoint tail of step i overlaps the image pipeline of step i+1.
     # Timing: CUDA events on the launching stream of context 0, bracketed by full-device synchronisation.
-    NCTX = int(os.environ.get("CVB_BENCH_CONTEXTS", "8"))          # contexts pipelined in the device-resident measurement
-    NHOST = min(NCTX, int(os.environ.get("CVB_BENCH_HOST_THREADS", "8")))   # host threads (one context each) in the e2e measurement
+    NCTX = int(os.environ.get("CVB_BENCH_CONTEXTS", "12"))          # contexts pipelined in the device-resident measurement
+    NHOST = min(NCTX, int(os.environ.get("CVB_BENCH_HOST_THREADS", "12")))   # host threads (one context each) in the e2e measurement
     ctxs = [cv_b200.Context(local_rank) for _ in range(NCTX)]
     ctx = ctxs[0]
     lib = ctx.lib
@@ -192,7 +231,12 @@ def main():
             step_dev(i, c)
     barrier()
     n_kp = outs[0].n.cpu().numpy().tolist()
-    sampler = ClockSampler(local_rank)
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        pci = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+    except Exception:
+        pci = None
+    sampler = ClockSampler(local_rank, pci)
     sampler.start()
     l0 = sum(cx.launch_count() for cx in ctxs)
     barrier()
@@ -222,16 +266,21 @@ def main():
             self.pairs = torch.empty(cap * 2, dtype=torch.int32).pin_memory()
             self.npairs = C.c_uint32()
             self.h2d = self.d2h = 0
+            self.t_extract = self.t_match = 0.0
+            self.steps = 0
     houts = [HostOut() for _ in range(NHOST)]
 
     def step_host(i, c):
         cx, o = ctxs[c], houts[c]
         img = h_pool[i % POOL_PAIRS]
+        t0 = time.perf_counter()
         cx.check(lib.cvb_akaze_extract_batch(cx.handle, C.byref(cfg), img.data_ptr(), 2, W, H, o.kp.data_ptr(), o.desc.data_ptr(),
                                              cap, o.n.data_ptr()))
+        t1 = time.perf_counter()
         na, nb = int(o.n[0]), int(o.n[1])
         cx.check(lib.cvb_match_symmetric(cx.handle, o.desc.data_ptr(), na, o.desc.data_ptr() + cap * 64, nb, BETTER_BY,
                                          o.pairs.data_ptr(), cap, C.byref(o.npairs)))
+        o.t_extract += t1 - t0; o.t_match += time.perf_counter() - t1; o.steps += 1
         o.h2d = 2 * W * H * 4 + (na + nb) * 64
         o.d2h = 8 + 4 + (na + nb) * (KP_DTYPE.itemsize + 64) + na * 4
         return o.npairs.value
@@ -263,6 +312,8 @@ def main():
     nm = houts[0].npairs.value
     barrier()
     t0 = time.perf_counter()
+    for o in houts:
+        o.t_extract = o.t_match = 0.0; o.steps = 0
     run_host(Wm, K)
     ms_e2e = (time.perf_counter() - t0) * 1e3     # blocking host API: wall clock over the K steps (all results on the host)
     barrier()
@@ -346,7 +397,10 @@ def main():
                            "detector_threshold": 0.001, "better_by": BETTER_BY,
                            "pipelining": f"{NCTX} contexts (CUDA streams + workspaces) alternate steps, CUDA graph per context; e2e: {NHOST} host threads",
                            "l2": f"inputs rotate over a pool of {2 * POOL_PAIRS} distinct frames ({2 * POOL_PAIRS * W * H * 4 / 1e6:.0f} MB > 126 MB L2)"},
-                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "host_threads": NHOST, "mean_call_ms": {"extract_batch": 1e3 * sum(o.t_extract for o in houts) / max(sum(o.steps for o in houts), 1),
+                                                               "match_symmetric": 1e3 * sum(o.t_match for o in houts) / max(sum(o.steps for o in houts), 1)},
+                        "steps_per_thread": [o.steps for o in houts]},
                 "gpu_launches": int(launches), "roofline": roofline, "hamming_Gcmp_per_s": gcmp, "ransac_two_view": ransac, "cpu_baseline": cpu,
                 "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)

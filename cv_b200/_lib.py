@@ -66,6 +66,8 @@ def load_library():
     if not os.path.exists(p):
         raise CvbError(CVB_ENODEV, f"{p} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                    f"or `make -C cv_b200/csrc`")
+    # one hardware queue per stream when many contexts are pipelined (effective only if CUDA is not initialised yet)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     L = C.CDLL(p)
     vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
     L.cvb_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]

@@ -744,10 +744,13 @@ int cvb_akaze_extract_batch(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, const float 
     const unsigned cap_dev = ws->cap_out;
     rc = run_extract(ctx, ws->img, batch, ws->kp_out, ws->desc_out, cap_dev, ws->n_out);
     if (rc) return rc;
-    unsigned ovf = 0;
-    CVB_CUDA(ctx, cudaMemcpyAsync(n_out, ws->n_out, sizeof(unsigned) * batch, cudaMemcpyDeviceToHost, st));
-    CVB_CUDA(ctx, cudaMemcpyAsync(&ovf, ws->overflow, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    unsigned *hs = (unsigned *)cvb_pinned(ctx, sizeof(unsigned) * ((size_t)batch + 1));
+    if (!hs) return cvb_set_error(ctx, CVB_ENOMEM, "page-locked scratch");
+    CVB_CUDA(ctx, cudaMemcpyAsync(hs, ws->n_out, sizeof(unsigned) * batch, cudaMemcpyDeviceToHost, st));
+    CVB_CUDA(ctx, cudaMemcpyAsync(hs + batch, ws->overflow, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CVB_CUDA(ctx, cudaStreamSynchronize(st));
+    const unsigned ovf = hs[batch];
+    for (uint32_t b = 0; b < batch; b++) n_out[b] = hs[b];
     if (ovf) {
         cudaMemsetAsync(ws->overflow, 0, sizeof(unsigned), st);
         if (ovf == 3) return cvb_set_error(ctx, CVB_ECAP, "output capacity %u too small", cap);

@@ -1262,29 +1262,44 @@ __global__ void __launch_bounds__(NT) k_filter_upper(const cvb_keypoint *__restr
                                                      unsigned char *__restrict__ keep) {
     __shared__ float s_x[NT], s_y[NT], s_r[NT];
     __shared__ unsigned s_c[NT];
+    __shared__ unsigned s_lo[NT / 32], s_hi[NT / 32];
     const int b = blockIdx.z;
     const unsigned n = ncache[b];
     const cvb_keypoint *kc = cache + (size_t)b * capk;
     const unsigned nchunks = (n + NT - 1) / NT;
-    for (unsigned ic = blockIdx.x; ic < nchunks; ic += gridDim.x)
+    for (unsigned ic = blockIdx.x; ic < nchunks; ic += gridDim.x) {
+        const unsigned i = ic * NT + threadIdx.x;
+        cvb_keypoint a = {};
+        if (i < n) a = kc[i];
+        // class range of this i-chunk: the cache is almost sorted by class, so most j-chunks hold no class this chunk's
+        // keypoints compare against (class + 1) and are skipped after one vote
+        unsigned lo = i < n ? a.class_id : 0xffffffffu, hi = i < n ? a.class_id : 0u;
+        lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+        __syncthreads();
+        for (int k = 0; k < NT / 32; k++) { lo = min(lo, s_lo[k]); hi = max(hi, s_hi[k]); }
+        const float s2 = a.size * a.size;
+        bool rep = false;
         for (unsigned jc = ic + blockIdx.y; jc < nchunks; jc += gridDim.y) {
-            const unsigned i = ic * NT + threadIdx.x, j = jc * NT + threadIdx.x;
-            __syncthreads();
-            if (j < n) { const cvb_keypoint q = kc[j]; s_x[threadIdx.x] = q.x; s_y[threadIdx.x] = q.y; s_r[threadIdx.x] = q.response; s_c[threadIdx.x] = q.class_id; }
+            const unsigned j = jc * NT + threadIdx.x;
+            cvb_keypoint q = {};
+            bool relevant = false;
+            if (j < n) { q = kc[j]; relevant = q.class_id >= lo + 1 && q.class_id <= hi + 1; }
+            if (!__syncthreads_or(relevant)) continue;          // also orders the previous round's reads before the stores below
+            if (j < n) { s_x[threadIdx.x] = q.x; s_y[threadIdx.x] = q.y; s_r[threadIdx.x] = q.response; s_c[threadIdx.x] = q.class_id; }
             __syncthreads();
             if (i >= n) continue;
-            const cvb_keypoint a = kc[i];
-            const float s2 = a.size * a.size;
             const unsigned lim = min((unsigned)NT, n - jc * NT);
-            bool rep = false;
             for (unsigned u = 0; u < lim; u++) {
                 if (jc * NT + u <= i || s_c[u] != a.class_id + 1) continue;
                 float dx = a.x - s_x[u], dy = a.y - s_y[u];
                 float dist = dx * dx + dy * dy;
                 if (dist <= s2 && a.response <= s_r[u]) rep = true;
             }
-            if (rep) keep[(size_t)b * capk + i] = 0;
         }
+        if (rep) keep[(size_t)b * capk + i] = 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -21,6 +21,10 @@ struct cvb_ctx {
     AkazeWorkspace *akaze = nullptr;
     MatchWorkspace *match = nullptr;
     GeomWorkspace *geom = nullptr;
+    // page-locked host scratch for the small device->host results of the host API (a D2H copy into pageable memory is
+    // staged synchronously inside the driver and stalls the other contexts' launches)
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
     // optional per-kernel CUDA-event profiling (bench.py roofline pass); off by default
     bool prof = false;
     std::vector<cudaEvent_t> prof_pool;
@@ -30,6 +34,7 @@ struct cvb_ctx {
 };
 
 cudaEvent_t cvb_prof_event(cvb_ctx *ctx);
+void *cvb_pinned(cvb_ctx *ctx, size_t bytes);   // >= bytes of page-locked scratch (nullptr on failure); valid until the next call
 struct CvbProfScope {
     cvb_ctx *ctx; const char *name; double bytes; cudaEvent_t e0 = nullptr;
     CvbProfScope(cvb_ctx *c, const char *n, double b) : ctx(c), name(n), bytes(b) {

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 #include "common.cuh"
 
@@ -22,6 +23,15 @@ cudaEvent_t cvb_prof_event(cvb_ctx *ctx) {
         ctx->prof_pool.push_back(e);
     }
     return ctx->prof_pool[ctx->prof_used++];
+}
+
+void *cvb_pinned(cvb_ctx *ctx, size_t bytes) {
+    if (ctx->pinned && ctx->pinned_bytes >= bytes) return ctx->pinned;
+    if (ctx->pinned) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
+    const size_t n = std::max<size_t>(bytes, 64 * 1024);
+    if (cudaHostAlloc(&ctx->pinned, n, cudaHostAllocDefault) != cudaSuccess) { ctx->pinned = nullptr; return nullptr; }
+    ctx->pinned_bytes = n;
+    return ctx->pinned;
 }
 
 extern "C" {
@@ -97,6 +107,7 @@ void cvb_ctx_destroy(cvb_ctx *ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     delete ctx;
 }
 

@@ -529,8 +529,9 @@ int cvb_match_symmetric(cvb_ctx *ctx, const uint8_t *a, uint32_t n, const uint8_
     if ((rc = knn_dev(ctx, ws->db, nullptr, m, ws->q, nullptr, n, 2, ws->idx2, ws->dist2))) return rc;
     k_symmetric<<<cdiv(n, 256), 256, 0, st>>>(ws->idx, ws->dist, ws->idx2, ws->dist2, n, m, better_by, ws->flag);
     CVB_LAUNCH_CHECK(ctx);
-    std::vector<uint32_t> flag(n);
-    CVB_CUDA(ctx, cudaMemcpyAsync(flag.data(), ws->flag, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    const uint32_t *flag = (const uint32_t *)cvb_pinned(ctx, sizeof(uint32_t) * (size_t)n);
+    if (!flag) return cvb_set_error(ctx, CVB_ENOMEM, "page-locked scratch");
+    CVB_CUDA(ctx, cudaMemcpyAsync((void *)flag, ws->flag, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
     CVB_CUDA(ctx, cudaStreamSynchronize(st));
     uint32_t cnt = 0;
     for (uint32_t i = 0; i < n; i++)
