@@ -104,6 +104,7 @@ struct AkazeWorkspace {
     float *img = nullptr;
     float *Lt = nullptr, *Lsm = nullptr, *Lx = nullptr, *Ly = nullptr, *Lflow = nullptr, *Ldet = nullptr;
     float *tmpA = nullptr, *tmpB = nullptr, *tmpC = nullptr;
+    bool fuse_blur_scharr = true;   // one launch per evolution for Lsmooth + Lflow (CVB_NO_FUSE_BLUR=1: the two separate kernels)
     double *g2 = nullptr;
     unsigned long long *gmax = nullptr;
     unsigned *hist = nullptr, *npoints = nullptr;
@@ -362,6 +363,8 @@ int ensure_workspace(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, uint32_t batch, uin
         ws->use_graph = !(env && env[0] == '1');
         env = getenv("CVB_NO_AUX_STREAM");
         ws->use_aux = !(env && env[0] == '1');
+        env = getenv("CVB_NO_FUSE_BLUR");
+        ws->fuse_blur_scharr = !(env && env[0] == '1');
         cudaStreamCreateWithFlags(&ws->aux, cudaStreamNonBlocking);
         for (auto &e : ws->ev_fork) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ws->ev_join, cudaEventDisableTiming);
@@ -553,14 +556,20 @@ int run_extract_eager(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoin
             CVB_LAUNCH_CHECK(ctx); }
             src = ws->tmpC; src_bs = P0;
         }
-        // Lsmooth = gaussian_blur(Lt, 1.0)
-        rc = launch_separable(ctx, src, src_bs, ws->Lsm + e.off, PF, e.w, e.h, B, ws->g1, ws->g1);
-        if (rc) return rc;
-        // Lflow = pm_g2(simple_scharr_x(Lsmooth), simple_scharr_y(Lsmooth), contrast)
-        { CVB_PROF(ctx, "k_scharr_pm", 8.0 * e.w * e.h * B);
-        k_scharr_pm_v3<0><<<dim3(cdiv((unsigned)e.w, SW3), cdiv((unsigned)e.h, SH3), B), NT, 0, st>>>(ws->Lsm + e.off, ws->Lflow + e.off, nullptr, nullptr, e.w, e.h, PF, PF,
-                                                             ws->inv_k + i, MAX_EVO);
-        CVB_LAUNCH_CHECK(ctx); }
+        // Lsmooth = gaussian_blur(Lt, 1.0); Lflow = pm_g2(simple_scharr_x(Lsmooth), simple_scharr_y(Lsmooth), contrast)
+        if (ws->fuse_blur_scharr && ws->g1.ks == 5) {
+            CVB_PROF(ctx, "k_blur_scharr", 16.0 * e.w * e.h * B);
+            k_blur_scharr_pm<<<dim3(cdiv((unsigned)e.w, SW3), cdiv((unsigned)e.h, SH3), B), NT, 0, st>>>(
+                src, ws->Lsm + e.off, ws->Lflow + e.off, e.w, e.h, src_bs, PF, PF, ws->g1, ws->inv_k + i, MAX_EVO);
+            CVB_LAUNCH_CHECK(ctx);
+        } else {
+            rc = launch_separable(ctx, src, src_bs, ws->Lsm + e.off, PF, e.w, e.h, B, ws->g1, ws->g1);
+            if (rc) return rc;
+            { CVB_PROF(ctx, "k_scharr_pm", 8.0 * e.w * e.h * B);
+            k_scharr_pm_v3<0><<<dim3(cdiv((unsigned)e.w, SW3), cdiv((unsigned)e.h, SH3), B), NT, 0, st>>>(ws->Lsm + e.off, ws->Lflow + e.off, nullptr, nullptr, e.w, e.h, PF, PF,
+                                                                 ws->inv_k + i, MAX_EVO);
+            CVB_LAUNCH_CHECK(ctx); }
+        }
         // FED steps: nl launches of at most FED_SMAX fused steps (balanced split); the chain ends in Lt_i
         const int n = (int)e.tau.size();
         const int fed_fuse = fed_fuse_steps();

@@ -681,6 +681,76 @@ __global__ void __launch_bounds__(NT) k_scharr_pm_v3(const float *__restrict__ i
 }
 
 // ---------------------------------------------------------------------------------------------
+// Lsmooth = gaussian_blur(L, 1.0) and Lflow = pm_g2(scharr(Lsmooth)) of one evolution in ONE launch (lib.rs:225-246).
+// The 5-tap blur runs over the 32 x 64 tile plus a one-pixel ring (34 x 66 values kept in shared memory, the tile part also
+// written to the Lsmooth plane); the Scharr stage is the body of k_scharr_pm_v3<0> reading that ring tile.  Ring positions
+// outside the image take the value of the clamped position, which is what the separate kernel's replicate-border staging of
+// the Lsmooth plane reads.  Same helpers and orders as the two separate kernels -> same bits.
+__global__ void __launch_bounds__(NT) k_blur_scharr_pm(const float *__restrict__ in, float *__restrict__ out_lsm,
+                                                       float *__restrict__ out_flow, int w, int h, size_t in_bstride,
+                                                       size_t lsm_bstride, size_t flow_bstride, Taps tk,
+                                                       const float *__restrict__ inv_k, int inv_k_stride) {
+    constexpr int RWI = SW3 + 6, RHI = SH3 + 6, LW = SW3 + 2, LH = SH3 + 2;
+    constexpr int BSTRIP = 10, NSTRIPS = (LH + BSTRIP - 1) / BSTRIP;     // 34 columns x 7 strips = 238 blur tasks
+    static_assert(LW * NSTRIPS <= NT, "one blur task per thread");
+    __shared__ float s_in[RHI * RWI];
+    __shared__ float s_l[LH * LW];
+    const int x0 = blockIdx.x * SW3, y0 = blockIdx.y * SH3;
+    stage_region<3, 3>(in + (size_t)blockIdx.z * in_bstride, w, h, x0, y0, s_in);
+    __syncthreads();
+    if (threadIdx.x < LW * NSTRIPS) {
+        const int sidx = threadIdx.x / LW, c = threadIdx.x - sidx * LW;
+        const int gx = x0 - 1 + c;
+        if (gx >= 0 && gx < w) {
+            float *lsm = out_lsm + (size_t)blockIdx.z * lsm_bstride;
+            const float *col = s_in + (sidx * BSTRIP) * RWI + c;   // ring row lr needs staged rows lr .. lr + 4, columns c .. c + 4
+            float hv[BSTRIP + 4];
+#pragma unroll
+            for (int r = 0; r < BSTRIP + 4; r++) {
+                hv[r] = sidx * BSTRIP + r < RHI ? lane_dot_static<5>(col + r * RWI, 1, tk.k) : 0.f;
+                if (r >= 4) {
+                    const int lr = sidx * BSTRIP + r - 4, gy = y0 - 1 + lr;
+                    if (lr < LH && gy >= 0 && gy < h) {
+                        const float v = lane_dot_regs<5>(hv + (r - 4), tk.k);
+                        s_l[lr * LW + c] = v;
+                        if (lr >= 1 && lr <= SH3 && c >= 1 && c <= SW3) lsm[(size_t)gy * w + gx] = v;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (x0 < 1 || y0 < 1 || x0 + SW3 + 1 > w || y0 + SH3 + 1 > h) {      // the ring leaves the image (CTA-uniform)
+        for (int p = threadIdx.x; p < LH * LW; p += NT) {
+            const int lr = p / LW, lc = p - lr * LW, gy = y0 - 1 + lr, gx = x0 - 1 + lc;
+            if (gx < 0 || gx >= w || gy < 0 || gy >= h)
+                s_l[p] = s_l[(clampi(gy, 0, h - 1) - (y0 - 1)) * LW + (clampi(gx, 0, w - 1) - (x0 - 1))];
+        }
+        __syncthreads();
+    }
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int gx = x0 + tx;
+    if (gx >= w) return;
+    const float ik = inv_k[(size_t)blockIdx.z * inv_k_stride];
+    const float *col = s_l + (ty * STRIP) * LW + tx;
+    float hm[STRIP + 2], ho[STRIP + 2];
+#pragma unroll
+    for (int r = 0; r < STRIP + 2; r++) {
+        const float a = col[r * LW], m = col[r * LW + 1], z = col[r * LW + 2];
+        hm[r] = dot2<0, 2>(a, -1.0f, z, 1.0f);                 // H [-1,0,1]
+        ho[r] = dot3<0, 1, 2>(a, 3.0f, m, 10.0f, z, 3.0f);     // H [3,10,3]
+        if (r >= 2) {
+            const int o = r - 2, gy = y0 + ty * STRIP + o;
+            if (gy < h) {
+                const float dx = dot3<0, 1, 2>(hm[o], 3.0f, hm[o + 1], 10.0f, hm[o + 2], 3.0f);   // V [3,10,3]
+                const float dy = dot2<0, 2>(ho[o], -1.0f, ho[o + 2], 1.0f);                        // V [-1,0,1]
+                out_flow[(size_t)blockIdx.z * flow_bstride + (size_t)gy * w + gx] = 1.0f / (1.0f + ik * (dx * dx + dy * dy));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Extrema detection: one pass over Ldet in 32 x 64 column-strip tiles produces a 1-bit-per-pixel mask
 // (strict 3x3 maximum above the threshold on interior pixels, scale_space_extrema.rs:49-59: v > each of the
 // eight neighbours <=> v > their maximum) plus per-row counts; a second, tiny pass turns mask words into the
