@@ -244,6 +244,7 @@ def main():
     ctx.timer_begin()
     for i in range(K):
         step_dev(Wm + i)
+    enqueue_ms = (time.perf_counter() - t0) * 1e3      # host time to launch all K steps (one thread); must stay below the device time
     for cx in ctxs[1:]:
         cx.sync()                 # the other stream has drained before the end event is recorded
     ms = ctx.timer_end()          # CUDA events on context 0's launching stream; waits for the end event
@@ -391,7 +392,7 @@ def main():
                          "OpenMP only at the reference's rayon sites"}
     if rank == 0:
         line = {"metric": "vSLAM frames/s (AKAZE+match, 1080p ~5k kp)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
-                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "ms_per_step": ms_max / K, "enqueue_ms_per_step": enqueue_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "configs[1]: AKAZE extract x2 + symmetric Hamming 2-NN, 2 frames 1920x1080 f32, ~5k kp/frame",
                            "frames_per_step_per_gpu": 2, "keypoints_per_frame": n_kp, "matches": int(nm), "maximum_features": MAXF,
                            "detector_threshold": 0.001, "better_by": BETTER_BY,

@@ -1369,6 +1369,19 @@ int estimate_host(cvb_ctx *ctx, int kind, const double *a, const double *b, uint
     return 0;
 }
 
+// poses (g->out) and per-problem update counts (g->ok) through page-locked scratch to the caller's (possibly pageable) arrays
+int download_poses_updates(cvb_ctx *ctx, GeomWorkspace *g, cvb_pose *poses_out, size_t nposes, uint32_t *updates_out, uint32_t B) {
+    const size_t pb = sizeof(cvb_pose) * nposes, ub = sizeof(uint32_t) * (size_t)B;
+    unsigned char *hs = (unsigned char *)cvb_pinned(ctx, pb + ub);
+    if (!hs) return cvb_set_error(ctx, CVB_ENOMEM, "page-locked scratch");
+    CVB_CUDA(ctx, cudaMemcpyAsync(hs, g->out.p, pb, cudaMemcpyDeviceToHost, ctx->stream));
+    CVB_CUDA(ctx, cudaMemcpyAsync(hs + pb, g->ok.p, ub, cudaMemcpyDeviceToHost, ctx->stream));
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(poses_out, hs, pb);
+    if (updates_out) memcpy(updates_out, hs + pb, ub);
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1521,12 +1534,7 @@ int cvb_single_view_optimize_l2(cvb_ctx *ctx, const cvb_pose *poses, uint32_t B,
                                                          (uint32_t *)g->ok.p);
         CVB_LAUNCH_CHECK(ctx);
     }
-    CVB_CUDA(ctx, cudaMemcpyAsync(poses_out, g->out.p, sizeof(cvb_pose) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
-    std::vector<uint32_t> upd(B);
-    CVB_CUDA(ctx, cudaMemcpyAsync(upd.data(), g->ok.p, sizeof(uint32_t) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (updates_out) memcpy(updates_out, upd.data(), sizeof(uint32_t) * (size_t)B);
-    return 0;
+    return download_poses_updates(ctx, g, poses_out, (size_t)B, updates_out, B);
 }
 
 int cvb_three_view_optimize_l2(cvb_ctx *ctx, const cvb_pose *poses, uint32_t B, int32_t adaptive, double optimization_rate,
@@ -1553,12 +1561,7 @@ int cvb_three_view_optimize_l2(cvb_ctx *ctx, const cvb_pose *poses, uint32_t B, 
                                                         adaptive ? 1 : 0, optimization_rate, iterations, (cvb_pose *)g->out.p, (uint32_t *)g->ok.p);
         CVB_LAUNCH_CHECK(ctx);
     }
-    CVB_CUDA(ctx, cudaMemcpyAsync(poses_out, g->out.p, sizeof(cvb_pose) * 2 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
-    std::vector<uint32_t> upd(B);
-    CVB_CUDA(ctx, cudaMemcpyAsync(upd.data(), g->ok.p, sizeof(uint32_t) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (updates_out) memcpy(updates_out, upd.data(), sizeof(uint32_t) * (size_t)B);
-    return 0;
+    return download_poses_updates(ctx, g, poses_out, 2 * (size_t)B, updates_out, B);
 }
 
 int cvb_observation_losses(cvb_ctx *ctx, const cvb_pose *poses, const double *bearings, const uint32_t *offsets, uint32_t L,
