@@ -1443,20 +1443,28 @@ __global__ void __launch_bounds__(NT) k_refine_orient(const cvb_keypoint *__rest
         __syncwarp();
         float best_val = 0.f, best_sx = 0.f, best_sy = 0.f;
         int best_w = 0x7fffffff;
-        for (int wi = lane; wi < OT->nwin; wi += 32) {
-            const float ang1 = OT->ang1[wi];
-            const float ang2 = (ang1 + PI / 3.0f > two_pi) ? ang1 - 5.0f * PI / 3.0f : ang1 + PI / 3.0f;
-            float sum_x = 0.f, sum_y = 0.f;
+        // two consecutive windows per lane in ONE pass over the samples (42 windows -> lanes 0..20; one window per lane needed a
+        // second, mostly idle pass for windows 32..41); each window still adds its samples in sample order
+        for (int wa = 2 * lane; wa < OT->nwin; wa += 64) {
+            const int wb = wa + 1;
+            const bool hasb = wb < OT->nwin;
+            const float a1 = OT->ang1[wa], b1 = hasb ? OT->ang1[wb] : 0.f;
+            const float a2 = (a1 + PI / 3.0f > two_pi) ? a1 - 5.0f * PI / 3.0f : a1 + PI / 3.0f;
+            const float b2 = (b1 + PI / 3.0f > two_pi) ? b1 - 5.0f * PI / 3.0f : b1 + PI / 3.0f;
+            float sxa = 0.f, sya = 0.f, sxb = 0.f, syb = 0.f;
             for (int k = 0; k < 109; k++) {
-                float ang = s_an[wid][k];
-                if ((ang1 < ang2 && ang1 < ang && ang < ang2) ||
-                    (ang2 < ang1 && ((ang > 0.f && ang < ang2) || (ang > ang1 && ang < two_pi)))) {
-                    sum_x += s_rx[wid][k];
-                    sum_y += s_ry[wid][k];
-                }
+                const float ang = s_an[wid][k], rx = s_rx[wid][k], ry = s_ry[wid][k];
+                const bool ina = (a1 < a2 && a1 < ang && ang < a2) || (a2 < a1 && ((ang > 0.f && ang < a2) || (ang > a1 && ang < two_pi)));
+                const bool inb = (b1 < b2 && b1 < ang && ang < b2) || (b2 < b1 && ((ang > 0.f && ang < b2) || (ang > b1 && ang < two_pi)));
+                if (ina) { sxa += rx; sya += ry; }
+                if (inb) { sxb += rx; syb += ry; }
             }
-            float val = sum_x * sum_x + sum_y * sum_y;
-            if (val > best_val) { best_val = val; best_sx = sum_x; best_sy = sum_y; best_w = wi; }
+            const float va = sxa * sxa + sya * sya;
+            if (va > best_val) { best_val = va; best_sx = sxa; best_sy = sya; best_w = wa; }
+            if (hasb) {
+                const float vb = sxb * sxb + syb * syb;
+                if (vb > best_val) { best_val = vb; best_sx = sxb; best_sy = syb; best_w = wb; }
+            }
         }
         // sequential `if val > max` == first window attaining the maximum (when > 0)
         for (int o = 16; o; o >>= 1) {
