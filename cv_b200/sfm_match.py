@@ -11,7 +11,7 @@ import numpy as np
 from .knn import hamming_knn
 
 
-def landmark_matches(new_descriptors, views, better_by=24, landmark_views=None, landmark_observations=None, ctx=None):
+def landmark_matches(new_descriptors, views, better_by=24, landmark_views=None, landmark_observations=None, ctx=None, knn=None):
     """new_descriptors[N, 64]; views = [(descriptors[M_v, 64], landmarks[M_v] int), ...] for every matched view.
 
     Returns [(landmarks, feature)] with landmarks a 1- or 2-tuple:
@@ -19,7 +19,8 @@ def landmark_matches(new_descriptors, views, better_by=24, landmark_views=None, 
       * the best two when `d1 + better_by <= d2` and they share no view (`landmark_views`: landmark -> iterable of view
         keys; omitted = never sharing) -- a merge candidate;
     then drops every match whose landmark is claimed by more than one feature, and stable-sorts by the summed observation
-    count of its landmarks, descending (`landmark_observations`: landmark -> count; omitted = keep order)."""
+    count of its landmarks, descending (`landmark_observations`: landmark -> count; omitted = keep order).
+    `knn(queries, database, k) -> (idx, dist)` replaces the GPU matcher (host-logic tests only)."""
     q = np.ascontiguousarray(new_descriptors, np.uint8)
     if len(views) == 0 or len(q) == 0:
         return []
@@ -28,7 +29,7 @@ def landmark_matches(new_descriptors, views, better_by=24, landmark_views=None, 
         landmarks = np.asarray(landmarks, np.int64)
         if len(landmarks) != len(desc):
             raise ValueError("one landmark per view feature expected")
-        idx, d = hamming_knn(q, desc, 3, ctx)                      # one N x M launch per view
+        idx, d = knn(q, desc, 3) if knn else hamming_knn(q, desc, 3, ctx)      # one N x M launch per view
         missing = idx == 0xFFFFFFFF
         lm.append(np.where(missing, -1, landmarks[np.where(missing, 0, idx)]))
         dist.append(np.where(missing, 1 << 20, d).astype(np.int64))
