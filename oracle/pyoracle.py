@@ -484,3 +484,19 @@ def landmark_matches_ref(new_descriptors, views, better_by=24, landmark_views=No
     if landmark_observations is not None:
         kept = sorted(kept, key=lambda m: -sum(landmark_observations[l] for l in m[0]))
     return kept
+
+
+def fp_o1(a, b):
+    """nister-stewenius o1: product of two linear polynomials (x, y, z, 1 coefficients) in the 20-term basis"""
+    a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64); r = np.zeros(20)
+    L = _geom(); L.ref_fp_o1.argtypes = [C.POINTER(C.c_double)] * 3
+    L.ref_fp_o1(_dp(a), _dp(b), _dp(r))
+    return r
+
+
+def fp_o2(a, b):
+    """nister-stewenius o2: (degree <= 2 polynomial in the 20-term layout) x (linear polynomial)"""
+    a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64); r = np.zeros(20)
+    L = _geom(); L.ref_fp_o2.argtypes = [C.POINTER(C.c_double)] * 3
+    L.ref_fp_o2(_dp(a), _dp(b), _dp(r))
+    return r

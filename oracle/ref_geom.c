@@ -733,6 +733,10 @@ int ref_p3p(const double *bearings, const double *world, ref_pose out[4]) {
     return nl;
 }
 
+/* exported for the tests that mirror nister-stewenius/src/lib.rs:368-417 (o1_manual, o2_manual) */
+void ref_fp_o1(const double *a, const double *b, double *r) { fp_o1(a, b, r); }
+void ref_fp_o2(const double *a, const double *b, double *r) { fp_o2(a, b, r); }
+
 /* ------------------------------------------------------------------ triangulation */
 /* cv-geom/src/triangulation.rs:82-130: n (pose, bearing) observations -> homogeneous world point; returns 1 = Some */
 int ref_triangulate_linear_eigen(const ref_pose *poses, const double *bearings, int n, double *out) {

@@ -23,6 +23,8 @@ int ref_real_eigenvalues10(const double *A, double *wr, double *wi);
 int ref_five_point_essentials(const double *a, const double *b, double *Es);
 int ref_five_point(const double *a, const double *b, ref_pose *out);
 void ref_five_point_set_row0(int r0);
+void ref_fp_o1(const double *a, const double *b, double *r);   /* degree-1 x degree-1 -> 20-term basis */
+void ref_fp_o2(const double *a, const double *b, double *r);   /* degree-2 (20-term layout) x degree-1 */
 double ref_essential_residual(const double *E, const double *a, const double *b);
 double ref_residual_c2c(const ref_pose *P, const double *a, const double *b);
 double ref_residual_w2c(const ref_pose *P, const double *bearing, const double *world);

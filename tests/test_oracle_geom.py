@@ -180,3 +180,44 @@ def test_five_point_restatement_and_reference_quirk():
         assert hits() == 0
     finally:
         O.five_point_set_row0(5)
+
+
+# ---- the two unit tests the reference holds for the five-point solver's polynomial products (nister-stewenius/src/lib.rs:336-417)
+_BASIS = dict(XXX=0, XXY=1, XYY=2, YYY=3, XXZ=4, XYZ=5, YYZ=6, XZZ=7, YZZ=8, ZZZ=9, XX=10, XY=11, YY=12, XZ=13, YZ=14, ZZ=15, X=16, Y=17, Z=18, ONE=19)
+
+
+def _eval_polynomial(p, x, y, z):
+    B = _BASIS
+    return (p[B["XXX"]] * x * x * x + p[B["XXY"]] * x * x * y + p[B["XXZ"]] * x * x * z + p[B["XYY"]] * x * y * y + p[B["XYZ"]] * x * y * z
+            + p[B["XZZ"]] * x * z * z + p[B["YYY"]] * y * y * y + p[B["YYZ"]] * y * y * z + p[B["YZZ"]] * y * z * z + p[B["ZZZ"]] * z * z * z
+            + p[B["XX"]] * x * x + p[B["XY"]] * x * y + p[B["XZ"]] * x * z + p[B["YY"]] * y * y + p[B["YZ"]] * y * z + p[B["ZZ"]] * z * z
+            + p[B["X"]] * x + p[B["Y"]] * y + p[B["Z"]] * z + p[B["ONE"]])
+
+
+def _vec_to_poly_basis(v):
+    p = np.zeros(20)
+    p[_BASIS["X"]], p[_BASIS["Y"]], p[_BASIS["Z"]], p[_BASIS["ONE"]] = v
+    return p
+
+
+def test_o1_manual_reference_unit_test():
+    p1, p2 = np.array([0.1, 0.8, 0.3, 0.2]), np.array([0.5, 0.45, 0.82, 0.15])
+    p3 = O.fp_o1(p1, p2)
+    for z in range(-5, 5):
+        for y in range(-5, 5):
+            for x in range(-5, 5):
+                want = _eval_polynomial(_vec_to_poly_basis(p1), x, y, z) * _eval_polynomial(_vec_to_poly_basis(p2), x, y, z)
+                assert abs(_eval_polynomial(p3, x, y, z) - want) < 1e-6
+
+
+def test_o2_manual_reference_unit_test():
+    p1 = np.zeros(20)
+    for name, v in (("XX", 0.2), ("XY", 0.81), ("XZ", 0.66), ("YY", 0.91), ("YZ", 0.88), ("ZZ", 0.14), ("X", 0.97), ("Y", 0.3), ("Z", 0.38), ("ONE", 0.72)):
+        p1[_BASIS[name]] = v
+    p2 = np.array([0.5, 0.45, 0.82, 0.15])
+    p3 = O.fp_o2(p1, p2)
+    for z in range(-5, 5):
+        for y in range(-5, 5):
+            for x in range(-5, 5):
+                want = _eval_polynomial(p1, x, y, z) * _eval_polynomial(_vec_to_poly_basis(p2), x, y, z)
+                assert abs(_eval_polynomial(p3, x, y, z) - want) < 1e-8
