@@ -309,6 +309,8 @@ int build_tables(cvb_ctx *ctx, AkazeWorkspace *ws) {
     return 0;
 }
 
+int build_workspace(cvb_ctx *ctx, AkazeWorkspace *ws, const cvb_akaze_cfg *cfg, uint32_t batch, uint32_t w, uint32_t h, unsigned cap_out);
+
 int ensure_workspace(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, uint32_t batch, uint32_t w, uint32_t h, unsigned cap_out) {
     AkazeWorkspace *ws = ctx->akaze;
     if (ws && same_cfg(ws->cfg, *cfg) && ws->w == w && ws->h == h && ws->batch >= batch && ws->cap_out >= cap_out) return 0;
@@ -318,8 +320,16 @@ int ensure_workspace(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, uint32_t batch, uin
     if (cfg->num_sublevels < 1) return cvb_set_error(ctx, CVB_EINVAL, "num_sublevels must be >= 1");
     if (!(cfg->base_scale_offset > 0.0)) return cvb_set_error(ctx, CVB_EINVAL, "sigma must be > 0.0");   // image.rs:384
     ws = new AkazeWorkspace();
-    ctx->akaze = ws;
     ws->cfg = *cfg; ws->w = w; ws->h = h; ws->batch = batch; ws->cap_out = cap_out;
+    // the workspace is published on the context only when it is complete: a failed build must not satisfy the
+    // fast path of the next call with identical arguments
+    int rc = build_workspace(ctx, ws, cfg, batch, w, h, cap_out);
+    if (rc) { cudaStreamSynchronize(ctx->stream); akaze_workspace_free(ws); return rc; }
+    ctx->akaze = ws;
+    return 0;
+}
+
+int build_workspace(cvb_ctx *ctx, AkazeWorkspace *ws, const cvb_akaze_cfg *cfg, uint32_t batch, uint32_t w, uint32_t h, unsigned cap_out) {
     int rc = plan_evolutions(ctx, ws);
     if (rc) return rc;
     if (make_gauss_taps((float)cfg->base_scale_offset, &ws->g0)) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "base_scale_offset too large");

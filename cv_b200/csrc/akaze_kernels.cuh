@@ -1708,7 +1708,8 @@ __global__ void __launch_bounds__(1024) k_compact_final(const cvb_keypoint *__re
         if (threadIdx.x == 1023) s_carry = pos + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) n_out[b] = s_carry;
+    // the count never exceeds the capacity (the overflow flag reports the truncation): downstream kernels index by it
+    if (threadIdx.x == 0) n_out[b] = min(s_carry, cap_out);
 }
 
 }  // namespace akz

@@ -1,0 +1,638 @@
+// cv_b200/csrc/arrsac_dev.cuh -- arrsac::Arrsac::model_inliers entirely on the device (included by geom.cu).
+//
+// The reference loop (external crate arrsac 0.10.0, restated for the CPU checker under the test tree; call sites
+// cv-sfm/src/lib.rs:1394-1406, vslam-sandbox/src/main.rs:105-117, akaze/tests/estimate_pose.rs:63-75) is sequential in
+// three places: the random draws, the adaptive likelihood-ratio test over the initial hypotheses, and the block loop
+// (score, stable sort, halve, re-estimate from the best inlier set).  Round 1 ran that bookkeeping on the host with
+// ~3 stream synchronisations per 64-datum block.  Here nothing returns to the host between enqueue and result:
+//
+//   k_ars_begin     minimal samples of all initial hypotheses from a pre-generated stream of raw u32 draws (the modulo and
+//                   the rejection of repeats need n, which may only exist on the device); one warp, 32 draws per step
+//   k_ars_estimate  eight-point / P3P / five-point per hypothesis (k_estimate's device functions)
+//   k_ars_score     one warp per (model, 32 data): inlier bits by ballot.  CameraToCamera bits come from the exact-predicate
+//                   filter (c2c_filter.cuh) with the Jacobi evaluation as fallback
+//   k_ars_sprt      one CTA: the adaptive SPRT over all initial models in order.  1024 models are walked concurrently under a
+//                   BOX of possible (epsilon, delta) states; f32 multiplication is monotone, so a model whose walk ends at the
+//                   same datum for both corners of the box has that outcome for every state inside.  Prefix sums over the
+//                   chunk then give the exact state in front of every model; everything up to the first model whose state
+//                   leaves the box (or whose corners disagree, or which raises epsilon) is committed, and the next chunk starts
+//                   there with a new box.  Then: stable top-max_candidate selection (histogram + ordered compaction + bitonic).
+//   k_ars_book      one CTA per block of data: accept the new hypotheses that beat the bar, stable sort, truncate, termination
+//                   test, add the next block's inliers, stable sort, halve, inlier pool of the best, next minimal samples.
+//   k_ars_final     inlier list of the winner.
+// The candidate table is double buffered (rows = pose + inlier count + inlier bit mask); every k_ars_book writes the
+// surviving rows in sorted order into the other buffer, so there is no free list and no indirection.
+#pragma once
+
+#define ARS_SORT_CAP 4096u     // max_candidate_hypotheses + estimations_per_block * models_per_sample must fit
+#define ARS_BOOK_NT 1024
+#define ARS_BOOK_SMEM (14u * ARS_SORT_CAP)
+
+struct ArrsacCtl {
+    uint32_t n, init_n, Mv, npass;
+    uint32_t Hn, cur, blk_lo, blk_hi;
+    uint32_t acc_hi, n_new, worst, done;
+    uint32_t found, iters, nraw, pad0;
+    uint64_t rng_pos, gen_pos;
+    cvb_rng gen;                 // generator positioned at raw index gen_pos (continues the stream when it is exhausted)
+    cvb_pose winner;
+    uint32_t n_inliers, overflow;
+    uint32_t stat_chunks, stat_pass;
+};
+
+struct ArrsacParams {            // launch-constant configuration (by value)
+    uint32_t K, MM, kind;        // MIN_SAMPLES, models per sample, estimator kind
+    uint32_t H0, ib, bs, max_cand, G;
+    uint32_t W0;                 // mask words per model of the initialisation (ceil(bs * ib / 32))
+    uint32_t NW;                 // mask words per candidate row (ceil(NMAX / 32))
+    uint32_t NMAX;               // data capacity
+    uint32_t rows;               // candidate rows per table (max_cand + G * MM)
+    float lr_thr, eps0, delta0;
+    double thr;
+    int row0;
+};
+
+__device__ __forceinline__ uint64_t ars_rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+__device__ uint32_t ars_rng_next_u32(cvb_rng *r) {
+    if (r->kind == 0) {
+        uint64_t *s = r->s;
+        const uint64_t result = ars_rotl64(s[0] + s[3], 23) + s[0];
+        const uint64_t t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = ars_rotl64(s[3], 45);
+        return (uint32_t)(result >> 32);
+    }
+    unsigned __int128 state = (unsigned __int128)r->s[0] | ((unsigned __int128)r->s[1] << 64);
+    const unsigned __int128 incr = (unsigned __int128)r->s[2] | ((unsigned __int128)r->s[3] << 64);
+    const unsigned __int128 MUL = ((unsigned __int128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+    state = state * MUL + incr;
+    r->s[0] = (uint64_t)state; r->s[1] = (uint64_t)(state >> 64);
+    const uint32_t rot = (uint32_t)(state >> 122);
+    const uint64_t xsl = (uint64_t)(state >> 64) ^ (uint64_t)state;
+    return (uint32_t)((xsl >> rot) | (xsl << ((64 - rot) & 63)));
+}
+
+// raw draw number pos of the caller's generator (sequential consumers only: pos never decreases)
+__device__ uint32_t ars_raw_at(ArrsacCtl *ctl, const uint32_t *raw, uint64_t pos) {
+    if (pos < ctl->nraw) return raw[pos];
+    uint32_t v = 0;
+    while (ctl->gen_pos <= pos) { v = ars_rng_next_u32(&ctl->gen); ctl->gen_pos++; }
+    return v;
+}
+
+// `count` minimal samples of K distinct indices below len: next_u32() % len with rejection of repeats, exactly in the
+// reference's draw order.  Executed by one full warp.  32/K samples per step are taken from 32 consecutive draws when none
+// of them repeats inside its sample (the common case); a sample with a repeat is redone draw by draw by lane 0.
+__device__ void ars_sample_warp(ArrsacCtl *ctl, const uint32_t *raw, uint32_t len, uint32_t K, uint32_t count, uint32_t *out,
+                                const uint32_t *map) {
+    const unsigned full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31, hps = 32 / K;
+    const uint32_t g = lane / K, k = lane % K;
+    uint64_t pos = ctl->rng_pos;
+    const uint32_t nraw = ctl->nraw;
+    uint32_t h = 0;
+    while (h < count) {
+        if (pos + 32 <= nraw) {
+            const uint32_t ng = min(hps, count - h);
+            const bool act = g < ng;
+            const uint32_t s = raw[pos + lane] % len;
+            bool dup = false;
+            for (uint32_t j = 1; j < K; j++) {
+                const uint32_t o = __shfl_sync(full, s, (lane - j) & 31);
+                if (k >= j && o == s) dup = true;
+            }
+            const unsigned dm = __ballot_sync(full, act && dup);
+            const uint32_t good = dm ? (uint32_t)(__ffs(dm) - 1) / K : ng;
+            if (act && g < good) out[(size_t)(h + g) * K + k] = map ? map[s] : s;
+            h += good; pos += (uint64_t)good * K;
+            if (good == ng) continue;
+        }
+        if (lane == 0) {
+            uint32_t loc[8];
+            for (uint32_t c = 0; c < K;) {
+                const uint32_t s = ars_raw_at(ctl, raw, pos) % len;
+                pos++;
+                bool dup = false;
+                for (uint32_t j = 0; j < c; j++) dup |= loc[j] == s;
+                if (!dup) { loc[c] = s; out[(size_t)h * K + c] = map ? map[s] : s; c++; }
+            }
+        }
+        pos = __shfl_sync(full, pos, 0);
+        h++;
+    }
+    if (lane == 0) ctl->rng_pos = pos;
+    __syncwarp();
+}
+
+// ---- k_ars_begin ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_ars_begin(ArrsacCtl *ctl, ArrsacParams P, const uint32_t *n_dev, uint32_t n_host,
+                                                  const uint32_t *raw, uint32_t *samples0) {
+    const uint32_t n = min(n_dev ? *n_dev : n_host, P.NMAX);
+    if (threadIdx.x == 0) {
+        ctl->n = n;
+        ctl->init_n = min(P.bs * P.ib, n);
+        ctl->Mv = 0; ctl->npass = 0; ctl->Hn = 0; ctl->cur = 0; ctl->blk_lo = ctl->blk_hi = ctl->acc_hi = 0;
+        ctl->n_new = 0; ctl->worst = 0; ctl->found = 0; ctl->iters = 0; ctl->n_inliers = 0; ctl->overflow = 0;
+        ctl->stat_chunks = 0; ctl->stat_pass = 0;
+        ctl->done = (n < P.K || P.H0 == 0) ? 1u : 0u;
+    }
+    __syncwarp();
+    if (n < P.K || P.H0 == 0) return;
+    ars_sample_warp(ctl, raw, n, P.K, P.H0, samples0, nullptr);
+}
+
+// ---- k_ars_estimate ------------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(128) k_ars_estimate(const ArrsacCtl *ctl, int phase, uint32_t H_init, const double *__restrict__ a,
+                                                      const double *__restrict__ b, const uint32_t *__restrict__ samples,
+                                                      cvb_pose *poses, uint8_t *nposes, int row0) {
+    if (ctl->done) return;
+    const uint32_t H = phase == 0 ? H_init : ctl->n_new;
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    if (KIND == 2) { nposes[h] = (uint8_t)five_point(a, b, samples + (size_t)h * 5, row0, poses + (size_t)h * 40); return; }
+    cvb_pose out[4];
+    int n;
+    if (KIND == 0) n = eight_point(a, b, samples + (size_t)h * 8, out);
+    else n = p3p(a, b, samples + (size_t)h * 3, out);
+    for (int k = 0; k < n; k++) poses[(size_t)h * 4 + k] = out[k];
+    nposes[h] = (uint8_t)n;
+}
+
+// ---- k_ars_score ---------------------------------------------------------------------------------------------------------
+template <int RES>
+__device__ __forceinline__ bool ars_inlier(const cvb_pose &Pz, const double *__restrict__ a, const double *__restrict__ b, uint32_t i,
+                                           double thr) {
+    if (RES == 1) return residual_w2c(Pz, a + 3 * (size_t)i, b + 4 * (size_t)i) < thr;
+    const double *pa = a + 3 * (size_t)i, *pb = b + 3 * (size_t)i;
+    int f = c2c_inlier_filter(Pz.r, Pz.t, pa, pb, thr);
+    if (f < 0) f = residual_c2c(Pz, pa, pb) < thr ? 1 : 0;
+    return f != 0;
+}
+
+// phase 0: every initial model on data [0, init_n) -> masks0[model * W0 + w]
+// phase 1: kept candidate rows on [blk_lo, blk_hi) merged into their mask rows; new models on [0, blk_hi) -> newmask rows
+template <int RES>
+__global__ void __launch_bounds__(256) k_ars_score(const ArrsacCtl *ctl, ArrsacParams P, int phase, const double *__restrict__ a,
+                                                   const double *__restrict__ b, const cvb_pose *__restrict__ poses0,
+                                                   const uint8_t *__restrict__ nposes0, uint32_t *__restrict__ masks0,
+                                                   const cvb_pose *__restrict__ tposes, uint32_t *__restrict__ tmasks,
+                                                   const cvb_pose *__restrict__ newposes, const uint8_t *__restrict__ nposes_new,
+                                                   uint32_t *__restrict__ newmask) {
+    if (ctl->done) return;
+    const unsigned full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    if (phase == 0) {
+        const uint32_t init_n = ctl->init_n, W = (init_n + 31) >> 5;
+        const uint32_t units = P.H0 * P.MM * W;
+        for (uint32_t u = warp; u < units; u += nwarps) {
+            const uint32_t m = u / W, w = u % W;
+            if ((m % P.MM) >= nposes0[m / P.MM]) continue;
+            const uint32_t i = w * 32 + lane;
+            bool bit = false;
+            if (i < init_n) bit = ars_inlier<RES>(poses0[m], a, b, i, P.thr);
+            const unsigned bits = __ballot_sync(full, bit);
+            if (lane == 0) masks0[(size_t)m * P.W0 + w] = bits;
+        }
+        return;
+    }
+    const uint32_t lo = ctl->blk_lo, hi = ctl->blk_hi, Hn = ctl->Hn, cur = ctl->cur;
+    const uint32_t wlo = lo >> 5, nwb = hi > lo ? ((hi - 1) >> 5) - wlo + 1 : 0;
+    const uint32_t kept_units = Hn * nwb;
+    const uint32_t nnew = ctl->n_new * P.MM, nwn = (hi + 31) >> 5;
+    const uint32_t units = kept_units + nnew * nwn;
+    const cvb_pose *tp = tposes + (size_t)cur * P.rows;
+    uint32_t *tm = tmasks + (size_t)cur * P.rows * P.NW;
+    for (uint32_t u = warp; u < units; u += nwarps) {
+        if (u < kept_units) {
+            const uint32_t r = u / nwb, w = wlo + u % nwb;
+            const uint32_t i = w * 32 + lane;
+            const bool act = i >= lo && i < hi;
+            bool bit = false;
+            if (act) bit = ars_inlier<RES>(tp[r], a, b, i, P.thr);
+            const unsigned bits = __ballot_sync(full, bit), range = __ballot_sync(full, act);
+            if (lane == 0) { uint32_t *p = tm + (size_t)r * P.NW + w; *p = (*p & ~range) | bits; }
+        } else {
+            const uint32_t v = u - kept_units;
+            const uint32_t j = v / nwn, w = v % nwn;
+            if ((j % P.MM) >= nposes_new[j / P.MM]) continue;
+            const uint32_t i = w * 32 + lane;
+            bool bit = false;
+            if (i < hi) bit = ars_inlier<RES>(newposes[j], a, b, i, P.thr);
+            const unsigned bits = __ballot_sync(full, bit);
+            if (lane == 0) newmask[(size_t)j * P.NW + w] = bits;
+        }
+    }
+}
+
+// ---- block-wide helpers (ARS_BOOK_NT threads) ----------------------------------------------------------------------------
+// inclusive scan of three u32 values per thread; total of component k in tot[k]
+__device__ void ars_scan3(uint32_t &a, uint32_t &b, uint32_t &c, uint32_t *sm /* 3 * 32 */, uint32_t *tot /* 3 */) {
+    const unsigned full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(full, a, o), y = __shfl_up_sync(full, b, o), z = __shfl_up_sync(full, c, o);
+        if ((int)lane >= o) { a += x; b += y; c += z; }
+    }
+    __syncthreads();     // protects sm / tot against the previous call's readers
+    if (lane == 31) { sm[wid] = a; sm[32 + wid] = b; sm[64 + wid] = c; }
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t x = sm[lane], y = sm[32 + lane], z = sm[64 + lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t p = __shfl_up_sync(full, x, o), q = __shfl_up_sync(full, y, o), r = __shfl_up_sync(full, z, o);
+            if ((int)lane >= o) { x += p; y += q; z += r; }
+        }
+        sm[lane] = x; sm[32 + lane] = y; sm[64 + lane] = z;
+        if (lane == 31) { tot[0] = x; tot[1] = y; tot[2] = z; }
+    }
+    __syncthreads();
+    if (wid > 0) { a += sm[wid - 1]; b += sm[32 + wid - 1]; c += sm[64 + wid - 1]; }
+}
+
+__device__ uint32_t ars_block_min(uint32_t v, uint32_t *sm /* 32 */) {
+    const unsigned full = 0xffffffffu;
+    for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(full, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t r = sm[threadIdx.x & 31];
+    for (int o = 16; o; o >>= 1) r = min(r, __shfl_xor_sync(full, r, o));
+    return r;
+}
+__device__ uint32_t ars_block_max(uint32_t v, uint32_t *sm) { return ~ars_block_min(~v, sm); }
+
+// ascending bitonic sort of the first P2 (power of two) u64 keys in shared memory
+__device__ void ars_bitonic(uint64_t *keys, uint32_t P2) {
+    for (uint32_t k = 2; k <= P2; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < P2; i += blockDim.x) {
+                const uint32_t l = i ^ j;
+                if (l > i) {
+                    const uint64_t x = keys[i], y = keys[l];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { keys[i] = y; keys[l] = x; }
+                }
+            }
+        }
+    __syncthreads();
+}
+// stable "descending by inliers" order as ascending u64 keys: (inliers desc, previous position asc); payload = source id
+__device__ __forceinline__ uint64_t ars_key(uint32_t inl, uint32_t pos, uint32_t src) {
+    return ((uint64_t)(0xfffffu - inl) << 32) | ((uint64_t)pos << 16) | (uint64_t)src;
+}
+__device__ __forceinline__ uint32_t ars_pow2(uint32_t n) { uint32_t p = 2; while (p < n) p <<= 1; return p; }
+
+// number of set bits of a mask row in data [lo, hi)
+__device__ uint32_t ars_popc_range(const uint32_t *row, uint32_t lo, uint32_t hi) {
+    if (hi <= lo) return 0;
+    uint32_t c = 0;
+    for (uint32_t w = lo >> 5; w <= (hi - 1) >> 5; w++) {
+        uint32_t x = row[w];
+        const uint32_t b0 = w * 32;
+        if (b0 < lo) x &= ~0u << (lo - b0);
+        if (b0 + 32 > hi) x &= ~0u >> (b0 + 32 - hi);
+        c += __popc(x);
+    }
+    return c;
+}
+
+// SPRT walk of one model over its initialisation mask (the reference's inner loop, f32 in data order).
+// Returns tested (the 1-based datum at which the ratio exceeded the threshold) or 0 when the model passes.
+__device__ uint32_t ars_sprt_walk(const uint32_t *__restrict__ words, uint32_t init_n, float pos, float neg, float thr, uint32_t *inl_out) {
+    float ratio = 1.0f;
+    uint32_t inl = 0;
+    for (uint32_t w = 0; w * 32 < init_n; w++) {
+        const uint32_t x = words[w];
+        const uint32_t cnt = min(32u, init_n - w * 32);
+        if (ratio == 0.0f) { inl += __popc(cnt < 32 ? (x & ((1u << cnt) - 1)) : x); continue; }   // 0 * finite stays 0: never rejected
+        for (uint32_t k = 0; k < cnt; k++) {
+            if ((x >> k) & 1u) { inl++; ratio *= pos; }
+            else ratio *= neg;
+            if (ratio > thr) { *inl_out = inl; return w * 32 + k + 1; }
+        }
+    }
+    *inl_out = inl;
+    return 0;
+}
+
+// ---- k_ars_sprt ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, ArrsacParams P, const cvb_pose *__restrict__ poses0,
+                                                           const uint8_t *__restrict__ nposes0, const uint32_t *__restrict__ masks0,
+                                                           uint32_t *__restrict__ vm, uint32_t *__restrict__ pass_id,
+                                                           uint32_t *__restrict__ pass_inl, cvb_pose *tposes, uint32_t *tinl,
+                                                           uint32_t *tmasks) {
+    if (ctl->done) return;
+    __shared__ uint32_t sm[96], tot[3];
+    __shared__ uint64_t keys[ARS_SORT_CAP];
+    __shared__ float s_eps, s_delta;
+    __shared__ uint32_t s_best, s_cursor, s_npass, s_stop, s_chunks;
+    __shared__ unsigned long long s_rej_inl, s_rej_tested;
+    const uint32_t tid = threadIdx.x, NT = blockDim.x;
+    const uint32_t init_n = ctl->init_n;
+    // A. models in reference order (sample-major, solution-minor), skipping the slots an estimator left empty
+    uint32_t base = 0;
+    for (uint32_t h0 = 0; h0 < P.H0; h0 += NT) {
+        const uint32_t h = h0 + tid;
+        const uint32_t cnt = h < P.H0 ? nposes0[h] : 0;
+        uint32_t x = cnt, y = 0, z = 0;
+        ars_scan3(x, y, z, sm, tot);
+        const uint32_t off = base + x - cnt;
+        for (uint32_t k = 0; k < cnt; k++) vm[off + k] = h * P.MM + k;
+        base += tot[0];
+        __syncthreads();
+    }
+    const uint32_t Mv = base;
+    if (tid == 0) {
+        ctl->Mv = Mv;
+        s_eps = P.eps0; s_delta = P.delta0; s_best = 0; s_cursor = 0; s_npass = 0; s_rej_inl = 0; s_rej_tested = 0; s_chunks = 0;
+    }
+    __syncthreads();
+    // B. adaptive SPRT, chunks of NT models under a box of states
+    while (true) {
+        const uint32_t c0 = s_cursor;
+        if (c0 >= Mv) break;
+        const float eps = s_eps, delta = s_delta;
+        const uint32_t best0 = s_best;
+        const unsigned long long ri0 = s_rej_inl, rt0 = s_rej_tested;
+        const float d_lo = delta * (1.0f - 1.0f / 64.0f), d_hi = delta * (1.0f + 1.0f / 64.0f);
+        const uint32_t j = tid, cnt = min(NT, Mv - c0);
+        uint32_t tested = 0, inl = 0;
+        bool robust = true, have = j < cnt;
+        uint32_t id = 0;
+        if (have) {
+            id = vm[c0 + j];
+            const uint32_t *row = masks0 + (size_t)id * P.W0;
+            if (j == 0) {
+                tested = ars_sprt_walk(row, init_n, delta / eps, (1.0f - delta) / (1.0f - eps), P.lr_thr, &inl);
+            } else {
+                uint32_t inl2;
+                tested = ars_sprt_walk(row, init_n, d_hi / eps, (1.0f - d_lo) / (1.0f - eps), P.lr_thr, &inl);
+                const uint32_t t2 = ars_sprt_walk(row, init_n, d_lo / eps, (1.0f - d_hi) / (1.0f - eps), P.lr_thr, &inl2);
+                robust = t2 == tested;
+            }
+        }
+        const bool pass = have && tested == 0, rej = have && tested != 0;
+        uint32_t a_ri = rej ? inl : 0, a_rt = rej ? tested : 0, a_pc = pass ? 1 : 0;
+        ars_scan3(a_ri, a_rt, a_pc, sm, tot);                                  // inclusive
+        // events that end the committed range: before j (corners disagree) or after j (epsilon changes / delta leaves the box)
+        uint32_t stop = cnt;
+        if (have) {
+            if (!robust) stop = j;
+            else if (pass && inl > best0) stop = j + 1;
+            else if (rej) {
+                const float d = (float)(ri0 + a_ri) / (float)(rt0 + a_rt);
+                if (d > 0.0f && d < eps && (d < d_lo || d > d_hi)) stop = j + 1;
+            }
+        }
+        const uint32_t ce = ars_block_min(stop, sm);                           // commit models [0, ce)
+        // last committed rejection with a valid delta estimate
+        uint32_t lastv = 0;                                                    // 1-based index
+        if (have && rej && j < ce) {
+            const float d = (float)(ri0 + a_ri) / (float)(rt0 + a_rt);
+            if (d > 0.0f && d < eps) lastv = j + 1;
+        }
+        const uint32_t lv = ars_block_max(lastv, sm);
+        __syncthreads();
+        if (have && j < ce && pass) {
+            const uint32_t p = s_npass + a_pc - 1;
+            pass_id[p] = id; pass_inl[p] = inl;
+        }
+        if (have && j + 1 == ce) {      // the last committed model publishes the sums
+            s_rej_inl = ri0 + a_ri; s_rej_tested = rt0 + a_rt;
+            s_npass = s_npass + a_pc;
+            s_cursor = c0 + ce;
+            s_chunks++;
+            if (pass && inl > best0) {
+                s_best = inl;
+                const float e = (float)inl / (float)init_n;
+                if (e > eps && e < 1.0f) s_eps = e; else if (e >= 1.0f) s_eps = 0.999f;
+            }
+        }
+        if (have && lv && j + 1 == lv) s_delta = (float)(ri0 + a_ri) / (float)(rt0 + a_rt);
+        __syncthreads();
+    }
+    // C. stable top-max_cand by inliers: threshold from a histogram, ordered compaction, bitonic on (inliers desc, order asc)
+    const uint32_t npass = s_npass;
+    uint32_t *hist = (uint32_t *)keys;      // init_n + 1 <= 32 * W0 + 1 bins (host guarantees <= 2 * ARS_SORT_CAP)
+    for (uint32_t i = tid; i <= init_n; i += NT) hist[i] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < npass; i += NT) atomicAdd(&hist[pass_inl[i]], 1u);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t T = 0, need = 0;
+        if (npass > P.max_cand) {
+            uint32_t cum = 0;
+            for (int v = (int)init_n; v >= 0; v--) {
+                if (cum + hist[v] >= P.max_cand) { T = (uint32_t)v; need = P.max_cand - cum; break; }
+                cum += hist[v];
+            }
+        }
+        s_stop = T; s_best = need;        // reuse: threshold value, how many of the entries equal to it are taken
+        ctl->npass = npass; ctl->stat_chunks = s_chunks;
+    }
+    __syncthreads();
+    const uint32_t T = s_stop, need = s_best;
+    const bool all = npass <= P.max_cand;
+    __syncthreads();
+    uint32_t ngt = 0, neq = 0;
+    for (uint32_t i0 = 0; i0 < npass; i0 += NT) {
+        const uint32_t i = i0 + tid;
+        const uint32_t v = i < npass ? pass_inl[i] : 0;
+        const bool gt = i < npass && (all || v > T), eq = i < npass && !all && v == T;
+        uint32_t x = gt ? 1 : 0, y = eq ? 1 : 0, z = 0;
+        ars_scan3(x, y, z, sm, tot);
+        // position among the selected = (greater-than entries before) + min(equal entries before, need)
+        const uint32_t eq_before = neq + y - (eq ? 1 : 0);
+        const bool take = gt || (eq && eq_before < need);
+        if (take) {
+            const uint32_t p = ngt + (x - (gt ? 1 : 0)) + min(eq_before, need);
+            keys[p] = ars_key(v, p, 0);
+            vm[p] = pass_id[i];                    // vm is free again: model id by selection position
+        }
+        ngt += tot[0];
+        neq += tot[1];
+        __syncthreads();
+    }
+    const uint32_t nsel = ngt + min(neq, need);
+    // NOTE: selection positions are already in pass order, i.e. keys carry (inliers, position); sort them
+    const uint32_t Hn = nsel;
+    const uint32_t P2 = ars_pow2(max(Hn, 2u));
+    for (uint32_t i = Hn + tid; i < P2; i += NT) keys[i] = ~0ull;
+    ars_bitonic(keys, P2);
+    // D. candidate table 0 in sorted order: pose, inliers, mask (initialisation words, rest zero)
+    for (uint32_t r = tid / 32; r < Hn; r += NT / 32) {
+        const uint32_t lane = tid & 31;
+        const uint64_t kx = keys[r];
+        const uint32_t p = (uint32_t)(kx >> 16) & 0xffffu;
+        const uint32_t id = vm[p];
+        const double *src = (const double *)(poses0 + id);
+        double *dst = (double *)(tposes + r);
+        if (lane < 12) dst[lane] = src[lane];
+        if (lane == 0) tinl[r] = 0xfffffu - (uint32_t)(kx >> 32);
+        for (uint32_t w = lane; w < P.NW; w += 32) tmasks[(size_t)r * P.NW + w] = w < P.W0 ? masks0[(size_t)id * P.W0 + w] : 0u;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t n = ctl->n;
+        ctl->Hn = Hn; ctl->cur = 0; ctl->stat_pass = npass;
+        ctl->acc_hi = init_n; ctl->blk_lo = init_n; ctl->blk_hi = min(init_n + P.bs, n);
+        ctl->n_new = 0; ctl->worst = 0;
+        if (!(init_n < n && Hn > 1)) {
+            ctl->done = 1; ctl->found = Hn >= 1 ? 1 : 0;
+            if (Hn >= 1) ctl->winner = tposes[0];
+        }
+    }
+}
+
+// ---- k_ars_book ----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_book(ArrsacCtl *ctl, ArrsacParams P, const uint32_t *__restrict__ raw,
+                                                           cvb_pose *tposes, uint32_t *tinl, uint32_t *tmasks,
+                                                           const cvb_pose *__restrict__ newposes, const uint8_t *__restrict__ nposes_new,
+                                                           const uint32_t *__restrict__ newmask, uint32_t *__restrict__ pool,
+                                                           uint32_t *__restrict__ samples_new) {
+    if (ctl->done) return;
+    __shared__ uint32_t sm[96], tot[3];
+    extern __shared__ __align__(16) unsigned char ars_dyn[];     // ARS_BOOK_SMEM bytes
+    uint64_t *keys = (uint64_t *)ars_dyn;                                        // [ARS_SORT_CAP]
+    uint32_t *e_inl = (uint32_t *)(ars_dyn + 8 * ARS_SORT_CAP);                  // inliers by entry position (part 1 order)
+    uint16_t *e_src = (uint16_t *)(ars_dyn + 12 * ARS_SORT_CAP);                 // source: < rows -> kept row of the current table, else rows + new model
+    const uint32_t tid = threadIdx.x, NT = blockDim.x;
+    const uint32_t cur = ctl->cur, Hk = ctl->Hn, n = ctl->n;
+    const uint32_t acc_hi = ctl->acc_hi, lo = ctl->blk_lo, hi = ctl->blk_hi, worst = ctl->worst;
+    const uint32_t nnew = ctl->n_new * P.MM;
+    const cvb_pose *tp = tposes + (size_t)cur * P.rows;
+    const uint32_t *ti = tinl + (size_t)cur * P.rows;
+    const uint32_t *tm = tmasks + (size_t)cur * P.rows * P.NW;
+    // ---- part 1: new hypotheses that beat the bar join the candidates (in generation order), stable sort, truncate
+    for (uint32_t r = tid; r < Hk; r += NT) { e_inl[r] = ti[r]; e_src[r] = (uint16_t)r; keys[r] = ars_key(ti[r], r, r); }
+    uint32_t total = Hk;
+    for (uint32_t j0 = 0; j0 < nnew; j0 += NT) {
+        const uint32_t j = j0 + tid;
+        uint32_t inl = 0;
+        bool acc = false;
+        if (j < nnew && (j % P.MM) < nposes_new[j / P.MM]) {
+            inl = ars_popc_range(newmask + (size_t)j * P.NW, 0, acc_hi);
+            acc = inl > worst;
+        }
+        uint32_t x = acc ? 1 : 0, y = 0, z = 0;
+        ars_scan3(x, y, z, sm, tot);
+        if (acc) {
+            const uint32_t p = total + x - 1;
+            if (p < ARS_SORT_CAP) { e_inl[p] = inl; e_src[p] = (uint16_t)(P.rows + j); keys[p] = ars_key(inl, p, p); }
+        }
+        total += tot[0];
+        __syncthreads();
+    }
+    uint32_t P2 = ars_pow2(max(total, 2u));
+    for (uint32_t i = total + tid; i < P2; i += NT) keys[i] = ~0ull;
+    ars_bitonic(keys, P2);
+    const uint32_t Hn1 = min(total, P.max_cand);
+    // termination test of the reference's loop head (start < n && H.n > 1)
+    if (!(lo < n && Hn1 > 1)) {
+        if (tid == 0) {
+            ctl->done = 1; ctl->found = Hn1 >= 1 ? 1 : 0;
+            if (Hn1 >= 1) {
+                const uint32_t src = e_src[(uint32_t)keys[0] & 0xffffu];
+                ctl->winner = src < P.rows ? tp[src] : newposes[src - P.rows];
+            }
+        }
+        return;
+    }
+    // ---- part 2: add this block's inliers, stable sort, halve
+    // entry positions of the survivors of part 1 in their sorted order -> new keys (inliers + block count, rank, entry)
+    __syncthreads();
+    uint64_t mykeys[ARS_SORT_CAP / ARS_BOOK_NT];
+    uint32_t nk = 0;
+    for (uint32_t r = tid; r < Hn1; r += NT) {
+        const uint32_t e = (uint32_t)keys[r] & 0xffffu;
+        const uint32_t src = e_src[e];
+        const uint32_t *row = src < P.rows ? tm + (size_t)src * P.NW : newmask + (size_t)(src - P.rows) * P.NW;
+        const uint32_t inl = e_inl[e] + ars_popc_range(row, lo, hi);
+        e_inl[e] = inl;
+        mykeys[nk++] = ars_key(inl, r, e);
+    }
+    __syncthreads();
+    nk = 0;
+    for (uint32_t r = tid; r < Hn1; r += NT) keys[r] = mykeys[nk++];
+    P2 = ars_pow2(max(Hn1, 2u));
+    for (uint32_t i = Hn1 + tid; i < P2; i += NT) keys[i] = ~0ull;
+    ars_bitonic(keys, P2);
+    const uint32_t keep = max(Hn1 / 2, 1u);
+    // surviving rows, in order, into the other table
+    cvb_pose *np_ = tposes + (size_t)(cur ^ 1) * P.rows;
+    uint32_t *ni = tinl + (size_t)(cur ^ 1) * P.rows;
+    uint32_t *nm = tmasks + (size_t)(cur ^ 1) * P.rows * P.NW;
+    const uint32_t nwords = (hi + 31) >> 5;
+    for (uint32_t r = tid / 32; r < keep; r += NT / 32) {
+        const uint32_t lane = tid & 31;
+        const uint32_t e = (uint32_t)keys[r] & 0xffffu;
+        const uint32_t src = e_src[e];
+        const double *ps = (const double *)(src < P.rows ? tp + src : newposes + (src - P.rows));
+        const uint32_t *row = src < P.rows ? tm + (size_t)src * P.NW : newmask + (size_t)(src - P.rows) * P.NW;
+        double *pd = (double *)(np_ + r);
+        if (lane < 12) pd[lane] = ps[lane];
+        if (lane == 0) ni[r] = e_inl[e];
+        for (uint32_t w = lane; w < P.NW; w += 32) nm[(size_t)r * P.NW + w] = w < nwords ? row[w] : 0u;
+    }
+    __syncthreads();
+    // inlier pool of the best candidate over [0, hi)
+    uint32_t npool = 0;
+    for (uint32_t w0 = 0; w0 < nwords; w0 += NT) {
+        const uint32_t w = w0 + tid;
+        uint32_t x = 0;
+        if (w < nwords) {
+            x = nm[w];
+            if (w * 32 + 32 > hi) x &= ~0u >> (w * 32 + 32 - hi);
+        }
+        uint32_t c = __popc(x), y = 0, z = 0;
+        const uint32_t mine = c;
+        ars_scan3(c, y, z, sm, tot);
+        uint32_t p = npool + c - mine;
+        while (x) { const int b = __ffs(x) - 1; x &= x - 1; pool[p++] = w * 32 + b; }
+        npool += tot[0];
+        __syncthreads();
+    }
+    const bool gen = npool >= P.K && P.G > 0;
+    if (gen && tid < 32) ars_sample_warp(ctl, raw, npool, P.K, P.G, samples_new, pool);
+    __syncthreads();
+    if (tid == 0) {
+        ctl->worst = e_inl[(uint32_t)keys[keep - 1] & 0xffffu];
+        ctl->n_new = gen ? P.G : 0;
+        ctl->cur = cur ^ 1; ctl->Hn = keep;
+        ctl->acc_hi = hi; ctl->blk_lo = hi; ctl->blk_hi = min(hi + P.bs, n);
+        ctl->iters++;
+    }
+}
+
+// ---- k_ars_final ---------------------------------------------------------------------------------------------------------
+template <int RES>
+__global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_final(ArrsacCtl *ctl, ArrsacParams P, const double *__restrict__ a,
+                                                            const double *__restrict__ b, cvb_pose *model_out, uint32_t *inliers_out,
+                                                            uint32_t cap, uint32_t *n_inliers_out, int32_t *found_out) {
+    __shared__ uint32_t sm[96], tot[3];
+    const uint32_t tid = threadIdx.x, NT = blockDim.x;
+    const uint32_t n = ctl->n;
+    const bool found = ctl->found != 0;
+    uint32_t cnt = 0;
+    if (found) {
+        const cvb_pose W = ctl->winner;
+        if (tid == 0 && model_out) *model_out = W;
+        for (uint32_t i0 = 0; i0 < n; i0 += NT) {
+            const uint32_t i = i0 + tid;
+            const bool in = i < n && ars_inlier<RES>(W, a, b, i, P.thr);
+            uint32_t x = in ? 1 : 0, y = 0, z = 0;
+            ars_scan3(x, y, z, sm, tot);
+            if (in) { const uint32_t p = cnt + x - 1; if (inliers_out && p < cap) inliers_out[p] = i; }
+            cnt += tot[0];
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        ctl->n_inliers = cnt;
+        ctl->overflow = (inliers_out && cnt > cap) ? 1u : 0u;
+        if (n_inliers_out) *n_inliers_out = cnt;
+        if (found_out) *found_out = found ? 1 : 0;
+    }
+}

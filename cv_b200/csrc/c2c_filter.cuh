@@ -1,0 +1,145 @@
+// cv_b200/csrc/c2c_filter.cuh -- floating-point filter for the consensus predicate
+//     CameraToCamera::residual(pose, FeatureMatch(a, b)) < inlier_threshold        (cv-core/src/pose.rs:249-296)
+//
+// ARRSAC consumes only that one bit per (hypothesis, datum).  The reference obtains it from a full 4x4 symmetric
+// eigen-decomposition (residual_c2c in geom.cu restates it with cyclic Jacobi: ~6 k FP64 instructions).  This filter
+// decides the same bit with ~0.8 k instructions whenever the decision is provably insensitive to rounding, and
+// returns "undecided" otherwise; the caller then runs the exact routine.  It is an exact-predicate filter in the
+// computational-geometry sense, not an approximation of the result:
+//
+//   D = A_a + A_b (the 4x4 two-view design matrix of pose.rs:256-277), eigenvalues 0 <= l1 <= l2 <= l3 <= l4.
+//   (1) residual >= l1 / (4 (1 + |t|^2))     [for the minimiser X: l1 = |X_xyz|^2 sin^2(alpha) + |P X|^2 sin^2(beta),
+//        |X_xyz| <= 1, |P X|^2 <= 1 + |t|^2, residual = sin^2(alpha/2) + sin^2(beta/2) >= (sin^2 alpha + sin^2 beta)/4]
+//       => with s_lo = 8 (1 + |t|^2) thr:  l1 >= s_lo  implies  residual >= 2 thr: certain outlier.
+//   (2) the number of negative pivots of an LDL^T factorisation of D - s I equals the number of eigenvalues below s
+//       (Sylvester's law of inertia).  Exactly one negative pivot at s_lo and exactly one at s_hi = min(1024 s_lo, 0.01)
+//       (>= 16 s_lo, else the filter declines) gives l1 < s_lo < s_hi < l2: inverse iteration with shift s_lo then contracts
+//       the error by <= s_lo / (s_hi - s_lo) <= 1/15 per step (1e-3 at the production threshold 1e-7), and a final step that
+//       moves the unit vector by < 1e-11 certifies the eigenvector to ~1e-12.
+//   (3) the residual of that eigenvector is computed with the reference's formula; if it is further from the threshold
+//       than 1e-11 + 1e-4 thr (orders of magnitude above the rounding of either evaluation) the comparison is decided.
+//   Anything else (tiny pivots, l2 < s_hi, non-finite values, slow convergence, residual inside the band, thresholds so
+//   large that s_hi is not small) returns -1.
+//
+// Compiles for the device (nvcc) and for the host (g++; only the CPU tests do that, to compare every decision with the exact CPU evaluation).
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define C2C_HD __host__ __device__ __forceinline__
+#else
+#define C2C_HD static inline
+#endif
+
+// LDL^T of the symmetric 4x4 matrix m (full storage, row-major) minus s*I.  d[] = pivots, l[] = the six multipliers
+// (l10 l20 l30 l21 l31 l32).  Returns the number of negative pivots, or -1 when a pivot is too small to trust its sign.
+C2C_HD int c2c_ldl4(const double *m, double s, double *d, double *l) {
+    const double tiny = 1e-11;
+    const double m00 = m[0] - s, m11 = m[5] - s, m22 = m[10] - s, m33 = m[15] - s;
+    const double m10 = m[4], m20 = m[8], m30 = m[12], m21 = m[9], m31 = m[13], m32 = m[14];
+    int neg = 0;
+    d[0] = m00;
+    if (!(fabs(d[0]) > tiny)) return -1;
+    neg += d[0] < 0.0;
+    const double i0 = 1.0 / d[0];
+    l[0] = m10 * i0; l[1] = m20 * i0; l[2] = m30 * i0;
+    d[1] = m11 - l[0] * m10;
+    if (!(fabs(d[1]) > tiny)) return -1;
+    neg += d[1] < 0.0;
+    const double i1 = 1.0 / d[1];
+    const double u21 = m21 - l[1] * m10, u31 = m31 - l[2] * m10;
+    l[3] = u21 * i1; l[4] = u31 * i1;
+    d[2] = m22 - l[1] * m20 - l[3] * u21;
+    if (!(fabs(d[2]) > tiny)) return -1;
+    neg += d[2] < 0.0;
+    const double i2 = 1.0 / d[2];
+    const double u32 = m32 - l[2] * m20 - l[4] * u21;
+    l[5] = u32 * i2;
+    d[3] = m33 - l[2] * m30 - l[4] * u31 - l[5] * u32;
+    if (!(fabs(d[3]) > 0.0)) return -1;      // the last pivot may be arbitrarily small (l1 close to s): its sign is not used by callers that see 0 or 1 above
+    neg += d[3] < 0.0;
+    return neg;
+}
+
+// x <- (L D L^T)^-1 x
+C2C_HD void c2c_ldl4_solve(const double *id, const double *l, double *x) {
+    x[1] -= l[0] * x[0];
+    x[2] -= l[1] * x[0] + l[3] * x[1];
+    x[3] -= l[2] * x[0] + l[4] * x[1] + l[5] * x[2];
+    x[0] *= id[0]; x[1] *= id[1]; x[2] *= id[2]; x[3] *= id[3];
+    x[2] -= l[5] * x[3];
+    x[1] -= l[3] * x[2] + l[4] * x[3];
+    x[0] -= l[0] * x[1] + l[1] * x[2] + l[2] * x[3];
+}
+
+C2C_HD double c2c_normalise4(double *x) {
+    const double n = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+    const double in = 1.0 / n;
+    x[0] *= in; x[1] *= in; x[2] *= in; x[3] *= in;
+    return n;
+}
+
+// R row-major 3x3, t[3]: the CameraToCamera pose; a, b: unit bearings of the match.
+// Returns 1 (residual < thr), 0 (residual >= thr) or -1 (undecided: evaluate exactly).
+C2C_HD int c2c_inlier_filter(const double *R, const double *t, const double *a, const double *b, double thr) {
+    const double tt = 1.0 + (t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+    const double s_lo = 8.0 * tt * thr, s_hi = fmin(1024.0 * s_lo, 0.01);
+    if (!(s_hi >= 16.0 * s_lo) || !(thr > 0.0)) return -1;      // contraction <= 1/15 per step, or no filter
+    // D = sum over the two views of (M - b b^T M)^T (M - b b^T M), M = [I | 0] resp. [R | t]   (pose.rs:256-277)
+    double D[16];
+    {
+        // view a: columns c = 0..2 are e_c - a a_c, column 3 is zero
+        double Ta[3][3];
+        for (int c = 0; c < 3; c++)
+            for (int r = 0; r < 3; r++) Ta[r][c] = (r == c ? 1.0 : 0.0) - a[r] * a[c];
+        double Tb[3][4];
+        for (int c = 0; c < 4; c++) {
+            const double m0 = c < 3 ? R[c] : t[0], m1 = c < 3 ? R[3 + c] : t[1], m2 = c < 3 ? R[6 + c] : t[2];
+            const double btm = b[0] * m0 + b[1] * m1 + b[2] * m2;
+            Tb[0][c] = m0 - b[0] * btm; Tb[1][c] = m1 - b[1] * btm; Tb[2][c] = m2 - b[2] * btm;
+        }
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j <= i; j++) {
+                double v = Tb[0][i] * Tb[0][j] + Tb[1][i] * Tb[1][j] + Tb[2][i] * Tb[2][j];
+                if (i < 3) v += Ta[0][i] * Ta[0][j] + Ta[1][i] * Ta[1][j] + Ta[2][i] * Ta[2][j];
+                D[i * 4 + j] = v; D[j * 4 + i] = v;
+            }
+    }
+    double d[4], l[6], dh[4], lh[6];
+    const int c_lo = c2c_ldl4(D, s_lo, d, l);
+    if (c_lo == 0) return 0;                       // l1 > s_lo: residual >= 2 thr
+    if (c_lo != 1) return -1;
+    if (c2c_ldl4(D, s_hi, dh, lh) != 1) return -1; // need l2 > s_hi for the contraction bound
+    const double id[4] = {1.0 / d[0], 1.0 / d[1], 1.0 / d[2], 1.0 / d[3]};
+    double x[4] = {0.5, 0.5, 0.5, 0.5};
+    c2c_ldl4_solve(id, l, x);
+    c2c_normalise4(x);
+    c2c_ldl4_solve(id, l, x);
+    c2c_normalise4(x);
+    double delta = 1.0;
+    for (int it = 0; it < 6 && delta > 1e-11; it++) {
+        double y[4] = {x[0], x[1], x[2], x[3]};
+        c2c_ldl4_solve(id, l, y);
+        c2c_normalise4(y);
+        // the shifted operator has a negative dominant eigenvalue when l1 < s_lo: successive iterates alternate in sign
+        const double sg = (x[0] * y[0] + x[1] * y[1] + x[2] * y[2] + x[3] * y[3]) < 0.0 ? -1.0 : 1.0;
+        double e = 0.0;
+        for (int k = 0; k < 4; k++) { const double df = sg * y[k] - x[k]; e += df * df; x[k] = sg * y[k]; }
+        delta = sqrt(e);
+    }
+    if (!(delta <= 1e-11)) return -1;
+    // pose.rs:284-295: from_homogeneous (sign of w, unit xyz), transform, cosine distances
+    double p[4] = {x[0], x[1], x[2], x[3]};
+    if (signbit(p[3])) { p[0] = -p[0]; p[1] = -p[1]; p[2] = -p[2]; p[3] = -p[3]; }
+    const double pn = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+    if (!(pn > 1e-9)) return -1;
+    p[0] /= pn; p[1] /= pn; p[2] /= pn; p[3] /= pn;
+    double q[3];
+    for (int r = 0; r < 3; r++) q[r] = R[3 * r] * p[0] + R[3 * r + 1] * p[1] + R[3 * r + 2] * p[2] + t[r] * p[3];
+    const double qn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    if (!(qn > 1e-9)) return -1;
+    const double res = 0.5 * (1.0 - (a[0] * p[0] + a[1] * p[1] + a[2] * p[2]) + 1.0 - (b[0] * q[0] + b[1] * q[1] + b[2] * q[2]) / qn);
+    if (!isfinite(res)) return -1;
+    if (fabs(res - thr) <= 1e-11 + 1e-4 * thr) return -1;
+    return res < thr ? 1 : 0;
+}

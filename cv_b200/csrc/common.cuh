@@ -9,6 +9,7 @@
 struct AkazeWorkspace;
 struct MatchWorkspace;
 struct GeomWorkspace;
+struct PairWorkspace;
 
 struct cvb_ctx {
     int device = 0;
@@ -21,6 +22,7 @@ struct cvb_ctx {
     AkazeWorkspace *akaze = nullptr;
     MatchWorkspace *match = nullptr;
     GeomWorkspace *geom = nullptr;
+    PairWorkspace *pair = nullptr;
     // page-locked host scratch for the small device->host results of the host API (a D2H copy into pageable memory is
     // staged synchronously inside the driver and stalls the other contexts' launches)
     void *pinned = nullptr;
@@ -51,6 +53,7 @@ int cvb_set_error(cvb_ctx *ctx, int code, const char *fmt, ...);
 void akaze_workspace_free(AkazeWorkspace *ws);
 void match_workspace_free(MatchWorkspace *ws);
 void geom_workspace_free(GeomWorkspace *ws);
+void pair_workspace_free(PairWorkspace *ws);
 
 #define CVB_CUDA(ctx, call)                                                                          \
     do {                                                                                             \

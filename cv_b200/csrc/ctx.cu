@@ -103,6 +103,7 @@ void cvb_ctx_destroy(cvb_ctx *ctx) {
     akaze_workspace_free(ctx->akaze);
     match_workspace_free(ctx->match);
     geom_workspace_free(ctx->geom);
+    pair_workspace_free(ctx->pair);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);

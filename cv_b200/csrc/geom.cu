@@ -8,10 +8,12 @@
 // here as cyclic Jacobi / closed forms; f64 results are held to 1e-6 relative (BASELINE north_star) in the parity tests.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
 #include "common.cuh"
+#include "c2c_filter.cuh"
 
 namespace {
 
@@ -757,6 +759,27 @@ __global__ void __launch_bounds__(128) k_triangulate(const cvb_pose *__restrict_
     for (int i = 0; i < 4; i++) xyzw[(size_t)l * 4 + i] = good ? p[i] : 0.0;
 }
 
+// cv-sfm keeps calibrated bearings per feature (CameraModel::calibrate, cv-pinhole/src/lib.rs:108-116, on
+// akaze::KeyPoint's ImagePoint, akaze/src/lib.rs:95-99); a FeatureMatch is the bearing pair of a match (cv-sfm/src/lib.rs:1400).
+// One thread per match: both bearings in f64 with the reference's operation order (no distortion: k1 = 0).
+__device__ __forceinline__ void calibrate_px(const cvb_intrinsics K, double px, double py, double *o) {
+    const double y = (py - K.cy) / K.fy;
+    const double x = (px - K.cx - K.skew * y) / K.fx;
+    const double n = sqrt(x * x + y * y + 1.0);
+    o[0] = x / n; o[1] = y / n; o[2] = 1.0 / n;
+}
+__global__ void __launch_bounds__(256) k_pair_bearings(const cvb_keypoint *__restrict__ kpa, const cvb_keypoint *__restrict__ kpb,
+                                                       const uint32_t *__restrict__ pairs, const uint32_t *__restrict__ npairs,
+                                                       uint32_t cap, cvb_intrinsics K, double *__restrict__ a, double *__restrict__ b) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(*npairs, cap)) return;
+    const cvb_keypoint ka = kpa[pairs[2 * i]], kb = kpb[pairs[2 * i + 1]];
+    calibrate_px(K, (double)ka.x, (double)ka.y, a + 3 * (size_t)i);
+    calibrate_px(K, (double)kb.x, (double)kb.y, b + 3 * (size_t)i);
+}
+
+#include "arrsac_dev.cuh"
+
 // ------------------------------------------------------------------------------------------ post-consensus refinement
 // cv-optimize single_view_simple_optimize_l2 / three_view_{simple,adaptive}_optimize_l2 with cv-geom's epipolar gradients,
 // and cv-sfm's robustness checks.  One CTA per problem iterates to completion on the device: every iteration the threads
@@ -1087,13 +1110,37 @@ struct DevBuf {
 
 }  // namespace
 
+// device-resident ARRSAC (arrsac_dev.cuh): buffers + page-locked staging of one context
+struct ArsWorkspace {
+    DevBuf ctl, raw, samples0, poses0, nposes0, masks0, vm, pass_id, pass_inl, tposes, tinl, tmasks, newposes, nposes_new, newmask,
+        pool, samples_new, res;
+    uint32_t *h_raw = nullptr;      // page-locked: raw draws + ArrsacCtl header
+    size_t h_raw_cap = 0;
+    unsigned char *h_res = nullptr; // page-locked result block
+    cudaEvent_t up_done = nullptr;  // the staging buffer may be rewritten once this has fired
+    std::vector<cvb_rng> snaps;     // generator state every ARS_SNAP draws of the staged stream
+    cvb_rng rng0;                   // generator state at draw 0 of the staged stream
+    uint32_t nraw = 0;
+    bool pending = false;           // a run whose draw count has not been committed to the caller's generator yet
+};
 struct GeomWorkspace {
     DevBuf a, b, samples, poses, nposes, out, masks, offsets, ok;
+    ArsWorkspace *ars = nullptr;
 };
 void geom_workspace_free(GeomWorkspace *g) {
     if (!g) return;
     DevBuf *bufs[] = {&g->a, &g->b, &g->samples, &g->poses, &g->nposes, &g->out, &g->masks, &g->offsets, &g->ok};
     for (DevBuf *d : bufs) if (d->p) cudaFree(d->p);
+    if (g->ars) {
+        ArsWorkspace *w = g->ars;
+        DevBuf *ab[] = {&w->ctl, &w->raw, &w->samples0, &w->poses0, &w->nposes0, &w->masks0, &w->vm, &w->pass_id, &w->pass_inl, &w->tposes,
+                        &w->tinl, &w->tmasks, &w->newposes, &w->nposes_new, &w->newmask, &w->pool, &w->samples_new, &w->res};
+        for (DevBuf *d : ab) if (d->p) cudaFree(d->p);
+        if (w->h_raw) cudaFreeHost(w->h_raw);
+        if (w->h_res) cudaFreeHost(w->h_res);
+        if (w->up_done) cudaEventDestroy(w->up_done);
+        delete w;
+    }
     delete g;
 }
 
@@ -1324,6 +1371,216 @@ int arrsac_run(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const double *
     return 0;
 }
 
+
+// ---- device-resident ARRSAC driver (kernels: arrsac_dev.cuh).  Enqueues everything on the context stream and returns;
+// no host synchronisation between the first kernel and the result.
+#define ARS_SNAP 4096u
+ArsWorkspace *arsws(cvb_ctx *ctx) {
+    GeomWorkspace *g = gws(ctx);
+    if (!g->ars) g->ars = new ArsWorkspace();
+    return g->ars;
+}
+
+int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const double *a_dev, const double *b_dev, const uint32_t *n_dev,
+                   uint32_t n_host, uint32_t nmax, const cvb_rng *rng, cvb_pose *model_dev, uint32_t *inl_dev, uint32_t cap,
+                   uint32_t *ninl_dev, int32_t *found_dev, int row0) {
+    if (cfg->block_size == 0 || cfg->initialization_blocks == 0) return cvb_set_error(ctx, CVB_EINVAL, "block_size / initialization_blocks must be > 0");
+    ArrsacParams P;
+    memset(&P, 0, sizeof(P));
+    P.K = kind_K(kind); P.MM = kind_M(kind); P.kind = (uint32_t)kind;
+    P.H0 = cfg->initialization_hypotheses; P.ib = cfg->initialization_blocks; P.bs = cfg->block_size;
+    P.max_cand = cfg->max_candidate_hypotheses; P.G = cfg->estimations_per_block;
+    P.NMAX = std::max<uint32_t>(nmax, 1);
+    P.W0 = cdiv(P.bs * P.ib, 32); P.NW = cdiv(P.NMAX, 32);
+    P.rows = P.max_cand + P.G * P.MM;
+    P.lr_thr = cfg->likelihood_ratio_threshold; P.eps0 = cfg->initial_epsilon; P.delta0 = cfg->initial_delta;
+    P.thr = cfg->inlier_threshold; P.row0 = row0;
+    if (P.max_cand == 0 || P.rows > ARS_SORT_CAP)
+        return cvb_set_error(ctx, CVB_EUNSUPPORTED, "max_candidate_hypotheses + estimations_per_block * %u must be in 1..%u", P.MM, ARS_SORT_CAP);
+    if ((uint64_t)P.bs * P.ib + 1 > 2ull * ARS_SORT_CAP) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "block_size * initialization_blocks too large");
+    if (P.NMAX >= (1u << 20)) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "more than 2^20 data");
+    ArsWorkspace *w = arsws(ctx);
+    const uint32_t nb_max = cdiv(P.NMAX, P.bs) + 1;
+    const uint32_t nraw = P.H0 * P.K + P.H0 * P.K / 4 + 64 + nb_max * (P.G * P.K + P.G * P.K / 4 + 64);
+    const size_t nmodels0 = (size_t)P.H0 * P.MM, nnew = (size_t)std::max<uint32_t>(P.G, 1) * P.MM;
+    int rc;
+    if ((rc = w->ctl.ensure(ctx, sizeof(ArrsacCtl)))) return rc;
+    if ((rc = w->raw.ensure(ctx, sizeof(uint32_t) * (size_t)nraw))) return rc;
+    if ((rc = w->samples0.ensure(ctx, sizeof(uint32_t) * (size_t)std::max<uint32_t>(P.H0, 1) * P.K))) return rc;
+    if ((rc = w->poses0.ensure(ctx, sizeof(cvb_pose) * std::max<size_t>(nmodels0, 1)))) return rc;
+    if ((rc = w->nposes0.ensure(ctx, std::max<uint32_t>(P.H0, 1)))) return rc;
+    if ((rc = w->masks0.ensure(ctx, sizeof(uint32_t) * std::max<size_t>(nmodels0, 1) * P.W0))) return rc;
+    if ((rc = w->vm.ensure(ctx, sizeof(uint32_t) * std::max<size_t>(nmodels0, ARS_SORT_CAP)))) return rc;
+    if ((rc = w->pass_id.ensure(ctx, sizeof(uint32_t) * std::max<size_t>(nmodels0, 1)))) return rc;
+    if ((rc = w->pass_inl.ensure(ctx, sizeof(uint32_t) * std::max<size_t>(nmodels0, 1)))) return rc;
+    if ((rc = w->tposes.ensure(ctx, sizeof(cvb_pose) * 2 * (size_t)P.rows))) return rc;
+    if ((rc = w->tinl.ensure(ctx, sizeof(uint32_t) * 2 * (size_t)P.rows))) return rc;
+    if ((rc = w->tmasks.ensure(ctx, sizeof(uint32_t) * 2 * (size_t)P.rows * P.NW))) return rc;
+    if ((rc = w->newposes.ensure(ctx, sizeof(cvb_pose) * nnew))) return rc;
+    if ((rc = w->nposes_new.ensure(ctx, std::max<uint32_t>(P.G, 1)))) return rc;
+    if ((rc = w->newmask.ensure(ctx, sizeof(uint32_t) * nnew * P.NW))) return rc;
+    if ((rc = w->pool.ensure(ctx, sizeof(uint32_t) * (size_t)P.NMAX))) return rc;
+    if ((rc = w->samples_new.ensure(ctx, sizeof(uint32_t) * (size_t)std::max<uint32_t>(P.G, 1) * P.K))) return rc;
+    // page-locked staging: [ArrsacCtl header | raw draws]
+    const size_t hdr = (sizeof(ArrsacCtl) + 15) / 16 * 16, stage_bytes = hdr + sizeof(uint32_t) * (size_t)nraw;
+    if (w->h_raw_cap < stage_bytes) {
+        if (w->h_raw) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(w->h_raw); w->h_raw = nullptr; w->h_raw_cap = 0; }
+        if (cudaHostAlloc((void **)&w->h_raw, stage_bytes, cudaHostAllocDefault) != cudaSuccess) return cvb_set_error(ctx, CVB_ENOMEM, "page-locked staging");
+        w->h_raw_cap = stage_bytes;
+    }
+    if (!w->h_res && cudaHostAlloc((void **)&w->h_res, sizeof(ArrsacCtl) + sizeof(cvb_pose) + 64, cudaHostAllocDefault) != cudaSuccess)
+        return cvb_set_error(ctx, CVB_ENOMEM, "page-locked staging");
+    if (!w->up_done) CVB_CUDA(ctx, cudaEventCreateWithFlags(&w->up_done, cudaEventDisableTiming));
+    else CVB_CUDA(ctx, cudaEventSynchronize(w->up_done));       // previous upload has left the staging buffer
+    {
+        cvb_rng g = *rng;
+        w->rng0 = g;
+        w->snaps.clear();
+        uint32_t *raw = (uint32_t *)((unsigned char *)w->h_raw + hdr);
+        for (uint32_t i = 0; i < nraw; i++) {
+            if (i % ARS_SNAP == 0) w->snaps.push_back(g);
+            raw[i] = cvb_rng_next_u32(&g);
+        }
+        ArrsacCtl *h = (ArrsacCtl *)w->h_raw;
+        memset(h, 0, sizeof(*h));
+        h->nraw = nraw; h->gen = g; h->gen_pos = nraw; h->rng_pos = 0;
+        w->nraw = nraw;
+    }
+    cudaStream_t st = ctx->stream;
+    CVB_CUDA(ctx, cudaMemcpyAsync(w->ctl.p, w->h_raw, sizeof(ArrsacCtl), cudaMemcpyHostToDevice, st));
+    CVB_CUDA(ctx, cudaMemcpyAsync(w->raw.p, (unsigned char *)w->h_raw + hdr, sizeof(uint32_t) * (size_t)nraw, cudaMemcpyHostToDevice, st));
+    CVB_CUDA(ctx, cudaEventRecord(w->up_done, st));
+    ArrsacCtl *ctl = (ArrsacCtl *)w->ctl.p;
+    const uint32_t *raw = (const uint32_t *)w->raw.p;
+    const int res = kind_res(kind);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_ars_book, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ARS_BOOK_SMEM); attr_set = true; }
+    {
+        CVB_PROF(ctx, "k_ars_begin", 0);
+        k_ars_begin<<<1, 32, 0, st>>>(ctl, P, n_dev, n_host, raw, (uint32_t *)w->samples0.p);
+        CVB_LAUNCH_CHECK(ctx);
+    }
+    auto estimate = [&](int phase, uint32_t H, const uint32_t *samples, cvb_pose *poses, uint8_t *nposes) -> int {
+        if (H == 0) return 0;
+        CVB_PROF(ctx, phase == 0 ? "k_ars_estimate_init" : "k_ars_estimate_block", 0);
+        if (kind == 0) k_ars_estimate<0><<<cdiv(H, 128), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
+        else if (kind == 1) k_ars_estimate<1><<<cdiv(H, 128), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
+        else k_ars_estimate<2><<<cdiv(H, 128), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
+        CVB_LAUNCH_CHECK(ctx);
+        return 0;
+    };
+    const uint32_t sgrid = (uint32_t)ctx->num_sms * 4;
+    auto score = [&](int phase) -> int {
+        CVB_PROF(ctx, phase == 0 ? "k_ars_score_init" : "k_ars_score_block", 0);
+        if (res == 0)
+            k_ars_score<0><<<sgrid, 256, 0, st>>>(ctl, P, phase, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p,
+                                                  (uint32_t *)w->masks0.p, (const cvb_pose *)w->tposes.p, (uint32_t *)w->tmasks.p,
+                                                  (const cvb_pose *)w->newposes.p, (const uint8_t *)w->nposes_new.p, (uint32_t *)w->newmask.p);
+        else
+            k_ars_score<1><<<sgrid, 256, 0, st>>>(ctl, P, phase, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p,
+                                                  (uint32_t *)w->masks0.p, (const cvb_pose *)w->tposes.p, (uint32_t *)w->tmasks.p,
+                                                  (const cvb_pose *)w->newposes.p, (const uint8_t *)w->nposes_new.p, (uint32_t *)w->newmask.p);
+        CVB_LAUNCH_CHECK(ctx);
+        return 0;
+    };
+    if ((rc = estimate(0, P.H0, (const uint32_t *)w->samples0.p, (cvb_pose *)w->poses0.p, (uint8_t *)w->nposes0.p))) return rc;
+    if ((rc = score(0))) return rc;
+    {
+        CVB_PROF(ctx, "k_ars_sprt", 0);
+        k_ars_sprt<<<1, ARS_BOOK_NT, 0, st>>>(ctl, P, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p, (const uint32_t *)w->masks0.p,
+                                             (uint32_t *)w->vm.p, (uint32_t *)w->pass_id.p, (uint32_t *)w->pass_inl.p, (cvb_pose *)w->tposes.p,
+                                             (uint32_t *)w->tinl.p, (uint32_t *)w->tmasks.p);
+        CVB_LAUNCH_CHECK(ctx);
+    }
+    // block loop: the number of launches follows the data count when the host knows it, the capacity otherwise;
+    // kernels behind the loop's end return at once (ctl->done)
+    const uint32_t n_bound = n_dev ? P.NMAX : std::min(n_host, P.NMAX);
+    const uint32_t init_n = std::min(P.bs * P.ib, n_bound);
+    const uint32_t nb = n_bound > init_n ? cdiv(n_bound - init_n, P.bs) : 0;
+    for (uint32_t it = 0; it <= nb; it++) {
+        if ((rc = score(1))) return rc;
+        {
+            CVB_PROF(ctx, "k_ars_book", 0);
+            k_ars_book<<<1, ARS_BOOK_NT, ARS_BOOK_SMEM, st>>>(ctl, P, raw, (cvb_pose *)w->tposes.p, (uint32_t *)w->tinl.p, (uint32_t *)w->tmasks.p,
+                                                              (const cvb_pose *)w->newposes.p, (const uint8_t *)w->nposes_new.p,
+                                                              (const uint32_t *)w->newmask.p, (uint32_t *)w->pool.p, (uint32_t *)w->samples_new.p);
+            CVB_LAUNCH_CHECK(ctx);
+        }
+        if (it < nb && P.G)
+            if ((rc = estimate(1, P.G, (const uint32_t *)w->samples_new.p, (cvb_pose *)w->newposes.p, (uint8_t *)w->nposes_new.p))) return rc;
+    }
+    {
+        CVB_PROF(ctx, "k_ars_final", 0);
+        if (res == 0) k_ars_final<0><<<1, ARS_BOOK_NT, 0, st>>>(ctl, P, a_dev, b_dev, model_dev, inl_dev, cap, ninl_dev, found_dev);
+        else k_ars_final<1><<<1, ARS_BOOK_NT, 0, st>>>(ctl, P, a_dev, b_dev, model_dev, inl_dev, cap, ninl_dev, found_dev);
+        CVB_LAUNCH_CHECK(ctx);
+    }
+    CVB_CUDA(ctx, cudaMemcpyAsync(w->h_res, w->ctl.p, sizeof(ArrsacCtl), cudaMemcpyDeviceToHost, st));
+    w->pending = true;
+    return 0;
+}
+
+// after the stream has drained: advance the caller's generator by the draws the run consumed (state in == state the
+// reference would hold after model_inliers)
+int arrsac_commit_rng(cvb_ctx *ctx, cvb_rng *rng, ArrsacCtl *stats_out = nullptr) {
+    ArsWorkspace *w = arsws(ctx);
+    if (!w->pending) return cvb_set_error(ctx, CVB_EINVAL, "no device ARRSAC run to commit");
+    const ArrsacCtl *h = (const ArrsacCtl *)w->h_res;
+    if (stats_out) *stats_out = *h;
+    w->pending = false;
+    if (!rng) return 0;
+    const uint64_t used = h->rng_pos;
+    if (used >= w->nraw) {
+        if (h->gen_pos != std::max<uint64_t>(used, w->nraw)) return cvb_set_error(ctx, CVB_ECUDA, "generator position mismatch");
+        *rng = h->gen;
+        return 0;
+    }
+    cvb_rng g = w->snaps[used / ARS_SNAP];
+    for (uint64_t i = used / ARS_SNAP * ARS_SNAP; i < used; i++) cvb_rng_next_u32(&g);
+    *rng = g;
+    return 0;
+}
+
+// host-pointer entry: upload, run on the device, one synchronisation at the end
+int arrsac_host(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const double *a, const double *b, uint32_t n, cvb_rng *rng,
+                cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers, int32_t *found, int row0 = 5) {
+    *found = 0;
+    if (n_inliers) *n_inliers = 0;
+    if (n < kind_K(kind) || cfg->initialization_hypotheses == 0) return 0;
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = upload_data(ctx, kind, a, b, n);
+    if (rc) return rc;
+    GeomWorkspace *g = gws(ctx);
+    ArsWorkspace *w = arsws(ctx);
+    const size_t res_bytes = sizeof(cvb_pose) + 16 + sizeof(uint32_t) * (size_t)n;
+    if ((rc = w->res.ensure(ctx, res_bytes))) return rc;
+    unsigned char *rd = (unsigned char *)w->res.p;
+    cvb_pose *model_dev = (cvb_pose *)rd;
+    uint32_t *ninl_dev = (uint32_t *)(rd + sizeof(cvb_pose));
+    int32_t *found_dev = (int32_t *)(rd + sizeof(cvb_pose) + 4);
+    uint32_t *inl_dev = (uint32_t *)(rd + sizeof(cvb_pose) + 16);
+    if ((rc = arrsac_run_dev(ctx, cfg, kind, (const double *)g->a.p, (const double *)g->b.p, nullptr, n, n, rng, model_dev, inl_dev, n, ninl_dev,
+                             found_dev, row0))) return rc;
+    unsigned char *hs = (unsigned char *)cvb_pinned(ctx, res_bytes);
+    if (!hs) return cvb_set_error(ctx, CVB_ENOMEM, "page-locked scratch");
+    CVB_CUDA(ctx, cudaMemcpyAsync(hs, rd, res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = arrsac_commit_rng(ctx, rng))) return rc;
+    const uint32_t c = *(const uint32_t *)(hs + sizeof(cvb_pose));
+    *found = *(const int32_t *)(hs + sizeof(cvb_pose) + 4);
+    if (!*found) return 0;
+    memcpy(model_out, hs, sizeof(cvb_pose));
+    if (n_inliers) *n_inliers = c;
+    if (inliers_out) memcpy(inliers_out, hs + sizeof(cvb_pose) + 16, sizeof(uint32_t) * std::min(c, cap));
+    if (inliers_out && c > cap) return cvb_set_error(ctx, CVB_ECAP, "inlier capacity %u too small (%u needed)", cap, c);
+    return 0;
+}
+
+bool arrsac_on_host() {     // CVB_ARRSAC_HOST=1: round-1 driver (bookkeeping on the host) kept for A/B tests
+    const char *e = getenv("CVB_ARRSAC_HOST");
+    return e && e[0] == '1';
+}
+
 int residuals_host(cvb_ctx *ctx, int kind, const cvb_pose *poses, uint32_t m, const double *a, const double *b, uint32_t n, double *out) {
     if (!ctx) return CVB_EINVAL;
     if ((m && !poses) || (n && (!a || !b)) || (m && n && !out)) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
@@ -1491,7 +1748,8 @@ int cvb_arrsac_eight_point(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double
                            cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers, int32_t *found) {
     if (!ctx) return CVB_EINVAL;
     if (!cfg || !rng || !model_out || !found || (n && (!a || !b))) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
-    return arrsac_run(ctx, cfg, 0, a, b, n, rng, model_out, inliers_out, cap, n_inliers, found);
+    if (arrsac_on_host()) return arrsac_run(ctx, cfg, 0, a, b, n, rng, model_out, inliers_out, cap, n_inliers, found);
+    return arrsac_host(ctx, cfg, 0, a, b, n, rng, model_out, inliers_out, cap, n_inliers, found);
 }
 int cvb_arrsac_five_point(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *a, const double *b, uint32_t n, cvb_rng *rng,
                           int32_t eigenvector_row0, cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers,
@@ -1499,13 +1757,59 @@ int cvb_arrsac_five_point(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double 
     if (!ctx) return CVB_EINVAL;
     if (!cfg || !rng || !model_out || !found || (n && (!a || !b))) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
     if (eigenvector_row0 != 5 && eigenvector_row0 != 6) return cvb_set_error(ctx, CVB_EINVAL, "eigenvector_row0 must be 5 (reference) or 6 (corrected)");
-    return arrsac_run(ctx, cfg, 2, a, b, n, rng, model_out, inliers_out, cap, n_inliers, found, eigenvector_row0);
+    if (arrsac_on_host()) return arrsac_run(ctx, cfg, 2, a, b, n, rng, model_out, inliers_out, cap, n_inliers, found, eigenvector_row0);
+    return arrsac_host(ctx, cfg, 2, a, b, n, rng, model_out, inliers_out, cap, n_inliers, found, eigenvector_row0);
 }
 int cvb_arrsac_p3p(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *bearings, const double *world, uint32_t n, cvb_rng *rng,
                    cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers, int32_t *found) {
     if (!ctx) return CVB_EINVAL;
     if (!cfg || !rng || !model_out || !found || (n && (!bearings || !world))) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
-    return arrsac_run(ctx, cfg, 1, bearings, world, n, rng, model_out, inliers_out, cap, n_inliers, found);
+    if (arrsac_on_host()) return arrsac_run(ctx, cfg, 1, bearings, world, n, rng, model_out, inliers_out, cap, n_inliers, found);
+    return arrsac_host(ctx, cfg, 1, bearings, world, n, rng, model_out, inliers_out, cap, n_inliers, found);
+}
+
+// ---- device-resident entry points (asynchronous on the context stream) -----------------------------------------------------
+int cvb_pair_bearings_dev(cvb_ctx *ctx, const cvb_keypoint *kp_a_dev, const cvb_keypoint *kp_b_dev, const uint32_t *pairs_dev,
+                          const uint32_t *n_pairs_dev, uint32_t cap, const cvb_intrinsics *intrinsics, double *a_out_dev, double *b_out_dev) {
+    if (!ctx) return CVB_EINVAL;
+    if (!kp_a_dev || !kp_b_dev || !pairs_dev || !n_pairs_dev || !intrinsics || !a_out_dev || !b_out_dev) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    if (cap == 0) return 0;
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CVB_PROF(ctx, "k_pair_bearings", 0);
+    k_pair_bearings<<<cdiv(cap, 256), 256, 0, ctx->stream>>>(kp_a_dev, kp_b_dev, pairs_dev, n_pairs_dev, cap, *intrinsics, a_out_dev, b_out_dev);
+    CVB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+static int arrsac_dev_entry(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const double *a_dev, const double *b_dev, const uint32_t *n_dev,
+                            uint32_t n_max, const cvb_rng *rng, cvb_pose *model_out_dev, uint32_t *inliers_out_dev, uint32_t cap,
+                            uint32_t *n_inliers_dev, int32_t *found_dev) {
+    if (!ctx) return CVB_EINVAL;
+    if (!cfg || !rng || !a_dev || !b_dev || !n_dev || !model_out_dev || !n_inliers_dev || !found_dev) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return arrsac_run_dev(ctx, cfg, kind, a_dev, b_dev, n_dev, 0, n_max, rng, model_out_dev, inliers_out_dev, cap, n_inliers_dev, found_dev, 5);
+}
+int cvb_arrsac_eight_point_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *a_dev, const double *b_dev, const uint32_t *n_dev,
+                               uint32_t n_max, const cvb_rng *rng, cvb_pose *model_out_dev, uint32_t *inliers_out_dev, uint32_t cap,
+                               uint32_t *n_inliers_dev, int32_t *found_dev) {
+    return arrsac_dev_entry(ctx, cfg, 0, a_dev, b_dev, n_dev, n_max, rng, model_out_dev, inliers_out_dev, cap, n_inliers_dev, found_dev);
+}
+int cvb_arrsac_p3p_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *bearings_dev, const double *world_dev, const uint32_t *n_dev,
+                       uint32_t n_max, const cvb_rng *rng, cvb_pose *model_out_dev, uint32_t *inliers_out_dev, uint32_t cap,
+                       uint32_t *n_inliers_dev, int32_t *found_dev) {
+    return arrsac_dev_entry(ctx, cfg, 1, bearings_dev, world_dev, n_dev, n_max, rng, model_out_dev, inliers_out_dev, cap, n_inliers_dev, found_dev);
+}
+int cvb_arrsac_commit_rng(cvb_ctx *ctx, cvb_rng *rng, uint32_t *stats_out) {
+    if (!ctx) return CVB_EINVAL;
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ArrsacCtl h;
+    int rc = arrsac_commit_rng(ctx, rng, &h);
+    if (rc) return rc;
+    if (stats_out) {   // n, valid initial models, models that passed the SPRT, SPRT chunks, block iterations, draws consumed (low word), inliers, found
+        stats_out[0] = h.n; stats_out[1] = h.Mv; stats_out[2] = h.npass; stats_out[3] = h.stat_chunks; stats_out[4] = h.iters;
+        stats_out[5] = (uint32_t)h.rng_pos; stats_out[6] = h.n_inliers; stats_out[7] = h.found;
+    }
+    return 0;
 }
 
 int cvb_single_view_optimize_l2(cvb_ctx *ctx, const cvb_pose *poses, uint32_t B, double optimization_rate, uint32_t iterations,

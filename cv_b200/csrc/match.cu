@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(QT) k_hamming_knn(const uint8_t *__restrict__ 
                                                     uint32_t *__restrict__ partial) {
     __shared__ __align__(128) uint8_t s_db[2][DTILE * 64];
     __shared__ __align__(8) uint64_t s_bar[2];
-    const uint32_t n = n_dev ? *n_dev : n_host, m = m_dev ? *m_dev : m_host;
+    const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host, m = m_dev ? min(*m_dev, m_host) : m_host;
     const uint32_t q = blockIdx.x * QT + threadIdx.x;
     if (blockIdx.x * QT >= n) return;
     const uint32_t lo = min(blockIdx.y * chunk, m), hi = min(lo + chunk, m);
@@ -144,7 +144,7 @@ constexpr size_t IM_SMEM = 2 * (size_t)IM_DT * IM_ROWB + 2 * IM_DT * sizeof(uint
 // one warp per descriptor: 512 bits -> 512 bytes (0/1) + population count
 __global__ void __launch_bounds__(256) k_unpack_bits(const uint8_t *__restrict__ desc, const uint32_t *__restrict__ n_dev,
                                                      uint32_t n_host, uint8_t *__restrict__ U, uint16_t *__restrict__ pc) {
-    const uint32_t n = n_dev ? *n_dev : n_host;
+    const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
     const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= n) return;
     const uint32_t bits = ((const uint16_t *)(desc + (size_t)row * 64))[lane];   // bits 16*lane .. 16*lane+15
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32) k_hamming_imma(const uint8_t *_
     extern __shared__ __align__(128) uint8_t smraw[];
     uint8_t *s_db = smraw;                                              // [2][IM_DT][IM_ROWB]
     uint16_t *s_pb = (uint16_t *)(smraw + 2 * (size_t)IM_DT * IM_ROWB);   // [2][IM_DT]
-    const uint32_t n = n_dev ? *n_dev : n_host, m = m_dev ? *m_dev : m_host;
+    const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host, m = m_dev ? min(*m_dev, m_host) : m_host;
     if (blockIdx.x * IM_QT >= n) return;
     const uint32_t lo = min(blockIdx.y * chunk, m), hi = min(lo + chunk, m), cnt = hi - lo;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(IM_WARPS * 32) k_hamming_imma(const uint8_t *_
 template <int K>
 __global__ void k_knn_merge(const uint32_t *__restrict__ partial, const uint32_t *__restrict__ n_dev, uint32_t n_host,
                             uint32_t splits, uint32_t chunk, uint32_t *__restrict__ idx_out, uint32_t *__restrict__ dist_out) {
-    const uint32_t n = n_dev ? *n_dev : n_host;
+    const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     uint64_t best[K];
@@ -307,6 +307,52 @@ __global__ void k_symmetric(const uint32_t *__restrict__ fidx, const uint32_t *_
         }
     }
     flag[a] = f;
+}
+
+
+// symmetric rule with device-resident counts, followed by an ordered compaction into (a, b) index pairs (ascending a):
+// one CTA walks the n <= n_max queries in chunks of 1024 (cv-sfm/src/lib.rs:3097-3133)
+__global__ void __launch_bounds__(1024) k_symmetric_pairs(const uint32_t *__restrict__ fidx, const uint32_t *__restrict__ fdist,
+                                                          const uint32_t *__restrict__ ridx, const uint32_t *__restrict__ rdist,
+                                                          const uint32_t *__restrict__ n_dev, uint32_t n_max,
+                                                          const uint32_t *__restrict__ m_dev, uint32_t m_max, uint32_t better_by,
+                                                          uint32_t *__restrict__ pairs, uint32_t cap, uint32_t *__restrict__ npairs,
+                                                          uint32_t *__restrict__ overflow) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t n = min(*n_dev, n_max), m = min(*m_dev, m_max);
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t a = base + threadIdx.x;
+        uint32_t f = 0xffffffffu;
+        if (a < n && n >= 2 && m >= 2 && fdist[2 * a] + better_by <= fdist[2 * a + 1]) {
+            const uint32_t bix = fidx[2 * a];
+            if (rdist[2 * bix] + better_by <= rdist[2 * bix + 1] && ridx[2 * bix] == a) f = bix;
+        }
+        const uint32_t v = f != 0xffffffffu ? 1u : 0u;
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, x, o); if ((int)lane >= o) x += t; }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            const uint32_t y = s_warp[lane];
+            uint32_t z = y;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, z, o); if ((int)lane >= o) z += t; }
+            s_warp[lane] = z - y;
+        }
+        __syncthreads();
+        const uint32_t pos = s_carry + s_warp[wid] + x - v;
+        if (v) {
+            if (pos < cap) { pairs[2 * pos] = a; pairs[2 * pos + 1] = f; }
+            else if (overflow) *overflow = 1u;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = pos + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *npairs = min(s_carry, cap);
 }
 
 }  // namespace
@@ -501,6 +547,32 @@ int cvb_match_symmetric_dev(cvb_ctx *ctx, const uint8_t *a_dev, uint32_t n, cons
     if ((rc = knn_dev(ctx, a_dev, nullptr, n, b_dev, nullptr, m, 2, ws->idx, ws->dist))) return rc;
     if ((rc = knn_dev(ctx, b_dev, nullptr, m, a_dev, nullptr, n, 2, ws->idx2, ws->dist2))) return rc;
     k_symmetric<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ws->idx, ws->dist, ws->idx2, ws->dist2, n, m, better_by, match_out_dev);
+    CVB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int cvb_match_symmetric_pairs_dev(cvb_ctx *ctx, const uint8_t *a_dev, const uint32_t *n_dev, uint32_t n_max, const uint8_t *b_dev,
+                                  const uint32_t *m_dev, uint32_t m_max, uint32_t better_by, uint32_t *pairs_out_dev, uint32_t cap,
+                                  uint32_t *n_pairs_dev) {
+    if (!ctx) return CVB_EINVAL;
+    if (!a_dev || !b_dev || !n_dev || !m_dev || !pairs_out_dev || !n_pairs_dev) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_max < 2 || m_max < 2) {   // cv-sfm/src/lib.rs:3099-3101: no matches at all
+        CVB_CUDA(ctx, cudaMemsetAsync(n_pairs_dev, 0, sizeof(uint32_t), ctx->stream));
+        return 0;
+    }
+    if (!ctx->match) ctx->match = new MatchWorkspace();
+    MatchWorkspace *ws = ctx->match;
+    int rc;
+    if ((rc = grow(ctx, &ws->idx, &ws->idx_elems, (size_t)n_max * 2))) return rc;
+    if ((rc = grow(ctx, &ws->dist, &ws->dist_elems, (size_t)n_max * 2))) return rc;
+    if ((rc = grow(ctx, &ws->idx2, &ws->idx2_elems, (size_t)m_max * 2))) return rc;
+    if ((rc = grow(ctx, &ws->dist2, &ws->dist2_elems, (size_t)m_max * 2))) return rc;
+    if ((rc = knn_dev(ctx, a_dev, n_dev, n_max, b_dev, m_dev, m_max, 2, ws->idx, ws->dist))) return rc;
+    if ((rc = knn_dev(ctx, b_dev, m_dev, m_max, a_dev, n_dev, n_max, 2, ws->idx2, ws->dist2))) return rc;
+    CVB_PROF(ctx, "k_symmetric_pairs", 0);
+    k_symmetric_pairs<<<1, 1024, 0, ctx->stream>>>(ws->idx, ws->dist, ws->idx2, ws->dist2, n_dev, n_max, m_dev, m_max, better_by,
+                                                   pairs_out_dev, cap, n_pairs_dev, nullptr);
     CVB_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -160,8 +160,12 @@ int cvb_match_symmetric_dev(cvb_ctx *ctx, const uint8_t *a_dev, uint32_t n, cons
  *                                   cv-sfm/src/lib.rs:1394-1406,1619-1622, vslam-sandbox/src/main.rs:105-117)
  * Data: FeatureMatch = two unit bearings (a[i*3..], b[i*3..]); FeatureWorldMatch = unit bearing + homogeneous world
  * point xyzw (xyz unit, w = 1/distance >= 0).  All pointers are HOST pointers; every model hypothesis and every
- * (hypothesis, datum) residual is evaluated on the GPU; only ARRSAC's sequential bookkeeping (likelihood-ratio
- * test, sort/truncate, RNG draws) runs on the host, exactly in the restated reference order. */
+ * (hypothesis, datum) residual is evaluated on the GPU; ARRSAC's sequential bookkeeping (likelihood-ratio test, stable sort / truncate,
+ * consumption of the RNG draws) also runs on the device (cv_b200/csrc/arrsac_dev.cuh), in the order of the restated reference loop
+ * (oracle/ref_geom.c::ref_arrsac).  The arrsac crate's source is not available here: the control flow is a restatement, its
+ * inlier-set parity with the crate is unpinned; GPU and oracle agree bit for bit on inlier sets.
+ * Degenerate case: the 3x3 SVD of the essential matrix returns no poses when the second singular value is <= 1e-12 * s0, where
+ * nalgebra's SVD would still return four. */
 typedef struct { double r[9]; double t[3]; } cvb_pose;      /* IsometryMatrix3<f64>: rotation row-major, translation */
 typedef struct { int32_t kind; uint64_t s[4]; } cvb_rng;   /* kind 0: xoshiro256++ (SmallRng / Xoshiro256PlusPlus), 1: Pcg64 */
 typedef struct {
@@ -202,6 +206,52 @@ int cvb_arrsac_five_point(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double 
                           uint32_t *n_inliers, int32_t *found);
 int cvb_arrsac_p3p(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *bearings, const double *world, uint32_t n,
                    cvb_rng *rng, cvb_pose *model_out, uint32_t *inliers_out, uint32_t cap, uint32_t *n_inliers, int32_t *found);
+
+/* ---- device-resident geometric verification: nothing returns to the host between enqueue and result ---------------------------
+ * cv-sfm's two-view initialisation of one frame pair (cv-sfm/src/lib.rs:1375-1412): symmetric_matching (:3097-3133) -> FeatureMatch
+ * bearings of the matched keypoints (CameraModel::calibrate, cv-pinhole/src/lib.rs:108-116) -> Consensus::model_inliers
+ * (arrsac::Arrsac, configuration vslam-sandbox/src/main.rs:105-117).  All pointers below are DEVICE pointers unless stated; every call is
+ * asynchronous on the context stream.  ARRSAC's random draws come from a stream of raw next_u32() values generated on the host from
+ * *rng at call time (the generator is sequential; modulo and rejection run on the device because they need the datum count); the
+ * caller's generator is advanced by the number of draws actually consumed with cvb_arrsac_commit_rng after the stream has drained. */
+typedef struct { double fx, fy, cx, cy, skew; } cvb_intrinsics;   /* cv_pinhole::CameraIntrinsics (cv-pinhole/src/lib.rs:32-41), k1 = 0 */
+
+/* counts read from device memory (the n_out_dev of cvb_akaze_extract_batch_dev); pairs_out_dev: up to cap (a, b) index pairs in
+ * ascending a; *n_pairs_dev <= cap */
+int cvb_match_symmetric_pairs_dev(cvb_ctx *ctx, const uint8_t *a_dev, const uint32_t *n_dev, uint32_t n_max, const uint8_t *b_dev,
+                                  const uint32_t *m_dev, uint32_t m_max, uint32_t better_by, uint32_t *pairs_out_dev, uint32_t cap,
+                                  uint32_t *n_pairs_dev);
+/* a_out_dev[i*3..], b_out_dev[i*3..]: unit bearings of match i (keypoint pixel coordinates widened to f64, akaze/src/lib.rs:95-99) */
+int cvb_pair_bearings_dev(cvb_ctx *ctx, const cvb_keypoint *kp_a_dev, const cvb_keypoint *kp_b_dev, const uint32_t *pairs_dev,
+                          const uint32_t *n_pairs_dev, uint32_t cap, const cvb_intrinsics *intrinsics /* host */, double *a_out_dev,
+                          double *b_out_dev);
+/* Consensus::model_inliers with device data: a_dev/b_dev hold n_max rows, *n_dev of them valid.  cfg and rng are HOST pointers.
+ * *found_dev = 0 -> None.  inliers_out_dev (may be NULL): ascending datum indices, at most cap written; *n_inliers_dev = their number. */
+int cvb_arrsac_eight_point_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *a_dev, const double *b_dev, const uint32_t *n_dev,
+                               uint32_t n_max, const cvb_rng *rng, cvb_pose *model_out_dev, uint32_t *inliers_out_dev, uint32_t cap,
+                               uint32_t *n_inliers_dev, int32_t *found_dev);
+int cvb_arrsac_p3p_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *bearings_dev, const double *world_dev, const uint32_t *n_dev,
+                       uint32_t n_max, const cvb_rng *rng, cvb_pose *model_out_dev, uint32_t *inliers_out_dev, uint32_t cap,
+                       uint32_t *n_inliers_dev, int32_t *found_dev);
+/* Synchronises the context stream and advances *rng (host, may be NULL) past the draws the last cvb_arrsac_*_dev /
+ * cvb_two_view_* call consumed.  stats_out (host, 8 words, may be NULL): data, valid initial models, models that passed the SPRT,
+ * SPRT commit rounds, block iterations, draws consumed, inliers, found. */
+int cvb_arrsac_commit_rng(cvb_ctx *ctx, cvb_rng *rng, uint32_t *stats_out);
+
+/* One frame pair end to end on the device: symmetric match of the two descriptor sets, bearings, ARRSAC + eight-point.
+ * kp/desc/n: the two frames' extraction results (device).  pairs_out_dev: cap x 2; inliers_out_dev: cap (indices into pairs). */
+int cvb_two_view_pair_dev(cvb_ctx *ctx, const cvb_keypoint *kp_a_dev, const uint8_t *desc_a_dev, const uint32_t *n_a_dev,
+                          const cvb_keypoint *kp_b_dev, const uint8_t *desc_b_dev, const uint32_t *n_b_dev, uint32_t n_max,
+                          uint32_t better_by, const cvb_intrinsics *intrinsics, const cvb_arrsac_cfg *cfg, const cvb_rng *rng,
+                          uint32_t *pairs_out_dev, uint32_t cap, uint32_t *n_pairs_dev, cvb_pose *model_out_dev,
+                          uint32_t *inliers_out_dev, uint32_t *n_inliers_dev, int32_t *found_dev);
+/* The same from two HOST frames (f32, w x h each, contiguous) to HOST results, one synchronisation at the end: AKAZE extract of both
+ * frames (one batched pass), then cvb_two_view_pair_dev.  kp_out: 2 x cap, desc_out: 2 x cap x 64, n_out: 2, pairs_out: cap x 2,
+ * inliers_out: cap.  *rng is advanced like the reference's generator.  Page-locked output buffers avoid staged copies. */
+int cvb_two_view_frames(cvb_ctx *ctx, const cvb_akaze_cfg *akaze, const float *frames, uint32_t w, uint32_t h, uint32_t better_by,
+                        const cvb_intrinsics *intrinsics, const cvb_arrsac_cfg *cfg, cvb_rng *rng, cvb_keypoint *kp_out, uint8_t *desc_out,
+                        uint32_t cap, uint32_t *n_out, uint32_t *pairs_out, uint32_t *n_pairs, cvb_pose *model_out, uint32_t *inliers_out,
+                        uint32_t *n_inliers, int32_t *found);
 
 /* ---- post-consensus refinement and robustness checks ------------------------------
  *   cvb_single_view_optimize_l2 <- cv_optimize::single_view_simple_optimize_l2   cv-optimize/src/single_view_optimizer.rs:80-135

@@ -1,0 +1,90 @@
+"""CPU: the exact-predicate filter that replaces most CameraToCamera::residual evaluations inside ARRSAC
+(cv_b200/csrc/c2c_filter.cuh, compiled for the host by tests/csrc/c2c_filter_host.c) never contradicts the oracle's exact
+evaluation of `residual < threshold` (cv-core/src/pose.rs:249-296), and leaves only a small fraction undecided."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from tests.geom_util import two_view_scene
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def filt():
+    out = os.path.join(HERE, "csrc", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libc2c_filter_host.so")
+    src = os.path.join(HERE, "csrc", "c2c_filter_host.c")
+    hdr = os.path.join(HERE, "..", "cv_b200", "csrc", "c2c_filter.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c", src, "-o", so, "-lm"])
+    L = C.CDLL(so)
+    L.c2c_filter_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_void_p]
+    L.c2c_filter_batch.restype = None
+    return L
+
+
+def _poses(a, b, rng, nh, pool=None):
+    out = []
+    n = len(a) if pool is None else len(pool)
+    for _ in range(nh):
+        idx = rng.choice(n, 8, replace=False)
+        if pool is not None:
+            idx = pool[idx]
+        out += O.eight_point(a[idx], b[idx])
+    return out
+
+
+def _check(filt, poses, a, b, thr):
+    P = np.ascontiguousarray([np.concatenate([R.reshape(9), t]) for R, t in poses], np.float64)
+    out = np.zeros((len(P), len(a)), np.int8)
+    filt.c2c_filter_batch(P.ctypes.data, len(P), a.ctypes.data, b.ctypes.data, len(a), thr, out.ctypes.data)
+    exact = np.array([[O.residual_c2c(R, t, a[i], b[i]) < thr for i in range(len(a))] for R, t in poses])
+    decided = out >= 0
+    assert np.array_equal(out[decided] == 1, exact[decided])
+    return decided.mean(), exact.mean()
+
+
+def test_filter_agrees_with_exact_predicate_on_bench_pair(filt):
+    z = np.load(os.path.join(HERE, "golden", "bench_pair0.npz"))
+    a, b = np.ascontiguousarray(z["ba"][:600]), np.ascontiguousarray(z["bb"][:600])
+    rng = np.random.default_rng(0)
+    poses = _poses(a, b, rng, 12)
+    dec, inl = _check(filt, poses, a, b, 1e-7)
+    assert dec > 0.98
+    # hypotheses generated from the inliers of a good model: most data sit close to the threshold
+    best = max(poses, key=lambda p: sum(O.residual_c2c(p[0], p[1], a[i], b[i]) < 1e-7 for i in range(len(a))))
+    pool = np.array([i for i in range(len(a)) if O.residual_c2c(best[0], best[1], a[i], b[i]) < 1e-7])
+    assert len(pool) > 100
+    dec, inl = _check(filt, _poses(a, b, rng, 12, pool), a, b, 1e-7)
+    assert dec > 0.97 and inl > 0.05
+
+
+@pytest.mark.parametrize("thr,noise", [(1e-7, 5e-5), (1e-6, 2e-4), (1e-9, 0.0), (1e-5, 1e-3)])
+def test_filter_agrees_on_synthetic_scenes(filt, thr, noise):
+    rng = np.random.default_rng(int(-np.log10(thr)))
+    R, t, a, b, good = two_view_scene(rng, 300, outlier_frac=0.3, noise=noise)
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    poses = _poses(a, b, rng, 10) + [(R, t)]
+    dec, _ = _check(filt, poses, a, b, thr)
+    assert dec > 0.9
+
+
+def test_filter_declines_large_thresholds_and_degenerate_input(filt):
+    rng = np.random.default_rng(3)
+    R, t, a, b, _ = two_view_scene(rng, 50)
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    P = np.ascontiguousarray([np.concatenate([R.reshape(9), t])], np.float64)
+    out = np.zeros((1, 50), np.int8)
+    filt.c2c_filter_batch(P.ctypes.data, 1, a.ctypes.data, b.ctypes.data, 50, 0.1, out.ctypes.data)     # akaze/tests/estimate_pose.rs:63
+    assert (out == -1).all()
+    Pz = np.ascontiguousarray([np.concatenate([np.eye(3).reshape(9), np.zeros(3)])], np.float64)       # t = 0: rank-deficient design
+    filt.c2c_filter_batch(Pz.ctypes.data, 1, a.ctypes.data, a.ctypes.data, 50, 1e-7, out.ctypes.data)
+    exact = np.array([O.residual_c2c(np.eye(3), np.zeros(3), a[i], a[i]) < 1e-7 for i in range(50)])
+    d = out[0] >= 0
+    assert np.array_equal(out[0][d] == 1, exact[d])
