@@ -1,20 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the hot path (BASELINE.json configs[1]).
+"""bench.py -- headline benchmark: BASELINE.json's metric, "vSLAM frames/s (AKAZE+match+RANSAC, 1080p ~5k kp)".
 
-Workload ("step"): one frame PAIR of synthetic 1920x1080 f32 images, ~5k keypoints each:
-  AKAZE extract on both frames (one batched pass) -> symmetric brute-force Hamming 2-NN match
-  (forward + reverse, cv-sfm rule d0 + 24 <= d1 with cross-check).
-metric = frames/s (2 frames per step per GPU).  N>1: every rank runs its own frame pairs
-(frames are independent -> weak scaling, no data-path collective).
+One frame PAIR of the workload is the sequence cv-sfm runs for a two-view initialisation (cv-sfm/src/lib.rs:2200-2204, 1375-1412):
+  AKAZE extract of both 1920x1080 f32 frames (~5k keypoints each, one batched pass)
+  -> symmetric brute-force Hamming 2-NN match (rule d0 + 24 <= d1, cross-check)
+  -> calibrated bearings of the matched keypoints (f = 1000 px, c = (960, 540))
+  -> Arrsac(1e-7, Xoshiro256++).initialization_hypotheses(8192).max_candidate_hypotheses(1024) + EightPoint
+     (the two-view consensus of vslam-sandbox/src/main.rs:112-117), every stage on the GPU, nothing returns to the host in between.
+A "step" is one batch of PAIRS_PER_STEP such pairs (declared in config); metric = frames/s = 2 * pairs / time.
+N>1: every rank processes its own frame pairs (independent -> weak scaling, no data-path collective).
 
-  value : device-resident inputs/outputs (inputs already in HBM), CUDA-event timed, max over ranks
-  e2e   : the same step through the reference-facing host API (pinned HOST buffers in, keypoints /
-          descriptors / match pairs back on the host), copies inside the timed region
-  roofline : dominant kernel, algorithmic bytes / CUDA-event duration from an instrumented pass
-  cpu_baseline : the CPU oracle (restated reference) timed on this box's host cores, bounded sample
+  value : device-resident frames, results stay in HBM; CUDA events, max over ranks
+  e2e   : the host entry point cvb_two_view_frames: pinned HOST frames in, keypoints / descriptors / matches / pose / inliers back
+          on the host, copies inside the timed region
+  roofline : dominant HBM-modelled kernel: algorithmic bytes / CUDA-event duration (instrumented pass) + the RANSAC kernels' figures
+  cpu_baseline : the CPU oracle (restated reference, -O3) on this box's host cores, bounded sample, all-core and 1-thread
 
-`--impl reference` times the reference's CPU implementation (the oracle port; the Rust original cannot
-be built: no cargo/rustc in the image) on the same config and prints the same JSON line.
+`--impl reference` times the reference's CPU implementation (the oracle port; the Rust original cannot be built: no cargo/rustc
+in the image) on the same workload and prints the same JSON line.
 """
 import argparse
 import ctypes as C
@@ -34,11 +37,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "vSLAM frames/s (AKAZE+match+RANSAC, 1080p ~5k kp) at 1/2/4/8 B200"     # BASELINE.json, verbatim
 W, H = 1920, 1080
 MAXF = 5000            # maximum_features -> exactly "~5k keypoints" per frame
 BETTER_BY = 24         # cv-sfm/src/settings.rs:397-399
 POOL_PAIRS = 8         # 16 distinct frames = 133 MB > 126 MB L2: step inputs are never L2-resident
+PAIRS_PER_STEP = 16    # one step = one batch of 16 frame pairs (32 frames)
+FOCAL, CX, CY = 1000.0, 960.0, 540.0
+ARRSAC = dict(threshold=1e-7, initialization_hypotheses=8192, max_candidate_hypotheses=1024)      # vslam-sandbox/src/main.rs:112-117
 ALG_BYTES_PER_FRAME = 4 * (13 * 11016000 + 3 * 40759200 + 4 * 2073600)   # 1.095 GB
+WORKLOAD = ("configs[1]+[2]: AKAZE extract x2 + symmetric Hamming 2-NN + ARRSAC(1e-7, init 8192, max_cand 1024)/eight-point, "
+            "2 frames 1920x1080 f32, ~5k kp/frame")
 
 
 def make_pool(npairs, seed0=0):
@@ -51,7 +60,7 @@ def make_pool(npairs, seed0=0):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """NVML clocks / throttle reasons sampled during the timed regions."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -97,43 +106,60 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def cpu_reference_step(frames, reps):
-    """The reference's CPU path (oracle port): extract both frames, symmetric 2-NN match. Returns seconds/step."""
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_pair(pair, threads):
+    """The reference's CPU path (oracle port) on one frame pair: extract both frames, symmetric 2-NN match, calibrate, ARRSAC +
+    eight-point.  Returns (seconds, matches, inliers or None, bearings)."""
     from oracle import pyoracle as O
-    O.set_num_threads(os.cpu_count())      # torchrun exports OMP_NUM_THREADS=1; the CPU arm may use every host thread
+    O.set_num_threads(threads)      # torchrun exports OMP_NUM_THREADS=1; the CPU arm may use every host thread
     t0 = time.perf_counter()
-    for r in range(reps):
-        pair = frames[r % len(frames)]
-        ds = []
-        for f in pair:
-            ak = O.Akaze(maximum_features=MAXF)
-            _, d = ak.extract(f)
-            ds.append(d)
-        fi, fd = O.hamming_knn(ds[0], ds[1], 2)
-        ri, rd = O.hamming_knn(ds[1], ds[0], 2)
-        fwd = np.where(fd[:, 0] + BETTER_BY <= fd[:, 1], fi[:, 0].astype(np.int64), -1)
-        rev = np.where(rd[:, 0] + BETTER_BY <= rd[:, 1], ri[:, 0].astype(np.int64), -1)
-        _ = [(i, j) for i, j in enumerate(fwd) if j >= 0 and rev[j] == i]
-    return (time.perf_counter() - t0) / reps
+    ks, ds = [], []
+    for f in pair:
+        k, d = O.Akaze(maximum_features=MAXF).extract(f)
+        ks.append(k); ds.append(d)
+    fi, fd = O.hamming_knn(ds[0], ds[1], 2)
+    ri, rd = O.hamming_knn(ds[1], ds[0], 2)
+    fwd = np.where(fd[:, 0] + BETTER_BY <= fd[:, 1], fi[:, 0].astype(np.int64), -1)
+    rev = np.where(rd[:, 0] + BETTER_BY <= rd[:, 1], ri[:, 0].astype(np.int64), -1)
+    pairs = np.array([(i, j) for i, j in enumerate(fwd) if j >= 0 and rev[j] == i], np.int64).reshape(-1, 2)
+    ba, bb = calibrate_np(ks[0][pairs[:, 0]]), calibrate_np(ks[1][pairs[:, 1]])
+    cfg = O.arrsac_cfg(ARRSAC["threshold"], initialization_hypotheses=ARRSAC["initialization_hypotheses"],
+                       max_candidate_hypotheses=ARRSAC["max_candidate_hypotheses"])
+    r = O.arrsac(cfg, 0, ba, bb, O.rng_xoshiro(0)) if len(pairs) else None
+    return time.perf_counter() - t0, len(pairs), (None if r is None else r[2]), (ba, bb)
+
+
+def calibrate_np(kps):
+    """cv-pinhole CameraIntrinsics::calibrate, identical to cv_b200/pinhole.py (no import of the product in the CPU arm)."""
+    y = (kps["y"].astype(np.float64) - CY) / FOCAL
+    x = (kps["x"].astype(np.float64) - CX - 0.0 * y) / FOCAL
+    n = np.sqrt(x * x + y * y + 1.0)
+    return np.stack([x / n, y / n, 1.0 / n], 1)
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    frames = make_pool(1)
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_step(frames, 1)
-    steps = max(1, min(args.steps, 3))       # bounded sample: ~5 s of CPU work per step
-    sec = cpu_reference_step(frames, steps)
-    fps = 2.0 / sec
+    frames = make_pool(2)
     cores = os.cpu_count()
-    line = {"metric": "vSLAM frames/s (AKAZE+match, 1080p ~5k kp)", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+    for i in range(min(args.warmup, 1)):
+        cpu_reference_pair(frames[i % 2], cores)
+    steps = max(1, min(args.steps, 4))       # bounded sample: one frame pair (~5 s of CPU work) per step
+    t = [cpu_reference_pair(frames[i % 2], cores) for i in range(steps)]
+    sec = sum(x[0] for x in t) / steps
+    fps = 2.0 / sec
+    sec1 = cpu_reference_pair(frames[0], 1)[0]      # the reference's default build is unthreaded (akaze/README.md:22)
+    line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "configs[1]: AKAZE extract x2 + symmetric Hamming 2-NN, 2 frames 1920x1080 f32, ~5k kp/frame",
-                       "maximum_features": MAXF, "detector_threshold": 0.001, "better_by": BETTER_BY},
+            "config": {"workload": WORKLOAD, "maximum_features": MAXF, "detector_threshold": 0.001, "better_by": BETTER_BY, "arrsac": ARRSAC,
+                       "pairs_per_step": 1, "note": "bounded sample: one frame pair per step (the GPU arm's step is a batch of "
+                                                    f"{PAIRS_PER_STEP} pairs); frames/s is step-size independent"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"{steps} frame pair(s); C restatement of rust-cv akaze/space (oracle/), OpenMP at the reference's rayon sites"},
+                             "single_thread_value": 2.0 / sec1,
+                             "sample": f"{steps} frame pair(s), matches {t[0][1]}, inliers {0 if t[0][2] is None else len(t[0][2])}; C restatement of "
+                                       "rust-cv akaze/space/arrsac/eight-point (oracle/, -O3 -march=x86-64-v3 -ffp-contract=off), OpenMP at the reference's "
+                                       "rayon sites and over independent hypotheses; single_thread_value = the same pair on 1 thread"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -173,6 +199,8 @@ def main():
     import torch.distributed as dist
     import cv_b200
     from cv_b200._lib import KP_DTYPE
+    from cv_b200.geom import ArrsacCfg, Pose, Rng, _lib as geom_lib
+    from cv_b200.pair import Intrinsics, bind as pair_bind
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
@@ -181,42 +209,90 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    # every distinct input buffer gets its CUDA graph captured during warm-up, never inside the timed region
-    K, Wm = args.steps, max(args.warmup, 3, POOL_PAIRS)
+    K, Wm = max(args.steps, 1), max(args.warmup, 3)          # timing rule: at least 3 warm-up steps
+    NCTX = int(os.environ.get("CVB_BENCH_CONTEXTS", "16"))   # contexts (stream + workspace + host thread each) pipelined on the GPU
 
     frames = make_pool(POOL_PAIRS, seed0=100 * rank)
-    # Two independent contexts (each owns a CUDA stream + workspace; the ABI makes distinct contexts independent)
-    # alternate steps, so the latency-bound keypoint tail of step i overlaps the image pipeline of step i+1.
-    # Timing: CUDA events on the launching stream of context 0, bracketed by full-device synchronisation.
-    NCTX = int(os.environ.get("CVB_BENCH_CONTEXTS", "12"))          # contexts pipelined in the device-resident measurement
-    NHOST = min(NCTX, int(os.environ.get("CVB_BENCH_HOST_THREADS", "12")))   # host threads (one context each) in the e2e measurement
     ctxs = [cv_b200.Context(local_rank) for _ in range(NCTX)]
     ctx = ctxs[0]
     lib = ctx.lib
-    cfg = cv_b200.AkazeConfig(maximum_features=MAXF).to_c()
-    cap = 8192
-    # ---- device-resident buffers (one output set per context)
+    geom_lib(ctx)
+    pair_bind(lib)
+    akaze_cfg = cv_b200.AkazeConfig(maximum_features=MAXF).to_c()
+    intr = Intrinsics(FOCAL, FOCAL, CX, CY, 0.0)
+    acfg = ArrsacCfg()
+    lib.cvb_arrsac_default_cfg(C.byref(acfg), ARRSAC["threshold"])
+    acfg.initialization_hypotheses = ARRSAC["initialization_hypotheses"]
+    acfg.max_candidate_hypotheses = ARRSAC["max_candidate_hypotheses"]
+    cap = MAXF
     d_pool = [torch.from_numpy(p).to(dev) for p in frames]
+    h_pool = [torch.from_numpy(p).pin_memory() for p in frames]
 
-    class Out:
+    class Slot:
+        """Everything one context owns: device result buffers, pinned host result buffers, its consensus generator (the
+        two_view_consensus object of a VSlam instance keeps its generator across frame pairs)."""
         def __init__(self):
             self.kp = torch.empty(2 * cap * KP_DTYPE.itemsize, dtype=torch.uint8, device=dev)
             self.desc = torch.zeros(2 * cap * 64, dtype=torch.uint8, device=dev)
             self.n = torch.zeros(2, dtype=torch.int32, device=dev)
-            self.fi = torch.empty(cap * 2, dtype=torch.int32, device=dev); self.fd = torch.empty_like(self.fi)
-            self.ri = torch.empty(cap * 2, dtype=torch.int32, device=dev); self.rd = torch.empty_like(self.ri)
-    outs = [Out() for _ in range(NCTX)]
+            self.pairs = torch.zeros(cap * 2, dtype=torch.int32, device=dev)
+            self.inl = torch.zeros(cap, dtype=torch.int32, device=dev)
+            self.cnt = torch.zeros(4, dtype=torch.int32, device=dev)      # n_pairs, n_inliers, found
+            self.model = torch.zeros(12, dtype=torch.float64, device=dev)
+            self.h_kp = torch.empty(2 * cap * KP_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+            self.h_desc = torch.empty(2 * cap * 64, dtype=torch.uint8).pin_memory()
+            self.h_pairs = torch.empty(cap * 2, dtype=torch.int32).pin_memory()
+            self.h_inl = torch.empty(cap, dtype=torch.int32).pin_memory()
+            self.h_n = (C.c_uint32 * 2)()
+            self.h_np, self.h_ni, self.h_found = C.c_uint32(), C.c_uint32(), C.c_int32()
+            self.h_model = Pose()
+            self.rng = Rng()
+            lib.cvb_rng_seed_xoshiro256pp(C.byref(self.rng), 0)
+            self.stats = (C.c_uint32 * 8)()
+            self.pairs_done = 0
+            self.t_busy = 0.0
+    slots = [Slot() for _ in range(NCTX)]
 
-    def step_dev(i, c=None):
-        c = i % NCTX if c is None else c
-        cx, o = ctxs[c], outs[c]
+    def pair_dev(i, c):
+        """device-resident: frames already in HBM, results stay in HBM; one synchronisation (the generator commit)"""
+        cx, s = ctxs[c], slots[c]
         img = d_pool[i % POOL_PAIRS]
-        cx.check(lib.cvb_akaze_extract_batch_dev(cx.handle, C.byref(cfg), img.data_ptr(), 2, W, H, o.kp.data_ptr(),
-                                                 o.desc.data_ptr(), cap, o.n.data_ptr()))
-        da, db = o.desc.data_ptr(), o.desc.data_ptr() + cap * 64
-        na, nb = o.n.data_ptr(), o.n.data_ptr() + 4
-        cx.check(lib.cvb_hamming_knn_dev_counts(cx.handle, da, na, MAXF, db, nb, MAXF, 2, o.fi.data_ptr(), o.fd.data_ptr()))
-        cx.check(lib.cvb_hamming_knn_dev_counts(cx.handle, db, nb, MAXF, da, na, MAXF, 2, o.ri.data_ptr(), o.rd.data_ptr()))
+        cx.check(lib.cvb_akaze_extract_batch_dev(cx.handle, C.byref(akaze_cfg), img.data_ptr(), 2, W, H, s.kp.data_ptr(), s.desc.data_ptr(), cap,
+                                                 s.n.data_ptr()))
+        cx.check(lib.cvb_two_view_pair_dev(cx.handle, s.kp.data_ptr(), s.desc.data_ptr(), s.n.data_ptr(),
+                                           s.kp.data_ptr() + cap * KP_DTYPE.itemsize, s.desc.data_ptr() + cap * 64, s.n.data_ptr() + 4, cap,
+                                           BETTER_BY, C.byref(intr), C.addressof(acfg), C.addressof(s.rng), s.pairs.data_ptr(), cap,
+                                           s.cnt.data_ptr(), s.model.data_ptr(), s.inl.data_ptr(), s.cnt.data_ptr() + 4, s.cnt.data_ptr() + 8))
+        cx.check(lib.cvb_arrsac_commit_rng(cx.handle, C.addressof(s.rng), s.stats))
+
+    def pair_host(i, c):
+        """end to end: pinned host frames in, every result back on the host"""
+        cx, s = ctxs[c], slots[c]
+        img = h_pool[i % POOL_PAIRS]
+        cx.check(lib.cvb_two_view_frames(cx.handle, C.addressof(akaze_cfg), img.data_ptr(), W, H, BETTER_BY, C.byref(intr), C.addressof(acfg),
+                                         C.addressof(s.rng), s.h_kp.data_ptr(), s.h_desc.data_ptr(), cap, s.h_n, s.h_pairs.data_ptr(),
+                                         C.byref(s.h_np), C.byref(s.h_model), s.h_inl.data_ptr(), C.byref(s.h_ni), C.byref(s.h_found)))
+
+    def run_pairs(fn, first, count, nthreads=NCTX):
+        """`count` pairs handed out dynamically to one host thread per context (the blocking C calls release the GIL)"""
+        lock, nxt = threading.Lock(), [first]
+
+        def worker(c):
+            while True:
+                with lock:
+                    i = nxt[0]
+                    if i >= first + count:
+                        return
+                    nxt[0] = i + 1
+                t0 = time.perf_counter()
+                fn(i, c)
+                slots[c].t_busy += time.perf_counter() - t0
+                slots[c].pairs_done += 1
+        th = [threading.Thread(target=worker, args=(c,)) for c in range(nthreads)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
 
     def barrier():
         for cx in ctxs:
@@ -226,11 +302,16 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for c in range(NCTX):                      # every (context, input buffer) pair captures its CUDA graph here
-        for i in range(max(Wm, POOL_PAIRS)):
-            step_dev(i, c)
+    def reset_rngs():
+        for s in slots:
+            lib.cvb_rng_seed_xoshiro256pp(C.byref(s.rng), 0)
+            s.pairs_done = 0; s.t_busy = 0.0
+
+    # ---- setup (not a warm-up step): every (context, input buffer) pair captures its extraction graph; workspaces are allocated
+    for c in range(NCTX):
+        for i in range(POOL_PAIRS):
+            pair_dev(i, c)
     barrier()
-    n_kp = outs[0].n.cpu().numpy().tolist()
     try:
         pr = torch.cuda.get_device_properties(local_rank)
         pci = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
@@ -238,96 +319,86 @@ def main():
         pci = None
     sampler = ClockSampler(local_rank, pci)
     sampler.start()
-    l0 = sum(cx.launch_count() for cx in ctxs)
+
+    # ---- value: device-resident, W warm-up steps then exactly K timed steps of PAIRS_PER_STEP pairs
+    reset_rngs()
+    run_pairs(pair_dev, 0, Wm * PAIRS_PER_STEP)
     barrier()
+    l0 = sum(cx.launch_count() for cx in ctxs)
+    for s in slots:
+        s.pairs_done = 0; s.t_busy = 0.0
     t0 = time.perf_counter()
-    ctx.timer_begin()
-    for i in range(K):
-        step_dev(Wm + i)
-    enqueue_ms = (time.perf_counter() - t0) * 1e3      # host time to launch all K steps (one thread); must stay below the device time
-    for cx in ctxs[1:]:
-        cx.sync()                 # the other stream has drained before the end event is recorded
-    ms = ctx.timer_end()          # CUDA events on context 0's launching stream; waits for the end event
+    ctx.timer_begin()                      # CUDA events on context 0's stream, which is idle here and again at timer_end
+    run_pairs(pair_dev, Wm * PAIRS_PER_STEP, K * PAIRS_PER_STEP)     # every worker returns with its stream drained (generator commit)
+    ms = ctx.timer_end()
     wall_ms = (time.perf_counter() - t0) * 1e3
     barrier()
     assert ms > 0.5 * wall_ms or wall_ms < 1.0, f"device timer {ms} ms disagrees with wall clock {wall_ms} ms"
     launches = sum(cx.launch_count() for cx in ctxs) - l0
     from cv_b200 import dist as D
-    value, ms_max = D.aggregate_throughput(2.0 * K, ms, dev)      # units of all ranks / max-over-ranks device time
+    value, ms_max = D.aggregate_throughput(2.0 * K * PAIRS_PER_STEP, ms, dev)      # frames of all ranks / max-over-ranks device time
+    dev_busy = [round(s.t_busy / max(s.pairs_done, 1) * 1e3, 3) for s in slots]
+    stats0 = [int(x) for x in slots[0].stats]
+    n_kp = slots[0].n.cpu().numpy().tolist()
+    cnt0 = slots[0].cnt.cpu().numpy().tolist()
 
-    # ---- e2e: host API with pinned host buffers (H2D frames, D2H keypoints/descriptors, H2D descriptors, D2H pairs).
-    # One host thread per context (the blocking C calls release the GIL), steps alternate between them.
-    h_pool = [torch.from_numpy(p).pin_memory() for p in frames]
-
-    class HostOut:
-        def __init__(self):
-            self.kp = torch.empty(2 * cap * KP_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-            self.desc = torch.empty(2 * cap * 64, dtype=torch.uint8).pin_memory()
-            self.n = torch.zeros(2, dtype=torch.int32).pin_memory()
-            self.pairs = torch.empty(cap * 2, dtype=torch.int32).pin_memory()
-            self.npairs = C.c_uint32()
-            self.h2d = self.d2h = 0
-            self.t_extract = self.t_match = 0.0
-            self.steps = 0
-    houts = [HostOut() for _ in range(NHOST)]
-
-    def step_host(i, c):
-        cx, o = ctxs[c], houts[c]
-        img = h_pool[i % POOL_PAIRS]
-        t0 = time.perf_counter()
-        cx.check(lib.cvb_akaze_extract_batch(cx.handle, C.byref(cfg), img.data_ptr(), 2, W, H, o.kp.data_ptr(), o.desc.data_ptr(),
-                                             cap, o.n.data_ptr()))
-        t1 = time.perf_counter()
-        na, nb = int(o.n[0]), int(o.n[1])
-        cx.check(lib.cvb_match_symmetric(cx.handle, o.desc.data_ptr(), na, o.desc.data_ptr() + cap * 64, nb, BETTER_BY,
-                                         o.pairs.data_ptr(), cap, C.byref(o.npairs)))
-        o.t_extract += t1 - t0; o.t_match += time.perf_counter() - t1; o.steps += 1
-        o.h2d = 2 * W * H * 4 + (na + nb) * 64
-        o.d2h = 8 + 4 + (na + nb) * (KP_DTYPE.itemsize + 64) + na * 4
-        return o.npairs.value
-
-    def host_worker(c, take):
-        while True:              # steps are handed out dynamically: a thread that finishes early takes the next one
-            i = take()
-            if i is None:
-                return
-            step_host(i, c)
-
-    def run_host(first, count):
-        lock, nxt = threading.Lock(), [first]
-
-        def take():
-            with lock:
-                i = nxt[0]
-                if i >= first + count:
-                    return None
-                nxt[0] = i + 1
-                return i
-        th = [threading.Thread(target=host_worker, args=(c, take)) for c in range(NHOST)]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-
-    run_host(0, max(Wm, 3 * NHOST))          # every host thread / context has run a few steps before the timed region
-    nm = houts[0].npairs.value
+    # ---- e2e: host entry point, pinned host buffers, copies inside the timed region
+    reset_rngs()
+    run_pairs(pair_host, 0, Wm * PAIRS_PER_STEP)
     barrier()
+    for s in slots:
+        s.pairs_done = 0; s.t_busy = 0.0
     t0 = time.perf_counter()
-    for o in houts:
-        o.t_extract = o.t_match = 0.0; o.steps = 0
-    run_host(Wm, K)
+    run_pairs(pair_host, Wm * PAIRS_PER_STEP, K * PAIRS_PER_STEP)
     ms_e2e = (time.perf_counter() - t0) * 1e3     # blocking host API: wall clock over the K steps (all results on the host)
     barrier()
-    h2d, d2h = houts[0].h2d, houts[0].d2h
-    e2e_value, _ = D.aggregate_throughput(2.0 * K, ms_e2e, dev)
+    s0 = slots[0]
+    nb_max = (cap + 63) // 64 + 1
+    nraw = 8192 * 8 + 8192 * 8 // 4 + 64 + nb_max * (64 * 8 + 64 * 8 // 4 + 64)     # geom.cu: arrsac_run_dev
+    h2d_step = PAIRS_PER_STEP * (2 * W * H * 4 + 4 * nraw + 160)                  # frames + the consensus generator's draw stream + control block
+    d2h_step = PAIRS_PER_STEP * (2 * cap * (KP_DTYPE.itemsize + 64) + cap * 8 + cap * 4 + 16 + 96 + 8 + 160)
+    e2e_value, _ = D.aggregate_throughput(2.0 * K * PAIRS_PER_STEP, ms_e2e, dev)
+    e2e_busy = [round(s.t_busy / max(s.pairs_done, 1) * 1e3, 3) for s in slots]
+    e2e_pairs = [s.pairs_done for s in slots]
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # ---- parity of the benchmarked result: pair 0 through the host entry point vs the CPU oracle on the same bearings
+    inliers_equal_oracle = None
+    ransac = None
+    if rank == 0:
+        try:
+            lib.cvb_rng_seed_xoshiro256pp(C.byref(s0.rng), 0)
+            pair_host(0, 0)
+            npairs, ninl = int(s0.h_np.value), int(s0.h_ni.value)
+            kp = np.frombuffer(s0.h_kp.numpy().tobytes(), dtype=KP_DTYPE)
+            pr_ = s0.h_pairs.numpy()[:2 * npairs].reshape(-1, 2).astype(np.int64)
+            ba, bb = calibrate_np(kp[:cap][pr_[:, 0]]), calibrate_np(kp[cap:2 * cap][pr_[:, 1]])
+            gpu_inl = s0.h_inl.numpy()[:ninl].astype(np.int64)
+            from oracle import pyoracle as O      # checker only
+            O.set_num_threads(os.cpu_count())
+            want = O.arrsac(O.arrsac_cfg(ARRSAC["threshold"], initialization_hypotheses=ARRSAC["initialization_hypotheses"],
+                                         max_candidate_hypotheses=ARRSAC["max_candidate_hypotheses"]), 0, ba, bb, O.rng_xoshiro(0))
+            inliers_equal_oracle = bool(want is not None and int(s0.h_found.value) == 1 and np.array_equal(want[2].astype(np.int64), gpu_inl))
+            # single-call latencies of the consensus stage alone (host API, data upload included)
+            ars = cv_b200.Arrsac(ARRSAC["threshold"], cv_b200.Xoshiro256PlusPlus(0), ctx=ctx).initialization_hypotheses(
+                ARRSAC["initialization_hypotheses"]).max_candidate_hypotheses(ARRSAC["max_candidate_hypotheses"])
+            ars.model_inliers(cv_b200.EightPoint(), ba, bb)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                ars.model_inliers(cv_b200.EightPoint(), ba, bb)
+            ransac = {"config": "Arrsac(1e-7, Xoshiro256++).initialization_hypotheses(8192).max_candidate_hypotheses(1024) + EightPoint",
+                      "matches": npairs, "inliers": ninl, "single_call_latency_ms": (time.perf_counter() - t0) / 5 * 1e3,
+                      "note": "one isolated call through the host API (upload, every kernel, download); inside the pipelined step its kernels overlap other pairs"}
+        except Exception as ex:   # never fail the headline line on the cross-check
+            ransac = {"error": repr(ex)}
+
     # ---- roofline: instrumented pass (per-kernel CUDA events on the launching stream, one context, no overlap)
     ctx.profile(True)
-    PK = min(K, 10)
+    PK = 6
+    lib.cvb_rng_seed_xoshiro256pp(C.byref(slots[0].rng), 0)
     for i in range(PK):
-        step_dev(i, 0)
+        pair_dev(i, 0)
     rep = ctx.profile_report()
     ctx.profile(False)
     peaks = {}
@@ -339,10 +410,9 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     tot_ms = sum(v["ms"] for v in rep.values())
     top = max(rep.items(), key=lambda kv: kv[1]["ms"]) if rep else (None, None)
-    kernels = {k: {"launches_per_step": v["launches"] / PK, "ms_per_step": v["ms"] / PK, "share": v["ms"] / tot_ms if tot_ms else 0,
+    kernels = {k: {"launches_per_pair": v["launches"] / PK, "ms_per_pair": v["ms"] / PK, "share": v["ms"] / tot_ms if tot_ms else 0,
                    "alg_GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] > 0 else None} for k, v in rep.items()}
-    # dominant kernel among those with an HBM-traffic model
-    hb = {k: v for k, v in rep.items() if v["bytes"] > 0}
+    hb = {k: v for k, v in rep.items() if v["bytes"] > 0 and k != "k_hamming_knn"}      # the matcher's 64 B/cmp is a streaming model, not traffic
     dom = max(hb.items(), key=lambda kv: kv[1]["ms"])
     achieved = dom[1]["bytes"] / (dom[1]["ms"] * 1e-3) / 1e9
     traffic, traffic_src = None, None
@@ -352,57 +422,48 @@ def main():
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     except Exception:
         pass
+    fps_rank = value / world
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "launch_ms": dom[1]["ms"] / dom[1]["launches"], "bytes_per_launch": dom[1]["bytes"] / dom[1]["launches"],
-                "timing": "per-kernel CUDA events on the launching stream, separate instrumented pass of the same steps",
-                "pipeline_alg_GBps": value / world * ALG_BYTES_PER_FRAME / 1e9, "pipeline_frac": value / world * ALG_BYTES_PER_FRAME / 1e9 / hbm_peak,
+                "timing": "per-kernel CUDA events on the launching stream, separate instrumented pass of the same pairs (one context, no overlap)",
+                "pipeline_alg_GBps": fps_rank * ALG_BYTES_PER_FRAME / 1e9, "pipeline_frac": fps_rank * ALG_BYTES_PER_FRAME / 1e9 / hbm_peak,
                 "top_kernel_by_time": top[0], "kernels": kernels}
     knn = rep.get("k_hamming_knn")
     gcmp = (knn["bytes"] / 64.0) / (knn["ms"] * 1e-3) / 1e9 if knn and knn["ms"] > 0 else None
-
-    # ---- secondary measurement (BASELINE configs[2]): two-view geometric verification of this pair's matches,
-    # ARRSAC + eight-point in the vslam-sandbox configuration (vslam-sandbox/src/main.rs:112-117)
-    ransac = None
-    if rank == 0:
-        try:
-            o = houts[0]
-            na = int(o.n[0]); npairs_h = int(o.npairs.value)
-            pr = o.pairs.numpy()[:2 * npairs_h].reshape(-1, 2).astype(np.int64)
-            kpa = np.frombuffer(o.kp.numpy().tobytes(), dtype=KP_DTYPE)
-            Kc = cv_b200.CameraIntrinsics(focals=(1000.0, 1000.0), principal_point=(960.0, 540.0))
-            ba = Kc.calibrate_keypoints(kpa[:cap][pr[:, 0]])
-            bb = Kc.calibrate_keypoints(kpa[cap:2 * cap][pr[:, 1]])
-            def run_arrsac():
-                ars = cv_b200.Arrsac(1e-7, cv_b200.Xoshiro256PlusPlus(0), ctx=ctx).initialization_hypotheses(8192).max_candidate_hypotheses(1024)
-                t0 = time.perf_counter(); r = ars.model_inliers(cv_b200.EightPoint(), ba, bb); return r, (time.perf_counter() - t0) * 1e3
-            run_arrsac()
-            r, ms_r = run_arrsac()
-            ransac = {"config": "Arrsac(1e-7, Xoshiro256++(0)).initialization_hypotheses(8192).max_candidate_hypotheses(1024) + EightPoint",
-                      "matches": int(npairs_h), "inliers": int(len(r[2])) if r else 0, "ms": ms_r,
-                      "note": "host API wall clock incl. all copies; every hypothesis and residual on the GPU, ARRSAC bookkeeping on the host"}
-        except Exception as ex:   # secondary figure only: never fail the headline line
-            ransac = {"error": repr(ex)}
+    # RANSAC scoring figure: (hypothesis, datum) predicates per second of the scoring kernels
+    sc = [rep.get("k_ars_score_init"), rep.get("k_ars_score_block")]
+    ransac_scoring = None
+    if sc[0] and stats0[1]:
+        init_pairs = stats0[1] * min(256, stats0[0])
+        ransac_scoring = {"init_models": stats0[1], "init_predicates": init_pairs, "score_init_ms": sc[0]["ms"] / PK,
+                          "predicates_per_s": init_pairs / (sc[0]["ms"] / PK * 1e-3) if sc[0]["ms"] > 0 else None,
+                          "sprt_pass": stats0[2], "sprt_commit_rounds": stats0[3], "block_iterations": stats0[4], "draws": stats0[5]}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        sec = cpu_reference_step(frames[:1], 2)     # ~10 s of CPU work
-        cpu = {"value": 2.0 / sec, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "2 frame pairs (4 extracts + 2 symmetric matches) of the same workload; C restatement of the reference (oracle/), "
-                         "OpenMP only at the reference's rayon sites"}
+        sec, nm_cpu, inl_cpu, _ = cpu_reference_pair(frames[0], os.cpu_count())      # ~5 s of CPU work
+        sec1 = cpu_reference_pair(frames[0], 1)[0]                                  # ~20 s: the reference's default build is unthreaded
+        cpu = {"value": 2.0 / sec, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "single_thread_value": 2.0 / sec1,
+               "sample": f"1 frame pair of the same workload (2 extracts, symmetric match, ARRSAC: {nm_cpu} matches, "
+                         f"{0 if inl_cpu is None else len(inl_cpu)} inliers) on all host threads, and the same pair on 1 thread; C restatement of the "
+                         "reference (oracle/, -O3), OpenMP at the reference's rayon sites and over independent hypotheses"}
     if rank == 0:
-        line = {"metric": "vSLAM frames/s (AKAZE+match, 1080p ~5k kp)", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
-                "ms_per_step": ms_max / K, "enqueue_ms_per_step": enqueue_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "configs[1]: AKAZE extract x2 + symmetric Hamming 2-NN, 2 frames 1920x1080 f32, ~5k kp/frame",
-                           "frames_per_step_per_gpu": 2, "keypoints_per_frame": n_kp, "matches": int(nm), "maximum_features": MAXF,
-                           "detector_threshold": 0.001, "better_by": BETTER_BY,
-                           "pipelining": f"{NCTX} contexts (CUDA streams + workspaces) alternate steps, CUDA graph per context; e2e: {NHOST} host threads",
-                           "l2": f"inputs rotate over a pool of {2 * POOL_PAIRS} distinct frames ({2 * POOL_PAIRS * W * H * 4 / 1e6:.0f} MB > 126 MB L2)"},
-                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "host_threads": NHOST, "mean_call_ms": {"extract_batch": 1e3 * sum(o.t_extract for o in houts) / max(sum(o.steps for o in houts), 1),
-                                                               "match_symmetric": 1e3 * sum(o.t_match for o in houts) / max(sum(o.steps for o in houts), 1)},
-                        "steps_per_thread": [o.steps for o in houts]},
-                "gpu_launches": int(launches), "roofline": roofline, "hamming_Gcmp_per_s": gcmp, "ransac_two_view": ransac, "cpu_baseline": cpu,
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "pairs_per_step": PAIRS_PER_STEP, "frames_per_step_per_gpu": 2 * PAIRS_PER_STEP,
+                           "keypoints_per_frame": n_kp, "matches": cnt0[0], "inliers": cnt0[1], "maximum_features": MAXF,
+                           "detector_threshold": 0.001, "better_by": BETTER_BY, "arrsac": ARRSAC, "intrinsics": [FOCAL, FOCAL, CX, CY],
+                           "pipelining": f"{NCTX} contexts (CUDA stream + workspace + host thread + consensus generator each) take pairs from a "
+                                         "shared queue; extraction is one CUDA graph per context",
+                           "l2": f"inputs rotate over a pool of {2 * POOL_PAIRS} distinct frames ({2 * POOL_PAIRS * W * H * 4 / 1e6:.0f} MB > 126 MB L2)",
+                           "setup": "graph capture / allocation pass over every (context, input) pair before the warm-up steps"},
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+                        "host_threads": NCTX, "timed_region_ms": ms_e2e, "mean_call_ms": sum(e2e_busy) / len(e2e_busy),
+                        "pairs_per_thread": e2e_pairs},
+                "timed_region_ms": ms_max, "mean_pair_latency_ms": sum(dev_busy) / len(dev_busy),
+                "gpu_launches": int(launches), "roofline": roofline, "hamming_Gcmp_per_s": gcmp, "ransac_two_view": ransac,
+                "ransac_scoring": ransac_scoring, "inliers_equal_oracle": inliers_equal_oracle, "cpu_baseline": cpu,
                 "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -911,6 +911,8 @@ int ref_arrsac(const ref_arrsac_cfg *cfg, int kind, const double *a, const doubl
     uint32_t *pool = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)n);
     for (uint32_t start = init_n; start < n && H.n > 1; start += cfg->block_size) {
         uint32_t end = start + cfg->block_size < n ? start + cfg->block_size : n;
+        /* (the per-hypothesis counts are independent: OpenMP over hypotheses does not change any result) */
+#pragma omp parallel for schedule(dynamic, 4)
         for (size_t h = 0; h < H.n; h++)
             for (uint32_t i = start; i < end; i++)
                 if (model_residual(kind, &H.v[h].m, a, b, i) < thr) H.v[h].inliers++;
@@ -923,18 +925,31 @@ int ref_arrsac(const ref_arrsac_cfg *cfg, int kind, const double *a, const doubl
             if (model_residual(kind, &H.v[0].m, a, b, i) < thr) pool[np++] = i;
         if (np >= K) {
             const uint32_t worst = H.v[H.n - 1].inliers;   /* bar a new hypothesis has to beat */
-            for (uint32_t g = 0; g < cfg->estimations_per_block; g++) {
+            const uint32_t G = cfg->estimations_per_block;
+            /* the draws are sequential; estimation and scoring of the G samples are independent of each other */
+            uint32_t *gidx = (uint32_t *)malloc(sizeof(uint32_t) * 8 * (size_t)(G ? G : 1));
+            ref_pose *gm = (ref_pose *)malloc(sizeof(ref_pose) * 40 * (size_t)(G ? G : 1));
+            int *gnm = (int *)malloc(sizeof(int) * (size_t)(G ? G : 1));
+            uint32_t *ginl = (uint32_t *)malloc(sizeof(uint32_t) * 40 * (size_t)(G ? G : 1));
+            for (uint32_t g = 0; g < G; g++) {
                 uint32_t loc[8];
                 populate_samples(rng, K, np, loc);
-                for (uint32_t k = 0; k < K; k++) idx[k] = pool[loc[k]];
-                int nm = model_estimate(kind, a, b, idx, models);
-                for (int m = 0; m < nm; m++) {
+                for (uint32_t k = 0; k < K; k++) gidx[8 * (size_t)g + k] = pool[loc[k]];
+            }
+#pragma omp parallel for schedule(dynamic, 1)
+            for (uint32_t g = 0; g < G; g++) {
+                gnm[g] = model_estimate(kind, a, b, gidx + 8 * (size_t)g, gm + 40 * (size_t)g);
+                for (int m = 0; m < gnm[g]; m++) {
                     uint32_t inl = 0;
                     for (uint32_t i = 0; i < end; i++)
-                        if (model_residual(kind, &models[m], a, b, i) < thr) inl++;
-                    if (inl > worst) hv_push(&H, &models[m], inl);
+                        if (model_residual(kind, &gm[40 * (size_t)g + m], a, b, i) < thr) inl++;
+                    ginl[40 * (size_t)g + m] = inl;
                 }
             }
+            for (uint32_t g = 0; g < G; g++)
+                for (int m = 0; m < gnm[g]; m++)
+                    if (ginl[40 * (size_t)g + m] > worst) hv_push(&H, &gm[40 * (size_t)g + m], ginl[40 * (size_t)g + m]);
+            free(gidx); free(gm); free(gnm); free(ginl);
             hv_sort(&H);
             if (H.n > cfg->max_candidate_hypotheses) H.n = cfg->max_candidate_hypotheses;
         }

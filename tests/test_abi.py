@@ -28,11 +28,47 @@ def test_library_exports_every_header_symbol():
     assert b"sm_100a" in L.cvb_version()
 
 
+def _build_abi_smoke():
+    import subprocess
+    out = os.path.join(ROOT, "tests", "csrc", "_build")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "abi_smoke")
+    libdir = os.path.join(ROOT, "cv_b200")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "tests", "csrc", "abi_smoke.c"),
+                           "-I" + os.path.join(ROOT, "include"), "-L" + libdir, "-lcvb200", "-lm", "-Wl,-rpath," + libdir, "-o", exe])
+    return exe
+
+
+def test_c_program_compiles_against_header_and_calls_every_entry_point():
+    """tests/csrc/abi_smoke.c includes include/cvb200.h and calls every declared function: a C compiler (-Werror) checks the
+    prototypes that a Rust / cgo binding transcribes; without a GPU every call must fail cleanly (no crash, no CPU fallback)."""
+    import subprocess
+    _ensure_built()
+    exe = _build_abi_smoke()
+    src = open(os.path.join(ROOT, "tests", "csrc", "abi_smoke.c")).read()
+    header = open(os.path.join(ROOT, "include", "cvb200.h")).read()
+    for sym in set(re.findall(r"\b(cvb_[a-z0-9_]+)\s*\(", header)):
+        assert re.search(r"\b" + sym + r"\s*\(", src), f"{sym} is not called by abi_smoke.c"
+    r = subprocess.run([exe, "0"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_c_program_gpu_workflow():
+    import subprocess
+    _ensure_built()
+    r = subprocess.run([_build_abi_smoke(), "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "GPU workflow ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_struct_layouts_match_header():
     import ctypes as C
     from cv_b200._lib import KP_DTYPE, AkazeCfg
     assert C.sizeof(AkazeCfg) == 80
     assert KP_DTYPE.itemsize == 28
+    from cv_b200.geom import ArrsacCfg, Pose, Rng
+    from cv_b200.pair import Intrinsics
+    assert C.sizeof(Pose) == 96 and C.sizeof(Rng) == 40 and C.sizeof(ArrsacCfg) == 40 and C.sizeof(Intrinsics) == 40
 
 
 def test_no_cpu_fallback_without_gpu():
