@@ -165,6 +165,45 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def allpairs64(rank, world, local_rank, dev, cap):
+    """BASELINE configs[3]: 64 synthetic 1080p frames sharded round-robin, extract all, ONE packed all-gather of descriptors, all
+    2 016 frame pairs matched symmetrically (pairs partitioned over the ranks).  CUDA-event times, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from cv_b200 import AkazeConfig, dist as D, multi
+    from tests.synth import synth_frame, warp_frame
+    F = 64
+    mine = D.shard_frames(F, rank, world)
+    bases = {}
+    frames = []
+    for g in mine:        # 4 base textures, every frame a distinct warp (smooth camera path); content only has to yield ~5k keypoints
+        b = g % 4
+        if b not in bases:
+            bases[b] = synth_frame(500 + b)
+        frames.append(bases[b] if g < 4 else warp_frame(bases[b], 2000 + g, shift=(0.9 * (g // 4), -0.6 * (g // 4))))
+    imgs = torch.from_numpy(np.stack(frames)).to(dev)
+    ctx = multi.make_context(local_rank)
+    cfg = AkazeConfig(maximum_features=cap)
+    tm = {}
+    multi.extract_and_match_all_pairs(ctx, cfg, imgs, F, cap=cap, better_by=BETTER_BY, timing=tm)        # warm-up: workspaces, graphs
+    if world > 1:
+        dist.barrier()
+    tm = {}
+    counts, res = multi.extract_and_match_all_pairs(ctx, cfg, imgs, F, cap=cap, better_by=BETTER_BY, timing=tm)
+    t = torch.tensor([tm["extract_ms"], tm["match_ms"], tm["gather_ms"], tm["total_ms"]], dtype=torch.float64, device=dev)
+    c = torch.tensor([tm["comparisons"], float(sum(len(v) for v in res.values()))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    t, c = t.cpu().numpy(), c.cpu().numpy()
+    ctx.close()
+    return {"frames": F, "frame_pairs": F * (F - 1) // 2, "keypoints_per_frame_mean": float(np.mean(list(counts.values()))),
+            "extract_frames_per_s": F / (t[0] * 1e-3), "match_Gcmp_per_s": c[0] / (t[1] * 1e-3) / 1e9, "comparisons": c[0], "matches_total": int(c[1]),
+            "extract_ms": t[0], "match_ms": t[1], "total_ms": t[3], "collective": "one all_gather_into_tensor of the packed descriptors (NCCL over NVLink)",
+            "collective_us": t[2] * 1e3, "collective_bytes": tm["gather_bytes"], "pairs_this_rank": tm["pairs"], "pairs_matched_during_gather": tm["local_pairs"],
+            "timing": "CUDA events on the rank's stream, max over ranks; the match time includes waiting for the all-gather"}
+
+
 def bind_to_gpu_numa_node(props):
     """Run this process (and the pinned buffers it first-touches) on the CPUs local to the GPU's PCIe root, like a deployed
     service would; silently skipped when sysfs does not expose the topology."""
@@ -393,6 +432,14 @@ def main():
         except Exception as ex:   # never fail the headline line on the cross-check
             ransac = {"error": repr(ex)}
 
+    # ---- BASELINE configs[3] (multi-frame all-pairs workload; the one place the path has a collective)
+    ap64 = None
+    if os.environ.get("CVB_BENCH_ALLPAIRS", "1") == "1":
+        try:
+            ap64 = allpairs64(rank, world, local_rank, dev, cap)
+        except Exception as ex:      # secondary block: never fail the headline line
+            ap64 = {"error": repr(ex)}
+
     # ---- roofline: instrumented pass (per-kernel CUDA events on the launching stream, one context, no overlap)
     ctx.profile(True)
     PK = 6
@@ -463,7 +510,7 @@ def main():
                         "pairs_per_thread": e2e_pairs},
                 "timed_region_ms": ms_max, "mean_pair_latency_ms": sum(dev_busy) / len(dev_busy),
                 "gpu_launches": int(launches), "roofline": roofline, "hamming_Gcmp_per_s": gcmp, "ransac_two_view": ransac,
-                "ransac_scoring": ransac_scoring, "inliers_equal_oracle": inliers_equal_oracle, "cpu_baseline": cpu,
+                "ransac_scoring": ransac_scoring, "allpairs64": ap64, "inliers_equal_oracle": inliers_equal_oracle, "cpu_baseline": cpu,
                 "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)
     if world > 1:

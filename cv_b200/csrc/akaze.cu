@@ -117,6 +117,8 @@ struct AkazeWorkspace {
     unsigned *ncache = nullptr, *nsorted = nullptr, *nvalid = nullptr, *rank = nullptr;
     unsigned char *keep = nullptr, *valid = nullptr, *ok = nullptr, *desc_tmp = nullptr;
     unsigned *overflow = nullptr;
+    CUtensorMap *tmaps = nullptr;      // device: [3][MAX_EVO] per-evolution maps (deriv1 source, Lx, Ly) for the TMA-staged tiles
+    bool use_tma = false;
     SupScratch sup{};
     bool suppress_seq = false;   // CVB_SUPPRESS_SEQ=1: serial reference kernel (debug / A-B check)
     bool suppress_par_only = false;   // CVB_SUPPRESS_GLOBAL=1: force the global-memory parallel kernel
@@ -156,6 +158,39 @@ void akaze_workspace_free(AkazeWorkspace *ws) {
 }
 
 namespace {
+
+// ---- TMA tensor maps (cuTensorMapEncodeTiled resolved through the runtime: libcvb200.so keeps no link dependency on libcuda)
+#ifndef CVB_TMA_DEFAULT
+#define CVB_TMA_DEFAULT 0          // CVB_TMA=1 / 0 overrides at run time
+#endif
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// 3-D f32 map (x, y, frame) of `B` planes of w x h floats, `bstride` floats apart; box = boxw x boxh x 1.  false: TMA not usable here
+bool make_tmap(CUtensorMap *out, const float *base, int w, int h, unsigned B, size_t bstride, int boxw, int boxh) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    memset(out, 0, sizeof(*out));
+    if (!fn || ((uintptr_t)base & 15) || (w & 3) || (bstride & 3) || boxw > 256 || boxh > 256 || w < 1 || h < 1) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)std::max(B, 1u)};
+    const cuuint64_t strides[2] = {(cuuint64_t)w * 4, (cuuint64_t)(B > 1 ? bstride : (size_t)w * h) * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)boxh, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 
 // fused FED steps per launch (halo grows with it); CVB_FED_FUSE=1..FED_SMAX overrides for experiments
 int fed_fuse_steps() {
@@ -381,8 +416,27 @@ int build_workspace(cvb_ctx *ctx, AkazeWorkspace *ws, const cvb_akaze_cfg *cfg, 
         cudaFuncSetAttribute(k_suppress_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SUP_SMEM);
     }
     DA(ot, 1); DA(dt, 1);
+    DA(tmaps, 3 * MAX_EVO);
     DA(kp_out, B * (size_t)cap_out); DA(desc_out, B * (size_t)cap_out * 64); DA(n_out, B);
 #undef DA
+    {   // TMA-staged tiles: per-evolution maps of the planes the derivative kernels read (CVB_TMA=0 / 1 overrides the default)
+        const char *env = getenv("CVB_TMA");
+        ws->use_tma = env ? env[0] == '1' : (CVB_TMA_DEFAULT != 0);
+        std::vector<CUtensorMap> hm(3 * MAX_EVO);
+        memset(hm.data(), 0, sizeof(CUtensorMap) * hm.size());
+        for (size_t i = 0; i < ws->evo.size() && ws->use_tma; i++) {
+            const EvoHost &e = ws->evo[i];
+            const int S = std::min<int>((int)e.sigma, 5);
+            if ((int)e.sigma > 5) { ws->use_tma = false; break; }
+            const float *src1 = (i == 0 ? ws->Lt : ws->Lsm) + e.off;
+            const bool ok = make_tmap(&hm[i], src1, e.w, e.h, batch, PF, pitch3(S), SH3 + 2 * S)
+                         && make_tmap(&hm[MAX_EVO + i], ws->Lx + e.off, e.w, e.h, batch, PF, pitch3(S), SH3 + 2 * S)
+                         && make_tmap(&hm[2 * MAX_EVO + i], ws->Ly + e.off, e.w, e.h, batch, PF, pitch3(S), SH3 + 2 * S);
+            if (!ok) ws->use_tma = false;        // e.g. a level width that is not a multiple of 4 floats: every kernel keeps the classic path
+        }
+        CVB_CUDA(ctx, cudaMemcpyAsync(ws->tmaps, hm.data(), sizeof(CUtensorMap) * hm.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     {
         std::vector<unsigned char> te((size_t)std::max(ws->table.total_tiles, 1), 0);
         ws->deriv_v3 = true;
@@ -428,8 +482,12 @@ int launch_separable(cvb_ctx *ctx, const float *in, size_t in_bs, float *out, si
     if (hk.ks == vk.ks && (hk.ks == 5 || hk.ks == 9) && memcmp(hk.k, vk.k, sizeof(float) * hk.ks) == 0) {
         CVB_PROF(ctx, "k_blur", 8.0 * w * h * B);
         dim3 g(cdiv((unsigned)w, SW3), cdiv((unsigned)h, SH3), B);
-        if (hk.ks == 5) k_blur_v3<5><<<g, NT, 0, ctx->stream>>>(in, out, w, h, in_bs, out_bs, hk);
-        else k_blur_v3<9><<<g, NT, 0, ctx->stream>>>(in, out, w, h, in_bs, out_bs, hk);
+        CUtensorMap tm;
+        const int R = hk.ks / 2;
+        const int use_tma = ctx->akaze && ctx->akaze->use_tma && make_tmap(&tm, in, w, h, B, in_bs, pitch3(R), SH3 + 2 * R) ? 1 : 0;
+        if (!use_tma) memset(&tm, 0, sizeof(tm));
+        if (hk.ks == 5) k_blur_v3<5><<<g, NT, 0, ctx->stream>>>(in, out, w, h, in_bs, out_bs, hk, tm, use_tma);
+        else k_blur_v3<9><<<g, NT, 0, ctx->stream>>>(in, out, w, h, in_bs, out_bs, hk, tm, use_tma);
         CVB_LAUNCH_CHECK(ctx);
         return 0;
     }
@@ -506,13 +564,15 @@ int run_extract_eager(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoin
         double px = 0;
         for (int e = e0; e < e1; e++) px += (double)ws->evo[e].w * ws->evo[e].h;
         if (ws->deriv_v3) {
-            const size_t region = (size_t)(SW3 + 2 * smax) * (SH3 + 2 * smax);
+            const size_t region = (((size_t)pitch3(smax) * (SH3 + 2 * smax)) + 31) & ~(size_t)31;
             dim3 g((unsigned)(t1 - t0), 1, B);
             { CVB_PROF(ctx, "k_deriv1", 12.0 * px * B);
-            k_deriv1_v3<<<g, NT, sizeof(float) * region, ds>>>(ws->Lsm, ws->Lt, ws->Lx, ws->Ly, PF, ws->table, ws->tile_evo, t0);
+            k_deriv1_v3<<<g, NT, sizeof(float) * region, ds>>>(ws->Lsm, ws->Lt, ws->Lx, ws->Ly, PF, ws->table, ws->tile_evo, t0,
+                                                               ws->use_tma ? ws->tmaps : nullptr);
             CVB_LAUNCH_CHECK(ctx); }
             { CVB_PROF(ctx, "k_deriv2_det", 12.0 * px * B);
-            k_deriv2_v3<<<g, NT, sizeof(float) * 2 * region, ds>>>(ws->Lx, ws->Ly, ws->Ldet, PF, ws->table, ws->tile_evo, t0);
+            k_deriv2_v3<<<g, NT, sizeof(float) * 2 * region, ds>>>(ws->Lx, ws->Ly, ws->Ldet, PF, ws->table, ws->tile_evo, t0,
+                                                                   ws->use_tma ? ws->tmaps + MAX_EVO : nullptr, ws->use_tma ? ws->tmaps + 2 * MAX_EVO : nullptr);
             CVB_LAUNCH_CHECK(ctx); }
         } else {   // generic two-pass tiles, one launch pair per evolution (derivative sigma > 5)
             cudaStream_t keep = ctx->stream;
@@ -569,8 +629,11 @@ int run_extract_eager(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoin
         // Lsmooth = gaussian_blur(Lt, 1.0); Lflow = pm_g2(simple_scharr_x(Lsmooth), simple_scharr_y(Lsmooth), contrast)
         if (ws->fuse_blur_scharr && ws->g1.ks == 5) {
             CVB_PROF(ctx, "k_blur_scharr", 16.0 * e.w * e.h * B);
+            CUtensorMap tm;
+            const int use_tma = ws->use_tma && make_tmap(&tm, src, e.w, e.h, B, src_bs, pitch3(3), SH3 + 6) ? 1 : 0;
+            if (!use_tma) memset(&tm, 0, sizeof(tm));
             k_blur_scharr_pm<<<dim3(cdiv((unsigned)e.w, SW3), cdiv((unsigned)e.h, SH3), B), NT, 0, st>>>(
-                src, ws->Lsm + e.off, ws->Lflow + e.off, e.w, e.h, src_bs, PF, PF, ws->g1, ws->inv_k + i, MAX_EVO);
+                src, ws->Lsm + e.off, ws->Lflow + e.off, e.w, e.h, src_bs, PF, PF, ws->g1, ws->inv_k + i, MAX_EVO, tm, use_tma);
             CVB_LAUNCH_CHECK(ctx);
         } else {
             rc = launch_separable(ctx, src, src_bs, ws->Lsm + e.off, PF, e.w, e.h, B, ws->g1, ws->g1);

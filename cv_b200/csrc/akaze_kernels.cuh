@@ -6,6 +6,7 @@
 // each intermediate is rounded to f32 exactly where the reference materialises it.
 // Compile with -fmad=false.  Reference line numbers are relative to /root/reference/akaze/src.
 #pragma once
+#include <cuda.h>            // CUtensorMap (types only: the encode entry point is resolved at run time, no libcuda link dependency)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "device_libm.cuh"
@@ -455,13 +456,50 @@ __device__ __forceinline__ float lane_dot_regs(const float *v, const float *k) {
 // The arithmetic of every output is unchanged (same helpers, same order) -> still bit-exact.
 constexpr int SW3 = 32, SH3 = 64, STRIP = 8;
 
-template <int RX, int RY>
-__device__ __forceinline__ void stage_region(const float *__restrict__ src, int w, int h, int x0, int y0, float *s_in) {
+// ---- TMA staging of interior tiles (BASELINE north_star: "TMA-staged tiles in shared memory").  A tile whose halo lies inside the
+// image is fetched by ONE 3-D cp.async.bulk.tensor (x, y, frame) issued by one thread and awaited on an mbarrier; tiles that touch the
+// border keep the clamped path below, because TMA fills out-of-bounds elements with zero while the reference replicates the border
+// (image.rs:233-235,289-296).  The box is `pitch3(R)` floats wide (row bytes must be a multiple of 16); the padding columns are
+// never read.  Shared-memory contents of the halo region are identical in both paths.
+__host__ __device__ constexpr int pitch3(int r) { return (SW3 + 2 * r + 3) & ~3; }
+__device__ __forceinline__ uint32_t ak_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ak_tma_tile(float *dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar, unsigned bytes) {
+    // called by one thread after the barrier has been initialised and made visible
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ak_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(ak_smem_u32(dst)),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(ak_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void ak_mbar_wait0(uint64_t *bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(ak_smem_u32(bar)) : "memory");
+}
+
+template <int RX, int RY, int RW = SW3 + 2 * RX>
+__device__ __forceinline__ void stage_region(const float *__restrict__ src, int w, int h, int x0, int y0, float *s_in,
+                                             const CUtensorMap *tm = nullptr, int frame = 0, uint64_t *bar = nullptr) {
     // all of a thread's global loads are issued before the first shared store (a rolled load->store loop waits one
     // DRAM latency per row: ncu showed 36 % of the blur kernel's stall samples on that store)
-    constexpr int RW = SW3 + 2 * RX, RH = SH3 + 2 * RY, NI = (RH + 7) / 8;
+    constexpr int RH = SH3 + 2 * RY, NI = (RH + 7) / 8;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const bool interior = x0 - RX >= 0 && x0 + SW3 + RX <= w && y0 - RY >= 0 && y0 + SH3 + RY <= h;
+    if (tm != nullptr && interior) {          // CTA-uniform
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ak_smem_u32(bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) ak_tma_tile(s_in, tm, x0 - RX, y0 - RY, frame, bar, (unsigned)(RW * RH * sizeof(float)));
+        ak_mbar_wait0(bar);
+        return;
+    }
     const bool tail = tx < 2 * RX;
     float a[NI], b[NI];
     if (interior) {
@@ -506,9 +544,9 @@ __device__ __forceinline__ void tile_origin_v3(const EvoDev &ev, int gtile, int 
 // first derivatives, sigma = S (detector_response.rs:60-65): Lx = V_off(H_main(Ls)), Ly = V_main(H_off(Ls))
 template <int S>
 __device__ __forceinline__ void deriv1_body(const float *__restrict__ src, float *__restrict__ Lx, float *__restrict__ Ly,
-                                            const EvoDev &ev, int x0, int y0, float *s_in) {
-    constexpr int RW = SW3 + 2 * S;
-    stage_region<S, S>(src, ev.w, ev.h, x0, y0, s_in);
+                                            const EvoDev &ev, int x0, int y0, float *s_in, const CUtensorMap *tm, uint64_t *bar) {
+    constexpr int RW = pitch3(S);
+    stage_region<S, S, RW>(src, ev.w, ev.h, x0, y0, s_in, tm, (int)blockIdx.z, bar);
     __syncthreads();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int gx = x0 + tx;
@@ -533,8 +571,10 @@ __device__ __forceinline__ void deriv1_body(const float *__restrict__ src, float
 
 __global__ void __launch_bounds__(NT) k_deriv1_v3(const float *__restrict__ Ls, const float *__restrict__ Lt0,
                                                   float *__restrict__ Lx, float *__restrict__ Ly, size_t bstride, EvoTable T,
-                                                  const unsigned char *__restrict__ tile_evo, int tile_offset) {
-    extern __shared__ float sm[];
+                                                  const unsigned char *__restrict__ tile_evo, int tile_offset,
+                                                  const CUtensorMap *__restrict__ maps) {
+    extern __shared__ __align__(128) float sm[];
+    __shared__ __align__(8) uint64_t s_bar[1];
     const int gtile = blockIdx.x + tile_offset;
     const int e = tile_evo[gtile];
     const EvoDev ev = T.e[e];
@@ -542,23 +582,25 @@ __global__ void __launch_bounds__(NT) k_deriv1_v3(const float *__restrict__ Ls, 
     tile_origin_v3(ev, gtile, x0, y0);
     const size_t base = (size_t)blockIdx.z * bstride + ev.off;
     const float *src = (e == 0 ? Lt0 : Ls) + base;   // evolution 0: Lsmooth IS Lt (lib.rs:201)
+    const CUtensorMap *tm = maps ? maps + e : nullptr;   // per-evolution map of the source plane (all frames)
     switch (ev.sigma) {
-    case 1: deriv1_body<1>(src, Lx + base, Ly + base, ev, x0, y0, sm); break;
-    case 2: deriv1_body<2>(src, Lx + base, Ly + base, ev, x0, y0, sm); break;
-    case 3: deriv1_body<3>(src, Lx + base, Ly + base, ev, x0, y0, sm); break;
-    case 4: deriv1_body<4>(src, Lx + base, Ly + base, ev, x0, y0, sm); break;
-    default: deriv1_body<5>(src, Lx + base, Ly + base, ev, x0, y0, sm); break;
+    case 1: deriv1_body<1>(src, Lx + base, Ly + base, ev, x0, y0, sm, tm, s_bar); break;
+    case 2: deriv1_body<2>(src, Lx + base, Ly + base, ev, x0, y0, sm, tm, s_bar); break;
+    case 3: deriv1_body<3>(src, Lx + base, Ly + base, ev, x0, y0, sm, tm, s_bar); break;
+    case 4: deriv1_body<4>(src, Lx + base, Ly + base, ev, x0, y0, sm, tm, s_bar); break;
+    default: deriv1_body<5>(src, Lx + base, Ly + base, ev, x0, y0, sm, tm, s_bar); break;
     }
 }
 
 // second derivatives + Hessian determinant (detector_response.rs:40-47,66-68)
 template <int S>
 __device__ __forceinline__ void deriv2_body(const float *__restrict__ px, const float *__restrict__ py, float *__restrict__ Ldet,
-                                            const EvoDev &ev, int x0, int y0, float *sm) {
-    constexpr int RW = SW3 + 2 * S, RH = SH3 + 2 * S;
-    float *s_x = sm, *s_y = sm + RW * RH;
-    stage_region<S, S>(px, ev.w, ev.h, x0, y0, s_x);
-    stage_region<S, S>(py, ev.w, ev.h, x0, y0, s_y);
+                                            const EvoDev &ev, int x0, int y0, float *sm, const CUtensorMap *tmx, const CUtensorMap *tmy,
+                                            uint64_t *bar) {
+    constexpr int RW = pitch3(S), RH = SH3 + 2 * S;
+    float *s_x = sm, *s_y = sm + ((RW * RH + 31) & ~31);      // second buffer 128-byte aligned
+    stage_region<S, S, RW>(px, ev.w, ev.h, x0, y0, s_x, tmx, (int)blockIdx.z, bar);
+    stage_region<S, S, RW>(py, ev.w, ev.h, x0, y0, s_y, tmy, (int)blockIdx.z, bar + 1);
     __syncthreads();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int gx = x0 + tx;
@@ -585,31 +627,36 @@ __device__ __forceinline__ void deriv2_body(const float *__restrict__ px, const 
 
 __global__ void __launch_bounds__(NT) k_deriv2_v3(const float *__restrict__ Lx, const float *__restrict__ Ly,
                                                   float *__restrict__ Ldet, size_t bstride, EvoTable T,
-                                                  const unsigned char *__restrict__ tile_evo, int tile_offset) {
-    extern __shared__ float sm[];
+                                                  const unsigned char *__restrict__ tile_evo, int tile_offset,
+                                                  const CUtensorMap *__restrict__ maps_x, const CUtensorMap *__restrict__ maps_y) {
+    extern __shared__ __align__(128) float sm[];
+    __shared__ __align__(8) uint64_t s_bar[2];
     const int gtile = blockIdx.x + tile_offset;
     const int e = tile_evo[gtile];
     const EvoDev ev = T.e[e];
     int x0, y0;
     tile_origin_v3(ev, gtile, x0, y0);
     const size_t base = (size_t)blockIdx.z * bstride + ev.off;
+    const CUtensorMap *tmx = maps_x ? maps_x + e : nullptr, *tmy = maps_y ? maps_y + e : nullptr;
     switch (ev.sigma) {
-    case 1: deriv2_body<1>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sm); break;
-    case 2: deriv2_body<2>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sm); break;
-    case 3: deriv2_body<3>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sm); break;
-    case 4: deriv2_body<4>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sm); break;
-    default: deriv2_body<5>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sm); break;
+    case 1: deriv2_body<1>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sm, tmx, tmy, s_bar); break;
+    case 2: deriv2_body<2>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sm, tmx, tmy, s_bar); break;
+    case 3: deriv2_body<3>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sm, tmx, tmy, s_bar); break;
+    case 4: deriv2_body<4>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sm, tmx, tmy, s_bar); break;
+    default: deriv2_body<5>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sm, tmx, tmy, s_bar); break;
     }
 }
 
 // Gaussian blur, column strips (image.rs:202-340, 383-389).  grid = (ceil(w/32), ceil(h/64), B)
 template <int KS>
 __global__ void __launch_bounds__(NT) k_blur_v3(const float *__restrict__ in, float *__restrict__ out, int w, int h,
-                                                size_t in_bstride, size_t out_bstride, Taps tk) {
-    constexpr int R = KS / 2, RW = SW3 + 2 * R;
-    __shared__ float s_in[(SH3 + 2 * R) * RW];
+                                                size_t in_bstride, size_t out_bstride, Taps tk,
+                                                const __grid_constant__ CUtensorMap tmap, int use_tma) {
+    constexpr int R = KS / 2, RW = pitch3(R);
+    __shared__ __align__(128) float s_in[(SH3 + 2 * R) * RW];
+    __shared__ __align__(8) uint64_t s_bar[1];
     const int x0 = blockIdx.x * SW3, y0 = blockIdx.y * SH3;
-    stage_region<R, R>(in + (size_t)blockIdx.z * in_bstride, w, h, x0, y0, s_in);
+    stage_region<R, R, RW>(in + (size_t)blockIdx.z * in_bstride, w, h, x0, y0, s_in, use_tma ? &tmap : nullptr, (int)blockIdx.z, s_bar);
     __syncthreads();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int gx = x0 + tx;
@@ -689,14 +736,16 @@ __global__ void __launch_bounds__(NT) k_scharr_pm_v3(const float *__restrict__ i
 __global__ void __launch_bounds__(NT) k_blur_scharr_pm(const float *__restrict__ in, float *__restrict__ out_lsm,
                                                        float *__restrict__ out_flow, int w, int h, size_t in_bstride,
                                                        size_t lsm_bstride, size_t flow_bstride, Taps tk,
-                                                       const float *__restrict__ inv_k, int inv_k_stride) {
-    constexpr int RWI = SW3 + 6, RHI = SH3 + 6, LW = SW3 + 2, LH = SH3 + 2;
+                                                       const float *__restrict__ inv_k, int inv_k_stride,
+                                                       const __grid_constant__ CUtensorMap tmap, int use_tma) {
+    constexpr int RWI = pitch3(3), RHI = SH3 + 6, LW = SW3 + 2, LH = SH3 + 2;
     constexpr int BSTRIP = 10, NSTRIPS = (LH + BSTRIP - 1) / BSTRIP;     // 34 columns x 7 strips = 238 blur tasks
     static_assert(LW * NSTRIPS <= NT, "one blur task per thread");
-    __shared__ float s_in[RHI * RWI];
+    __shared__ __align__(128) float s_in[RHI * RWI];
     __shared__ float s_l[LH * LW];
+    __shared__ __align__(8) uint64_t s_bar[1];
     const int x0 = blockIdx.x * SW3, y0 = blockIdx.y * SH3;
-    stage_region<3, 3>(in + (size_t)blockIdx.z * in_bstride, w, h, x0, y0, s_in);
+    stage_region<3, 3, RWI>(in + (size_t)blockIdx.z * in_bstride, w, h, x0, y0, s_in, use_tma ? &tmap : nullptr, (int)blockIdx.z, s_bar);
     __syncthreads();
     if (threadIdx.x < LW * NSTRIPS) {
         const int sidx = threadIdx.x / LW, c = threadIdx.x - sidx * LW;

@@ -16,13 +16,14 @@ from tests.synth import synth_frame, warp_frame  # noqa: E402
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-F = 2 * world
+F = 2 * world + 1          # uneven shards: the last rank(s) hold one frame less (padded)
 base = synth_frame(11, h=360, w=480, nblobs=900)
 frames = [base] + [warp_frame(base, g, shift=(1.0 + g, 0.5 * g)) for g in range(1, F)]
 mine = D.shard_frames(F, rank, world)
-ctx = cv_b200.Context(lr)
+ctx = multi.make_context(lr)
 cfg = cv_b200.AkazeConfig(detector_threshold=0.001)
-counts, res = multi.extract_and_match_all_pairs(ctx, cfg, torch.from_numpy(np.stack([frames[g] for g in mine])).cuda(), num_frames=F, cap=4096)
+tm = {}
+counts, res = multi.extract_and_match_all_pairs(ctx, cfg, torch.from_numpy(np.stack([frames[g] for g in mine])).cuda(), num_frames=F, cap=4096, timing=tm)
 gathered = [None] * world
 dist.all_gather_object(gathered, {k: v.tolist() for k, v in res.items()})
 if rank == 0:
@@ -35,5 +36,5 @@ if rank == 0:
     assert [counts[g] for g in range(F)] == [len(d) for d in descs]
     for (i, j), pairs in allres.items():
         assert cv_b200.symmetric_matching(descs[i], descs[j], 24, ctx=ctx).tolist() == pairs, (i, j)
-    print(f"multi-GPU check ok: world {world}, {F} frames, {len(allres)} pairs, one NCCL all-gather of {F} x 4096 x 64 B")
+    print(f"multi-GPU check ok: world {world}, {F} frames, {len(allres)} pairs, one NCCL all-gather of {tm['gather_bytes']} B in {tm['gather_ms']:.3f} ms; rank 0 timing {tm}")
 dist.destroy_process_group()

@@ -54,3 +54,20 @@ def test_landmark_matches_edge_cases():
         landmark_matches(new, [(views[0][0], views[0][1][:-1])], knn=O.hamming_knn)
     with pytest.raises(ValueError):           # fewer than three distinct candidate landmarks: the reference unwraps (panics)
         landmark_matches(new[:5], [(views[0][0][:2], views[0][1][:2])], knn=O.hamming_knn)
+
+
+def test_pack_layout_uneven_shards():
+    """config 4 with num_frames % world != 0: padded frames have count 0 and occupy no rows of the packed all-gather."""
+    from cv_b200.multi import pack_layout
+    from cv_b200 import dist as D
+    world, F = 4, 10
+    per = -(-F // world)
+    counts = np.zeros((world, per), np.int64)
+    for g in range(F):
+        counts[g % world, g // world] = 100 + g
+    off, maxtot = pack_layout(counts)
+    assert maxtot == int(counts.sum(1).max()) and off.shape == (world, per + 1)
+    for r in range(world):
+        assert off[r, 0] == 0 and (np.diff(off[r]) == counts[r]).all()
+    assert counts[2, 2] == 0 and counts[3, 2] == 0              # ranks 2, 3 hold two frames: their third slot is padding
+    assert sorted(sum((D.shard_frames(F, r, world) for r in range(world)), [])) == list(range(F))
