@@ -80,52 +80,73 @@ __device__ uint32_t ars_raw_at(ArrsacCtl *ctl, const uint32_t *raw, uint64_t pos
 }
 
 // `count` minimal samples of K distinct indices below len: next_u32() % len with rejection of repeats, exactly in the
-// reference's draw order.  Executed by one full warp.  32/K samples per step are taken from 32 consecutive draws when none
-// of them repeats inside its sample (the common case); a sample with a repeat is redone draw by draw by lane 0.
-__device__ void ars_sample_warp(ArrsacCtl *ctl, const uint32_t *raw, uint32_t len, uint32_t K, uint32_t count, uint32_t *out,
-                                const uint32_t *map) {
+// reference's draw order.  Called by EVERY thread of the CTA: the raw draws are staged through a shared-memory window (cooperative,
+// coalesced loads; the consumer's position depends on the data, so reading them from global memory one warp-step at a time costs
+// an L2 round trip per step), and warp 0 consumes them: 32/K samples per step are taken from 32 consecutive draws when none of
+// them repeats inside its sample (the common case); a sample with a repeat is redone draw by draw by lane 0.
+#define ARS_WIN 4096u
+__device__ void ars_sample_block(ArrsacCtl *ctl, const uint32_t *raw, uint32_t len, uint32_t K, uint32_t count, uint32_t *out,
+                                 const uint32_t *map, uint32_t *win /* ARS_WIN words of shared memory */, uint32_t *sh /* 4 shared words */) {
     const unsigned full = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31, hps = 32 / K;
     const uint32_t g = lane / K, k = lane % K;
-    uint64_t pos = ctl->rng_pos;
     const uint32_t nraw = ctl->nraw;
-    uint32_t h = 0;
-    while (h < count) {
-        if (pos + 32 <= nraw) {
-            const uint32_t ng = min(hps, count - h);
-            const bool act = g < ng;
-            const uint32_t s = raw[pos + lane] % len;
-            bool dup = false;
-            for (uint32_t j = 1; j < K; j++) {
-                const uint32_t o = __shfl_sync(full, s, (lane - j) & 31);
-                if (k >= j && o == s) dup = true;
+    if (threadIdx.x == 0) { sh[0] = 0; *(uint64_t *)(sh + 2) = ctl->rng_pos; }
+    __syncthreads();
+    while (true) {
+        const uint32_t h0 = sh[0];
+        const uint64_t wbase = *(const uint64_t *)(sh + 2);
+        if (h0 >= count) break;
+        for (uint32_t i = threadIdx.x; i < ARS_WIN; i += blockDim.x) win[i] = wbase + i < nraw ? raw[wbase + i] : 0u;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint64_t pos = wbase;
+            uint32_t h = h0;
+            while (h < count) {
+                const bool in_win = pos + 32 <= wbase + ARS_WIN && pos + 32 <= nraw;
+                if (!in_win && pos + 32 <= nraw) break;             // refill the window at pos
+                if (in_win) {
+                    const uint32_t ng = min(hps, count - h);
+                    const bool act = g < ng;
+                    const uint32_t s = win[(uint32_t)(pos - wbase) + lane] % len;
+                    bool dup = false;
+                    for (uint32_t j = 1; j < K; j++) {
+                        const uint32_t o = __shfl_sync(full, s, (lane - j) & 31);
+                        if (k >= j && o == s) dup = true;
+                    }
+                    const unsigned dm = __ballot_sync(full, act && dup);
+                    const uint32_t good = dm ? (uint32_t)(__ffs(dm) - 1) / K : ng;
+                    if (act && g < good) out[(size_t)(h + g) * K + k] = map ? map[s] : s;
+                    h += good; pos += (uint64_t)good * K;
+                    if (good == ng) continue;
+                }
+                if (lane == 0) {      // one sample draw by draw (a repeat inside it, or the tail of the staged stream)
+                    uint32_t loc[8];
+                    for (uint32_t c = 0; c < K;) {
+                        const uint32_t r = (pos >= wbase && pos < wbase + ARS_WIN && pos < nraw) ? win[(uint32_t)(pos - wbase)] : ars_raw_at(ctl, raw, pos);
+                        const uint32_t s = r % len;
+                        pos++;
+                        bool dup = false;
+                        for (uint32_t j = 0; j < c; j++) dup |= loc[j] == s;
+                        if (!dup) { loc[c] = s; out[(size_t)h * K + c] = map ? map[s] : s; c++; }
+                    }
+                }
+                pos = __shfl_sync(full, pos, 0);
+                h++;
             }
-            const unsigned dm = __ballot_sync(full, act && dup);
-            const uint32_t good = dm ? (uint32_t)(__ffs(dm) - 1) / K : ng;
-            if (act && g < good) out[(size_t)(h + g) * K + k] = map ? map[s] : s;
-            h += good; pos += (uint64_t)good * K;
-            if (good == ng) continue;
+            if (lane == 0) { sh[0] = h; *(uint64_t *)(sh + 2) = pos; }
         }
-        if (lane == 0) {
-            uint32_t loc[8];
-            for (uint32_t c = 0; c < K;) {
-                const uint32_t s = ars_raw_at(ctl, raw, pos) % len;
-                pos++;
-                bool dup = false;
-                for (uint32_t j = 0; j < c; j++) dup |= loc[j] == s;
-                if (!dup) { loc[c] = s; out[(size_t)h * K + c] = map ? map[s] : s; c++; }
-            }
-        }
-        pos = __shfl_sync(full, pos, 0);
-        h++;
+        __syncthreads();
     }
-    if (lane == 0) ctl->rng_pos = pos;
-    __syncwarp();
+    if (threadIdx.x == 0) ctl->rng_pos = *(const uint64_t *)(sh + 2);
+    __syncthreads();
 }
 
 // ---- k_ars_begin ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_ars_begin(ArrsacCtl *ctl, ArrsacParams P, const uint32_t *n_dev, uint32_t n_host,
-                                                  const uint32_t *raw, uint32_t *samples0) {
+__global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_begin(ArrsacCtl *ctl, ArrsacParams P, const uint32_t *n_dev, uint32_t n_host,
+                                                            const uint32_t *raw, uint32_t *samples0) {
+    __shared__ uint32_t win[ARS_WIN];
+    __shared__ __align__(8) uint32_t sh[4];
     const uint32_t n = min(n_dev ? *n_dev : n_host, P.NMAX);
     if (threadIdx.x == 0) {
         ctl->n = n;
@@ -135,9 +156,9 @@ __global__ void __launch_bounds__(32) k_ars_begin(ArrsacCtl *ctl, ArrsacParams P
         ctl->stat_chunks = 0; ctl->stat_pass = 0;
         ctl->done = (n < P.K || P.H0 == 0) ? 1u : 0u;
     }
-    __syncwarp();
+    __syncthreads();
     if (n < P.K || P.H0 == 0) return;
-    ars_sample_warp(ctl, raw, n, P.K, P.H0, samples0, nullptr);
+    ars_sample_block(ctl, raw, n, P.K, P.H0, samples0, nullptr, win, sh);
 }
 
 // ---- k_ars_estimate ------------------------------------------------------------------------------------------------------
@@ -298,13 +319,13 @@ __device__ uint32_t ars_popc_range(const uint32_t *row, uint32_t lo, uint32_t hi
     return c;
 }
 
-// SPRT walk of one model over its initialisation mask (the reference's inner loop, f32 in data order).
-// Returns tested (the 1-based datum at which the ratio exceeded the threshold) or 0 when the model passes.
-__device__ uint32_t ars_sprt_walk(const uint32_t *__restrict__ words, uint32_t init_n, float pos, float neg, float thr, uint32_t *inl_out) {
+// SPRT walk of one model over its initialisation mask (the reference's inner loop, f32 in data order).  words[w * stride] = mask
+// word w.  Returns tested (the 1-based datum at which the ratio exceeded the threshold) or 0 when the model passes.
+__device__ uint32_t ars_sprt_walk(const uint32_t *words, uint32_t stride, uint32_t init_n, float pos, float neg, float thr, uint32_t *inl_out) {
     float ratio = 1.0f;
     uint32_t inl = 0;
     for (uint32_t w = 0; w * 32 < init_n; w++) {
-        const uint32_t x = words[w];
+        const uint32_t x = words[w * stride];
         const uint32_t cnt = min(32u, init_n - w * 32);
         if (ratio == 0.0f) { inl += __popc(cnt < 32 ? (x & ((1u << cnt) - 1)) : x); continue; }   // 0 * finite stays 0: never rejected
         for (uint32_t k = 0; k < cnt; k++) {
@@ -315,6 +336,24 @@ __device__ uint32_t ars_sprt_walk(const uint32_t *__restrict__ words, uint32_t i
     }
     *inl_out = inl;
     return 0;
+}
+
+// inclusive block-wide max scan (ARS_BOOK_NT threads)
+__device__ uint32_t ars_scan_max(uint32_t v, uint32_t *sm /* 32 */) {
+    const unsigned full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(full, v, o); if ((int)lane >= o) v = max(v, x); }
+    __syncthreads();
+    if (lane == 31) sm[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t x = sm[lane];
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(full, x, o); if ((int)lane >= o) x = max(x, y); }
+        sm[lane] = x;
+    }
+    __syncthreads();
+    if (wid > 0) v = max(v, sm[wid - 1]);
+    return v;
 }
 
 // ---- k_ars_sprt ----------------------------------------------------------------------------------------------------------
@@ -349,70 +388,92 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
         s_eps = P.eps0; s_delta = P.delta0; s_best = 0; s_cursor = 0; s_npass = 0; s_rej_inl = 0; s_rej_tested = 0; s_chunks = 0;
     }
     __syncthreads();
-    // B. adaptive SPRT, chunks of NT models under a box of states
+    // B. adaptive SPRT.  NT models are walked concurrently; every model gets its OWN box of delta values around the current one
+    // (the widest of +-1/4, 1/16, 1/64, 1/256 for which the walks at both corners stop at the same datum -- f32 multiplication is
+    // monotone, so the outcome is then the same for every delta inside; epsilon is fixed inside a chunk).  Prefix sums over the
+    // chunk give the exact delta in front of every model; models are committed up to the first one whose delta lies outside its
+    // box (it becomes model 0 of the next chunk, which is always walked with the exact state) or which raises epsilon.
+    uint32_t *smw = (uint32_t *)keys;                    // [8][NT] mask words of the chunk's models (keys[] is free until phase C)
+    __shared__ float d_arr[ARS_BOOK_NT];                 // delta estimate after each rejected model (0 = none / invalid)
+    const bool words_in_smem = P.W0 <= 8;
     while (true) {
         const uint32_t c0 = s_cursor;
         if (c0 >= Mv) break;
         const float eps = s_eps, delta = s_delta;
-        const uint32_t best0 = s_best;
+        const uint32_t best0 = s_best, np0 = s_npass;
         const unsigned long long ri0 = s_rej_inl, rt0 = s_rej_tested;
-        const float d_lo = delta * (1.0f - 1.0f / 64.0f), d_hi = delta * (1.0f + 1.0f / 64.0f);
         const uint32_t j = tid, cnt = min(NT, Mv - c0);
         uint32_t tested = 0, inl = 0;
-        bool robust = true, have = j < cnt;
+        const bool have = j < cnt;
+        float box_lo = delta, box_hi = delta;            // degenerate box: only the exact current delta
         uint32_t id = 0;
         if (have) {
             id = vm[c0 + j];
             const uint32_t *row = masks0 + (size_t)id * P.W0;
-            if (j == 0) {
-                tested = ars_sprt_walk(row, init_n, delta / eps, (1.0f - delta) / (1.0f - eps), P.lr_thr, &inl);
-            } else {
-                uint32_t inl2;
-                tested = ars_sprt_walk(row, init_n, d_hi / eps, (1.0f - d_lo) / (1.0f - eps), P.lr_thr, &inl);
-                const uint32_t t2 = ars_sprt_walk(row, init_n, d_lo / eps, (1.0f - d_hi) / (1.0f - eps), P.lr_thr, &inl2);
-                robust = t2 == tested;
+            uint32_t stride = 1;
+            if (words_in_smem) {
+                for (uint32_t w = 0; w < P.W0; w++) smw[w * NT + tid] = row[w];
+                row = smw + tid; stride = NT;
             }
+            const float one_m_eps = 1.0f - eps;
+            bool boxed = false;
+            if (j != 0) {
+                float wdt = 0.25f;
+                for (int t = 0; t < 4 && !boxed; t++, wdt *= 0.25f) {
+                    const float lo = delta * (1.0f - wdt), hi = delta * (1.0f + wdt);
+                    if (!(hi < 1.0f)) continue;           // keeps both multipliers positive (the monotonicity argument needs it)
+                    uint32_t inl2;
+                    const uint32_t t1 = ars_sprt_walk(row, stride, init_n, hi / eps, (1.0f - lo) / one_m_eps, P.lr_thr, &inl);
+                    const uint32_t t2 = ars_sprt_walk(row, stride, init_n, lo / eps, (1.0f - hi) / one_m_eps, P.lr_thr, &inl2);
+                    if (t1 == t2) { boxed = true; tested = t1; box_lo = lo; box_hi = hi; }
+                }
+            }
+            if (!boxed) tested = ars_sprt_walk(row, stride, init_n, delta / eps, (1.0f - delta) / one_m_eps, P.lr_thr, &inl);
         }
         const bool pass = have && tested == 0, rej = have && tested != 0;
         uint32_t a_ri = rej ? inl : 0, a_rt = rej ? tested : 0, a_pc = pass ? 1 : 0;
         ars_scan3(a_ri, a_rt, a_pc, sm, tot);                                  // inclusive
-        // events that end the committed range: before j (corners disagree) or after j (epsilon changes / delta leaves the box)
+        // delta estimate right after model j (valid ones only, as in the reference: d > 0 && d < epsilon)
+        float dj = 0.0f;
+        if (rej) {
+            const float d = (float)(ri0 + a_ri) / (float)(rt0 + a_rt);
+            if (d > 0.0f && d < eps) dj = d;
+        }
+        d_arr[tid] = dj;
+        const uint32_t lastv_inc = ars_scan_max(dj != 0.0f ? j + 1 : 0u, sm);  // 1-based index of the last valid estimate in [0, j]
+        const uint32_t lastv_exc = __shfl_up_sync(0xffffffffu, lastv_inc, 1);
+        __syncthreads();                                                        // d_arr complete; sm reusable
+        if ((tid & 31) == 31) sm[tid >> 5] = lastv_inc;
+        __syncthreads();
+        const uint32_t lv_before = (tid & 31) ? lastv_exc : (tid ? sm[(tid >> 5) - 1] : 0u);   // ... in [0, j)
+        const float delta_before = lv_before ? d_arr[lv_before - 1] : delta;
+        const float delta_after = lastv_inc ? d_arr[lastv_inc - 1] : delta;
         uint32_t stop = cnt;
         if (have) {
-            if (!robust) stop = j;
-            else if (pass && inl > best0) stop = j + 1;
-            else if (rej) {
-                const float d = (float)(ri0 + a_ri) / (float)(rt0 + a_rt);
-                if (d > 0.0f && d < eps && (d < d_lo || d > d_hi)) stop = j + 1;
-            }
+            if (j != 0 && !(delta_before >= box_lo && delta_before <= box_hi)) stop = j;      // walked under a state that is not its own
+            else if (pass && inl > best0) stop = j + 1;                                       // epsilon changes after this model
         }
         const uint32_t ce = ars_block_min(stop, sm);                           // commit models [0, ce)
-        // last committed rejection with a valid delta estimate
-        uint32_t lastv = 0;                                                    // 1-based index
-        if (have && rej && j < ce) {
-            const float d = (float)(ri0 + a_ri) / (float)(rt0 + a_rt);
-            if (d > 0.0f && d < eps) lastv = j + 1;
-        }
-        const uint32_t lv = ars_block_max(lastv, sm);
-        __syncthreads();
         if (have && j < ce && pass) {
-            const uint32_t p = s_npass + a_pc - 1;
+            const uint32_t p = np0 + a_pc - 1;
             pass_id[p] = id; pass_inl[p] = inl;
         }
-        if (have && j + 1 == ce) {      // the last committed model publishes the sums
+        __syncthreads();
+        if (have && j + 1 == ce) {      // the last committed model publishes the state
             s_rej_inl = ri0 + a_ri; s_rej_tested = rt0 + a_rt;
-            s_npass = s_npass + a_pc;
+            s_npass = np0 + a_pc;
             s_cursor = c0 + ce;
             s_chunks++;
+            s_delta = delta_after;
             if (pass && inl > best0) {
                 s_best = inl;
                 const float e = (float)inl / (float)init_n;
                 if (e > eps && e < 1.0f) s_eps = e; else if (e >= 1.0f) s_eps = 0.999f;
             }
         }
-        if (have && lv && j + 1 == lv) s_delta = (float)(ri0 + a_ri) / (float)(rt0 + a_rt);
         __syncthreads();
     }
+    __syncthreads();
     // C. stable top-max_cand by inliers: threshold from a histogram, ordered compaction, bitonic on (inliers desc, order asc)
     const uint32_t npass = s_npass;
     uint32_t *hist = (uint32_t *)keys;      // init_n + 1 <= 32 * W0 + 1 bins (host guarantees <= 2 * ARS_SORT_CAP)
@@ -493,7 +554,8 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_book(ArrsacCtl *ctl, Arrsac
                                                            const uint32_t *__restrict__ newmask, uint32_t *__restrict__ pool,
                                                            uint32_t *__restrict__ samples_new) {
     if (ctl->done) return;
-    __shared__ uint32_t sm[96], tot[3];
+    __shared__ __align__(8) uint32_t sm[96];
+    __shared__ uint32_t tot[3];
     extern __shared__ __align__(16) unsigned char ars_dyn[];     // ARS_BOOK_SMEM bytes
     uint64_t *keys = (uint64_t *)ars_dyn;                                        // [ARS_SORT_CAP]
     uint32_t *e_inl = (uint32_t *)(ars_dyn + 8 * ARS_SORT_CAP);                  // inliers by entry position (part 1 order)
@@ -560,6 +622,7 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_book(ArrsacCtl *ctl, Arrsac
     for (uint32_t i = Hn1 + tid; i < P2; i += NT) keys[i] = ~0ull;
     ars_bitonic(keys, P2);
     const uint32_t keep = max(Hn1 / 2, 1u);
+    const uint32_t worst_next = e_inl[(uint32_t)keys[keep - 1] & 0xffffu];      // the bar of this block's new hypotheses (read before keys[] is reused)
     // surviving rows, in order, into the other table
     cvb_pose *np_ = tposes + (size_t)(cur ^ 1) * P.rows;
     uint32_t *ni = tinl + (size_t)(cur ^ 1) * P.rows;
@@ -595,10 +658,10 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_book(ArrsacCtl *ctl, Arrsac
         __syncthreads();
     }
     const bool gen = npool >= P.K && P.G > 0;
-    if (gen && tid < 32) ars_sample_warp(ctl, raw, npool, P.K, P.G, samples_new, pool);
+    if (gen) ars_sample_block(ctl, raw, npool, P.K, P.G, samples_new, pool, (uint32_t *)keys /* free: the keys were consumed above */, sm + 64);
     __syncthreads();
     if (tid == 0) {
-        ctl->worst = e_inl[(uint32_t)keys[keep - 1] & 0xffffu];
+        ctl->worst = worst_next;
         ctl->n_new = gen ? P.G : 0;
         ctl->cur = cur ^ 1; ctl->Hn = keep;
         ctl->acc_hi = hi; ctl->blk_lo = hi; ctl->blk_hi = min(hi + P.bs, n);

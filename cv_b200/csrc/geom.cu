@@ -1457,7 +1457,7 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
     if (!attr_set) { cudaFuncSetAttribute(k_ars_book, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ARS_BOOK_SMEM); attr_set = true; }
     {
         CVB_PROF(ctx, "k_ars_begin", 0);
-        k_ars_begin<<<1, 32, 0, st>>>(ctl, P, n_dev, n_host, raw, (uint32_t *)w->samples0.p);
+        k_ars_begin<<<1, ARS_BOOK_NT, 0, st>>>(ctl, P, n_dev, n_host, raw, (uint32_t *)w->samples0.p);
         CVB_LAUNCH_CHECK(ctx);
     }
     auto estimate = [&](int phase, uint32_t H, const uint32_t *samples, cvb_pose *poses, uint8_t *nposes) -> int {

@@ -24,7 +24,7 @@ constexpr int QT = 128;          // queries per CTA (1 per thread)
 constexpr int DTILE = 128;       // database descriptors per shared-memory tile (8 KB)
 constexpr int MAXKNN = 8;
 #ifndef CVB_KNN_DEFAULT_MODE
-#define CVB_KNN_DEFAULT_MODE 1     // 1: mma.sync int8, 2: tcgen05 (CVB_KNN_UMMA=1 / =0 override at run time)
+#define CVB_KNN_DEFAULT_MODE 2     // 1: mma.sync int8, 2: tcgen05 (CVB_KNN_UMMA=1 / =0 override at run time)
 #endif
 constexpr unsigned IDX_BITS = 22;
 constexpr unsigned IDX_MASK = (1u << IDX_BITS) - 1u;

@@ -14,7 +14,7 @@ def test_extract_and_match_all_pairs_single_rank():
     from tests.synth import synth_frame, warp_frame
     base = synth_frame(3, h=360, w=480, nblobs=900)
     frames = np.stack([base, warp_frame(base, 1, shift=(2.2, 1.1)), warp_frame(base, 2, shift=(-3.1, 0.7)), synth_frame(4, h=360, w=480, nblobs=900)])
-    ctx = cv_b200.Context(0)
+    ctx = multi.make_context(0)          # library kernels and torch ops (packing, NCCL) share this stream
     cfg = cv_b200.AkazeConfig(detector_threshold=0.001)
     counts, res = multi.extract_and_match_all_pairs(ctx, cfg, torch.from_numpy(frames).cuda(), num_frames=4, cap=4096)
     descs = []
