@@ -27,12 +27,14 @@
 #define ARS_SORT_CAP 4096u     // max_candidate_hypotheses + estimations_per_block * models_per_sample must fit
 #define ARS_BOOK_NT 1024
 #define ARS_BOOK_SMEM (14u * ARS_SORT_CAP)
+#define ARS_QCAP (1u << 20)    // queue of undecided predicates of the initial scoring (entries beyond it are evaluated in place)
 
 struct ArrsacCtl {
     uint32_t n, init_n, Mv, npass;
     uint32_t Hn, cur, blk_lo, blk_hi;
     uint32_t acc_hi, n_new, worst, done;
-    uint32_t found, iters, nraw, pad0;
+    uint32_t found, iters, nraw, q_count;     // q_count / q_count2: undecided (model, datum) predicates queued by the two initial scoring stages
+    uint32_t q_count2, stat_lazy;             // stat_lazy: mask words the SPRT had to compute itself
     uint64_t rng_pos, gen_pos;
     cvb_rng gen;                 // generator positioned at raw index gen_pos (continues the stream when it is exhausted)
     cvb_pose winner;
@@ -47,6 +49,8 @@ struct ArrsacParams {            // launch-constant configuration (by value)
     uint32_t NW;                 // mask words per candidate row (ceil(NMAX / 32))
     uint32_t NMAX;               // data capacity
     uint32_t rows;               // candidate rows per table (max_cand + G * MM)
+    uint32_t prefix, cmin;       // initial scoring in two stages: all words for the first `prefix` samples; for the rest, words >= 1 only
+                                 // when the first 32 data hold >= cmin inliers (the SPRT computes a missing word itself if it ever needs one)
     float lr_thr, eps0, delta0;
     double thr;
     int row0;
@@ -153,12 +157,145 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_begin(ArrsacCtl *ctl, Arrsa
         ctl->init_n = min(P.bs * P.ib, n);
         ctl->Mv = 0; ctl->npass = 0; ctl->Hn = 0; ctl->cur = 0; ctl->blk_lo = ctl->blk_hi = ctl->acc_hi = 0;
         ctl->n_new = 0; ctl->worst = 0; ctl->found = 0; ctl->iters = 0; ctl->n_inliers = 0; ctl->overflow = 0;
-        ctl->stat_chunks = 0; ctl->stat_pass = 0;
+        ctl->stat_chunks = 0; ctl->stat_pass = 0; ctl->q_count = 0; ctl->q_count2 = 0; ctl->stat_lazy = 0;
         ctl->done = (n < P.K || P.H0 == 0) ? 1u : 0u;
     }
     __syncthreads();
     if (n < P.K || P.H0 == 0) return;
     ars_sample_block(ctl, raw, n, P.K, P.H0, samples0, nullptr, win, sh);
+}
+
+// ---- eight-point on nine lanes ---------------------------------------------------------------------------------------------
+// eight_point() (geom.cu) runs one hypothesis per thread: its 9x9 cyclic Jacobi keeps 162 doubles in local memory and is a
+// ~600 k-cycle dependent chain, which is what a block's 64 re-estimations wait for.  Here nine lanes share one hypothesis: lane k
+// owns row k of the working matrix and of the eigenvector matrix in registers (every (p, q) rotation is unrolled, all indices
+// static), column and eigenvector updates touch each lane's own row, the row update of rows p and q exchanges the two rows by
+// shuffles.  Every element goes through exactly the operations of the one-thread version in the same order (the rotation
+// parameters are computed redundantly by all lanes from the same three broadcast values; the convergence sums are accumulated by
+// one lane in the serial order), so the poses are bit-identical to eight_point().  Three hypotheses per warp (lanes 27..31 idle).
+__device__ __forceinline__ double g9_shfl(double v, int src) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(0xffffffffu, lo, src); hi = __shfl_sync(0xffffffffu, hi, src);
+    return __hiloint2double(hi, lo);
+}
+template <int P_, int Q_>
+__device__ __forceinline__ void g9_rotate(double (&A)[9], double (&V)[9], int base, int k, bool active) {
+    const double apq = g9_shfl(A[Q_], base + P_);
+    const double app = g9_shfl(A[P_], base + P_), aqq = g9_shfl(A[Q_], base + Q_);
+    // (apq is uniform inside the group; lanes of other groups take their own branch: the shuffles above and below are executed
+    //  by the whole warp unconditionally, only the arithmetic is predicated)
+    const bool rot = active && apq != 0.0;
+    const double theta = (aqq - app) / (2.0 * apq);
+    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+    const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+    if (rot) {      // column update: A[k][p], A[k][q]
+        const double akp = A[P_], akq = A[Q_];
+        A[P_] = c * akp - s * akq;
+        A[Q_] = s * akp + c * akq;
+    }
+    // row update: rows p and q need each other's (column-updated) rows
+    const int other = k == P_ ? base + Q_ : (k == Q_ ? base + P_ : base + k);
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        const double o = g9_shfl(A[j], other);
+        if (rot) {
+            if (k == P_) A[j] = c * A[j] - s * o;          // A[p][j] = c * apk - s * aqk
+            else if (k == Q_) A[j] = s * o + c * A[j];     // A[q][j] = s * apk + c * aqk
+        }
+    }
+    if (rot) {      // eigenvectors: V[k][p], V[k][q]
+        const double vkp = V[P_], vkq = V[Q_];
+        V[P_] = c * vkp - s * vkq;
+        V[Q_] = s * vkp + c * vkq;
+    }
+}
+template <int P_>
+__device__ __forceinline__ void g9_sweep_row(double (&A)[9], double (&V)[9], int base, int k, bool active) {
+    if (P_ + 1 < 9) g9_rotate<P_, (P_ + 1 < 9 ? P_ + 1 : 8)>(A, V, base, k, active);
+    if (P_ + 2 < 9) g9_rotate<P_, (P_ + 2 < 9 ? P_ + 2 : 8)>(A, V, base, k, active);
+    if (P_ + 3 < 9) g9_rotate<P_, (P_ + 3 < 9 ? P_ + 3 : 8)>(A, V, base, k, active);
+    if (P_ + 4 < 9) g9_rotate<P_, (P_ + 4 < 9 ? P_ + 4 : 8)>(A, V, base, k, active);
+    if (P_ + 5 < 9) g9_rotate<P_, (P_ + 5 < 9 ? P_ + 5 : 8)>(A, V, base, k, active);
+    if (P_ + 6 < 9) g9_rotate<P_, (P_ + 6 < 9 ? P_ + 6 : 8)>(A, V, base, k, active);
+    if (P_ + 7 < 9) g9_rotate<P_, (P_ + 7 < 9 ? P_ + 7 : 8)>(A, V, base, k, active);
+    if (P_ + 8 < 9) g9_rotate<P_, (P_ + 8 < 9 ? P_ + 8 : 8)>(A, V, base, k, active);
+}
+
+// All 32 lanes call this; lanes base..base+8 (base = 9 * (lane / 9), groups 0..2) work on hypothesis `h` of their group; a group
+// whose `valid` is false (and lanes 27..31) only takes part in the shuffles.  Returns the number of poses (0 or 4) and out[4] in
+// the group's first lane.
+__device__ int eight_point_g9(const double *__restrict__ a, const double *__restrict__ b, const uint32_t *__restrict__ idx, bool valid,
+                              cvb_pose *out) {
+    const int lane = threadIdx.x & 31;
+    const int grp = lane / 9 < 3 ? lane / 9 : 2, base = grp * 9;
+    const int k = lane - base < 9 ? lane - base : 8;        // lanes 27..31 shadow row 8 of group 2 (results discarded)
+    double A[9], V[9];
+    {
+        // rows of the epipolar constraint (eight-point/src/lib.rs:11-24, incl. b / a.z) and row k of E^T E
+        double M[8][9];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t id = valid ? idx[i] : 0u;
+            const double *pa = a + 3 * (size_t)id, *pb = b + 3 * (size_t)id;
+            const double ap[3] = {pa[0] / pa[2], pa[1] / pa[2], pa[2] / pa[2]};
+            const double bp[3] = {pb[0] / pa[2], pb[1] / pa[2], pb[2] / pa[2]};
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) M[i][3 * j + c] = ap[j] * bp[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 9; c++) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                double mr = M[i][0];
+#pragma unroll
+                for (int r = 1; r < 9; r++) mr = k == r ? M[i][r] : mr;
+                s += mr * M[i][c];
+            }
+            A[c] = s;
+            V[c] = k == c ? 1.0 : 0.0;
+        }
+    }
+    // The three groups of a warp leave the iteration at different sweeps, but every shuffle is executed under the full mask: the
+    // warp iterates until all of its groups have converged; a converged (or invalid) group keeps shuffling with its arithmetic
+    // switched off, so its matrix stays exactly what the one-thread version returns.
+    bool converged = !valid;
+    int sweeps_left = 1000;
+    while (true) {
+        // convergence test in the serial order: diag += A[i][i]^2; off += A[i][j]^2 (i < j), row by row
+        double off = 0.0, diag = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            const double dii = g9_shfl(A[i], base + i);
+            diag += dii * dii;
+#pragma unroll
+            for (int j = i + 1; j < 9; j++) { const double v = g9_shfl(A[j], base + i); off += v * v; }
+        }
+        if (!converged && sweeps_left > 0 && (off <= 1e-12 * 1e-12 * diag || off == 0.0)) converged = true;
+        const bool active = !converged && sweeps_left > 0;
+        if (!__any_sync(0xffffffffu, active)) break;
+        g9_sweep_row<0>(A, V, base, k, active); g9_sweep_row<1>(A, V, base, k, active); g9_sweep_row<2>(A, V, base, k, active);
+        g9_sweep_row<3>(A, V, base, k, active); g9_sweep_row<4>(A, V, base, k, active); g9_sweep_row<5>(A, V, base, k, active);
+        g9_sweep_row<6>(A, V, base, k, active); g9_sweep_row<7>(A, V, base, k, active);
+        if (active) sweeps_left--;
+    }
+    double d[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) d[i] = g9_shfl(A[i], base + i);
+    int best = 0;
+#pragma unroll
+    for (int i = 1; i < 9; i++)
+        if (d[i] < d[best]) best = i;
+    double vb = V[0];
+#pragma unroll
+    for (int i = 1; i < 9; i++) vb = best == i ? V[i] : vb;      // V[k][best]
+    double E[9];
+#pragma unroll
+    for (int r = 0; r < 9; r++) E[(r % 3) * 3 + (r / 3)] = g9_shfl(vb, base + r);   // Matrix3::from_iterator is column-major
+    if (k != 0 || lane >= 27 || !valid || !converged) return 0;        // one lane per group finishes: SVD of E, the four poses
+    return essential_poses(E, out);
 }
 
 // ---- k_ars_estimate ------------------------------------------------------------------------------------------------------
@@ -168,13 +305,26 @@ __global__ void __launch_bounds__(128) k_ars_estimate(const ArrsacCtl *ctl, int 
                                                       cvb_pose *poses, uint8_t *nposes, int row0) {
     if (ctl->done) return;
     const uint32_t H = phase == 0 ? H_init : ctl->n_new;
+    if (KIND == 0) {
+        // eight-point: nine lanes per hypothesis, three hypotheses per warp (grid sized for 12 hypotheses per 128-thread CTA)
+        const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+        if (warp * 3 >= H) return;                       // warp-uniform
+        const uint32_t grp = lane / 9 < 3 ? lane / 9 : 2;
+        const uint32_t h = warp * 3 + grp;
+        const bool valid = h < H && lane < 27;
+        cvb_pose out[4];
+        const int n = eight_point_g9(a, b, samples + (size_t)min(h, H - 1) * 8, valid, out);
+        if (valid && lane == grp * 9) {
+            for (int k = 0; k < n; k++) poses[(size_t)h * 4 + k] = out[k];
+            nposes[h] = (uint8_t)n;
+        }
+        return;
+    }
     const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= H) return;
     if (KIND == 2) { nposes[h] = (uint8_t)five_point(a, b, samples + (size_t)h * 5, row0, poses + (size_t)h * 40); return; }
     cvb_pose out[4];
-    int n;
-    if (KIND == 0) n = eight_point(a, b, samples + (size_t)h * 8, out);
-    else n = p3p(a, b, samples + (size_t)h * 3, out);
+    const int n = p3p(a, b, samples + (size_t)h * 3, out);
     for (int k = 0; k < n; k++) poses[(size_t)h * 4 + k] = out[k];
     nposes[h] = (uint8_t)n;
 }
@@ -190,10 +340,17 @@ __device__ __forceinline__ bool ars_inlier(const cvb_pose &Pz, const double *__r
     return f != 0;
 }
 
-// phase 0: every initial model on data [0, init_n) -> masks0[model * W0 + w]
+// are the mask words >= 1 of an initial model computed by the scoring kernels?  (word0 = its final first mask word)
+__device__ __forceinline__ bool ars_ready(uint32_t word0, uint32_t init_n, uint32_t sample, const ArrsacParams &P) {
+    if (sample < P.prefix) return true;
+    const uint32_t c = min(32u, init_n);
+    return (uint32_t)__popc(c < 32 ? (word0 & ((1u << c) - 1)) : word0) >= P.cmin;
+}
+
+// phase 0 / 2: the initial models on data [0, init_n) -> masks0[model * W0 + w] (two stages, see ArrsacParams::prefix)
 // phase 1: kept candidate rows on [blk_lo, blk_hi) merged into their mask rows; new models on [0, blk_hi) -> newmask rows
 template <int RES>
-__global__ void __launch_bounds__(256) k_ars_score(const ArrsacCtl *ctl, ArrsacParams P, int phase, const double *__restrict__ a,
+__global__ void __launch_bounds__(256) k_ars_score(ArrsacCtl *ctl, uint2 *__restrict__ queue, ArrsacParams P, int phase, const double *__restrict__ a,
                                                    const double *__restrict__ b, const cvb_pose *__restrict__ poses0,
                                                    const uint8_t *__restrict__ nposes0, uint32_t *__restrict__ masks0,
                                                    const cvb_pose *__restrict__ tposes, uint32_t *__restrict__ tmasks,
@@ -203,15 +360,35 @@ __global__ void __launch_bounds__(256) k_ars_score(const ArrsacCtl *ctl, ArrsacP
     const unsigned full = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    if (phase == 0) {
+    if (phase == 0 || phase == 2) {
+        // phase 0: word 0 of every initial model, every word of the first P.prefix samples' models
+        // phase 2: words >= 1 of the remaining models whose first 32 data hold >= P.cmin inliers (after k_ars_resolve fixed word 0)
         const uint32_t init_n = ctl->init_n, W = (init_n + 31) >> 5;
         const uint32_t units = P.H0 * P.MM * W;
+        uint32_t *qc = phase == 0 ? &ctl->q_count : &ctl->q_count2;
+        uint2 *q = phase == 0 ? queue : queue + ARS_QCAP;
         for (uint32_t u = warp; u < units; u += nwarps) {
             const uint32_t m = u / W, w = u % W;
             if ((m % P.MM) >= nposes0[m / P.MM]) continue;
+            const bool early = w == 0 || m / P.MM < P.prefix;
+            if (phase == 0 ? !early : (early || !ars_ready(masks0[(size_t)m * P.W0], init_n, m / P.MM, P))) continue;
             const uint32_t i = w * 32 + lane;
             bool bit = false;
-            if (i < init_n) bit = ars_inlier<RES>(poses0[m], a, b, i, P.thr);
+            if (i < init_n) {
+                if (RES == 1) bit = ars_inlier<RES>(poses0[m], a, b, i, P.thr);
+                else {
+                    // the exact evaluation costs ~8x the filter: undecided pairs go to a queue that k_ars_resolve works off
+                    // without divergence (one undecided lane would otherwise stall its warp for the whole Jacobi iteration)
+                    const cvb_pose &Pz = poses0[m];
+                    const int f = c2c_inlier_filter(Pz.r, Pz.t, a + 3 * (size_t)i, b + 3 * (size_t)i, P.thr);
+                    if (f >= 0) bit = f != 0;
+                    else {
+                        const uint32_t slot = atomicAdd(qc, 1u);
+                        if (slot < ARS_QCAP) q[slot] = make_uint2(m, i);
+                        else bit = residual_c2c(Pz, a + 3 * (size_t)i, b + 3 * (size_t)i) < P.thr;
+                    }
+                }
+            }
             const unsigned bits = __ballot_sync(full, bit);
             if (lane == 0) masks0[(size_t)m * P.W0 + w] = bits;
         }
@@ -243,6 +420,20 @@ __global__ void __launch_bounds__(256) k_ars_score(const ArrsacCtl *ctl, ArrsacP
             const unsigned bits = __ballot_sync(full, bit);
             if (lane == 0) newmask[(size_t)j * P.NW + w] = bits;
         }
+    }
+}
+
+// exact evaluation of the queued predicates of the initial scoring; inliers are OR-ed into their mask word
+__global__ void __launch_bounds__(256) k_ars_resolve(const ArrsacCtl *ctl, const uint2 *__restrict__ queue, int stage, ArrsacParams P,
+                                                     const double *__restrict__ a, const double *__restrict__ b,
+                                                     const cvb_pose *__restrict__ poses0, uint32_t *__restrict__ masks0) {
+    if (ctl->done) return;
+    const uint32_t cnt = min(stage == 0 ? ctl->q_count : ctl->q_count2, ARS_QCAP);
+    queue += stage == 0 ? 0 : ARS_QCAP;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += gridDim.x * blockDim.x) {
+        const uint2 q = queue[e];
+        if (residual_c2c(poses0[q.x], a + 3 * (size_t)q.y, b + 3 * (size_t)q.y) < P.thr)
+            atomicOr(&masks0[(size_t)q.x * P.W0 + (q.y >> 5)], 1u << (q.y & 31));
     }
 }
 
@@ -320,13 +511,27 @@ __device__ uint32_t ars_popc_range(const uint32_t *row, uint32_t lo, uint32_t hi
 }
 
 // SPRT walk of one model over its initialisation mask (the reference's inner loop, f32 in data order).  words[w * stride] = mask
-// word w.  Returns tested (the 1-based datum at which the ratio exceeded the threshold) or 0 when the model passes.
-__device__ uint32_t ars_sprt_walk(const uint32_t *words, uint32_t stride, uint32_t init_n, float pos, float neg, float thr, uint32_t *inl_out) {
+// word w; words at and beyond `avail` have not been computed by the scoring kernels (two-stage initial scoring): the walk
+// evaluates such a word itself, stores it (walk copy and global row) and moves `avail` on.  Returns tested (the 1-based datum
+// at which the ratio exceeded the threshold) or 0 when the model passes.
+struct ArsLazy { const cvb_pose *pose; const double *a, *b; double thr; uint32_t *grow; uint32_t *counter; };
+template <int RES>
+__device__ uint32_t ars_sprt_walk(uint32_t *words, uint32_t stride, uint32_t init_n, float pos, float neg, float thr, uint32_t *inl_out,
+                                  uint32_t &avail, const ArsLazy &L) {
     float ratio = 1.0f;
     uint32_t inl = 0;
     for (uint32_t w = 0; w * 32 < init_n; w++) {
-        const uint32_t x = words[w * stride];
         const uint32_t cnt = min(32u, init_n - w * 32);
+        if (w >= avail) {
+            uint32_t bits = 0;
+            for (uint32_t k = 0; k < cnt; k++)
+                if (ars_inlier<RES>(*L.pose, L.a, L.b, w * 32 + k, L.thr)) bits |= 1u << k;
+            words[w * stride] = bits;
+            L.grow[w] = bits;
+            avail = w + 1;
+            atomicAdd(L.counter, 1u);
+        }
+        const uint32_t x = words[w * stride];
         if (ratio == 0.0f) { inl += __popc(cnt < 32 ? (x & ((1u << cnt) - 1)) : x); continue; }   // 0 * finite stays 0: never rejected
         for (uint32_t k = 0; k < cnt; k++) {
             if ((x >> k) & 1u) { inl++; ratio *= pos; }
@@ -357,8 +562,10 @@ __device__ uint32_t ars_scan_max(uint32_t v, uint32_t *sm /* 32 */) {
 }
 
 // ---- k_ars_sprt ----------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, ArrsacParams P, const cvb_pose *__restrict__ poses0,
-                                                           const uint8_t *__restrict__ nposes0, const uint32_t *__restrict__ masks0,
+template <int RES>
+__global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, ArrsacParams P, const double *__restrict__ a, const double *__restrict__ b,
+                                                           const cvb_pose *__restrict__ poses0,
+                                                           const uint8_t *__restrict__ nposes0, uint32_t *__restrict__ masks0,
                                                            uint32_t *__restrict__ vm, uint32_t *__restrict__ pass_id,
                                                            uint32_t *__restrict__ pass_inl, cvb_pose *tposes, uint32_t *tinl,
                                                            uint32_t *tmasks) {
@@ -409,12 +616,14 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
         uint32_t id = 0;
         if (have) {
             id = vm[c0 + j];
-            const uint32_t *row = masks0 + (size_t)id * P.W0;
+            uint32_t *grow = masks0 + (size_t)id * P.W0, *row = grow;
             uint32_t stride = 1;
+            uint32_t avail = ars_ready(grow[0], init_n, id / P.MM, P) ? P.W0 : 1u;     // words the scoring kernels computed
             if (words_in_smem) {
-                for (uint32_t w = 0; w < P.W0; w++) smw[w * NT + tid] = row[w];
+                for (uint32_t w = 0; w < avail; w++) smw[w * NT + tid] = grow[w];
                 row = smw + tid; stride = NT;
             }
+            const ArsLazy LZ = {poses0 + id, a, b, P.thr, grow, &ctl->stat_lazy};
             const float one_m_eps = 1.0f - eps;
             bool boxed = false;
             if (j != 0) {
@@ -423,12 +632,12 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
                     const float lo = delta * (1.0f - wdt), hi = delta * (1.0f + wdt);
                     if (!(hi < 1.0f)) continue;           // keeps both multipliers positive (the monotonicity argument needs it)
                     uint32_t inl2;
-                    const uint32_t t1 = ars_sprt_walk(row, stride, init_n, hi / eps, (1.0f - lo) / one_m_eps, P.lr_thr, &inl);
-                    const uint32_t t2 = ars_sprt_walk(row, stride, init_n, lo / eps, (1.0f - hi) / one_m_eps, P.lr_thr, &inl2);
+                    const uint32_t t1 = ars_sprt_walk<RES>(row, stride, init_n, hi / eps, (1.0f - lo) / one_m_eps, P.lr_thr, &inl, avail, LZ);
+                    const uint32_t t2 = ars_sprt_walk<RES>(row, stride, init_n, lo / eps, (1.0f - hi) / one_m_eps, P.lr_thr, &inl2, avail, LZ);
                     if (t1 == t2) { boxed = true; tested = t1; box_lo = lo; box_hi = hi; }
                 }
             }
-            if (!boxed) tested = ars_sprt_walk(row, stride, init_n, delta / eps, (1.0f - delta) / one_m_eps, P.lr_thr, &inl);
+            if (!boxed) tested = ars_sprt_walk<RES>(row, stride, init_n, delta / eps, (1.0f - delta) / one_m_eps, P.lr_thr, &inl, avail, LZ);
         }
         const bool pass = have && tested == 0, rej = have && tested != 0;
         uint32_t a_ri = rej ? inl : 0, a_rt = rej ? tested : 0, a_pc = pass ? 1 : 0;

@@ -30,6 +30,14 @@
 #else
 #define C2C_HD static inline
 #endif
+// The filter certifies its decisions by margins, not by bit-equality with anything, so the device build may contract a * b + c
+// into one DFMA (the library is compiled -fmad=false for the bit-exact kernels); the host build used by the CPU tests keeps
+// separate roundings.  Both are valid evaluations of the same bounds.
+#if defined(__CUDA_ARCH__)
+#define C2C_FMA(a, b, c) fma((a), (b), (c))
+#else
+#define C2C_FMA(a, b, c) ((a) * (b) + (c))
+#endif
 
 // LDL^T of the symmetric 4x4 matrix m (full storage, row-major) minus s*I.  d[] = pivots, l[] = the six multipliers
 // (l10 l20 l30 l21 l31 l32).  Returns the number of negative pivots, or -1 when a pivot is too small to trust its sign.
@@ -43,19 +51,19 @@ C2C_HD int c2c_ldl4(const double *m, double s, double *d, double *l) {
     neg += d[0] < 0.0;
     const double i0 = 1.0 / d[0];
     l[0] = m10 * i0; l[1] = m20 * i0; l[2] = m30 * i0;
-    d[1] = m11 - l[0] * m10;
+    d[1] = C2C_FMA(-l[0], m10, m11);
     if (!(fabs(d[1]) > tiny)) return -1;
     neg += d[1] < 0.0;
     const double i1 = 1.0 / d[1];
-    const double u21 = m21 - l[1] * m10, u31 = m31 - l[2] * m10;
+    const double u21 = C2C_FMA(-l[1], m10, m21), u31 = C2C_FMA(-l[2], m10, m31);
     l[3] = u21 * i1; l[4] = u31 * i1;
-    d[2] = m22 - l[1] * m20 - l[3] * u21;
+    d[2] = C2C_FMA(-l[3], u21, C2C_FMA(-l[1], m20, m22));
     if (!(fabs(d[2]) > tiny)) return -1;
     neg += d[2] < 0.0;
     const double i2 = 1.0 / d[2];
-    const double u32 = m32 - l[2] * m20 - l[4] * u21;
+    const double u32 = C2C_FMA(-l[4], u21, C2C_FMA(-l[2], m20, m32));
     l[5] = u32 * i2;
-    d[3] = m33 - l[2] * m30 - l[4] * u31 - l[5] * u32;
+    d[3] = C2C_FMA(-l[5], u32, C2C_FMA(-l[4], u31, C2C_FMA(-l[2], m30, m33)));
     if (!(fabs(d[3]) > 0.0)) return -1;      // the last pivot may be arbitrarily small (l1 close to s): its sign is not used by callers that see 0 or 1 above
     neg += d[3] < 0.0;
     return neg;
@@ -63,17 +71,17 @@ C2C_HD int c2c_ldl4(const double *m, double s, double *d, double *l) {
 
 // x <- (L D L^T)^-1 x
 C2C_HD void c2c_ldl4_solve(const double *id, const double *l, double *x) {
-    x[1] -= l[0] * x[0];
-    x[2] -= l[1] * x[0] + l[3] * x[1];
-    x[3] -= l[2] * x[0] + l[4] * x[1] + l[5] * x[2];
+    x[1] = C2C_FMA(-l[0], x[0], x[1]);
+    x[2] = C2C_FMA(-l[3], x[1], C2C_FMA(-l[1], x[0], x[2]));
+    x[3] = C2C_FMA(-l[5], x[2], C2C_FMA(-l[4], x[1], C2C_FMA(-l[2], x[0], x[3])));
     x[0] *= id[0]; x[1] *= id[1]; x[2] *= id[2]; x[3] *= id[3];
-    x[2] -= l[5] * x[3];
-    x[1] -= l[3] * x[2] + l[4] * x[3];
-    x[0] -= l[0] * x[1] + l[1] * x[2] + l[2] * x[3];
+    x[2] = C2C_FMA(-l[5], x[3], x[2]);
+    x[1] = C2C_FMA(-l[4], x[3], C2C_FMA(-l[3], x[2], x[1]));
+    x[0] = C2C_FMA(-l[2], x[3], C2C_FMA(-l[1], x[2], C2C_FMA(-l[0], x[1], x[0])));
 }
 
 C2C_HD double c2c_normalise4(double *x) {
-    const double n = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+    const double n = sqrt(C2C_FMA(x[3], x[3], C2C_FMA(x[2], x[2], C2C_FMA(x[1], x[1], x[0] * x[0]))));
     const double in = 1.0 / n;
     x[0] *= in; x[1] *= in; x[2] *= in; x[3] *= in;
     return n;
@@ -91,17 +99,17 @@ C2C_HD int c2c_inlier_filter(const double *R, const double *t, const double *a, 
         // view a: columns c = 0..2 are e_c - a a_c, column 3 is zero
         double Ta[3][3];
         for (int c = 0; c < 3; c++)
-            for (int r = 0; r < 3; r++) Ta[r][c] = (r == c ? 1.0 : 0.0) - a[r] * a[c];
+            for (int r = 0; r < 3; r++) Ta[r][c] = C2C_FMA(-a[r], a[c], r == c ? 1.0 : 0.0);
         double Tb[3][4];
         for (int c = 0; c < 4; c++) {
             const double m0 = c < 3 ? R[c] : t[0], m1 = c < 3 ? R[3 + c] : t[1], m2 = c < 3 ? R[6 + c] : t[2];
-            const double btm = b[0] * m0 + b[1] * m1 + b[2] * m2;
-            Tb[0][c] = m0 - b[0] * btm; Tb[1][c] = m1 - b[1] * btm; Tb[2][c] = m2 - b[2] * btm;
+            const double btm = C2C_FMA(b[2], m2, C2C_FMA(b[1], m1, b[0] * m0));
+            Tb[0][c] = C2C_FMA(-b[0], btm, m0); Tb[1][c] = C2C_FMA(-b[1], btm, m1); Tb[2][c] = C2C_FMA(-b[2], btm, m2);
         }
         for (int i = 0; i < 4; i++)
             for (int j = 0; j <= i; j++) {
-                double v = Tb[0][i] * Tb[0][j] + Tb[1][i] * Tb[1][j] + Tb[2][i] * Tb[2][j];
-                if (i < 3) v += Ta[0][i] * Ta[0][j] + Ta[1][i] * Ta[1][j] + Ta[2][i] * Ta[2][j];
+                double v = C2C_FMA(Tb[2][i], Tb[2][j], C2C_FMA(Tb[1][i], Tb[1][j], Tb[0][i] * Tb[0][j]));
+                if (i < 3) v = C2C_FMA(Ta[2][i], Ta[2][j], C2C_FMA(Ta[1][i], Ta[1][j], C2C_FMA(Ta[0][i], Ta[0][j], v)));
                 D[i * 4 + j] = v; D[j * 4 + i] = v;
             }
     }

@@ -1113,7 +1113,7 @@ struct DevBuf {
 // device-resident ARRSAC (arrsac_dev.cuh): buffers + page-locked staging of one context
 struct ArsWorkspace {
     DevBuf ctl, raw, samples0, poses0, nposes0, masks0, vm, pass_id, pass_inl, tposes, tinl, tmasks, newposes, nposes_new, newmask,
-        pool, samples_new, res;
+        pool, samples_new, res, queue;
     uint32_t *h_raw = nullptr;      // page-locked: raw draws + ArrsacCtl header
     size_t h_raw_cap = 0;
     unsigned char *h_res = nullptr; // page-locked result block
@@ -1134,7 +1134,7 @@ void geom_workspace_free(GeomWorkspace *g) {
     if (g->ars) {
         ArsWorkspace *w = g->ars;
         DevBuf *ab[] = {&w->ctl, &w->raw, &w->samples0, &w->poses0, &w->nposes0, &w->masks0, &w->vm, &w->pass_id, &w->pass_inl, &w->tposes,
-                        &w->tinl, &w->tmasks, &w->newposes, &w->nposes_new, &w->newmask, &w->pool, &w->samples_new, &w->res};
+                        &w->tinl, &w->tmasks, &w->newposes, &w->nposes_new, &w->newmask, &w->pool, &w->samples_new, &w->res, &w->queue};
         for (DevBuf *d : ab) if (d->p) cudaFree(d->p);
         if (w->h_raw) cudaFreeHost(w->h_raw);
         if (w->h_res) cudaFreeHost(w->h_res);
@@ -1395,6 +1395,9 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
     P.rows = P.max_cand + P.G * P.MM;
     P.lr_thr = cfg->likelihood_ratio_threshold; P.eps0 = cfg->initial_epsilon; P.delta0 = cfg->initial_delta;
     P.thr = cfg->inlier_threshold; P.row0 = row0;
+    // two-stage initial scoring only where a predicate is expensive (CameraToCamera residual); CVB_ARS_EAGER=1 scores everything up front
+    { const char *env = getenv("CVB_ARS_EAGER"); const bool eager = (env && env[0] == '1') || kind_res(kind) == 1;
+      P.prefix = eager ? P.H0 : std::min<uint32_t>(P.H0, 64); P.cmin = 2; }
     if (P.max_cand == 0 || P.rows > ARS_SORT_CAP)
         return cvb_set_error(ctx, CVB_EUNSUPPORTED, "max_candidate_hypotheses + estimations_per_block * %u must be in 1..%u", P.MM, ARS_SORT_CAP);
     if ((uint64_t)P.bs * P.ib + 1 > 2ull * ARS_SORT_CAP) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "block_size * initialization_blocks too large");
@@ -1421,6 +1424,7 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
     if ((rc = w->newmask.ensure(ctx, sizeof(uint32_t) * nnew * P.NW))) return rc;
     if ((rc = w->pool.ensure(ctx, sizeof(uint32_t) * (size_t)P.NMAX))) return rc;
     if ((rc = w->samples_new.ensure(ctx, sizeof(uint32_t) * (size_t)std::max<uint32_t>(P.G, 1) * P.K))) return rc;
+    if ((rc = w->queue.ensure(ctx, sizeof(uint2) * 2 * (size_t)ARS_QCAP))) return rc;
     // page-locked staging: [ArrsacCtl header | raw draws]
     const size_t hdr = (sizeof(ArrsacCtl) + 15) / 16 * 16, stage_bytes = hdr + sizeof(uint32_t) * (size_t)nraw;
     if (w->h_raw_cap < stage_bytes) {
@@ -1463,7 +1467,7 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
     auto estimate = [&](int phase, uint32_t H, const uint32_t *samples, cvb_pose *poses, uint8_t *nposes) -> int {
         if (H == 0) return 0;
         CVB_PROF(ctx, phase == 0 ? "k_ars_estimate_init" : "k_ars_estimate_block", 0);
-        if (kind == 0) k_ars_estimate<0><<<cdiv(H, 128), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
+        if (kind == 0) k_ars_estimate<0><<<cdiv(H, 12), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
         else if (kind == 1) k_ars_estimate<1><<<cdiv(H, 128), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
         else k_ars_estimate<2><<<cdiv(H, 128), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
         CVB_LAUNCH_CHECK(ctx);
@@ -1471,25 +1475,41 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
     };
     const uint32_t sgrid = (uint32_t)ctx->num_sms * 4;
     auto score = [&](int phase) -> int {
-        CVB_PROF(ctx, phase == 0 ? "k_ars_score_init" : "k_ars_score_block", 0);
+        CVB_PROF(ctx, phase == 1 ? "k_ars_score_block" : "k_ars_score_init", 0);
         if (res == 0)
-            k_ars_score<0><<<sgrid, 256, 0, st>>>(ctl, P, phase, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p,
+            k_ars_score<0><<<sgrid, 256, 0, st>>>(ctl, (uint2 *)w->queue.p, P, phase, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p,
                                                   (uint32_t *)w->masks0.p, (const cvb_pose *)w->tposes.p, (uint32_t *)w->tmasks.p,
                                                   (const cvb_pose *)w->newposes.p, (const uint8_t *)w->nposes_new.p, (uint32_t *)w->newmask.p);
         else
-            k_ars_score<1><<<sgrid, 256, 0, st>>>(ctl, P, phase, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p,
+            k_ars_score<1><<<sgrid, 256, 0, st>>>(ctl, (uint2 *)w->queue.p, P, phase, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p,
                                                   (uint32_t *)w->masks0.p, (const cvb_pose *)w->tposes.p, (uint32_t *)w->tmasks.p,
                                                   (const cvb_pose *)w->newposes.p, (const uint8_t *)w->nposes_new.p, (uint32_t *)w->newmask.p);
         CVB_LAUNCH_CHECK(ctx);
         return 0;
     };
     if ((rc = estimate(0, P.H0, (const uint32_t *)w->samples0.p, (cvb_pose *)w->poses0.p, (uint8_t *)w->nposes0.p))) return rc;
+    auto resolve = [&](int stage) -> int {
+        CVB_PROF(ctx, "k_ars_resolve", 0);
+        k_ars_resolve<<<sgrid, 256, 0, st>>>(ctl, (const uint2 *)w->queue.p, stage, P, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (uint32_t *)w->masks0.p);
+        CVB_LAUNCH_CHECK(ctx);
+        return 0;
+    };
     if ((rc = score(0))) return rc;
+    if (res == 0 && (rc = resolve(0))) return rc;
+    if (P.prefix < P.H0 && P.W0 > 1) {
+        if ((rc = score(2))) return rc;
+        if (res == 0 && (rc = resolve(1))) return rc;
+    }
     {
         CVB_PROF(ctx, "k_ars_sprt", 0);
-        k_ars_sprt<<<1, ARS_BOOK_NT, 0, st>>>(ctl, P, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p, (const uint32_t *)w->masks0.p,
-                                             (uint32_t *)w->vm.p, (uint32_t *)w->pass_id.p, (uint32_t *)w->pass_inl.p, (cvb_pose *)w->tposes.p,
-                                             (uint32_t *)w->tinl.p, (uint32_t *)w->tmasks.p);
+        if (res == 0)
+            k_ars_sprt<0><<<1, ARS_BOOK_NT, 0, st>>>(ctl, P, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p, (uint32_t *)w->masks0.p,
+                                                    (uint32_t *)w->vm.p, (uint32_t *)w->pass_id.p, (uint32_t *)w->pass_inl.p, (cvb_pose *)w->tposes.p,
+                                                    (uint32_t *)w->tinl.p, (uint32_t *)w->tmasks.p);
+        else
+            k_ars_sprt<1><<<1, ARS_BOOK_NT, 0, st>>>(ctl, P, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p, (uint32_t *)w->masks0.p,
+                                                    (uint32_t *)w->vm.p, (uint32_t *)w->pass_id.p, (uint32_t *)w->pass_inl.p, (cvb_pose *)w->tposes.p,
+                                                    (uint32_t *)w->tinl.p, (uint32_t *)w->tmasks.p);
         CVB_LAUNCH_CHECK(ctx);
     }
     // block loop: the number of launches follows the data count when the host knows it, the capacity otherwise;
