@@ -12,7 +12,7 @@ CvbError when the library or a Blackwell GPU is missing.
 """
 from ._lib import CvbError, Context, KP_DTYPE, lib_path, load_library  # noqa: F401
 from .akaze import Akaze, AkazeConfig  # noqa: F401
-from .knn import LinearKnn, hamming_knn, lowe_ratio_matches, matching, symmetric_matching  # noqa: F401
+from .knn import HammingHasher, LinearKnn, hamming_knn, lowe_ratio_matches, matching, symmetric_matching  # noqa: F401
 from .pinhole import CameraIntrinsics  # noqa: F401
 from .geom import (Arrsac, EightPoint, LambdaTwist, LinearEigenTriangulator, NisterStewenius, Pcg64, Xoshiro256PlusPlus,  # noqa: F401
                    residuals_camera_to_camera, residuals_world_to_camera)

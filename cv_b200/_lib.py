@@ -49,7 +49,7 @@ ABI_SYMBOLS = [
     "cvb_arrsac_default_cfg", "cvb_rng_seed_xoshiro256pp", "cvb_rng_seed_pcg64", "cvb_rng_next_u32",
     "cvb_eight_point_batch", "cvb_p3p_batch", "cvb_five_point_batch", "cvb_arrsac_five_point", "cvb_residuals_camera_to_camera", "cvb_residuals_world_to_camera",
     "cvb_triangulate_linear_eigen", "cvb_arrsac_eight_point", "cvb_arrsac_p3p",
-    "cvb_match_symmetric_pairs_dev", "cvb_pair_bearings_dev", "cvb_arrsac_eight_point_dev", "cvb_arrsac_p3p_dev", "cvb_arrsac_commit_rng",
+    "cvb_hash_bag", "cvb_hash_bag_dev", "cvb_match_symmetric_pairs_dev", "cvb_pair_bearings_dev", "cvb_arrsac_eight_point_dev", "cvb_arrsac_p3p_dev", "cvb_arrsac_commit_rng",
     "cvb_two_view_pair_dev", "cvb_two_view_frames",
     "cvb_single_view_optimize_l2", "cvb_three_view_optimize_l2", "cvb_observation_losses", "cvb_tri_landmarks_robust",
 ]
@@ -101,6 +101,8 @@ def load_library():
     L.cvb_hamming_knn_dev_counts.argtypes = [vp, vp, vp, u32, vp, vp, u32, u32, vp, vp]
     L.cvb_match_symmetric.argtypes = [vp, vp, u32, vp, u32, u32, vp, u32, C.POINTER(u32)]
     L.cvb_match_symmetric_dev.argtypes = [vp, vp, u32, vp, u32, u32, vp]
+    L.cvb_hash_bag.argtypes = [vp, vp, u32, vp, u32, vp]
+    L.cvb_hash_bag_dev.argtypes = [vp, vp, vp, u32, vp, u32, vp]
     _LIB = L
     return L
 

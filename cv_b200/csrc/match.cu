@@ -14,6 +14,7 @@
 // per-split lists in index order.  The bound is the integer popc pipe, not HBM (working set is L2 resident).
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <algorithm>
 #include <vector>
 #include "common.cuh"
@@ -360,6 +361,19 @@ __global__ void __launch_bounds__(1024) k_symmetric_pairs(const uint32_t *__rest
     if (threadIdx.x == 0) *npairs = min(s_carry, cap);
 }
 
+
+// HammingHasher::hash_bag (external crate hamming-lsh 0.3.2; call site cv-sfm/src/lib.rs:672 with the 4 096-codeword table of
+// cv-sfm/src/codewords.rs): every feature sets the bit of its nearest codeword (first minimum on ties, like Iterator::min_by_key).
+// The nearest codeword IS a 1-NN query of the matcher above; this kernel ORs the winners' bits into the hash.
+__global__ void __launch_bounds__(256) k_hash_set_bits(const uint32_t *__restrict__ nearest, const uint32_t *__restrict__ n_dev, uint32_t n_host,
+                                                       uint32_t ncode, uint32_t *__restrict__ hash_words) {
+    const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t ix = nearest[i];
+    if (ix < ncode) atomicOr(&hash_words[ix >> 5], 1u << (ix & 31));      // little-endian words: bit ix & 7 of byte ix >> 3
+}
+
 }  // namespace
 
 struct MatchWorkspace {
@@ -619,6 +633,55 @@ int cvb_match_symmetric_pairs_dev(cvb_ctx *ctx, const uint8_t *a_dev, const uint
     k_symmetric_pairs<<<1, 1024, 0, ctx->stream>>>(ws->idx, ws->dist, ws->idx2, ws->dist2, n_dev, n_max, m_dev, m_max, better_by,
                                                    pairs_out_dev, cap, n_pairs_dev, nullptr);
     CVB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int cvb_hash_bag_dev(cvb_ctx *ctx, const uint8_t *desc_dev, const uint32_t *n_dev, uint32_t n_max, const uint8_t *codewords_dev,
+                     uint32_t ncode, uint8_t *hash_out_dev) {
+    if (!ctx) return CVB_EINVAL;
+    if (!desc_dev || !codewords_dev || !hash_out_dev || !n_dev) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    if (ncode == 0 || (ncode & 31)) return cvb_set_error(ctx, CVB_EINVAL, "the number of codewords must be a positive multiple of 32");
+    if (((uintptr_t)hash_out_dev & 3)) return cvb_set_error(ctx, CVB_EINVAL, "hash output must be 4-byte aligned");
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CVB_CUDA(ctx, cudaMemsetAsync(hash_out_dev, 0, ncode / 8, ctx->stream));
+    if (n_max == 0) return 0;
+    if (!ctx->match) ctx->match = new MatchWorkspace();
+    MatchWorkspace *ws = ctx->match;
+    int rc;
+    if ((rc = grow(ctx, &ws->idx, &ws->idx_elems, (size_t)n_max * 2))) return rc;
+    if ((rc = grow(ctx, &ws->dist, &ws->dist_elems, (size_t)n_max * 2))) return rc;
+    if ((rc = knn_dev(ctx, desc_dev, n_dev, n_max, codewords_dev, nullptr, ncode, 1, ws->idx, ws->dist))) return rc;
+    CVB_PROF(ctx, "k_hash_set_bits", 0);
+    k_hash_set_bits<<<cdiv(n_max, 256), 256, 0, ctx->stream>>>(ws->idx, n_dev, n_max, ncode, (uint32_t *)hash_out_dev);
+    CVB_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int cvb_hash_bag(cvb_ctx *ctx, const uint8_t *desc, uint32_t n, const uint8_t *codewords, uint32_t ncode, uint8_t *hash_out) {
+    if (!ctx) return CVB_EINVAL;
+    if ((n && !desc) || !codewords || !hash_out) return cvb_set_error(ctx, CVB_EINVAL, "null argument");
+    if (ncode == 0 || (ncode & 31)) return cvb_set_error(ctx, CVB_EINVAL, "the number of codewords must be a positive multiple of 32");
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->match) ctx->match = new MatchWorkspace();
+    MatchWorkspace *ws = ctx->match;
+    int rc;
+    // layout of the staging buffers: q = features, db = [codewords | n (u32, 16-byte slot) | hash]
+    const size_t cw_bytes = (size_t)ncode * 64, extra = 16 + ncode / 8;
+    if ((rc = grow(ctx, &ws->q, &ws->q_bytes, (size_t)std::max<uint32_t>(n, 1) * 64))) return rc;
+    if ((rc = grow(ctx, &ws->db, &ws->db_bytes, cw_bytes + extra))) return rc;
+    cudaStream_t st = ctx->stream;
+    uint32_t *n_slot = (uint32_t *)(ws->db + cw_bytes);
+    uint8_t *hash_dev = ws->db + cw_bytes + 16;
+    uint32_t *hn = (uint32_t *)cvb_pinned(ctx, 16 + ncode / 8);
+    if (!hn) return cvb_set_error(ctx, CVB_ENOMEM, "page-locked scratch");
+    hn[0] = n;
+    if (n) CVB_CUDA(ctx, cudaMemcpyAsync(ws->q, desc, (size_t)n * 64, cudaMemcpyHostToDevice, st));
+    CVB_CUDA(ctx, cudaMemcpyAsync(ws->db, codewords, cw_bytes, cudaMemcpyHostToDevice, st));
+    CVB_CUDA(ctx, cudaMemcpyAsync(n_slot, hn, 4, cudaMemcpyHostToDevice, st));
+    if ((rc = cvb_hash_bag_dev(ctx, ws->q, n_slot, n, ws->db, ncode, hash_dev))) return rc;
+    CVB_CUDA(ctx, cudaMemcpyAsync(hn + 4, hash_dev, ncode / 8, cudaMemcpyDeviceToHost, st));
+    CVB_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(hash_out, hn + 4, ncode / 8);
     return 0;
 }
 

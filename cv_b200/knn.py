@@ -77,3 +77,21 @@ def symmetric_matching(a, b, better_by=24, ctx=None):
     ctx.check(ctx.lib.cvb_match_symmetric(ctx.handle, a.ctypes.data, len(a), b.ctypes.data, len(b), better_by,
                                           pairs.ctypes.data, cap, C.byref(n)))
     return pairs[:n.value].astype(np.int64)
+
+
+class HammingHasher:
+    """hamming_lsh::HammingHasher<64, H>::new_with_codewords(codewords) (cv-sfm/src/lib.rs:205,216): `hash_bag(features)` sets, for
+    every feature, the bit of its nearest codeword (first minimum on ties).  codewords: [H * 8, 64] uint8."""
+
+    def __init__(self, codewords, ctx=None):
+        self.codewords = _desc(codewords)
+        if len(self.codewords) == 0 or len(self.codewords) % 32:
+            raise ValueError("the number of codewords must be a positive multiple of 32")
+        self.ctx = ctx
+
+    def hash_bag(self, features):
+        f = np.ascontiguousarray(features, np.uint8).reshape(-1, 64)
+        ctx = self.ctx or default_context(0)
+        out = np.zeros(len(self.codewords) // 8, np.uint8)
+        ctx.check(ctx.lib.cvb_hash_bag(ctx.handle, f.ctypes.data, len(f), self.codewords.ctypes.data, len(self.codewords), out.ctypes.data))
+        return out

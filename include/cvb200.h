@@ -147,6 +147,15 @@ int cvb_match_symmetric(cvb_ctx *ctx, const uint8_t *desc_a, uint32_t n, const u
 int cvb_match_symmetric_dev(cvb_ctx *ctx, const uint8_t *a_dev, uint32_t n, const uint8_t *b_dev, uint32_t m,
                             uint32_t better_by, uint32_t *match_out_dev);
 
+/* HammingHasher::<64, H>::hash_bag (external crate hamming-lsh 0.3.2; cv-sfm/src/lib.rs:205,216,672): the frame-level place-recognition
+ * hash of a bag of descriptors.  Every descriptor sets the bit of its nearest codeword (Hamming distance, first minimum on ties);
+ * hash bit ix = bit ix & 7 of byte ix >> 3.  codewords: ncode x 64 bytes (cv-sfm passes the 4 096 entries of cv-sfm/src/codewords.rs,
+ * H = 512 bytes); hash_out: ncode / 8 bytes.  The crate source is not in the reference tree: restated from its documented behaviour,
+ * parity unpinned.  The nearest-codeword search is a 1-NN query of the matcher above (same kernels). */
+int cvb_hash_bag(cvb_ctx *ctx, const uint8_t *descriptors, uint32_t n, const uint8_t *codewords, uint32_t ncode, uint8_t *hash_out);
+int cvb_hash_bag_dev(cvb_ctx *ctx, const uint8_t *descriptors_dev, const uint32_t *n_dev, uint32_t n_max, const uint8_t *codewords_dev,
+                     uint32_t ncode, uint8_t *hash_out_dev);
+
 /* ---- geometric verification ------------------------------------------------------------------
  * sample_consensus::{Estimator, Model, Consensus} surfaces (external crate sample-consensus 1.0.2, re-exported at
  * cv-core/src/lib.rs:82) with the solvers and residuals of the reference:

@@ -46,6 +46,7 @@ static int no_gpu_checks(void) {
     CHECK(cvb_hamming_knn_dev_counts(NULL, desc, &n, 1, desc, &n, 1, 1, u, u + 1) == CVB_EINVAL);
     CHECK(cvb_match_symmetric(NULL, desc, 2, desc, 2, 24, u, 2, &n) == CVB_EINVAL);
     CHECK(cvb_match_symmetric_dev(NULL, desc, 2, desc, 2, 24, u) == CVB_EINVAL);
+    CHECK(cvb_hash_bag(NULL, desc, 1, desc, 32, desc) == CVB_EINVAL && cvb_hash_bag_dev(NULL, desc, &n, 1, desc, 32, desc) == CVB_EINVAL);
     CHECK(cvb_match_symmetric_pairs_dev(NULL, desc, &n, 2, desc, &n, 2, 24, u, 2, &n) == CVB_EINVAL);
     cvb_arrsac_cfg rc_;
     cvb_arrsac_default_cfg(&rc_, 1e-7);

@@ -111,3 +111,18 @@ def test_three_matcher_kernels_agree_with_oracle(mode, monkeypatch):
         oi, od = O.hamming_knn(q, db, k)
         assert np.array_equal(dist, od) and np.array_equal(idx, oi), (mode, n, m, k)
     ctx.close()
+
+
+def test_hash_bag_is_nearest_codeword_bag_of_words():
+    """HammingHasher::hash_bag (hamming-lsh, cv-sfm/src/lib.rs:672) restated: every feature sets its nearest codeword's bit."""
+    code = random_descriptors(4096, 77)            # same shape as cv-sfm/src/codewords.rs (4 096 x 64 bytes -> 512-byte hash)
+    feats = random_descriptors(3000, 78)
+    feats[:50] = code[100:150]; feats[:50, 7] ^= 3  # near-duplicates of known codewords
+    got = cv_b200.HammingHasher(code).hash_bag(feats)
+    oi, _ = O.hamming_knn(feats, code, 1)
+    want = np.zeros(512, np.uint8)
+    for ix in oi[:, 0]:
+        want[ix >> 3] |= 1 << (ix & 7)
+    assert np.array_equal(got, want)
+    assert all((got[ix >> 3] >> (ix & 7)) & 1 for ix in range(100, 150))
+    assert np.array_equal(cv_b200.HammingHasher(code).hash_bag(np.zeros((0, 64), np.uint8)), np.zeros(512, np.uint8))
