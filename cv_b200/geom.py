@@ -41,6 +41,11 @@ def _f64(a, cols):
     return a
 
 
+def _same_len(a, b, what="a, b"):
+    if len(a) != len(b):
+        raise ValueError(f"{what} must have the same number of rows ({len(a)} != {len(b)})")
+
+
 def _poses_in(poses):
     """accepts a POSE_DTYPE array or a list of (R[3,3], t[3])"""
     if isinstance(poses, np.ndarray) and poses.dtype == POSE_DTYPE:
@@ -110,6 +115,7 @@ class EightPoint:
     def estimate_batch(self, a, b, samples, ctx=None):
         ctx, L = _lib(ctx)
         a, b = _f64(a, 3), _f64(b, 3)
+        _same_len(a, b)
         s = np.ascontiguousarray(samples, np.uint32).reshape(-1, 8)
         poses = np.zeros((len(s), 4), POSE_DTYPE)
         cnt = np.zeros(len(s), np.uint8)
@@ -135,6 +141,7 @@ class NisterStewenius:
     def estimate_batch(self, a, b, samples, ctx=None):
         ctx, L = _lib(ctx)
         a, b = _f64(a, 3), _f64(b, 3)
+        _same_len(a, b)
         s = np.ascontiguousarray(samples, np.uint32).reshape(-1, 5)
         poses = np.zeros((len(s), 40), POSE_DTYPE)
         cnt = np.zeros(len(s), np.uint8)
@@ -154,6 +161,7 @@ class LambdaTwist:
     def estimate_batch(self, bearings, world, samples, ctx=None):
         ctx, L = _lib(ctx)
         a, b = _f64(bearings, 3), _f64(world, 4)
+        _same_len(a, b, "bearings, world")
         s = np.ascontiguousarray(samples, np.uint32).reshape(-1, 3)
         poses = np.zeros((len(s), 4), POSE_DTYPE)
         cnt = np.zeros(len(s), np.uint8)
@@ -169,6 +177,7 @@ def residuals_camera_to_camera(poses, a, b, ctx=None):
     """CameraToCamera::residual for every (pose, FeatureMatch): [M, N] float64."""
     ctx, L = _lib(ctx)
     p = _poses_in(poses); a, b = _f64(a, 3), _f64(b, 3)
+    _same_len(a, b)
     out = np.zeros((len(p), len(a)), np.float64)
     ctx.check(L.cvb_residuals_camera_to_camera(ctx.handle, p.ctypes.data, len(p), a.ctypes.data, b.ctypes.data, len(a), out.ctypes.data))
     return out
@@ -178,6 +187,7 @@ def residuals_world_to_camera(poses, bearings, world, ctx=None):
     """WorldToCamera::residual for every (pose, FeatureWorldMatch): [M, N] float64."""
     ctx, L = _lib(ctx)
     p = _poses_in(poses); a, b = _f64(bearings, 3), _f64(world, 4)
+    _same_len(a, b, "bearings, world")
     out = np.zeros((len(p), len(a)), np.float64)
     ctx.check(L.cvb_residuals_world_to_camera(ctx.handle, p.ctypes.data, len(p), a.ctypes.data, b.ctypes.data, len(a), out.ctypes.data))
     return out
@@ -190,6 +200,9 @@ class LinearEigenTriangulator:
         ctx, L = _lib(ctx)
         p = _poses_in(poses); b = _f64(bearings, 3)
         off = np.ascontiguousarray(offsets, np.uint32)
+        _same_len(p, b, "poses, bearings")
+        if len(off) < 1 or off[0] != 0 or (np.diff(off.astype(np.int64)) < 0).any() or off[-1] > len(p):
+            raise ValueError("offsets must start at 0, be non-decreasing and end within the observations")
         nl = len(off) - 1
         out = np.zeros((nl, 4), np.float64); ok = np.zeros(nl, np.uint8)
         ctx.check(L.cvb_triangulate_linear_eigen(ctx.handle, p.ctypes.data, b.ctypes.data, off.ctypes.data, nl, out.ctypes.data, ok.ctypes.data))
@@ -231,6 +244,7 @@ class Arrsac:
         LambdaTwist (a bearings, b homogeneous world points)."""
         two_view = isinstance(estimator, (EightPoint, NisterStewenius))
         a = _f64(a, 3); b = _f64(b, 3 if two_view else 4)
+        _same_len(a, b)
         n = len(a)
         model = Pose(); inl = np.zeros(max(n, 1), np.uint32); cnt = C.c_uint32(); found = C.c_int32()
         if isinstance(estimator, NisterStewenius):

@@ -56,3 +56,32 @@ def test_python_layer_rejects_bad_shapes():
     with pytest.raises(ValueError):
         cv_b200.Akaze().extract_batch(np.zeros((8, 8), np.float32))
     assert cv_b200.symmetric_matching(random_descriptors(1, 0), random_descriptors(5, 1)).shape == (0, 2)   # < 2 features: no matches
+
+
+def test_failed_workspace_build_is_not_cached():
+    """A configuration that fails while the workspace is being built (unsupported pattern size: the error comes AFTER the planes
+    are allocated) must fail identically when the same call is repeated, and must not poison the context."""
+    ctx = cv_b200.Context(0)
+    L = ctx.lib
+    n = C.c_uint32()
+    img = kitti_frame("0000000000")[:128, :160].copy()
+    kp = np.zeros(4096, KP_DTYPE); d = np.zeros((4096, 64), np.uint8)
+    bad = cv_b200.AkazeConfig(descriptor_pattern_size=40).to_c()
+    for _ in range(3):
+        assert L.cvb_akaze_extract(ctx.handle, C.byref(bad), img.ctypes.data, 160, 128, kp.ctypes.data, d.ctypes.data, 4096, C.byref(n)) == CVB_EUNSUPPORTED
+    good = cv_b200.AkazeConfig().to_c()
+    assert L.cvb_akaze_extract(ctx.handle, C.byref(good), img.ctypes.data, 160, 128, kp.ctypes.data, d.ctypes.data, 4096, C.byref(n)) == 0
+    assert n.value > 0
+
+
+def test_geometry_wrappers_validate_lengths():
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((20, 3)); b = rng.standard_normal((19, 3))
+    with pytest.raises(ValueError):
+        cv_b200.residuals_camera_to_camera([(np.eye(3), np.ones(3))], a, b)
+    with pytest.raises(ValueError):
+        cv_b200.Arrsac(1e-6, cv_b200.Xoshiro256PlusPlus(0)).model_inliers(cv_b200.EightPoint(), a, b)
+    with pytest.raises(ValueError):
+        cv_b200.LinearEigenTriangulator().triangulate_batch([(np.eye(3), np.zeros(3))] * 3, rng.standard_normal((3, 3)), [0, 2, 5])   # offsets past the data
+    with pytest.raises(ValueError):
+        cv_b200.LinearEigenTriangulator().triangulate_batch([(np.eye(3), np.zeros(3))] * 3, rng.standard_normal((3, 3)), [0, 2, 1])   # not monotone
