@@ -42,7 +42,7 @@ KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("response", "<f4"), ("size", "
 ABI_SYMBOLS = [
     "cvb_ctx_create", "cvb_ctx_create_on_stream", "cvb_ctx_destroy", "cvb_ctx_sync", "cvb_last_error", "cvb_version",
     "cvb_ctx_launch_count", "cvb_ctx_timer_begin", "cvb_ctx_timer_end", "cvb_ctx_profile", "cvb_ctx_profile_report",
-    "cvb_akaze_default_cfg", "cvb_akaze_extract", "cvb_akaze_extract_batch", "cvb_akaze_extract_batch_dev",
+    "cvb_akaze_default_cfg", "cvb_akaze_extract", "cvb_akaze_extract_batch", "cvb_akaze_extract_batch_dev", "cvb_akaze_dev_overflow",
     "cvb_akaze_debug_num_evolutions", "cvb_akaze_debug_evolution", "cvb_akaze_debug_plane", "cvb_akaze_debug_contrast",
     "cvb_akaze_debug_stage",
     "cvb_hamming_knn", "cvb_hamming_knn_dev", "cvb_hamming_knn_dev_counts", "cvb_match_symmetric", "cvb_match_symmetric_dev",
@@ -91,6 +91,7 @@ def load_library():
     L.cvb_akaze_extract.argtypes = [vp, C.POINTER(AkazeCfg), vp, u32, u32, vp, vp, u32, C.POINTER(u32)]
     L.cvb_akaze_extract_batch.argtypes = [vp, C.POINTER(AkazeCfg), vp, u32, u32, u32, vp, vp, u32, vp]
     L.cvb_akaze_extract_batch_dev.argtypes = [vp, C.POINTER(AkazeCfg), vp, u32, u32, u32, vp, vp, u32, vp]
+    L.cvb_akaze_dev_overflow.argtypes = [vp, C.POINTER(u32)]
     L.cvb_akaze_debug_num_evolutions.argtypes = [vp, C.POINTER(u32)]
     L.cvb_akaze_debug_evolution.argtypes = [vp, u32] + [C.POINTER(u32)] * 5
     L.cvb_akaze_debug_plane.argtypes = [vp, u32, u32, u32, vp]

@@ -812,6 +812,21 @@ int cvb_akaze_extract_batch_dev(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, const fl
     return run_extract(ctx, images_dev, batch, kp_out_dev, desc_out_dev, cap, n_out_dev);
 }
 
+int cvb_akaze_dev_overflow(cvb_ctx *ctx, uint32_t *flag_out) {
+    if (!ctx || !flag_out) return CVB_EINVAL;
+    *flag_out = 0;
+    AkazeWorkspace *ws = ctx->akaze;
+    if (!ws) return 0;
+    CVB_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned *hs = (unsigned *)cvb_pinned(ctx, sizeof(unsigned));
+    if (!hs) return cvb_set_error(ctx, CVB_ENOMEM, "page-locked scratch");
+    CVB_CUDA(ctx, cudaMemcpyAsync(hs, ws->overflow, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CVB_CUDA(ctx, cudaMemsetAsync(ws->overflow, 0, sizeof(unsigned), ctx->stream));
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *flag_out = hs[0];
+    return 0;
+}
+
 int cvb_akaze_extract_batch(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, const float *images, uint32_t batch, uint32_t w, uint32_t h,
                             cvb_keypoint *kp_out, uint8_t *desc_out, uint32_t cap, uint32_t *n_out) {
     int rc = check_args(ctx, cfg, images, batch, w, h);

@@ -108,6 +108,10 @@ int cvb_akaze_extract_batch(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, const float 
 int cvb_akaze_extract_batch_dev(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, const float *images_dev, uint32_t batch,
                                 uint32_t w, uint32_t h, cvb_keypoint *kp_out_dev, uint8_t *desc_out_dev,
                                 uint32_t cap, uint32_t *n_out_dev);
+/* The device-resident variant cannot return CVB_ECAP (nothing is read back): n_out_dev never exceeds cap, and a truncation
+ * sets a sticky flag.  This call synchronises the stream, returns the flag (0 none, 1/2 internal candidate / keypoint capacity,
+ * 3 output capacity) of the extract calls since the last query and clears it. */
+int cvb_akaze_dev_overflow(cvb_ctx *ctx, uint32_t *flag_out);
 
 /* Introspection of the last extract call (parity tests): copies one plane of one evolution of one
  * frame to host.  plane: 0 Lt, 1 Lsmooth, 2 Lx, 3 Ly, 4 Lflow, 5 Ldet.  out must hold w*h floats of

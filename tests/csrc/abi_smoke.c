@@ -35,6 +35,7 @@ static int no_gpu_checks(void) {
     CHECK(cvb_akaze_extract(NULL, &ac, img, 4, 4, kp, desc, 4, &n) == CVB_EINVAL);
     CHECK(cvb_akaze_extract_batch(NULL, &ac, img, 1, 4, 4, kp, desc, 4, &n) == CVB_EINVAL);
     CHECK(cvb_akaze_extract_batch_dev(NULL, &ac, img, 1, 4, 4, kp, desc, 4, &n) == CVB_EINVAL);
+    CHECK(cvb_akaze_dev_overflow(NULL, &n) == CVB_EINVAL);
     CHECK(cvb_akaze_debug_num_evolutions(NULL, &n) == CVB_EINVAL);
     CHECK(cvb_akaze_debug_evolution(NULL, 0, u, u + 1, u + 2, u + 3, u + 4) == CVB_EINVAL);
     CHECK(cvb_akaze_debug_plane(NULL, 0, 0, 0, img) == CVB_EINVAL);

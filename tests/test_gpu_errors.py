@@ -85,3 +85,23 @@ def test_geometry_wrappers_validate_lengths():
         cv_b200.LinearEigenTriangulator().triangulate_batch([(np.eye(3), np.zeros(3))] * 3, rng.standard_normal((3, 3)), [0, 2, 5])   # offsets past the data
     with pytest.raises(ValueError):
         cv_b200.LinearEigenTriangulator().triangulate_batch([(np.eye(3), np.zeros(3))] * 3, rng.standard_normal((3, 3)), [0, 2, 1])   # not monotone
+
+
+def test_device_resident_extract_clamps_and_flags_overflow():
+    """cvb_akaze_extract_batch_dev with too small an output capacity: the count is clamped (downstream kernels index by it) and the
+    truncation is reported by cvb_akaze_dev_overflow, once."""
+    import torch
+    ctx = cv_b200.Context(0)
+    L = ctx.lib
+    dev = torch.device("cuda", 0)
+    img = torch.from_numpy(kitti_frame("0000000000")[None].copy()).to(dev)
+    cap = 100
+    kp = torch.zeros(cap * KP_DTYPE.itemsize, dtype=torch.uint8, device=dev); d = torch.zeros(cap * 64, dtype=torch.uint8, device=dev)
+    n = torch.zeros(1, dtype=torch.int32, device=dev)
+    cfg = cv_b200.AkazeConfig().to_c()
+    ctx.check(L.cvb_akaze_extract_batch_dev(ctx.handle, C.byref(cfg), img.data_ptr(), 1, img.shape[2], img.shape[1], kp.data_ptr(), d.data_ptr(), cap, n.data_ptr()))
+    flag = C.c_uint32()
+    ctx.check(L.cvb_akaze_dev_overflow(ctx.handle, C.byref(flag)))
+    assert int(n.cpu()[0]) == cap and flag.value == 3
+    ctx.check(L.cvb_akaze_dev_overflow(ctx.handle, C.byref(flag)))
+    assert flag.value == 0
