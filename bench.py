@@ -249,7 +249,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, Wm = max(args.steps, 1), max(args.warmup, 3)          # timing rule: at least 3 warm-up steps
-    NCTX = int(os.environ.get("CVB_BENCH_CONTEXTS", "16"))   # contexts (stream + workspace + host thread each) pipelined on the GPU
+    NCTX = int(os.environ.get("CVB_BENCH_CONTEXTS", "32"))   # contexts (stream + workspace + host thread each) pipelined on the GPU
 
     frames = make_pool(POOL_PAIRS, seed0=100 * rank)
     ctxs = [cv_b200.Context(local_rank) for _ in range(NCTX)]
@@ -287,7 +287,7 @@ def main():
             self.h_model = Pose()
             self.rng = Rng()
             lib.cvb_rng_seed_xoshiro256pp(C.byref(self.rng), 0)
-            self.stats = (C.c_uint32 * 8)()
+            self.stats = (C.c_uint32 * 12)()
             self.pairs_done = 0
             self.t_busy = 0.0
     slots = [Slot() for _ in range(NCTX)]
@@ -482,10 +482,11 @@ def main():
     sc = [rep.get("k_ars_score_init"), rep.get("k_ars_score_block")]
     ransac_scoring = None
     if sc[0] and stats0[1]:
-        init_pairs = stats0[1] * min(256, stats0[0])
+        init_pairs = 32 * (stats0[8] + stats0[9])          # predicates the two scoring stages actually evaluated
         ransac_scoring = {"init_models": stats0[1], "init_predicates": init_pairs, "score_init_ms": sc[0]["ms"] / PK,
                           "predicates_per_s": init_pairs / (sc[0]["ms"] / PK * 1e-3) if sc[0]["ms"] > 0 else None,
-                          "sprt_pass": stats0[2], "sprt_commit_rounds": stats0[3], "block_iterations": stats0[4], "draws": stats0[5]}
+                          "sprt_pass": stats0[2], "sprt_commit_rounds": stats0[3], "block_iterations": stats0[4], "draws": stats0[5],
+                          "exact_fallbacks": stats0[10], "sprt_lazy_words": stats0[11]}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

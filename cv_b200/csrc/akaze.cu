@@ -119,6 +119,7 @@ struct AkazeWorkspace {
     unsigned *overflow = nullptr;
     CUtensorMap *tmaps = nullptr;      // device: [3][MAX_EVO] per-evolution maps (deriv1 source, Lx, Ly) for the TMA-staged tiles
     bool use_tma = false;
+    int tma_mask = 15;                 // CVB_TMA_MASK: 1 k_blur_v3, 2 k_blur_scharr_pm, 4 k_deriv1_v3, 8 k_deriv2_v3 (debugging)
     SupScratch sup{};
     bool suppress_seq = false;   // CVB_SUPPRESS_SEQ=1: serial reference kernel (debug / A-B check)
     bool suppress_par_only = false;   // CVB_SUPPRESS_GLOBAL=1: force the global-memory parallel kernel
@@ -422,6 +423,7 @@ int build_workspace(cvb_ctx *ctx, AkazeWorkspace *ws, const cvb_akaze_cfg *cfg, 
     {   // TMA-staged tiles: per-evolution maps of the planes the derivative kernels read (CVB_TMA=0 / 1 overrides the default)
         const char *env = getenv("CVB_TMA");
         ws->use_tma = env ? env[0] == '1' : (CVB_TMA_DEFAULT != 0);
+        if (const char *m = getenv("CVB_TMA_MASK")) ws->tma_mask = atoi(m);
         std::vector<CUtensorMap> hm(3 * MAX_EVO);
         memset(hm.data(), 0, sizeof(CUtensorMap) * hm.size());
         for (size_t i = 0; i < ws->evo.size() && ws->use_tma; i++) {
@@ -484,7 +486,7 @@ int launch_separable(cvb_ctx *ctx, const float *in, size_t in_bs, float *out, si
         dim3 g(cdiv((unsigned)w, SW3), cdiv((unsigned)h, SH3), B);
         CUtensorMap tm;
         const int R = hk.ks / 2;
-        const int use_tma = ctx->akaze && ctx->akaze->use_tma && make_tmap(&tm, in, w, h, B, in_bs, pitch3(R), SH3 + 2 * R) ? 1 : 0;
+        const int use_tma = ctx->akaze && ctx->akaze->use_tma && (ctx->akaze->tma_mask & 1) && make_tmap(&tm, in, w, h, B, in_bs, pitch3(R), SH3 + 2 * R) ? 1 : 0;
         if (!use_tma) memset(&tm, 0, sizeof(tm));
         if (hk.ks == 5) k_blur_v3<5><<<g, NT, 0, ctx->stream>>>(in, out, w, h, in_bs, out_bs, hk, tm, use_tma);
         else k_blur_v3<9><<<g, NT, 0, ctx->stream>>>(in, out, w, h, in_bs, out_bs, hk, tm, use_tma);
@@ -568,11 +570,11 @@ int run_extract_eager(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoin
             dim3 g((unsigned)(t1 - t0), 1, B);
             { CVB_PROF(ctx, "k_deriv1", 12.0 * px * B);
             k_deriv1_v3<<<g, NT, sizeof(float) * region, ds>>>(ws->Lsm, ws->Lt, ws->Lx, ws->Ly, PF, ws->table, ws->tile_evo, t0,
-                                                               ws->use_tma ? ws->tmaps : nullptr);
+                                                               ws->use_tma && (ws->tma_mask & 4) ? ws->tmaps : nullptr);
             CVB_LAUNCH_CHECK(ctx); }
             { CVB_PROF(ctx, "k_deriv2_det", 12.0 * px * B);
             k_deriv2_v3<<<g, NT, sizeof(float) * 2 * region, ds>>>(ws->Lx, ws->Ly, ws->Ldet, PF, ws->table, ws->tile_evo, t0,
-                                                                   ws->use_tma ? ws->tmaps + MAX_EVO : nullptr, ws->use_tma ? ws->tmaps + 2 * MAX_EVO : nullptr);
+                                                                   ws->use_tma && (ws->tma_mask & 8) ? ws->tmaps + MAX_EVO : nullptr, ws->use_tma && (ws->tma_mask & 8) ? ws->tmaps + 2 * MAX_EVO : nullptr);
             CVB_LAUNCH_CHECK(ctx); }
         } else {   // generic two-pass tiles, one launch pair per evolution (derivative sigma > 5)
             cudaStream_t keep = ctx->stream;
@@ -630,7 +632,7 @@ int run_extract_eager(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoin
         if (ws->fuse_blur_scharr && ws->g1.ks == 5) {
             CVB_PROF(ctx, "k_blur_scharr", 16.0 * e.w * e.h * B);
             CUtensorMap tm;
-            const int use_tma = ws->use_tma && make_tmap(&tm, src, e.w, e.h, B, src_bs, pitch3(3), SH3 + 6) ? 1 : 0;
+            const int use_tma = ws->use_tma && (ws->tma_mask & 2) && make_tmap(&tm, src, e.w, e.h, B, src_bs, pitch3(3), SH3 + 6) ? 1 : 0;
             if (!use_tma) memset(&tm, 0, sizeof(tm));
             k_blur_scharr_pm<<<dim3(cdiv((unsigned)e.w, SW3), cdiv((unsigned)e.h, SH3), B), NT, 0, st>>>(
                 src, ws->Lsm + e.off, ws->Lflow + e.off, e.w, e.h, src_bs, PF, PF, ws->g1, ws->inv_k + i, MAX_EVO, tm, use_tma);

@@ -484,7 +484,7 @@ __device__ __forceinline__ void ak_mbar_wait0(uint64_t *bar) {
 
 template <int RX, int RY, int RW = SW3 + 2 * RX>
 __device__ __forceinline__ void stage_region(const float *__restrict__ src, int w, int h, int x0, int y0, float *s_in,
-                                             const CUtensorMap *tm = nullptr, int frame = 0, uint64_t *bar = nullptr) {
+                                             const CUtensorMap *tm = nullptr, int frame = 0, uint64_t *bar = nullptr, bool tm_global = false) {
     // all of a thread's global loads are issued before the first shared store (a rolled load->store loop waits one
     // DRAM latency per row: ncu showed 36 % of the blur kernel's stall samples on that store)
     constexpr int RH = SH3 + 2 * RY, NI = (RH + 7) / 8;
@@ -496,7 +496,12 @@ __device__ __forceinline__ void stage_region(const float *__restrict__ src, int 
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        if (threadIdx.x == 0) ak_tma_tile(s_in, tm, x0 - RX, y0 - RY, frame, bar, (unsigned)(RW * RH * sizeof(float)));
+        if (threadIdx.x == 0) {
+            // a descriptor that lives in global memory was written through the generic proxy (cudaMemcpy): acquire it for the
+            // tensor-map proxy before the TMA unit reads it (harmless for descriptors in kernel-parameter space)
+            if (tm_global) asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm) : "memory");
+            ak_tma_tile(s_in, tm, x0 - RX, y0 - RY, frame, bar, (unsigned)(RW * RH * sizeof(float)));
+        }
         ak_mbar_wait0(bar);
         return;
     }
@@ -546,7 +551,7 @@ template <int S>
 __device__ __forceinline__ void deriv1_body(const float *__restrict__ src, float *__restrict__ Lx, float *__restrict__ Ly,
                                             const EvoDev &ev, int x0, int y0, float *s_in, const CUtensorMap *tm, uint64_t *bar) {
     constexpr int RW = pitch3(S);
-    stage_region<S, S, RW>(src, ev.w, ev.h, x0, y0, s_in, tm, (int)blockIdx.z, bar);
+    stage_region<S, S, RW>(src, ev.w, ev.h, x0, y0, s_in, tm, (int)blockIdx.z, bar, true);
     __syncthreads();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int gx = x0 + tx;
@@ -599,8 +604,8 @@ __device__ __forceinline__ void deriv2_body(const float *__restrict__ px, const 
                                             uint64_t *bar) {
     constexpr int RW = pitch3(S), RH = SH3 + 2 * S;
     float *s_x = sm, *s_y = sm + ((RW * RH + 31) & ~31);      // second buffer 128-byte aligned
-    stage_region<S, S, RW>(px, ev.w, ev.h, x0, y0, s_x, tmx, (int)blockIdx.z, bar);
-    stage_region<S, S, RW>(py, ev.w, ev.h, x0, y0, s_y, tmy, (int)blockIdx.z, bar + 1);
+    stage_region<S, S, RW>(px, ev.w, ev.h, x0, y0, s_x, tmx, (int)blockIdx.z, bar, true);
+    stage_region<S, S, RW>(py, ev.w, ev.h, x0, y0, s_y, tmy, (int)blockIdx.z, bar + 1, true);
     __syncthreads();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int gx = x0 + tx;

@@ -35,6 +35,7 @@ struct ArrsacCtl {
     uint32_t acc_hi, n_new, worst, done;
     uint32_t found, iters, nraw, q_count;     // q_count / q_count2: undecided (model, datum) predicates queued by the two initial scoring stages
     uint32_t q_count2, stat_lazy;             // stat_lazy: mask words the SPRT had to compute itself
+    uint32_t stat_units0, stat_units2;        // 32-datum units scored by the two initial stages
     uint64_t rng_pos, gen_pos;
     cvb_rng gen;                 // generator positioned at raw index gen_pos (continues the stream when it is exhausted)
     cvb_pose winner;
@@ -157,145 +158,12 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_begin(ArrsacCtl *ctl, Arrsa
         ctl->init_n = min(P.bs * P.ib, n);
         ctl->Mv = 0; ctl->npass = 0; ctl->Hn = 0; ctl->cur = 0; ctl->blk_lo = ctl->blk_hi = ctl->acc_hi = 0;
         ctl->n_new = 0; ctl->worst = 0; ctl->found = 0; ctl->iters = 0; ctl->n_inliers = 0; ctl->overflow = 0;
-        ctl->stat_chunks = 0; ctl->stat_pass = 0; ctl->q_count = 0; ctl->q_count2 = 0; ctl->stat_lazy = 0;
+        ctl->stat_chunks = 0; ctl->stat_pass = 0; ctl->q_count = 0; ctl->q_count2 = 0; ctl->stat_lazy = 0; ctl->stat_units0 = 0; ctl->stat_units2 = 0;
         ctl->done = (n < P.K || P.H0 == 0) ? 1u : 0u;
     }
     __syncthreads();
     if (n < P.K || P.H0 == 0) return;
     ars_sample_block(ctl, raw, n, P.K, P.H0, samples0, nullptr, win, sh);
-}
-
-// ---- eight-point on nine lanes ---------------------------------------------------------------------------------------------
-// eight_point() (geom.cu) runs one hypothesis per thread: its 9x9 cyclic Jacobi keeps 162 doubles in local memory and is a
-// ~600 k-cycle dependent chain, which is what a block's 64 re-estimations wait for.  Here nine lanes share one hypothesis: lane k
-// owns row k of the working matrix and of the eigenvector matrix in registers (every (p, q) rotation is unrolled, all indices
-// static), column and eigenvector updates touch each lane's own row, the row update of rows p and q exchanges the two rows by
-// shuffles.  Every element goes through exactly the operations of the one-thread version in the same order (the rotation
-// parameters are computed redundantly by all lanes from the same three broadcast values; the convergence sums are accumulated by
-// one lane in the serial order), so the poses are bit-identical to eight_point().  Three hypotheses per warp (lanes 27..31 idle).
-__device__ __forceinline__ double g9_shfl(double v, int src) {
-    int lo = __double2loint(v), hi = __double2hiint(v);
-    lo = __shfl_sync(0xffffffffu, lo, src); hi = __shfl_sync(0xffffffffu, hi, src);
-    return __hiloint2double(hi, lo);
-}
-template <int P_, int Q_>
-__device__ __forceinline__ void g9_rotate(double (&A)[9], double (&V)[9], int base, int k, bool active) {
-    const double apq = g9_shfl(A[Q_], base + P_);
-    const double app = g9_shfl(A[P_], base + P_), aqq = g9_shfl(A[Q_], base + Q_);
-    // (apq is uniform inside the group; lanes of other groups take their own branch: the shuffles above and below are executed
-    //  by the whole warp unconditionally, only the arithmetic is predicated)
-    const bool rot = active && apq != 0.0;
-    const double theta = (aqq - app) / (2.0 * apq);
-    const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-    const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-    if (rot) {      // column update: A[k][p], A[k][q]
-        const double akp = A[P_], akq = A[Q_];
-        A[P_] = c * akp - s * akq;
-        A[Q_] = s * akp + c * akq;
-    }
-    // row update: rows p and q need each other's (column-updated) rows
-    const int other = k == P_ ? base + Q_ : (k == Q_ ? base + P_ : base + k);
-#pragma unroll
-    for (int j = 0; j < 9; j++) {
-        const double o = g9_shfl(A[j], other);
-        if (rot) {
-            if (k == P_) A[j] = c * A[j] - s * o;          // A[p][j] = c * apk - s * aqk
-            else if (k == Q_) A[j] = s * o + c * A[j];     // A[q][j] = s * apk + c * aqk
-        }
-    }
-    if (rot) {      // eigenvectors: V[k][p], V[k][q]
-        const double vkp = V[P_], vkq = V[Q_];
-        V[P_] = c * vkp - s * vkq;
-        V[Q_] = s * vkp + c * vkq;
-    }
-}
-template <int P_>
-__device__ __forceinline__ void g9_sweep_row(double (&A)[9], double (&V)[9], int base, int k, bool active) {
-    if (P_ + 1 < 9) g9_rotate<P_, (P_ + 1 < 9 ? P_ + 1 : 8)>(A, V, base, k, active);
-    if (P_ + 2 < 9) g9_rotate<P_, (P_ + 2 < 9 ? P_ + 2 : 8)>(A, V, base, k, active);
-    if (P_ + 3 < 9) g9_rotate<P_, (P_ + 3 < 9 ? P_ + 3 : 8)>(A, V, base, k, active);
-    if (P_ + 4 < 9) g9_rotate<P_, (P_ + 4 < 9 ? P_ + 4 : 8)>(A, V, base, k, active);
-    if (P_ + 5 < 9) g9_rotate<P_, (P_ + 5 < 9 ? P_ + 5 : 8)>(A, V, base, k, active);
-    if (P_ + 6 < 9) g9_rotate<P_, (P_ + 6 < 9 ? P_ + 6 : 8)>(A, V, base, k, active);
-    if (P_ + 7 < 9) g9_rotate<P_, (P_ + 7 < 9 ? P_ + 7 : 8)>(A, V, base, k, active);
-    if (P_ + 8 < 9) g9_rotate<P_, (P_ + 8 < 9 ? P_ + 8 : 8)>(A, V, base, k, active);
-}
-
-// All 32 lanes call this; lanes base..base+8 (base = 9 * (lane / 9), groups 0..2) work on hypothesis `h` of their group; a group
-// whose `valid` is false (and lanes 27..31) only takes part in the shuffles.  Returns the number of poses (0 or 4) and out[4] in
-// the group's first lane.
-__device__ int eight_point_g9(const double *__restrict__ a, const double *__restrict__ b, const uint32_t *__restrict__ idx, bool valid,
-                              cvb_pose *out) {
-    const int lane = threadIdx.x & 31;
-    const int grp = lane / 9 < 3 ? lane / 9 : 2, base = grp * 9;
-    const int k = lane - base < 9 ? lane - base : 8;        // lanes 27..31 shadow row 8 of group 2 (results discarded)
-    double A[9], V[9];
-    {
-        // rows of the epipolar constraint (eight-point/src/lib.rs:11-24, incl. b / a.z) and row k of E^T E
-        double M[8][9];
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t id = valid ? idx[i] : 0u;
-            const double *pa = a + 3 * (size_t)id, *pb = b + 3 * (size_t)id;
-            const double ap[3] = {pa[0] / pa[2], pa[1] / pa[2], pa[2] / pa[2]};
-            const double bp[3] = {pb[0] / pa[2], pb[1] / pa[2], pb[2] / pa[2]};
-#pragma unroll
-            for (int j = 0; j < 3; j++)
-#pragma unroll
-                for (int c = 0; c < 3; c++) M[i][3 * j + c] = ap[j] * bp[c];
-        }
-#pragma unroll
-        for (int c = 0; c < 9; c++) {
-            double s = 0.0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                double mr = M[i][0];
-#pragma unroll
-                for (int r = 1; r < 9; r++) mr = k == r ? M[i][r] : mr;
-                s += mr * M[i][c];
-            }
-            A[c] = s;
-            V[c] = k == c ? 1.0 : 0.0;
-        }
-    }
-    // The three groups of a warp leave the iteration at different sweeps, but every shuffle is executed under the full mask: the
-    // warp iterates until all of its groups have converged; a converged (or invalid) group keeps shuffling with its arithmetic
-    // switched off, so its matrix stays exactly what the one-thread version returns.
-    bool converged = !valid;
-    int sweeps_left = 1000;
-    while (true) {
-        // convergence test in the serial order: diag += A[i][i]^2; off += A[i][j]^2 (i < j), row by row
-        double off = 0.0, diag = 0.0;
-#pragma unroll
-        for (int i = 0; i < 9; i++) {
-            const double dii = g9_shfl(A[i], base + i);
-            diag += dii * dii;
-#pragma unroll
-            for (int j = i + 1; j < 9; j++) { const double v = g9_shfl(A[j], base + i); off += v * v; }
-        }
-        if (!converged && sweeps_left > 0 && (off <= 1e-12 * 1e-12 * diag || off == 0.0)) converged = true;
-        const bool active = !converged && sweeps_left > 0;
-        if (!__any_sync(0xffffffffu, active)) break;
-        g9_sweep_row<0>(A, V, base, k, active); g9_sweep_row<1>(A, V, base, k, active); g9_sweep_row<2>(A, V, base, k, active);
-        g9_sweep_row<3>(A, V, base, k, active); g9_sweep_row<4>(A, V, base, k, active); g9_sweep_row<5>(A, V, base, k, active);
-        g9_sweep_row<6>(A, V, base, k, active); g9_sweep_row<7>(A, V, base, k, active);
-        if (active) sweeps_left--;
-    }
-    double d[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) d[i] = g9_shfl(A[i], base + i);
-    int best = 0;
-#pragma unroll
-    for (int i = 1; i < 9; i++)
-        if (d[i] < d[best]) best = i;
-    double vb = V[0];
-#pragma unroll
-    for (int i = 1; i < 9; i++) vb = best == i ? V[i] : vb;      // V[k][best]
-    double E[9];
-#pragma unroll
-    for (int r = 0; r < 9; r++) E[(r % 3) * 3 + (r / 3)] = g9_shfl(vb, base + r);   // Matrix3::from_iterator is column-major
-    if (k != 0 || lane >= 27 || !valid || !converged) return 0;        // one lane per group finishes: SVD of E, the four poses
-    return essential_poses(E, out);
 }
 
 // ---- k_ars_estimate ------------------------------------------------------------------------------------------------------
@@ -305,26 +173,13 @@ __global__ void __launch_bounds__(128) k_ars_estimate(const ArrsacCtl *ctl, int 
                                                       cvb_pose *poses, uint8_t *nposes, int row0) {
     if (ctl->done) return;
     const uint32_t H = phase == 0 ? H_init : ctl->n_new;
-    if (KIND == 0) {
-        // eight-point: nine lanes per hypothesis, three hypotheses per warp (grid sized for 12 hypotheses per 128-thread CTA)
-        const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-        if (warp * 3 >= H) return;                       // warp-uniform
-        const uint32_t grp = lane / 9 < 3 ? lane / 9 : 2;
-        const uint32_t h = warp * 3 + grp;
-        const bool valid = h < H && lane < 27;
-        cvb_pose out[4];
-        const int n = eight_point_g9(a, b, samples + (size_t)min(h, H - 1) * 8, valid, out);
-        if (valid && lane == grp * 9) {
-            for (int k = 0; k < n; k++) poses[(size_t)h * 4 + k] = out[k];
-            nposes[h] = (uint8_t)n;
-        }
-        return;
-    }
     const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= H) return;
     if (KIND == 2) { nposes[h] = (uint8_t)five_point(a, b, samples + (size_t)h * 5, row0, poses + (size_t)h * 40); return; }
     cvb_pose out[4];
-    const int n = p3p(a, b, samples + (size_t)h * 3, out);
+    // (a nine-lanes-per-hypothesis eight-point with the Jacobi matrix in registers was measured SLOWER on B200, 0.41 vs 0.23 ms per
+    //  64 hypotheses: the chain is dominated by the FP64 divide / square-root sequence of every rotation, which the lanes cannot share)
+    const int n = KIND == 0 ? eight_point(a, b, samples + (size_t)h * 8, out) : p3p(a, b, samples + (size_t)h * 3, out);
     for (int k = 0; k < n; k++) poses[(size_t)h * 4 + k] = out[k];
     nposes[h] = (uint8_t)n;
 }
@@ -390,7 +245,7 @@ __global__ void __launch_bounds__(256) k_ars_score(ArrsacCtl *ctl, uint2 *__rest
                 }
             }
             const unsigned bits = __ballot_sync(full, bit);
-            if (lane == 0) masks0[(size_t)m * P.W0 + w] = bits;
+            if (lane == 0) { masks0[(size_t)m * P.W0 + w] = bits; atomicAdd(phase == 0 ? &ctl->stat_units0 : &ctl->stat_units2, 1u); }
         }
         return;
     }
@@ -571,7 +426,8 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
                                                            uint32_t *tmasks) {
     if (ctl->done) return;
     __shared__ uint32_t sm[96], tot[3];
-    __shared__ uint64_t keys[ARS_SORT_CAP];
+    extern __shared__ __align__(16) unsigned char ars_dyn[];     // 8 * ARS_SORT_CAP bytes
+    uint64_t *keys = (uint64_t *)ars_dyn;                        // [ARS_SORT_CAP]
     __shared__ float s_eps, s_delta;
     __shared__ uint32_t s_best, s_cursor, s_npass, s_stop, s_chunks;
     __shared__ unsigned long long s_rej_inl, s_rej_tested;
@@ -595,77 +451,117 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
         s_eps = P.eps0; s_delta = P.delta0; s_best = 0; s_cursor = 0; s_npass = 0; s_rej_inl = 0; s_rej_tested = 0; s_chunks = 0;
     }
     __syncthreads();
-    // B. adaptive SPRT.  NT models are walked concurrently; every model gets its OWN box of delta values around the current one
-    // (the widest of +-1/4, 1/16, 1/64, 1/256 for which the walks at both corners stop at the same datum -- f32 multiplication is
-    // monotone, so the outcome is then the same for every delta inside; epsilon is fixed inside a chunk).  Prefix sums over the
-    // chunk give the exact delta in front of every model; models are committed up to the first one whose delta lies outside its
-    // box (it becomes model 0 of the next chunk, which is always walked with the exact state) or which raises epsilon.
-    uint32_t *smw = (uint32_t *)keys;                    // [8][NT] mask words of the chunk's models (keys[] is free until phase C)
+    // B. adaptive SPRT.  A chunk of models is walked concurrently; every model gets its OWN box of delta values around the current
+    // one (the widest of +-1/4, 1/16, 1/64, 1/256 for which the walks at both corners stop at the same datum -- f32 multiplication
+    // is monotone, so the outcome is then the same for every delta inside; epsilon is fixed inside a chunk).  Prefix sums over the
+    // chunk give the exact delta in front of every model.  The first model whose delta lies outside its box is walked again by its
+    // thread with that exact delta (everything in front of it is final) and the sums are redone; models are committed up to the
+    // first one that raises epsilon (the next chunk starts behind it).
+    //  * models are assigned to threads with the long walks (models the scoring kernels gave all their mask words) first, so that a
+    //    warp of quickly rejected models costs a few instructions instead of waiting for one long walk among its lanes;
+    //  * the chunk doubles (64 .. NT) while it is committed whole and restarts small after an epsilon change.
+    uint32_t *smw = (uint32_t *)keys;                    // [8][NT] mask words by chunk position (keys[] is free until phase C)
     __shared__ float d_arr[ARS_BOOK_NT];                 // delta estimate after each rejected model (0 = none / invalid)
+    __shared__ float o_lo[ARS_BOOK_NT], o_hi[ARS_BOOK_NT];
+    __shared__ uint32_t o_ti[ARS_BOOK_NT];               // outcome by position: tested << 16 | inliers at the stop (init_n < 8192)
+    __shared__ uint16_t perm[ARS_BOOK_NT];
+    __shared__ uint32_t s_fix, s_chunk;
     const bool words_in_smem = P.W0 <= 8;
+    if (tid == 0) s_chunk = 64;
+    __syncthreads();
     while (true) {
         const uint32_t c0 = s_cursor;
         if (c0 >= Mv) break;
         const float eps = s_eps, delta = s_delta;
         const uint32_t best0 = s_best, np0 = s_npass;
         const unsigned long long ri0 = s_rej_inl, rt0 = s_rej_tested;
-        const uint32_t j = tid, cnt = min(NT, Mv - c0);
-        uint32_t tested = 0, inl = 0;
-        const bool have = j < cnt;
-        float box_lo = delta, box_hi = delta;            // degenerate box: only the exact current delta
-        uint32_t id = 0;
-        if (have) {
-            id = vm[c0 + j];
+        const uint32_t j = tid, cnt = min(s_chunk, Mv - c0);
+        const float one_m_eps = 1.0f - eps;
+        // 1. positions with all mask words first
+        {
+            bool rdy = false;
+            if (j < cnt) { const uint32_t idj = vm[c0 + j]; rdy = ars_ready(masks0[(size_t)idj * P.W0], init_n, idj / P.MM, P); }
+            uint32_t x = (j < cnt && rdy) ? 1 : 0, y = (j < cnt && !rdy) ? 1 : 0, z = 0;
+            ars_scan3(x, y, z, sm, tot);
+            if (j < cnt) perm[rdy ? x - 1 : tot[0] + y - 1] = (uint16_t)j;
+            __syncthreads();
+        }
+        // 2. thread t walks position perm[t]
+        auto walk_position = [&](uint32_t pos, bool exact_only, float dl) {
+            const uint32_t id = vm[c0 + pos];
             uint32_t *grow = masks0 + (size_t)id * P.W0, *row = grow;
             uint32_t stride = 1;
             uint32_t avail = ars_ready(grow[0], init_n, id / P.MM, P) ? P.W0 : 1u;     // words the scoring kernels computed
             if (words_in_smem) {
-                for (uint32_t w = 0; w < avail; w++) smw[w * NT + tid] = grow[w];
-                row = smw + tid; stride = NT;
+                for (uint32_t w = 0; w < avail; w++) smw[w * NT + pos] = grow[w];
+                row = smw + pos; stride = NT;
             }
             const ArsLazy LZ = {poses0 + id, a, b, P.thr, grow, &ctl->stat_lazy};
-            const float one_m_eps = 1.0f - eps;
+            uint32_t tested = 0, inl = 0;
+            float blo = dl, bhi = dl;
             bool boxed = false;
-            if (j != 0) {
+            if (!exact_only) {
                 float wdt = 0.25f;
                 for (int t = 0; t < 4 && !boxed; t++, wdt *= 0.25f) {
-                    const float lo = delta * (1.0f - wdt), hi = delta * (1.0f + wdt);
+                    const float lo = dl * (1.0f - wdt), hi = dl * (1.0f + wdt);
                     if (!(hi < 1.0f)) continue;           // keeps both multipliers positive (the monotonicity argument needs it)
                     uint32_t inl2;
                     const uint32_t t1 = ars_sprt_walk<RES>(row, stride, init_n, hi / eps, (1.0f - lo) / one_m_eps, P.lr_thr, &inl, avail, LZ);
                     const uint32_t t2 = ars_sprt_walk<RES>(row, stride, init_n, lo / eps, (1.0f - hi) / one_m_eps, P.lr_thr, &inl2, avail, LZ);
-                    if (t1 == t2) { boxed = true; tested = t1; box_lo = lo; box_hi = hi; }
+                    if (t1 == t2) { boxed = true; tested = t1; blo = lo; bhi = hi; }
                 }
             }
-            if (!boxed) tested = ars_sprt_walk<RES>(row, stride, init_n, delta / eps, (1.0f - delta) / one_m_eps, P.lr_thr, &inl, avail, LZ);
-        }
-        const bool pass = have && tested == 0, rej = have && tested != 0;
-        uint32_t a_ri = rej ? inl : 0, a_rt = rej ? tested : 0, a_pc = pass ? 1 : 0;
-        ars_scan3(a_ri, a_rt, a_pc, sm, tot);                                  // inclusive
-        // delta estimate right after model j (valid ones only, as in the reference: d > 0 && d < epsilon)
-        float dj = 0.0f;
-        if (rej) {
-            const float d = (float)(ri0 + a_ri) / (float)(rt0 + a_rt);
-            if (d > 0.0f && d < eps) dj = d;
-        }
-        d_arr[tid] = dj;
-        const uint32_t lastv_inc = ars_scan_max(dj != 0.0f ? j + 1 : 0u, sm);  // 1-based index of the last valid estimate in [0, j]
-        const uint32_t lastv_exc = __shfl_up_sync(0xffffffffu, lastv_inc, 1);
-        __syncthreads();                                                        // d_arr complete; sm reusable
-        if ((tid & 31) == 31) sm[tid >> 5] = lastv_inc;
+            if (!boxed) tested = ars_sprt_walk<RES>(row, stride, init_n, dl / eps, (1.0f - dl) / one_m_eps, P.lr_thr, &inl, avail, LZ);
+            o_ti[pos] = (tested << 16) | inl;
+            o_lo[pos] = blo; o_hi[pos] = bhi;
+        };
+        if (tid < cnt) { const uint32_t pos = perm[tid]; walk_position(pos, pos == 0, delta); }
         __syncthreads();
-        const uint32_t lv_before = (tid & 31) ? lastv_exc : (tid ? sm[(tid >> 5) - 1] : 0u);   // ... in [0, j)
-        const float delta_before = lv_before ? d_arr[lv_before - 1] : delta;
-        const float delta_after = lastv_inc ? d_arr[lastv_inc - 1] : delta;
-        uint32_t stop = cnt;
-        if (have) {
-            if (j != 0 && !(delta_before >= box_lo && delta_before <= box_hi)) stop = j;      // walked under a state that is not its own
-            else if (pass && inl > best0) stop = j + 1;                                       // epsilon changes after this model
+        // 3. exact state in front of every position; repair the first position whose delta is not in its box; repeat
+        uint32_t ce = 0, a_ri = 0, a_rt = 0, a_pc = 0, tested = 0, inl = 0;
+        bool pass = false;
+        float delta_after = delta;
+        const bool have = j < cnt;
+        while (true) {
+            tested = have ? o_ti[j] >> 16 : 0; inl = have ? o_ti[j] & 0xffffu : 0;
+            pass = have && tested == 0;
+            const bool rej = have && tested != 0;
+            a_ri = rej ? inl : 0; a_rt = rej ? tested : 0; a_pc = pass ? 1 : 0;
+            ars_scan3(a_ri, a_rt, a_pc, sm, tot);                              // inclusive
+            float dj = 0.0f;                                                   // delta estimate right after model j (valid ones only)
+            if (rej) {
+                const float d = (float)(ri0 + a_ri) / (float)(rt0 + a_rt);
+                if (d > 0.0f && d < eps) dj = d;
+            }
+            d_arr[tid] = dj;
+            const uint32_t lastv_inc = ars_scan_max(dj != 0.0f ? j + 1 : 0u, sm);   // 1-based index of the last valid estimate in [0, j]
+            const uint32_t lastv_exc = __shfl_up_sync(0xffffffffu, lastv_inc, 1);
+            __syncthreads();                                                    // d_arr complete; sm reusable
+            if ((tid & 31) == 31) sm[tid >> 5] = lastv_inc;
+            __syncthreads();
+            const uint32_t lv_before = (tid & 31) ? lastv_exc : (tid ? sm[(tid >> 5) - 1] : 0u);   // ... in [0, j)
+            const float delta_before = lv_before ? d_arr[lv_before - 1] : delta;
+            delta_after = lastv_inc ? d_arr[lastv_inc - 1] : delta;
+            const bool viol = have && !(delta_before >= o_lo[j] && delta_before <= o_hi[j]);
+            uint32_t stop = cnt;
+            if (have) {
+                if (viol) stop = j;                                            // walked under a state that is not its own
+                else if (pass && inl > best0) stop = j + 1;                    // epsilon changes after this model
+            }
+            ce = ars_block_min(stop, sm);
+            if (tid == 0) s_fix = 0;
+            __syncthreads();
+            if (have && j == ce && viol) {                                     // everything in front of position ce is final
+                walk_position(j, true, delta_before);
+                s_fix = 1;
+            }
+            __syncthreads();
+            if (!s_fix) break;
         }
-        const uint32_t ce = ars_block_min(stop, sm);                           // commit models [0, ce)
+        // 4. commit models [0, ce)
         if (have && j < ce && pass) {
             const uint32_t p = np0 + a_pc - 1;
-            pass_id[p] = id; pass_inl[p] = inl;
+            pass_id[p] = vm[c0 + j]; pass_inl[p] = inl;
         }
         __syncthreads();
         if (have && j + 1 == ce) {      // the last committed model publishes the state
@@ -674,11 +570,13 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
             s_cursor = c0 + ce;
             s_chunks++;
             s_delta = delta_after;
-            if (pass && inl > best0) {
+            const bool eps_event = pass && inl > best0;
+            if (eps_event) {
                 s_best = inl;
                 const float e = (float)inl / (float)init_n;
                 if (e > eps && e < 1.0f) s_eps = e; else if (e >= 1.0f) s_eps = 0.999f;
             }
+            s_chunk = eps_event ? 64u : min((uint32_t)NT, 2u * cnt);
         }
         __syncthreads();
     }

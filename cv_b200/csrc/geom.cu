@@ -1458,7 +1458,12 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
     const uint32_t *raw = (const uint32_t *)w->raw.p;
     const int res = kind_res(kind);
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_ars_book, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ARS_BOOK_SMEM); attr_set = true; }
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_ars_book, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ARS_BOOK_SMEM);
+        cudaFuncSetAttribute(k_ars_sprt<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(k_ars_sprt<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_set = true;
+    }
     {
         CVB_PROF(ctx, "k_ars_begin", 0);
         k_ars_begin<<<1, ARS_BOOK_NT, 0, st>>>(ctl, P, n_dev, n_host, raw, (uint32_t *)w->samples0.p);
@@ -1467,7 +1472,7 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
     auto estimate = [&](int phase, uint32_t H, const uint32_t *samples, cvb_pose *poses, uint8_t *nposes) -> int {
         if (H == 0) return 0;
         CVB_PROF(ctx, phase == 0 ? "k_ars_estimate_init" : "k_ars_estimate_block", 0);
-        if (kind == 0) k_ars_estimate<0><<<cdiv(H, 12), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
+        if (kind == 0) k_ars_estimate<0><<<cdiv(H, 32), 32, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
         else if (kind == 1) k_ars_estimate<1><<<cdiv(H, 128), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
         else k_ars_estimate<2><<<cdiv(H, 128), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
         CVB_LAUNCH_CHECK(ctx);
@@ -1503,11 +1508,11 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
     {
         CVB_PROF(ctx, "k_ars_sprt", 0);
         if (res == 0)
-            k_ars_sprt<0><<<1, ARS_BOOK_NT, 0, st>>>(ctl, P, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p, (uint32_t *)w->masks0.p,
+            k_ars_sprt<0><<<1, ARS_BOOK_NT, 8 * ARS_SORT_CAP, st>>>(ctl, P, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p, (uint32_t *)w->masks0.p,
                                                     (uint32_t *)w->vm.p, (uint32_t *)w->pass_id.p, (uint32_t *)w->pass_inl.p, (cvb_pose *)w->tposes.p,
                                                     (uint32_t *)w->tinl.p, (uint32_t *)w->tmasks.p);
         else
-            k_ars_sprt<1><<<1, ARS_BOOK_NT, 0, st>>>(ctl, P, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p, (uint32_t *)w->masks0.p,
+            k_ars_sprt<1><<<1, ARS_BOOK_NT, 8 * ARS_SORT_CAP, st>>>(ctl, P, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p, (uint32_t *)w->masks0.p,
                                                     (uint32_t *)w->vm.p, (uint32_t *)w->pass_id.p, (uint32_t *)w->pass_inl.p, (cvb_pose *)w->tposes.p,
                                                     (uint32_t *)w->tinl.p, (uint32_t *)w->tmasks.p);
         CVB_LAUNCH_CHECK(ctx);
@@ -1825,9 +1830,11 @@ int cvb_arrsac_commit_rng(cvb_ctx *ctx, cvb_rng *rng, uint32_t *stats_out) {
     ArrsacCtl h;
     int rc = arrsac_commit_rng(ctx, rng, &h);
     if (rc) return rc;
-    if (stats_out) {   // n, valid initial models, models that passed the SPRT, SPRT chunks, block iterations, draws consumed (low word), inliers, found
+    if (stats_out) {   // 12 words: n, valid initial models, SPRT passes, SPRT commit rounds, block iterations, draws, inliers, found, 32-datum units
+                       // scored in stage 1 / stage 2, predicates resolved exactly from the queues, mask words computed by the SPRT itself
         stats_out[0] = h.n; stats_out[1] = h.Mv; stats_out[2] = h.npass; stats_out[3] = h.stat_chunks; stats_out[4] = h.iters;
         stats_out[5] = (uint32_t)h.rng_pos; stats_out[6] = h.n_inliers; stats_out[7] = h.found;
+        stats_out[8] = h.stat_units0; stats_out[9] = h.stat_units2; stats_out[10] = h.q_count + h.q_count2; stats_out[11] = h.stat_lazy;
     }
     return 0;
 }
