@@ -40,8 +40,9 @@
 #endif
 
 // LDL^T of the symmetric 4x4 matrix m (full storage, row-major) minus s*I.  d[] = pivots, l[] = the six multipliers
-// (l10 l20 l30 l21 l31 l32).  Returns the number of negative pivots, or -1 when a pivot is too small to trust its sign.
-C2C_HD int c2c_ldl4(const double *m, double s, double *d, double *l) {
+// (l10 l20 l30 l21 l31 l32), inv[0..2] = reciprocals of the first three pivots.  Returns the number of negative pivots, or -1 when a
+// pivot is too small to trust its sign.
+C2C_HD int c2c_ldl4(const double *m, double s, double *d, double *l, double *inv) {
     const double tiny = 1e-11;
     const double m00 = m[0] - s, m11 = m[5] - s, m22 = m[10] - s, m33 = m[15] - s;
     const double m10 = m[4], m20 = m[8], m30 = m[12], m21 = m[9], m31 = m[13], m32 = m[14];
@@ -50,17 +51,20 @@ C2C_HD int c2c_ldl4(const double *m, double s, double *d, double *l) {
     if (!(fabs(d[0]) > tiny)) return -1;
     neg += d[0] < 0.0;
     const double i0 = 1.0 / d[0];
+    inv[0] = i0;
     l[0] = m10 * i0; l[1] = m20 * i0; l[2] = m30 * i0;
     d[1] = C2C_FMA(-l[0], m10, m11);
     if (!(fabs(d[1]) > tiny)) return -1;
     neg += d[1] < 0.0;
     const double i1 = 1.0 / d[1];
+    inv[1] = i1;
     const double u21 = C2C_FMA(-l[1], m10, m21), u31 = C2C_FMA(-l[2], m10, m31);
     l[3] = u21 * i1; l[4] = u31 * i1;
     d[2] = C2C_FMA(-l[3], u21, C2C_FMA(-l[1], m20, m22));
     if (!(fabs(d[2]) > tiny)) return -1;
     neg += d[2] < 0.0;
     const double i2 = 1.0 / d[2];
+    inv[2] = i2;
     const double u32 = C2C_FMA(-l[4], u21, C2C_FMA(-l[2], m20, m32));
     l[5] = u32 * i2;
     d[3] = C2C_FMA(-l[5], u32, C2C_FMA(-l[4], u31, C2C_FMA(-l[2], m30, m33)));
@@ -113,35 +117,38 @@ C2C_HD int c2c_inlier_filter(const double *R, const double *t, const double *a, 
                 D[i * 4 + j] = v; D[j * 4 + i] = v;
             }
     }
-    double d[4], l[6], dh[4], lh[6];
-    const int c_lo = c2c_ldl4(D, s_lo, d, l);
+    double d[4], l[6], id[4], dh[4], lh[6], ih[4];
+    const int c_lo = c2c_ldl4(D, s_lo, d, l, id);
     if (c_lo == 0) return 0;                       // l1 > s_lo: residual >= 2 thr
     if (c_lo != 1) return -1;
-    if (c2c_ldl4(D, s_hi, dh, lh) != 1) return -1; // need l2 > s_hi for the contraction bound
-    const double id[4] = {1.0 / d[0], 1.0 / d[1], 1.0 / d[2], 1.0 / d[3]};
+    if (c2c_ldl4(D, s_hi, dh, lh, ih) != 1) return -1; // need l2 > s_hi for the contraction bound
+    id[3] = 1.0 / d[3];
+    // inverse iteration with shift s_lo.  Three solves without normalisation (growth <= 1 / |l1 - s_lo| per solve, harmless in
+    // f64), one normalisation, then a checked step: the unit vector must not move by more than 1e-11
     double x[4] = {0.5, 0.5, 0.5, 0.5};
     c2c_ldl4_solve(id, l, x);
-    c2c_normalise4(x);
+    c2c_ldl4_solve(id, l, x);
     c2c_ldl4_solve(id, l, x);
     c2c_normalise4(x);
-    double delta = 1.0;
-    for (int it = 0; it < 6 && delta > 1e-11; it++) {
+    double delta2 = 1.0;
+    for (int it = 0; it < 4 && delta2 > 1e-22; it++) {
         double y[4] = {x[0], x[1], x[2], x[3]};
         c2c_ldl4_solve(id, l, y);
         c2c_normalise4(y);
         // the shifted operator has a negative dominant eigenvalue when l1 < s_lo: successive iterates alternate in sign
         const double sg = (x[0] * y[0] + x[1] * y[1] + x[2] * y[2] + x[3] * y[3]) < 0.0 ? -1.0 : 1.0;
         double e = 0.0;
-        for (int k = 0; k < 4; k++) { const double df = sg * y[k] - x[k]; e += df * df; x[k] = sg * y[k]; }
-        delta = sqrt(e);
+        for (int k = 0; k < 4; k++) { const double df = sg * y[k] - x[k]; e = C2C_FMA(df, df, e); x[k] = sg * y[k]; }
+        delta2 = e;
     }
-    if (!(delta <= 1e-11)) return -1;
+    if (!(delta2 <= 1e-22)) return -1;
     // pose.rs:284-295: from_homogeneous (sign of w, unit xyz), transform, cosine distances
     double p[4] = {x[0], x[1], x[2], x[3]};
     if (signbit(p[3])) { p[0] = -p[0]; p[1] = -p[1]; p[2] = -p[2]; p[3] = -p[3]; }
     const double pn = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
     if (!(pn > 1e-9)) return -1;
-    p[0] /= pn; p[1] /= pn; p[2] /= pn; p[3] /= pn;
+    const double ipn = 1.0 / pn;
+    p[0] *= ipn; p[1] *= ipn; p[2] *= ipn; p[3] *= ipn;
     double q[3];
     for (int r = 0; r < 3; r++) q[r] = R[3 * r] * p[0] + R[3 * r + 1] * p[1] + R[3 * r + 2] * p[2] + t[r] * p[3];
     const double qn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
