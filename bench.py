@@ -249,7 +249,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, Wm = max(args.steps, 1), max(args.warmup, 3)          # timing rule: at least 3 warm-up steps
-    NCTX = int(os.environ.get("CVB_BENCH_CONTEXTS", "32"))   # contexts (stream + workspace + host thread each) pipelined on the GPU
+    NCTX = int(os.environ.get("CVB_BENCH_CONTEXTS", "16"))   # 16 contexts x (main + auxiliary stream) = the 32 hardware queues: more contexts alias queues   # contexts (stream + workspace + host thread each) pipelined on the GPU
 
     frames = make_pool(POOL_PAIRS, seed0=100 * rank)
     ctxs = [cv_b200.Context(local_rank) for _ in range(NCTX)]
@@ -388,8 +388,10 @@ def main():
     for s in slots:
         s.pairs_done = 0; s.t_busy = 0.0
     t0 = time.perf_counter()
+    cpu0 = time.process_time()
     run_pairs(pair_host, Wm * PAIRS_PER_STEP, K * PAIRS_PER_STEP)
     ms_e2e = (time.perf_counter() - t0) * 1e3     # blocking host API: wall clock over the K steps (all results on the host)
+    host_cpu_ms_per_pair = (time.process_time() - cpu0) * 1e3 / (K * PAIRS_PER_STEP)
     barrier()
     s0 = slots[0]
     nb_max = (cap + 63) // 64 + 1
@@ -397,6 +399,14 @@ def main():
     h2d_step = PAIRS_PER_STEP * (2 * W * H * 4 + 4 * nraw + 160)                  # frames + the consensus generator's draw stream + control block
     d2h_step = PAIRS_PER_STEP * (2 * cap * (KP_DTYPE.itemsize + 64) + cap * 8 + cap * 4 + 16 + 96 + 8 + 160)
     e2e_value, _ = D.aggregate_throughput(2.0 * K * PAIRS_PER_STEP, ms_e2e, dev)
+    per_rank = torch.tensor([2.0 * K * PAIRS_PER_STEP / (ms_e2e * 1e-3), h2d_step * K / (ms_e2e * 1e-3) / 1e9, host_cpu_ms_per_pair],
+                            dtype=torch.float64, device=dev)
+    per_rank_all = [torch.zeros_like(per_rank) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank_all, per_rank)
+    else:
+        per_rank_all = [per_rank]
+    per_rank_all = [[round(float(v), 3) for v in t.cpu().tolist()] for t in per_rank_all]
     e2e_busy = [round(s.t_busy / max(s.pairs_done, 1) * 1e3, 3) for s in slots]
     e2e_pairs = [s.pairs_done for s in slots]
     sampler.stop_flag = True
@@ -508,7 +518,8 @@ def main():
                            "setup": "graph capture / allocation pass over every (context, input) pair before the warm-up steps"},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
                         "host_threads": NCTX, "timed_region_ms": ms_e2e, "mean_call_ms": sum(e2e_busy) / len(e2e_busy),
-                        "pairs_per_thread": e2e_pairs},
+                        "pairs_per_thread": e2e_pairs,
+                        "per_rank": {"columns": ["frames_per_s", "h2d_GBps", "host_cpu_ms_per_pair"], "rows": per_rank_all}},
                 "timed_region_ms": ms_max, "mean_pair_latency_ms": sum(dev_busy) / len(dev_busy),
                 "gpu_launches": int(launches), "roofline": roofline, "hamming_Gcmp_per_s": gcmp, "ransac_two_view": ransac,
                 "ransac_scoring": ransac_scoring, "allpairs64": ap64, "inliers_equal_oracle": inliers_equal_oracle, "cpu_baseline": cpu,

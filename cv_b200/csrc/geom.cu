@@ -1478,8 +1478,11 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
         CVB_LAUNCH_CHECK(ctx);
         return 0;
     };
-    const uint32_t sgrid = (uint32_t)ctx->num_sms * 4;
+    // the initial scoring fills the machine; a block's scoring is a few thousand warp-units: a grid of the whole machine would
+    // spend more time scheduling empty CTAs (76 launches per pair) than computing
+    const uint32_t sgrid_full = (uint32_t)ctx->num_sms * 4, sgrid_block = 48;
     auto score = [&](int phase) -> int {
+        const uint32_t sgrid = phase == 1 ? sgrid_block : sgrid_full;
         CVB_PROF(ctx, phase == 1 ? "k_ars_score_block" : "k_ars_score_init", 0);
         if (res == 0)
             k_ars_score<0><<<sgrid, 256, 0, st>>>(ctl, (uint2 *)w->queue.p, P, phase, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p,
@@ -1495,7 +1498,7 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
     if ((rc = estimate(0, P.H0, (const uint32_t *)w->samples0.p, (cvb_pose *)w->poses0.p, (uint8_t *)w->nposes0.p))) return rc;
     auto resolve = [&](int stage) -> int {
         CVB_PROF(ctx, "k_ars_resolve", 0);
-        k_ars_resolve<<<sgrid, 256, 0, st>>>(ctl, (const uint2 *)w->queue.p, stage, P, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (uint32_t *)w->masks0.p);
+        k_ars_resolve<<<sgrid_full, 256, 0, st>>>(ctl, (const uint2 *)w->queue.p, stage, P, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (uint32_t *)w->masks0.p);
         CVB_LAUNCH_CHECK(ctx);
         return 0;
     };
