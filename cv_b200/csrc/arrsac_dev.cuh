@@ -185,13 +185,19 @@ __global__ void __launch_bounds__(128) k_ars_estimate(const ArrsacCtl *ctl, int 
 }
 
 // ---- k_ars_score ---------------------------------------------------------------------------------------------------------
+// the exact evaluation behind a call: inlining the 4x4 Jacobi into the scoring kernels cost 148 registers (one 256-thread CTA per SM,
+// FP64 pipe 30 % busy in ncu); out of line the filter path fits two CTAs per SM
+__device__ __noinline__ bool ars_exact_c2c(const cvb_pose *Pz, const double *pa, const double *pb, double thr) {
+    return residual_c2c(*Pz, pa, pb) < thr;
+}
+
 template <int RES>
 __device__ __forceinline__ bool ars_inlier(const cvb_pose &Pz, const double *__restrict__ a, const double *__restrict__ b, uint32_t i,
                                            double thr) {
     if (RES == 1) return residual_w2c(Pz, a + 3 * (size_t)i, b + 4 * (size_t)i) < thr;
     const double *pa = a + 3 * (size_t)i, *pb = b + 3 * (size_t)i;
     int f = c2c_inlier_filter(Pz.r, Pz.t, pa, pb, thr);
-    if (f < 0) f = residual_c2c(Pz, pa, pb) < thr ? 1 : 0;
+    if (f < 0) f = ars_exact_c2c(&Pz, pa, pb, thr) ? 1 : 0;
     return f != 0;
 }
 
@@ -205,7 +211,7 @@ __device__ __forceinline__ bool ars_ready(uint32_t word0, uint32_t init_n, uint3
 // phase 0 / 2: the initial models on data [0, init_n) -> masks0[model * W0 + w] (two stages, see ArrsacParams::prefix)
 // phase 1: kept candidate rows on [blk_lo, blk_hi) merged into their mask rows; new models on [0, blk_hi) -> newmask rows
 template <int RES>
-__global__ void __launch_bounds__(256) k_ars_score(ArrsacCtl *ctl, uint2 *__restrict__ queue, ArrsacParams P, int phase, const double *__restrict__ a,
+__global__ void __launch_bounds__(256, 2) k_ars_score(ArrsacCtl *ctl, uint2 *__restrict__ queue, ArrsacParams P, int phase, const double *__restrict__ a,
                                                    const double *__restrict__ b, const cvb_pose *__restrict__ poses0,
                                                    const uint8_t *__restrict__ nposes0, uint32_t *__restrict__ masks0,
                                                    const cvb_pose *__restrict__ tposes, uint32_t *__restrict__ tmasks,
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(256) k_ars_score(ArrsacCtl *ctl, uint2 *__rest
                     else {
                         const uint32_t slot = atomicAdd(qc, 1u);
                         if (slot < ARS_QCAP) q[slot] = make_uint2(m, i);
-                        else bit = residual_c2c(Pz, a + 3 * (size_t)i, b + 3 * (size_t)i) < P.thr;
+                        else bit = ars_exact_c2c(&Pz, a + 3 * (size_t)i, b + 3 * (size_t)i, P.thr);
                     }
                 }
             }
@@ -398,6 +404,41 @@ __device__ uint32_t ars_sprt_walk(uint32_t *words, uint32_t stride, uint32_t ini
     return 0;
 }
 
+// Both corners of a box in one pass (ratio_hi >= ratio_lo at every datum by monotonicity): returns true when the two walks stop at the
+// same datum (the outcome then holds for the whole box); *tested / *inl_out as in ars_sprt_walk.
+template <int RES>
+__device__ bool ars_sprt_walk_box(uint32_t *words, uint32_t stride, uint32_t init_n, float pos_hi, float neg_hi, float pos_lo, float neg_lo,
+                                  float thr, uint32_t *tested, uint32_t *inl_out, uint32_t &avail, const ArsLazy &L) {
+    float rh = 1.0f, rl = 1.0f;
+    uint32_t inl = 0;
+    for (uint32_t w = 0; w * 32 < init_n; w++) {
+        const uint32_t cnt = min(32u, init_n - w * 32);
+        if (w >= avail) {
+            uint32_t bits = 0;
+            for (uint32_t k = 0; k < cnt; k++)
+                if (ars_inlier<RES>(*L.pose, L.a, L.b, w * 32 + k, L.thr)) bits |= 1u << k;
+            words[w * stride] = bits;
+            L.grow[w] = bits;
+            avail = w + 1;
+            atomicAdd(L.counter, 1u);
+        }
+        const uint32_t x = words[w * stride];
+        if (rh == 0.0f) { inl += __popc(cnt < 32 ? (x & ((1u << cnt) - 1)) : x); continue; }      // rl <= rh: both stay 0, never rejected
+        for (uint32_t k = 0; k < cnt; k++) {
+            const bool in = (x >> k) & 1u;
+            inl += in ? 1u : 0u;
+            rh *= in ? pos_hi : neg_hi;
+            rl *= in ? pos_lo : neg_lo;
+            if (rh > thr) {                      // the upper corner stops here; the box is decided iff the lower corner stops here too
+                *tested = w * 32 + k + 1; *inl_out = inl;
+                return rl > thr;
+            }
+        }
+    }
+    *tested = 0; *inl_out = inl;                 // the upper corner passes, hence the lower corner as well
+    return true;
+}
+
 // inclusive block-wide max scan (ARS_BOOK_NT threads)
 __device__ uint32_t ars_scan_max(uint32_t v, uint32_t *sm /* 32 */) {
     const unsigned full = 0xffffffffu;
@@ -505,10 +546,9 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
                 for (int t = 0; t < 4 && !boxed; t++, wdt *= 0.25f) {
                     const float lo = dl * (1.0f - wdt), hi = dl * (1.0f + wdt);
                     if (!(hi < 1.0f)) continue;           // keeps both multipliers positive (the monotonicity argument needs it)
-                    uint32_t inl2;
-                    const uint32_t t1 = ars_sprt_walk<RES>(row, stride, init_n, hi / eps, (1.0f - lo) / one_m_eps, P.lr_thr, &inl, avail, LZ);
-                    const uint32_t t2 = ars_sprt_walk<RES>(row, stride, init_n, lo / eps, (1.0f - hi) / one_m_eps, P.lr_thr, &inl2, avail, LZ);
-                    if (t1 == t2) { boxed = true; tested = t1; blo = lo; bhi = hi; }
+                    uint32_t t1 = 0;
+                    if (ars_sprt_walk_box<RES>(row, stride, init_n, hi / eps, (1.0f - lo) / one_m_eps, lo / eps, (1.0f - hi) / one_m_eps, P.lr_thr,
+                                               &t1, &inl, avail, LZ)) { boxed = true; tested = t1; blo = lo; bhi = hi; }
                 }
             }
             if (!boxed) tested = ars_sprt_walk<RES>(row, stride, init_n, dl / eps, (1.0f - dl) / one_m_eps, P.lr_thr, &inl, avail, LZ);
