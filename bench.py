@@ -287,7 +287,7 @@ def main():
             self.h_model = Pose()
             self.rng = Rng()
             lib.cvb_rng_seed_xoshiro256pp(C.byref(self.rng), 0)
-            self.stats = (C.c_uint32 * 12)()
+            self.stats = (C.c_uint32 * 16)()
             self.pairs_done = 0
             self.t_busy = 0.0
     slots = [Slot() for _ in range(NCTX)]
@@ -496,7 +496,7 @@ def main():
         ransac_scoring = {"init_models": stats0[1], "init_predicates": init_pairs, "score_init_ms": sc[0]["ms"] / PK,
                           "predicates_per_s": init_pairs / (sc[0]["ms"] / PK * 1e-3) if sc[0]["ms"] > 0 else None,
                           "sprt_pass": stats0[2], "sprt_commit_rounds": stats0[3], "block_iterations": stats0[4], "draws": stats0[5],
-                          "exact_fallbacks": stats0[10], "sprt_lazy_words": stats0[11]}
+                          "exact_fallbacks": stats0[10], "sprt_lazy_words": stats0[11], "sprt_repairs": stats0[12], "sprt_walk_steps": stats0[13]}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

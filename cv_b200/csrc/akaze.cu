@@ -569,11 +569,11 @@ int run_extract_eager(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoin
             const size_t region = (((size_t)pitch3(smax) * (SH3 + 2 * smax)) + 31) & ~(size_t)31;
             dim3 g((unsigned)(t1 - t0), 1, B);
             { CVB_PROF(ctx, "k_deriv1", 12.0 * px * B);
-            k_deriv1_v3<<<g, NT, sizeof(float) * region, ds>>>(ws->Lsm, ws->Lt, ws->Lx, ws->Ly, PF, ws->table, ws->tile_evo, t0,
+            k_deriv1_v3<<<g, NT, sizeof(float) * region + 128, ds>>>(ws->Lsm, ws->Lt, ws->Lx, ws->Ly, PF, ws->table, ws->tile_evo, t0,
                                                                ws->use_tma && (ws->tma_mask & 4) ? ws->tmaps : nullptr);
             CVB_LAUNCH_CHECK(ctx); }
             { CVB_PROF(ctx, "k_deriv2_det", 12.0 * px * B);
-            k_deriv2_v3<<<g, NT, sizeof(float) * 2 * region, ds>>>(ws->Lx, ws->Ly, ws->Ldet, PF, ws->table, ws->tile_evo, t0,
+            k_deriv2_v3<<<g, NT, sizeof(float) * 2 * region + 128, ds>>>(ws->Lx, ws->Ly, ws->Ldet, PF, ws->table, ws->tile_evo, t0,
                                                                    ws->use_tma && (ws->tma_mask & 8) ? ws->tmaps + MAX_EVO : nullptr, ws->use_tma && (ws->tma_mask & 8) ? ws->tmaps + 2 * MAX_EVO : nullptr);
             CVB_LAUNCH_CHECK(ctx); }
         } else {   // generic two-pass tiles, one launch pair per evolution (derivative sigma > 5)

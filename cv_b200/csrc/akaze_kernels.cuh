@@ -7,6 +7,7 @@
 // Compile with -fmad=false.  Reference line numbers are relative to /root/reference/akaze/src.
 #pragma once
 #include <cuda.h>            // CUtensorMap (types only: the encode entry point is resolved at run time, no libcuda link dependency)
+#include <cuda/barrier>      // cuda::barrier + the cp.async.bulk.tensor wrappers (libcu++, header only)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "device_libm.cuh"
@@ -462,47 +463,38 @@ constexpr int SW3 = 32, SH3 = 64, STRIP = 8;
 // (image.rs:233-235,289-296).  The box is `pitch3(R)` floats wide (row bytes must be a multiple of 16); the padding columns are
 // never read.  Shared-memory contents of the halo region are identical in both paths.
 __host__ __device__ constexpr int pitch3(int r) { return (SW3 + 2 * r + 3) & ~3; }
-__device__ __forceinline__ uint32_t ak_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ak_tma_tile(float *dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar, unsigned bytes) {
-    // called by one thread after the barrier has been initialised and made visible
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ak_smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(ak_smem_u32(dst)),
-                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(ak_smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void ak_mbar_wait0(uint64_t *bar) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(ak_smem_u32(bar)) : "memory");
-}
+// The TMA path follows the CUDA programming guide's tensor-copy protocol through libcu++ (cuda::barrier in shared memory,
+// fence.proxy.async after its initialisation, every thread arrives, the issuing thread adds the transaction bytes): a hand-written
+// mbarrier.init / fence.mbarrier_init / expect_tx sequence that serves the 1-D bulk copies of the matcher raised "illegal
+// instruction" on UTMALDG on B200 (scratch probe), the guide's protocol does not.
+using ak_barrier = cuda::barrier<cuda::thread_scope_block>;
 
 template <int RX, int RY, int RW = SW3 + 2 * RX>
 __device__ __forceinline__ void stage_region(const float *__restrict__ src, int w, int h, int x0, int y0, float *s_in,
-                                             const CUtensorMap *tm = nullptr, int frame = 0, uint64_t *bar = nullptr, bool tm_global = false) {
+                                             const CUtensorMap *tm = nullptr, int frame = 0, ak_barrier *bar = nullptr, bool tm_global = false) {
     // all of a thread's global loads are issued before the first shared store (a rolled load->store loop waits one
     // DRAM latency per row: ncu showed 36 % of the blur kernel's stall samples on that store)
     constexpr int RH = SH3 + 2 * RY, NI = (RH + 7) / 8;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const bool interior = x0 - RX >= 0 && x0 + SW3 + RX <= w && y0 - RY >= 0 && y0 + SH3 + RY <= h;
     if (tm != nullptr && interior) {          // CTA-uniform
+        namespace cde = cuda::device::experimental;
         if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ak_smem_u32(bar)));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            init(bar, blockDim.x);
+            cde::fence_proxy_async_shared_cta();      // the initialised barrier becomes visible to the async proxy (TMA unit)
         }
         __syncthreads();
+        ak_barrier::arrival_token token;
         if (threadIdx.x == 0) {
             // a descriptor that lives in global memory was written through the generic proxy (cudaMemcpy): acquire it for the
-            // tensor-map proxy before the TMA unit reads it (harmless for descriptors in kernel-parameter space)
+            // tensor-map proxy before the TMA unit reads it
             if (tm_global) asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm) : "memory");
-            ak_tma_tile(s_in, tm, x0 - RX, y0 - RY, frame, bar, (unsigned)(RW * RH * sizeof(float)));
+            cde::cp_async_bulk_tensor_3d_global_to_shared(s_in, tm, x0 - RX, y0 - RY, frame, *bar);
+            token = cuda::device::barrier_arrive_tx(*bar, 1, (unsigned)(RW * RH * sizeof(float)));
+        } else {
+            token = bar->arrive();
         }
-        ak_mbar_wait0(bar);
+        bar->wait(std::move(token));
         return;
     }
     const bool tail = tx < 2 * RX;
@@ -549,7 +541,7 @@ __device__ __forceinline__ void tile_origin_v3(const EvoDev &ev, int gtile, int 
 // first derivatives, sigma = S (detector_response.rs:60-65): Lx = V_off(H_main(Ls)), Ly = V_main(H_off(Ls))
 template <int S>
 __device__ __forceinline__ void deriv1_body(const float *__restrict__ src, float *__restrict__ Lx, float *__restrict__ Ly,
-                                            const EvoDev &ev, int x0, int y0, float *s_in, const CUtensorMap *tm, uint64_t *bar) {
+                                            const EvoDev &ev, int x0, int y0, float *s_in, const CUtensorMap *tm, ak_barrier *bar) {
     constexpr int RW = pitch3(S);
     stage_region<S, S, RW>(src, ev.w, ev.h, x0, y0, s_in, tm, (int)blockIdx.z, bar, true);
     __syncthreads();
@@ -579,7 +571,8 @@ __global__ void __launch_bounds__(NT) k_deriv1_v3(const float *__restrict__ Ls, 
                                                   const unsigned char *__restrict__ tile_evo, int tile_offset,
                                                   const CUtensorMap *__restrict__ maps) {
     extern __shared__ __align__(128) float sm[];
-    __shared__ __align__(8) uint64_t s_bar[1];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+    __shared__ ak_barrier s_bar[1];
     const int gtile = blockIdx.x + tile_offset;
     const int e = tile_evo[gtile];
     const EvoDev ev = T.e[e];
@@ -588,12 +581,13 @@ __global__ void __launch_bounds__(NT) k_deriv1_v3(const float *__restrict__ Ls, 
     const size_t base = (size_t)blockIdx.z * bstride + ev.off;
     const float *src = (e == 0 ? Lt0 : Ls) + base;   // evolution 0: Lsmooth IS Lt (lib.rs:201)
     const CUtensorMap *tm = maps ? maps + e : nullptr;   // per-evolution map of the source plane (all frames)
+    float *sma = (float *)(((uintptr_t)sm + 127) & ~(uintptr_t)127);      // TMA destinations are 128-byte aligned
     switch (ev.sigma) {
-    case 1: deriv1_body<1>(src, Lx + base, Ly + base, ev, x0, y0, sm, tm, s_bar); break;
-    case 2: deriv1_body<2>(src, Lx + base, Ly + base, ev, x0, y0, sm, tm, s_bar); break;
-    case 3: deriv1_body<3>(src, Lx + base, Ly + base, ev, x0, y0, sm, tm, s_bar); break;
-    case 4: deriv1_body<4>(src, Lx + base, Ly + base, ev, x0, y0, sm, tm, s_bar); break;
-    default: deriv1_body<5>(src, Lx + base, Ly + base, ev, x0, y0, sm, tm, s_bar); break;
+    case 1: deriv1_body<1>(src, Lx + base, Ly + base, ev, x0, y0, sma, tm, s_bar); break;
+    case 2: deriv1_body<2>(src, Lx + base, Ly + base, ev, x0, y0, sma, tm, s_bar); break;
+    case 3: deriv1_body<3>(src, Lx + base, Ly + base, ev, x0, y0, sma, tm, s_bar); break;
+    case 4: deriv1_body<4>(src, Lx + base, Ly + base, ev, x0, y0, sma, tm, s_bar); break;
+    default: deriv1_body<5>(src, Lx + base, Ly + base, ev, x0, y0, sma, tm, s_bar); break;
     }
 }
 
@@ -601,7 +595,7 @@ __global__ void __launch_bounds__(NT) k_deriv1_v3(const float *__restrict__ Ls, 
 template <int S>
 __device__ __forceinline__ void deriv2_body(const float *__restrict__ px, const float *__restrict__ py, float *__restrict__ Ldet,
                                             const EvoDev &ev, int x0, int y0, float *sm, const CUtensorMap *tmx, const CUtensorMap *tmy,
-                                            uint64_t *bar) {
+                                            ak_barrier *bar) {
     constexpr int RW = pitch3(S), RH = SH3 + 2 * S;
     float *s_x = sm, *s_y = sm + ((RW * RH + 31) & ~31);      // second buffer 128-byte aligned
     stage_region<S, S, RW>(px, ev.w, ev.h, x0, y0, s_x, tmx, (int)blockIdx.z, bar, true);
@@ -635,7 +629,8 @@ __global__ void __launch_bounds__(NT) k_deriv2_v3(const float *__restrict__ Lx, 
                                                   const unsigned char *__restrict__ tile_evo, int tile_offset,
                                                   const CUtensorMap *__restrict__ maps_x, const CUtensorMap *__restrict__ maps_y) {
     extern __shared__ __align__(128) float sm[];
-    __shared__ __align__(8) uint64_t s_bar[2];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+    __shared__ ak_barrier s_bar[2];
     const int gtile = blockIdx.x + tile_offset;
     const int e = tile_evo[gtile];
     const EvoDev ev = T.e[e];
@@ -643,12 +638,13 @@ __global__ void __launch_bounds__(NT) k_deriv2_v3(const float *__restrict__ Lx, 
     tile_origin_v3(ev, gtile, x0, y0);
     const size_t base = (size_t)blockIdx.z * bstride + ev.off;
     const CUtensorMap *tmx = maps_x ? maps_x + e : nullptr, *tmy = maps_y ? maps_y + e : nullptr;
+    float *sma = (float *)(((uintptr_t)sm + 127) & ~(uintptr_t)127);
     switch (ev.sigma) {
-    case 1: deriv2_body<1>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sm, tmx, tmy, s_bar); break;
-    case 2: deriv2_body<2>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sm, tmx, tmy, s_bar); break;
-    case 3: deriv2_body<3>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sm, tmx, tmy, s_bar); break;
-    case 4: deriv2_body<4>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sm, tmx, tmy, s_bar); break;
-    default: deriv2_body<5>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sm, tmx, tmy, s_bar); break;
+    case 1: deriv2_body<1>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sma, tmx, tmy, s_bar); break;
+    case 2: deriv2_body<2>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sma, tmx, tmy, s_bar); break;
+    case 3: deriv2_body<3>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sma, tmx, tmy, s_bar); break;
+    case 4: deriv2_body<4>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sma, tmx, tmy, s_bar); break;
+    default: deriv2_body<5>(Lx + base, Ly + base, Ldet + base, ev, x0, y0, sma, tmx, tmy, s_bar); break;
     }
 }
 
@@ -659,7 +655,8 @@ __global__ void __launch_bounds__(NT) k_blur_v3(const float *__restrict__ in, fl
                                                 const __grid_constant__ CUtensorMap tmap, int use_tma) {
     constexpr int R = KS / 2, RW = pitch3(R);
     __shared__ __align__(128) float s_in[(SH3 + 2 * R) * RW];
-    __shared__ __align__(8) uint64_t s_bar[1];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+    __shared__ ak_barrier s_bar[1];
     const int x0 = blockIdx.x * SW3, y0 = blockIdx.y * SH3;
     stage_region<R, R, RW>(in + (size_t)blockIdx.z * in_bstride, w, h, x0, y0, s_in, use_tma ? &tmap : nullptr, (int)blockIdx.z, s_bar);
     __syncthreads();
@@ -748,7 +745,8 @@ __global__ void __launch_bounds__(NT) k_blur_scharr_pm(const float *__restrict__
     static_assert(LW * NSTRIPS <= NT, "one blur task per thread");
     __shared__ __align__(128) float s_in[RHI * RWI];
     __shared__ float s_l[LH * LW];
-    __shared__ __align__(8) uint64_t s_bar[1];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+    __shared__ ak_barrier s_bar[1];
     const int x0 = blockIdx.x * SW3, y0 = blockIdx.y * SH3;
     stage_region<3, 3, RWI>(in + (size_t)blockIdx.z * in_bstride, w, h, x0, y0, s_in, use_tma ? &tmap : nullptr, (int)blockIdx.z, s_bar);
     __syncthreads();

@@ -36,6 +36,7 @@ struct ArrsacCtl {
     uint32_t found, iters, nraw, q_count;     // q_count / q_count2: undecided (model, datum) predicates queued by the two initial scoring stages
     uint32_t q_count2, stat_lazy;             // stat_lazy: mask words the SPRT had to compute itself
     uint32_t stat_units0, stat_units2;        // 32-datum units scored by the two initial stages
+    uint32_t stat_repairs, stat_pad;          // SPRT: models walked again with their exact state
     uint64_t rng_pos, gen_pos;
     cvb_rng gen;                 // generator positioned at raw index gen_pos (continues the stream when it is exhausted)
     cvb_pose winner;
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_begin(ArrsacCtl *ctl, Arrsa
         ctl->init_n = min(P.bs * P.ib, n);
         ctl->Mv = 0; ctl->npass = 0; ctl->Hn = 0; ctl->cur = 0; ctl->blk_lo = ctl->blk_hi = ctl->acc_hi = 0;
         ctl->n_new = 0; ctl->worst = 0; ctl->found = 0; ctl->iters = 0; ctl->n_inliers = 0; ctl->overflow = 0;
-        ctl->stat_chunks = 0; ctl->stat_pass = 0; ctl->q_count = 0; ctl->q_count2 = 0; ctl->stat_lazy = 0; ctl->stat_units0 = 0; ctl->stat_units2 = 0;
+        ctl->stat_chunks = 0; ctl->stat_pass = 0; ctl->q_count = 0; ctl->q_count2 = 0; ctl->stat_lazy = 0; ctl->stat_units0 = 0; ctl->stat_units2 = 0; ctl->stat_repairs = 0; ctl->stat_pad = 0;
         ctl->done = (n < P.K || P.H0 == 0) ? 1u : 0u;
     }
     __syncthreads();
@@ -225,14 +226,18 @@ __global__ void __launch_bounds__(256, 2) k_ars_score(ArrsacCtl *ctl, uint2 *__r
         // phase 0: word 0 of every initial model, every word of the first P.prefix samples' models
         // phase 2: words >= 1 of the remaining models whose first 32 data hold >= P.cmin inliers (after k_ars_resolve fixed word 0)
         const uint32_t init_n = ctl->init_n, W = (init_n + 31) >> 5;
-        const uint32_t units = P.H0 * P.MM * W;
+        // compact unit spaces (no warp iterates over units of the other stage):
+        //   phase 0: [word 0 of every model | words 1.. of the prefix models]      phase 2: words 1.. of the other models
+        const uint32_t nmod = P.H0 * P.MM, npre = min(P.prefix, P.H0) * P.MM, W1 = W > 0 ? W - 1 : 0;
+        const uint32_t units = phase == 0 ? nmod + npre * W1 : (nmod - npre) * W1;
         uint32_t *qc = phase == 0 ? &ctl->q_count : &ctl->q_count2;
         uint2 *q = phase == 0 ? queue : queue + ARS_QCAP;
         for (uint32_t u = warp; u < units; u += nwarps) {
-            const uint32_t m = u / W, w = u % W;
+            uint32_t m, w;
+            if (phase == 0) { if (u < nmod) { m = u; w = 0; } else { m = (u - nmod) / W1; w = 1 + (u - nmod) % W1; } }
+            else { m = npre + u / W1; w = 1 + u % W1; }
             if ((m % P.MM) >= nposes0[m / P.MM]) continue;
-            const bool early = w == 0 || m / P.MM < P.prefix;
-            if (phase == 0 ? !early : (early || !ars_ready(masks0[(size_t)m * P.W0], init_n, m / P.MM, P))) continue;
+            if (phase == 2 && !ars_ready(masks0[(size_t)m * P.W0], init_n, m / P.MM, P)) continue;
             const uint32_t i = w * 32 + lane;
             bool bit = false;
             if (i < init_n) {
@@ -375,7 +380,7 @@ __device__ uint32_t ars_popc_range(const uint32_t *row, uint32_t lo, uint32_t hi
 // word w; words at and beyond `avail` have not been computed by the scoring kernels (two-stage initial scoring): the walk
 // evaluates such a word itself, stores it (walk copy and global row) and moves `avail` on.  Returns tested (the 1-based datum
 // at which the ratio exceeded the threshold) or 0 when the model passes.
-struct ArsLazy { const cvb_pose *pose; const double *a, *b; double thr; uint32_t *grow; uint32_t *counter; };
+struct ArsLazy { const cvb_pose *pose; const double *a, *b; double thr; uint32_t *grow; uint32_t *counter; uint32_t *steps; };
 template <int RES>
 __device__ uint32_t ars_sprt_walk(uint32_t *words, uint32_t stride, uint32_t init_n, float pos, float neg, float thr, uint32_t *inl_out,
                                   uint32_t &avail, const ArsLazy &L) {
@@ -431,11 +436,13 @@ __device__ bool ars_sprt_walk_box(uint32_t *words, uint32_t stride, uint32_t ini
             rl *= in ? pos_lo : neg_lo;
             if (rh > thr) {                      // the upper corner stops here; the box is decided iff the lower corner stops here too
                 *tested = w * 32 + k + 1; *inl_out = inl;
+                atomicAdd(L.steps, w * 32 + k + 1);
                 return rl > thr;
             }
         }
     }
     *tested = 0; *inl_out = inl;                 // the upper corner passes, hence the lower corner as well
+    atomicAdd(L.steps, init_n);
     return true;
 }
 
@@ -537,7 +544,7 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
                 for (uint32_t w = 0; w < avail; w++) smw[w * NT + pos] = grow[w];
                 row = smw + pos; stride = NT;
             }
-            const ArsLazy LZ = {poses0 + id, a, b, P.thr, grow, &ctl->stat_lazy};
+            const ArsLazy LZ = {poses0 + id, a, b, P.thr, grow, &ctl->stat_lazy, &ctl->stat_pad};
             uint32_t tested = 0, inl = 0;
             float blo = dl, bhi = dl;
             bool boxed = false;
@@ -594,6 +601,7 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
             if (have && j == ce && viol) {                                     // everything in front of position ce is final
                 walk_position(j, true, delta_before);
                 s_fix = 1;
+                ctl->stat_repairs++;
             }
             __syncthreads();
             if (!s_fix) break;

@@ -1833,11 +1833,12 @@ int cvb_arrsac_commit_rng(cvb_ctx *ctx, cvb_rng *rng, uint32_t *stats_out) {
     ArrsacCtl h;
     int rc = arrsac_commit_rng(ctx, rng, &h);
     if (rc) return rc;
-    if (stats_out) {   // 12 words: n, valid initial models, SPRT passes, SPRT commit rounds, block iterations, draws, inliers, found, 32-datum units
-                       // scored in stage 1 / stage 2, predicates resolved exactly from the queues, mask words computed by the SPRT itself
+    if (stats_out) {   // 16 words (13..15 reserved): n, valid initial models, SPRT passes, SPRT commit rounds, block iterations, draws, inliers, found, 32-datum units
+                       // scored in stage 1 / stage 2, predicates resolved exactly from the queues, mask words computed by the SPRT itself, SPRT repairs
         stats_out[0] = h.n; stats_out[1] = h.Mv; stats_out[2] = h.npass; stats_out[3] = h.stat_chunks; stats_out[4] = h.iters;
         stats_out[5] = (uint32_t)h.rng_pos; stats_out[6] = h.n_inliers; stats_out[7] = h.found;
         stats_out[8] = h.stat_units0; stats_out[9] = h.stat_units2; stats_out[10] = h.q_count + h.q_count2; stats_out[11] = h.stat_lazy;
+        stats_out[12] = h.stat_repairs; stats_out[13] = h.stat_pad /* data walked by the box walks */; stats_out[14] = stats_out[15] = 0;
     }
     return 0;
 }

@@ -247,9 +247,10 @@ int cvb_arrsac_p3p_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *be
                        uint32_t n_max, const cvb_rng *rng, cvb_pose *model_out_dev, uint32_t *inliers_out_dev, uint32_t cap,
                        uint32_t *n_inliers_dev, int32_t *found_dev);
 /* Synchronises the context stream and advances *rng (host, may be NULL) past the draws the last cvb_arrsac_*_dev /
- * cvb_two_view_* call consumed.  stats_out (host, 12 words, may be NULL): data, valid initial models, models that passed the SPRT,
+ * cvb_two_view_* call consumed.  stats_out (host, 16 words, may be NULL): data, valid initial models, models that passed the SPRT,
  * SPRT commit rounds, block iterations, draws consumed, inliers, found, 32-datum units scored by the two initial stages (2 words),
- * predicates the filter left to the exact evaluation, mask words the SPRT computed itself. */
+ * predicates the filter left to the exact evaluation, mask words the SPRT computed itself, models the SPRT walked again with their
+ * exact state; three reserved words. */
 int cvb_arrsac_commit_rng(cvb_ctx *ctx, cvb_rng *rng, uint32_t *stats_out);
 
 /* One frame pair end to end on the device: symmetric match of the two descriptor sets, bearings, ARRSAC + eight-point.

@@ -24,7 +24,7 @@ rng = Rng(); L.cvb_rng_seed_xoshiro256pp(C.byref(rng), 0)
 kp = torch.empty(2 * cap * KP_DTYPE.itemsize, dtype=torch.uint8, device=dev); desc = torch.zeros(2 * cap * 64, dtype=torch.uint8, device=dev)
 n = torch.zeros(2, dtype=torch.int32, device=dev); pr = torch.zeros(cap * 2, dtype=torch.int32, device=dev); inl = torch.zeros(cap, dtype=torch.int32, device=dev)
 cnt = torch.zeros(4, dtype=torch.int32, device=dev); model = torch.zeros(12, dtype=torch.float64, device=dev)
-stats = (C.c_uint32 * 12)()
+stats = (C.c_uint32 * 16)()
 def one(i):
     img = frames[i % 2]
     ctx.check(L.cvb_akaze_extract_batch_dev(ctx.handle, C.byref(cfg), img.data_ptr(), 2, 1920, 1080, kp.data_ptr(), desc.data_ptr(), cap, n.data_ptr()))

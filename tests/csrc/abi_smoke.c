@@ -31,7 +31,7 @@ static int no_gpu_checks(void) {
     float img[16] = {0};
     cvb_keypoint kp[4];
     uint8_t desc[4 * 64];
-    uint32_t n = 0, u[12];
+    uint32_t n = 0, u[16];
     CHECK(cvb_akaze_extract(NULL, &ac, img, 4, 4, kp, desc, 4, &n) == CVB_EINVAL);
     CHECK(cvb_akaze_extract_batch(NULL, &ac, img, 1, 4, 4, kp, desc, 4, &n) == CVB_EINVAL);
     CHECK(cvb_akaze_extract_batch_dev(NULL, &ac, img, 1, 4, 4, kp, desc, 4, &n) == CVB_EINVAL);
