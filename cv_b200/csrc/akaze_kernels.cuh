@@ -460,24 +460,29 @@ constexpr int SW3 = 32, SH3 = 64, STRIP = 8;
 // ---- TMA staging of interior tiles (BASELINE north_star: "TMA-staged tiles in shared memory").  A tile whose halo lies inside the
 // image is fetched by ONE 3-D cp.async.bulk.tensor (x, y, frame) issued by one thread and awaited on an mbarrier; tiles that touch the
 // border keep the clamped path below, because TMA fills out-of-bounds elements with zero while the reference replicates the border
-// (image.rs:233-235,289-296).  The box is `pitch3(R)` floats wide (row bytes must be a multiple of 16); the padding columns are
-// never read.  Shared-memory contents of the halo region are identical in both paths.
-__host__ __device__ constexpr int pitch3(int r) { return (SW3 + 2 * r + 3) & ~3; }
+// (image.rs:233-235,289-296).  The box is `pitch3(R)` floats wide; the padding columns are never read.  Shared-memory contents of the halo region are identical in both paths.
+// The TMA unit faults ("illegal instruction") when a box starts at an x coordinate that is not a multiple of 16 bytes (measured on
+// B200: x = 64 loads, x = 190 faults, 2-D and 3-D alike), so the staged box starts xpad3(R) >= R floats left of the tile, a multiple of
+// 4 floats, and the kernels read their halo region at column offset xoff3(R) inside it.
+__host__ __device__ constexpr int xpad3(int r) { return r <= 4 ? 4 : 8; }
+__host__ __device__ constexpr int xoff3(int r) { return xpad3(r) - r; }
+__host__ __device__ constexpr int pitch3(int r) { return SW3 + 2 * xpad3(r); }
 // The TMA path follows the CUDA programming guide's tensor-copy protocol through libcu++ (cuda::barrier in shared memory,
 // fence.proxy.async after its initialisation, every thread arrives, the issuing thread adds the transaction bytes): a hand-written
 // mbarrier.init / fence.mbarrier_init / expect_tx sequence that serves the 1-D bulk copies of the matcher raised "illegal
 // instruction" on UTMALDG on B200 (scratch probe), the guide's protocol does not.
 using ak_barrier = cuda::barrier<cuda::thread_scope_block>;
 
-template <int RX, int RY, int RW = SW3 + 2 * RX>
-__device__ __forceinline__ void stage_region(const float *__restrict__ src, int w, int h, int x0, int y0, float *s_in,
+template <int RX, int RY, int RW = SW3 + 2 * RX, int XOFF = 0>
+__device__ __forceinline__ void stage_region(const float *__restrict__ src, int w, int h, int x0, int y0, float *s_base,
                                              const CUtensorMap *tm = nullptr, int frame = 0, ak_barrier *bar = nullptr, bool tm_global = false) {
     // all of a thread's global loads are issued before the first shared store (a rolled load->store loop waits one
     // DRAM latency per row: ncu showed 36 % of the blur kernel's stall samples on that store)
     constexpr int RH = SH3 + 2 * RY, NI = (RH + 7) / 8;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const bool interior = x0 - RX >= 0 && x0 + SW3 + RX <= w && y0 - RY >= 0 && y0 + SH3 + RY <= h;
-    if (tm != nullptr && interior) {          // CTA-uniform
+    float *s_in = s_base + XOFF;              // the halo region (what the classic path fills and every consumer reads)
+    if (tm != nullptr && interior && x0 - (RX + XOFF) >= 0 && x0 + SW3 + RX + XOFF <= w) {          // CTA-uniform; the whole box inside the image
         namespace cde = cuda::device::experimental;
         if (threadIdx.x == 0) {
             init(bar, blockDim.x);
@@ -489,7 +494,7 @@ __device__ __forceinline__ void stage_region(const float *__restrict__ src, int 
             // a descriptor that lives in global memory was written through the generic proxy (cudaMemcpy): acquire it for the
             // tensor-map proxy before the TMA unit reads it
             if (tm_global) asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm) : "memory");
-            cde::cp_async_bulk_tensor_3d_global_to_shared(s_in, tm, x0 - RX, y0 - RY, frame, *bar);
+            cde::cp_async_bulk_tensor_3d_global_to_shared(s_base, tm, x0 - (RX + XOFF), y0 - RY, frame, *bar);
             token = cuda::device::barrier_arrive_tx(*bar, 1, (unsigned)(RW * RH * sizeof(float)));
         } else {
             token = bar->arrive();
@@ -542,13 +547,13 @@ __device__ __forceinline__ void tile_origin_v3(const EvoDev &ev, int gtile, int 
 template <int S>
 __device__ __forceinline__ void deriv1_body(const float *__restrict__ src, float *__restrict__ Lx, float *__restrict__ Ly,
                                             const EvoDev &ev, int x0, int y0, float *s_in, const CUtensorMap *tm, ak_barrier *bar) {
-    constexpr int RW = pitch3(S);
-    stage_region<S, S, RW>(src, ev.w, ev.h, x0, y0, s_in, tm, (int)blockIdx.z, bar, true);
+    constexpr int RW = pitch3(S), XO = xoff3(S);
+    stage_region<S, S, RW, XO>(src, ev.w, ev.h, x0, y0, s_in, tm, (int)blockIdx.z, bar, true);
     __syncthreads();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int gx = x0 + tx;
     if (gx >= ev.w) return;
-    const float *col = s_in + (ty * STRIP) * RW + tx;   // col[r * RW + {0, S, 2S}] = input row (y - S + r), x - S / x / x + S
+    const float *col = s_in + XO + (ty * STRIP) * RW + tx;   // col[r * RW + {0, S, 2S}] = input row (y - S + r), x - S / x / x + S
     float hm[STRIP + 2 * S], ho[STRIP + 2 * S];
 #pragma unroll
     for (int r = 0; r < STRIP + 2 * S; r++) {
@@ -596,15 +601,15 @@ template <int S>
 __device__ __forceinline__ void deriv2_body(const float *__restrict__ px, const float *__restrict__ py, float *__restrict__ Ldet,
                                             const EvoDev &ev, int x0, int y0, float *sm, const CUtensorMap *tmx, const CUtensorMap *tmy,
                                             ak_barrier *bar) {
-    constexpr int RW = pitch3(S), RH = SH3 + 2 * S;
+    constexpr int RW = pitch3(S), RH = SH3 + 2 * S, XO = xoff3(S);
     float *s_x = sm, *s_y = sm + ((RW * RH + 31) & ~31);      // second buffer 128-byte aligned
-    stage_region<S, S, RW>(px, ev.w, ev.h, x0, y0, s_x, tmx, (int)blockIdx.z, bar, true);
-    stage_region<S, S, RW>(py, ev.w, ev.h, x0, y0, s_y, tmy, (int)blockIdx.z, bar + 1, true);
+    stage_region<S, S, RW, XO>(px, ev.w, ev.h, x0, y0, s_x, tmx, (int)blockIdx.z, bar, true);
+    stage_region<S, S, RW, XO>(py, ev.w, ev.h, x0, y0, s_y, tmy, (int)blockIdx.z, bar + 1, true);
     __syncthreads();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int gx = x0 + tx;
     if (gx >= ev.w) return;
-    const float *cx = s_x + (ty * STRIP) * RW + tx, *cy = s_y + (ty * STRIP) * RW + tx;
+    const float *cx = s_x + XO + (ty * STRIP) * RW + tx, *cy = s_y + XO + (ty * STRIP) * RW + tx;
     float hmx[STRIP + 2 * S], hox[STRIP + 2 * S], hoy[STRIP + 2 * S];
 #pragma unroll
     for (int r = 0; r < STRIP + 2 * S; r++) {
@@ -653,18 +658,18 @@ template <int KS>
 __global__ void __launch_bounds__(NT) k_blur_v3(const float *__restrict__ in, float *__restrict__ out, int w, int h,
                                                 size_t in_bstride, size_t out_bstride, Taps tk,
                                                 const __grid_constant__ CUtensorMap tmap, int use_tma) {
-    constexpr int R = KS / 2, RW = pitch3(R);
+    constexpr int R = KS / 2, RW = pitch3(R), XO = xoff3(R);
     __shared__ __align__(128) float s_in[(SH3 + 2 * R) * RW];
 #pragma nv_diag_suppress static_var_with_dynamic_init
     __shared__ ak_barrier s_bar[1];
     const int x0 = blockIdx.x * SW3, y0 = blockIdx.y * SH3;
-    stage_region<R, R, RW>(in + (size_t)blockIdx.z * in_bstride, w, h, x0, y0, s_in, use_tma ? &tmap : nullptr, (int)blockIdx.z, s_bar);
+    stage_region<R, R, RW, XO>(in + (size_t)blockIdx.z * in_bstride, w, h, x0, y0, s_in, use_tma ? &tmap : nullptr, (int)blockIdx.z, s_bar);
     __syncthreads();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int gx = x0 + tx;
     if (gx >= w) return;
     float *dst = out + (size_t)blockIdx.z * out_bstride;
-    const float *col = s_in + (ty * STRIP) * RW + tx;
+    const float *col = s_in + XO + (ty * STRIP) * RW + tx;
     float hv[STRIP + 2 * R];
 #pragma unroll
     for (int r = 0; r < STRIP + 2 * R; r++) {
@@ -740,7 +745,7 @@ __global__ void __launch_bounds__(NT) k_blur_scharr_pm(const float *__restrict__
                                                        size_t lsm_bstride, size_t flow_bstride, Taps tk,
                                                        const float *__restrict__ inv_k, int inv_k_stride,
                                                        const __grid_constant__ CUtensorMap tmap, int use_tma) {
-    constexpr int RWI = pitch3(3), RHI = SH3 + 6, LW = SW3 + 2, LH = SH3 + 2;
+    constexpr int RWI = pitch3(3), RHI = SH3 + 6, LW = SW3 + 2, LH = SH3 + 2, XO = xoff3(3);
     constexpr int BSTRIP = 10, NSTRIPS = (LH + BSTRIP - 1) / BSTRIP;     // 34 columns x 7 strips = 238 blur tasks
     static_assert(LW * NSTRIPS <= NT, "one blur task per thread");
     __shared__ __align__(128) float s_in[RHI * RWI];
@@ -748,14 +753,14 @@ __global__ void __launch_bounds__(NT) k_blur_scharr_pm(const float *__restrict__
 #pragma nv_diag_suppress static_var_with_dynamic_init
     __shared__ ak_barrier s_bar[1];
     const int x0 = blockIdx.x * SW3, y0 = blockIdx.y * SH3;
-    stage_region<3, 3, RWI>(in + (size_t)blockIdx.z * in_bstride, w, h, x0, y0, s_in, use_tma ? &tmap : nullptr, (int)blockIdx.z, s_bar);
+    stage_region<3, 3, RWI, XO>(in + (size_t)blockIdx.z * in_bstride, w, h, x0, y0, s_in, use_tma ? &tmap : nullptr, (int)blockIdx.z, s_bar);
     __syncthreads();
     if (threadIdx.x < LW * NSTRIPS) {
         const int sidx = threadIdx.x / LW, c = threadIdx.x - sidx * LW;
         const int gx = x0 - 1 + c;
         if (gx >= 0 && gx < w) {
             float *lsm = out_lsm + (size_t)blockIdx.z * lsm_bstride;
-            const float *col = s_in + (sidx * BSTRIP) * RWI + c;   // ring row lr needs staged rows lr .. lr + 4, columns c .. c + 4
+            const float *col = s_in + XO + (sidx * BSTRIP) * RWI + c;   // ring row lr needs staged rows lr .. lr + 4, columns c .. c + 4
             float hv[BSTRIP + 4];
 #pragma unroll
             for (int r = 0; r < BSTRIP + 4; r++) {
