@@ -178,11 +178,31 @@ __global__ void __launch_bounds__(128) k_ars_estimate(const ArrsacCtl *ctl, int 
     if (h >= H) return;
     if (KIND == 2) { nposes[h] = (uint8_t)five_point(a, b, samples + (size_t)h * 5, row0, poses + (size_t)h * 40); return; }
     cvb_pose out[4];
-    // (a nine-lanes-per-hypothesis eight-point with the Jacobi matrix in registers was measured SLOWER on B200, 0.41 vs 0.23 ms per
-    //  64 hypotheses: the chain is dominated by the FP64 divide / square-root sequence of every rotation, which the lanes cannot share)
     const int n = KIND == 0 ? eight_point(a, b, samples + (size_t)h * 8, out) : p3p(a, b, samples + (size_t)h * 3, out);
     for (int k = 0; k < n; k++) poses[(size_t)h * 4 + k] = out[k];
     nposes[h] = (uint8_t)n;
+}
+
+// Eight-point with EIGHT_LANES lanes per hypothesis, the 9x9 matrix and its eigenvectors in shared memory (32 hypotheses per CTA).
+// The chain of 36 rotations x ~8 sweeps is what a block of the hypothesis loop waits for: a rotation is the FP64 divide / square-root
+// sequence (every lane) followed by the column and row updates (split over the lanes).  (A nine-lane version with the matrix in
+// REGISTERS and shuffles was measured slower than one thread; shared memory keeps the element exchange off the critical path.)
+__global__ void __launch_bounds__(128) k_ars_estimate8(const ArrsacCtl *ctl, int phase, uint32_t H_init, const double *__restrict__ a,
+                                                       const double *__restrict__ b, const uint32_t *__restrict__ samples,
+                                                       cvb_pose *poses, uint8_t *nposes) {
+    if (ctl->done) return;
+    __shared__ double sh[(128 / EIGHT_LANES) * EIGHT_SH];
+    const uint32_t H = phase == 0 ? H_init : ctl->n_new;
+    const uint32_t g = threadIdx.x / EIGHT_LANES, lane = threadIdx.x % EIGHT_LANES;
+    const uint32_t h = blockIdx.x * (128 / EIGHT_LANES) + g;
+    if (h >= H) return;                                          // whole lane groups leave together
+    const unsigned mask = ((1u << EIGHT_LANES) - 1u) << ((threadIdx.x & 31) / EIGHT_LANES * EIGHT_LANES);
+    cvb_pose out[4];
+    const int n = eight_point_lanes(a, b, samples + (size_t)h * 8, out, sh + g * EIGHT_SH, lane, mask);
+    if (lane == 0) {
+        for (int k = 0; k < n; k++) poses[(size_t)h * 4 + k] = out[k];
+        nposes[h] = (uint8_t)n;
+    }
 }
 
 // ---- k_ars_score ---------------------------------------------------------------------------------------------------------
@@ -509,11 +529,10 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
     //    warp of quickly rejected models costs a few instructions instead of waiting for one long walk among its lanes;
     //  * the chunk doubles (64 .. NT) while it is committed whole and restarts small after an epsilon change.
     uint32_t *smw = (uint32_t *)keys;                    // [8][NT] mask words by chunk position (keys[] is free until phase C)
-    __shared__ float d_arr[ARS_BOOK_NT];                 // delta estimate after each rejected model (0 = none / invalid)
     __shared__ float o_lo[ARS_BOOK_NT], o_hi[ARS_BOOK_NT];
     __shared__ uint32_t o_ti[ARS_BOOK_NT];               // outcome by position: tested << 16 | inliers at the stop (init_n < 8192)
     __shared__ uint16_t perm[ARS_BOOK_NT];
-    __shared__ uint32_t s_fix, s_chunk;
+    __shared__ uint32_t s_chunk;
     const bool words_in_smem = P.W0 <= 8;
     if (tid == 0) s_chunk = 64;
     __syncthreads();
@@ -524,6 +543,7 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
         const uint32_t best0 = s_best, np0 = s_npass;
         const unsigned long long ri0 = s_rej_inl, rt0 = s_rej_tested;
         const uint32_t j = tid, cnt = min(s_chunk, Mv - c0);
+        (void)np0;
         const float one_m_eps = 1.0f - eps;
         // 1. positions with all mask words first
         {
@@ -564,67 +584,74 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
         };
         if (tid < cnt) { const uint32_t pos = perm[tid]; walk_position(pos, pos == 0, delta); }
         __syncthreads();
-        // 3. exact state in front of every position; repair the first position whose delta is not in its box; repeat
-        uint32_t ce = 0, a_ri = 0, a_rt = 0, a_pc = 0, tested = 0, inl = 0;
-        bool pass = false;
-        float delta_after = delta;
-        const bool have = j < cnt;
-        while (true) {
-            tested = have ? o_ti[j] >> 16 : 0; inl = have ? o_ti[j] & 0xffffu : 0;
-            pass = have && tested == 0;
-            const bool rej = have && tested != 0;
-            a_ri = rej ? inl : 0; a_rt = rej ? tested : 0; a_pc = pass ? 1 : 0;
-            ars_scan3(a_ri, a_rt, a_pc, sm, tot);                              // inclusive
-            float dj = 0.0f;                                                   // delta estimate right after model j (valid ones only)
-            if (rej) {
-                const float d = (float)(ri0 + a_ri) / (float)(rt0 + a_rt);
-                if (d > 0.0f && d < eps) dj = d;
+        // 3. warp 0 commits the chunk in order, 32 positions at a time, carrying the exact state (rejected sums, delta, passes) in
+        //    registers: warp scans give the state in front of every lane's position; the first position whose delta is outside
+        //    its box is walked again by its lane with that exact delta (everything in front of it is final) and the group is
+        //    redone; the chunk ends behind the first model that raises epsilon.  No block-wide barrier inside.
+        if (tid < 32) {
+            const unsigned full = 0xffffffffu;
+            const uint32_t lane = tid;
+            unsigned long long ri = ri0, rt = rt0;
+            float dcur = delta;
+            uint32_t np = np0, ce = cnt, ev_inl = 0;
+            bool eps_event = false;
+            for (uint32_t g0 = 0; g0 < cnt && !eps_event; g0 += 32) {
+                const uint32_t jj = g0 + lane;
+                const bool hv = jj < cnt;
+                const uint32_t lastl_all = min(31u, cnt - g0 - 1);
+                while (true) {
+                    const uint32_t oti = hv ? o_ti[jj] : 0u;
+                    const uint32_t tested = oti >> 16, inl = oti & 0xffffu;
+                    const bool pass = hv && tested == 0, rej = hv && tested != 0;
+                    uint32_t a_ri = rej ? inl : 0, a_rt = rej ? tested : 0, a_pc = pass ? 1 : 0;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t x = __shfl_up_sync(full, a_ri, o), y = __shfl_up_sync(full, a_rt, o), z = __shfl_up_sync(full, a_pc, o);
+                        if ((int)lane >= o) { a_ri += x; a_rt += y; a_pc += z; }
+                    }
+                    float dj = 0.0f;                                           // delta estimate right after this position (valid ones only)
+                    if (rej) {
+                        const float d = (float)(ri + a_ri) / (float)(rt + a_rt);
+                        if (d > 0.0f && d < eps) dj = d;
+                    }
+                    uint32_t lv_inc = dj != 0.0f ? lane + 1 : 0u;              // 1-based lane of the last valid estimate in [0, lane]
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(full, lv_inc, o); if ((int)lane >= o) lv_inc = max(lv_inc, x); }
+                    uint32_t lv_exc = __shfl_up_sync(full, lv_inc, 1);
+                    if (lane == 0) lv_exc = 0;
+                    float db = __shfl_sync(full, dj, lv_exc ? lv_exc - 1 : 0);
+                    if (!lv_exc) db = dcur;
+                    const bool viol = hv && !(db >= o_lo[jj] && db <= o_hi[jj]);
+                    const bool e2 = pass && inl > best0;
+                    const unsigned vb = __ballot_sync(full, viol), eb = __ballot_sync(full, e2);
+                    const uint32_t fv = vb ? (uint32_t)__ffs(vb) - 1 : 32u, fe = eb ? (uint32_t)__ffs(eb) - 1 : 32u;
+                    if (fv < 32 && fv <= fe) {                                 // walked under a state that is not its own
+                        if (lane == fv) { walk_position(jj, true, db); ctl->stat_repairs++; }
+                        __syncwarp();
+                        continue;
+                    }
+                    const uint32_t lastl = min(fe, lastl_all);
+                    if (pass && lane <= lastl) { const uint32_t p = np + a_pc - 1; pass_id[p] = vm[c0 + jj]; pass_inl[p] = inl; }
+                    ri += __shfl_sync(full, a_ri, lastl); rt += __shfl_sync(full, a_rt, lastl); np += __shfl_sync(full, a_pc, lastl);
+                    const uint32_t lvl = __shfl_sync(full, lv_inc, lastl);
+                    const float dl = __shfl_sync(full, dj, lvl ? lvl - 1 : 0);
+                    if (lvl) dcur = dl;
+                    const uint32_t einl = __shfl_sync(full, inl, fe < 32 ? fe : 0);
+                    if (fe < 32) { eps_event = true; ev_inl = einl; ce = g0 + fe + 1; }
+                    break;
+                }
             }
-            d_arr[tid] = dj;
-            const uint32_t lastv_inc = ars_scan_max(dj != 0.0f ? j + 1 : 0u, sm);   // 1-based index of the last valid estimate in [0, j]
-            const uint32_t lastv_exc = __shfl_up_sync(0xffffffffu, lastv_inc, 1);
-            __syncthreads();                                                    // d_arr complete; sm reusable
-            if ((tid & 31) == 31) sm[tid >> 5] = lastv_inc;
-            __syncthreads();
-            const uint32_t lv_before = (tid & 31) ? lastv_exc : (tid ? sm[(tid >> 5) - 1] : 0u);   // ... in [0, j)
-            const float delta_before = lv_before ? d_arr[lv_before - 1] : delta;
-            delta_after = lastv_inc ? d_arr[lastv_inc - 1] : delta;
-            const bool viol = have && !(delta_before >= o_lo[j] && delta_before <= o_hi[j]);
-            uint32_t stop = cnt;
-            if (have) {
-                if (viol) stop = j;                                            // walked under a state that is not its own
-                else if (pass && inl > best0) stop = j + 1;                    // epsilon changes after this model
+            if (lane == 0) {                                                   // publish the state behind position ce - 1
+                s_rej_inl = ri; s_rej_tested = rt;
+                s_npass = np;
+                s_cursor = c0 + ce;
+                s_chunks++;
+                s_delta = dcur;
+                if (eps_event) {
+                    s_best = ev_inl;
+                    const float e = (float)ev_inl / (float)init_n;
+                    if (e > eps && e < 1.0f) s_eps = e; else if (e >= 1.0f) s_eps = 0.999f;
+                }
+                s_chunk = eps_event ? 64u : min((uint32_t)NT, 2u * cnt);
             }
-            ce = ars_block_min(stop, sm);
-            if (tid == 0) s_fix = 0;
-            __syncthreads();
-            if (have && j == ce && viol) {                                     // everything in front of position ce is final
-                walk_position(j, true, delta_before);
-                s_fix = 1;
-                ctl->stat_repairs++;
-            }
-            __syncthreads();
-            if (!s_fix) break;
-        }
-        // 4. commit models [0, ce)
-        if (have && j < ce && pass) {
-            const uint32_t p = np0 + a_pc - 1;
-            pass_id[p] = vm[c0 + j]; pass_inl[p] = inl;
-        }
-        __syncthreads();
-        if (have && j + 1 == ce) {      // the last committed model publishes the state
-            s_rej_inl = ri0 + a_ri; s_rej_tested = rt0 + a_rt;
-            s_npass = np0 + a_pc;
-            s_cursor = c0 + ce;
-            s_chunks++;
-            s_delta = delta_after;
-            const bool eps_event = pass && inl > best0;
-            if (eps_event) {
-                s_best = inl;
-                const float e = (float)inl / (float)init_n;
-                if (e > eps && e < 1.0f) s_eps = e; else if (e >= 1.0f) s_eps = 0.999f;
-            }
-            s_chunk = eps_event ? 64u : min((uint32_t)NT, 2u * cnt);
         }
         __syncthreads();
     }

@@ -18,6 +18,20 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------ device math
+// One cyclic Jacobi rotation, written with explicit roundings so that the one-thread and the lane-cooperative eigensolvers
+// (below) produce the same bits whatever the compiler would contract.
+__device__ __forceinline__ void jacobi_cs(double app, double aqq, double apq, double &c, double &s) {
+    const double theta = __ddiv_rn(__dsub_rn(aqq, app), __dmul_rn(2.0, apq));
+    const double t = __ddiv_rn(theta >= 0.0 ? 1.0 : -1.0, __dadd_rn(fabs(theta), __dsqrt_rn(__fma_rn(theta, theta, 1.0))));
+    c = __ddiv_rn(1.0, __dsqrt_rn(__fma_rn(t, t, 1.0)));
+    s = __dmul_rn(t, c);
+}
+__device__ __forceinline__ void jacobi_rot(double &x, double &y, double c, double s) {
+    const double a = x, b = y;
+    x = __fma_rn(c, a, -__dmul_rn(s, b));
+    y = __fma_rn(s, a, __dmul_rn(c, b));
+}
+
 template <int N>
 __device__ bool sym_eigen(const double *Ain, double eps, int max_sweeps, double *d, double *V) {
     double A[N * N];
@@ -28,8 +42,8 @@ __device__ bool sym_eigen(const double *Ain, double eps, int max_sweeps, double 
     for (int sweep = 0; sweep < max_sweeps; sweep++) {
         double off = 0.0, diag = 0.0;
         for (int i = 0; i < N; i++) {
-            diag += A[i * N + i] * A[i * N + i];
-            for (int j = i + 1; j < N; j++) off += A[i * N + j] * A[i * N + j];
+            diag = __fma_rn(A[i * N + i], A[i * N + i], diag);
+            for (int j = i + 1; j < N; j++) off = __fma_rn(A[i * N + j], A[i * N + j], off);
         }
         if (off <= eps * eps * diag || off == 0.0) {
             for (int i = 0; i < N; i++) d[i] = A[i * N + i];
@@ -39,28 +53,48 @@ __device__ bool sym_eigen(const double *Ain, double eps, int max_sweeps, double 
             for (int q = p + 1; q < N; q++) {
                 const double apq = A[p * N + q];
                 if (apq == 0.0) continue;
-                const double app = A[p * N + p], aqq = A[q * N + q];
-                const double theta = (aqq - app) / (2.0 * apq);
-                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < N; k++) {
-                    const double akp = A[k * N + p], akq = A[k * N + q];
-                    A[k * N + p] = c * akp - s * akq;
-                    A[k * N + q] = s * akp + c * akq;
-                }
-                for (int k = 0; k < N; k++) {
-                    const double apk = A[p * N + k], aqk = A[q * N + k];
-                    A[p * N + k] = c * apk - s * aqk;
-                    A[q * N + k] = s * apk + c * aqk;
-                }
-                for (int k = 0; k < N; k++) {
-                    const double vkp = V[k * N + p], vkq = V[k * N + q];
-                    V[k * N + p] = c * vkp - s * vkq;
-                    V[k * N + q] = s * vkp + c * vkq;
-                }
+                double c, s;
+                jacobi_cs(A[p * N + p], A[q * N + q], apq, c, s);
+                for (int k = 0; k < N; k++) jacobi_rot(A[k * N + p], A[k * N + q], c, s);
+                for (int k = 0; k < N; k++) jacobi_rot(A[p * N + k], A[q * N + k], c, s);
+                for (int k = 0; k < N; k++) jacobi_rot(V[k * N + p], V[k * N + q], c, s);
             }
     }
     for (int i = 0; i < N; i++) d[i] = A[i * N + i];
+    return false;
+}
+
+// The same 9x9 eigensolver shared by JL lanes of a warp (`mask` = those lanes, `lane` = 0..JL-1), A and V in shared memory: every lane
+// forms the rotation, the lanes split the nine column / row updates (they are independent inside a rotation).  Bit-identical to
+// sym_eigen<9>: same operations on every element, same order of the convergence sums.
+template <int JL>
+__device__ bool sym_eigen9_lanes(double *A, double *V, int lane, unsigned mask, double eps, int max_sweeps) {
+    constexpr int N = 9;
+    for (int e = lane; e < N * N; e += JL) V[e] = (e / N == e % N) ? 1.0 : 0.0;
+    __syncwarp(mask);
+    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < N; i++) {
+            diag = __fma_rn(A[i * N + i], A[i * N + i], diag);
+            for (int j = i + 1; j < N; j++) off = __fma_rn(A[i * N + j], A[i * N + j], off);
+        }
+        if (off <= eps * eps * diag || off == 0.0) return true;
+        for (int p = 0; p < N - 1; p++)
+            for (int q = p + 1; q < N; q++) {
+                const double apq = A[p * N + q], app = A[p * N + p], aqq = A[q * N + q];
+                __syncwarp(mask);                                  // every lane has read the pivot block before anyone writes it
+                if (apq == 0.0) continue;
+                double c, s;
+                jacobi_cs(app, aqq, apq, c, s);
+                for (int k = lane; k < N; k += JL) {
+                    jacobi_rot(A[k * N + p], A[k * N + q], c, s);
+                    jacobi_rot(V[k * N + p], V[k * N + q], c, s);
+                }
+                __syncwarp(mask);
+                for (int k = lane; k < N; k += JL) jacobi_rot(A[p * N + k], A[q * N + k], c, s);
+                __syncwarp(mask);
+            }
+    }
     return false;
 }
 
@@ -111,22 +145,20 @@ __device__ __noinline__ bool svd3(const double *M, double eps, int iters, double
 }
 
 // eight-point/src/lib.rs:11-24,43-58 (incl. b / a.z) + cv-pinhole/src/essential.rs:114-162,217-231
-__device__ int eight_point(const double *a, const double *b, const uint32_t *idx, cvb_pose *out) {
-    double A[8][9], EtE[81], d[9], V[81];
-    for (int i = 0; i < 8; i++) {
-        const double *pa = a + 3 * (size_t)idx[i], *pb = b + 3 * (size_t)idx[i];
-        const double ap[3] = {pa[0] / pa[2], pa[1] / pa[2], pa[2] / pa[2]};
-        const double bp[3] = {pb[0] / pa[2], pb[1] / pa[2], pb[2] / pa[2]};
-        for (int j = 0; j < 3; j++)
-            for (int k = 0; k < 3; k++) A[i][3 * j + k] = ap[j] * bp[k];
-    }
-    for (int r = 0; r < 9; r++)
-        for (int c = 0; c < 9; c++) {
-            double s = 0.0;
-            for (int i = 0; i < 8; i++) s += A[i][r] * A[i][c];
-            EtE[r * 9 + c] = s;
-        }
-    if (!sym_eigen<9>(EtE, 1e-12, 1000, d, V)) return 0;
+__device__ __forceinline__ void eight_point_row(const double *a, const double *b, uint32_t id, double *row /* 9 */) {
+    const double *pa = a + 3 * (size_t)id, *pb = b + 3 * (size_t)id;
+    const double ap[3] = {pa[0] / pa[2], pa[1] / pa[2], pa[2] / pa[2]};
+    const double bp[3] = {pb[0] / pa[2], pb[1] / pa[2], pb[2] / pa[2]};
+    for (int j = 0; j < 3; j++)
+        for (int k = 0; k < 3; k++) row[3 * j + k] = __dmul_rn(ap[j], bp[k]);
+}
+__device__ __forceinline__ double eight_point_gram(const double *D /* [8][9] */, int r, int c) {
+    double s = 0.0;
+    for (int i = 0; i < 8; i++) s = __fma_rn(D[i * 9 + r], D[i * 9 + c], s);
+    return s;
+}
+// the four poses from the eigenvectors (V column-stacked, d = diagonal after convergence)
+__device__ int eight_point_poses(const double *d, const double *V, cvb_pose *out) {
     int best = 0;
     for (int i = 1; i < 9; i++)
         if (d[i] < d[best]) best = i;
@@ -147,8 +179,34 @@ __device__ int eight_point(const double *a, const double *b, const uint32_t *idx
     }
     return 4;
 }
+__device__ int eight_point(const double *a, const double *b, const uint32_t *idx, cvb_pose *out) {
+    double D[72], EtE[81], d[9], V[81];
+    for (int i = 0; i < 8; i++) eight_point_row(a, b, idx[i], D + 9 * i);
+    for (int r = 0; r < 9; r++)
+        for (int c = 0; c < 9; c++) EtE[r * 9 + c] = eight_point_gram(D, r, c);
+    if (!sym_eigen<9>(EtE, 1e-12, 1000, d, V)) return 0;
+    return eight_point_poses(d, V, out);
+}
+// JL lanes per hypothesis; sh = 163 doubles of shared memory of this hypothesis (A | V, the design matrix lives in V's place first)
+#define EIGHT_LANES 4
+#define EIGHT_SH 163
+__device__ int eight_point_lanes(const double *a, const double *b, const uint32_t *idx, cvb_pose *out, double *sh, int lane, unsigned mask) {
+    double *A = sh, *V = sh + 81;
+    for (int i = lane; i < 8; i += EIGHT_LANES) eight_point_row(a, b, idx[i], V + 9 * i);
+    __syncwarp(mask);
+    for (int e = lane; e < 81; e += EIGHT_LANES) A[e] = eight_point_gram(V, e / 9, e % 9);
+    __syncwarp(mask);
+    const bool ok = sym_eigen9_lanes<EIGHT_LANES>(A, V, lane, mask, 1e-12, 1000);
+    __syncwarp(mask);
+    int n = 0;
+    if (ok && lane == 0) {
+        double d[9];
+        for (int i = 0; i < 9; i++) d[i] = A[i * 9 + i];
+        n = eight_point_poses(d, V, out);
+    }
+    return n;                                                    // valid on lane 0
+}
 
-// cv-core/src/point.rs:20-25
 __device__ __forceinline__ void from_homogeneous(double *p) {
     if (signbit(p[3])) { p[0] = -p[0]; p[1] = -p[1]; p[2] = -p[2]; p[3] = -p[3]; }
     const double n = norm3(p);
@@ -1472,7 +1530,7 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
     auto estimate = [&](int phase, uint32_t H, const uint32_t *samples, cvb_pose *poses, uint8_t *nposes) -> int {
         if (H == 0) return 0;
         CVB_PROF(ctx, phase == 0 ? "k_ars_estimate_init" : "k_ars_estimate_block", 0);
-        if (kind == 0) k_ars_estimate<0><<<cdiv(H, 32), 32, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
+        if (kind == 0) k_ars_estimate8<<<cdiv(H, 128 / EIGHT_LANES), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes);
         else if (kind == 1) k_ars_estimate<1><<<cdiv(H, 128), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
         else k_ars_estimate<2><<<cdiv(H, 128), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
         CVB_LAUNCH_CHECK(ctx);
