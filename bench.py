@@ -204,6 +204,65 @@ def allpairs64(rank, world, local_rank, dev, cap):
             "timing": "CUDA events on the rank's stream, max over ranks; the match time includes waiting for the all-gather"}
 
 
+def track256(rank, world, ctxs):
+    """BASELINE configs[4]: the cv-sfm registration loop over a 256-frame synthetic track -- per frame
+    Arrsac(1e-5, init 16384, max_cand 1024, est/block 256) + LambdaTwist on ~2 000 FeatureWorldMatches (20 % outliers), then
+    LinearEigenTriangulator on every landmark with >= 3 inlier observations.  Every rank runs its own track (replicas, weak scaling);
+    the frames of a track are independent registrations, handed to the contexts' host threads.  Host API (host pointers in, results
+    on the host), wall clock."""
+    import cv_b200
+    from tests.geom_util import world_homog
+    from tests.synth import helix_track, landmark_observations
+    F = int(os.environ.get("CVB_BENCH_TRACK_FRAMES", "256"))
+    cloud, frames = helix_track(1 + rank, F, 20000, 2000, 0.2)
+    worlds = [world_homog(cloud[fr["ids"]]) for fr in frames]
+    regs = [None] * F
+    nthreads = len(ctxs)
+
+    def register(k, c):
+        ars = (cv_b200.Arrsac(1e-5, cv_b200.Xoshiro256PlusPlus(100 + k), ctx=ctxs[c]).initialization_hypotheses(16384)
+               .max_candidate_hypotheses(1024).estimations_per_block(256))
+        regs[k] = ars.model_inliers(cv_b200.LambdaTwist(), frames[k]["bearing"], worlds[k])
+
+    def sweep(first, count):
+        lock, nxt = threading.Lock(), [first]
+
+        def worker(c):
+            while True:
+                with lock:
+                    k = nxt[0]
+                    if k >= first + count:
+                        return
+                    nxt[0] = k + 1
+                register(k, c)
+        th = [threading.Thread(target=worker, args=(c,)) for c in range(nthreads)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+    sweep(0, min(F, 2 * nthreads))                 # warm-up: workspaces of every context
+    t0 = time.perf_counter()
+    sweep(0, F)
+    t_reg = time.perf_counter() - t0
+    ids, poses, bearings, offsets = landmark_observations(frames, regs)
+    tri = cv_b200.LinearEigenTriangulator()
+    tri.triangulate_batch(poses, bearings, offsets)
+    t0 = time.perf_counter()
+    pts, ok = tri.triangulate_batch(poses, bearings, offsets)
+    t_tri = time.perf_counter() - t0
+    inl = [0 if r is None else len(r[2]) for r in regs]
+    good = [float(fr["good"][r[2]].mean()) for fr, r in zip(frames, regs) if r is not None and len(r[2])]
+    xyz = pts[ok, :3] / pts[ok, 3:4]
+    err = np.linalg.norm(xyz - cloud[np.array(ids)[ok]], axis=1) if ok.any() else np.array([np.nan])
+    return {"frames": F, "matches_per_frame": 2000, "outlier_fraction": 0.2, "registered": int(sum(r is not None for r in regs)),
+            "inliers_per_frame_mean": float(np.mean(inl)), "inlier_purity_mean": float(np.mean(good)) if good else None,
+            "registration_ms_total": t_reg * 1e3, "registrations_per_s": F / t_reg, "host_threads": nthreads,
+            "landmarks": len(ids), "observations": len(poses), "triangulated_ok": int(ok.sum()), "triangulation_ms": t_tri * 1e3,
+            "landmarks_per_s": len(ids) / t_tri if t_tri > 0 else None, "median_landmark_error": float(np.median(err)),
+            "arrsac": {"threshold": 1e-5, "initialization_hypotheses": 16384, "max_candidate_hypotheses": 1024, "estimations_per_block": 256},
+            "timing": "host API (host pointers in, results on the host), wall clock, this rank's replica"}
+
+
 def bind_to_gpu_numa_node(props):
     """Run this process (and the pinned buffers it first-touches) on the CPUs local to the GPU's PCIe root, like a deployed
     service would; silently skipped when sysfs does not expose the topology."""
@@ -450,6 +509,22 @@ def main():
         except Exception as ex:      # secondary block: never fail the headline line
             ap64 = {"error": repr(ex)}
 
+    # ---- BASELINE configs[4] (P3P registration + triangulation over a 256-frame track; one replica per rank)
+    tr256 = None
+    if os.environ.get("CVB_BENCH_TRACK", "1") == "1":
+        try:
+            tr256 = track256(rank, world, ctxs)
+        except Exception as ex:
+            tr256 = {"error": repr(ex)}
+        if world > 1:          # every rank takes part in the reduction, whatever happened to its replica
+            v = torch.tensor([tr256.get("registration_ms_total", 0.0), tr256.get("triangulation_ms", 0.0)], dtype=torch.float64, device=dev)
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            v = v.cpu().tolist()
+            if "error" not in tr256:
+                tr256["replicas"] = world
+                tr256["registrations_per_s_all_ranks"] = world * tr256["frames"] / (v[0] * 1e-3)
+                tr256["landmarks_per_s_all_ranks"] = world * tr256["landmarks"] / (v[1] * 1e-3) if v[1] > 0 else None
+
     # ---- roofline: instrumented pass (per-kernel CUDA events on the launching stream, one context, no overlap)
     ctx.profile(True)
     PK = 6
@@ -522,7 +597,7 @@ def main():
                         "per_rank": {"columns": ["frames_per_s", "h2d_GBps", "host_cpu_ms_per_pair"], "rows": per_rank_all}},
                 "timed_region_ms": ms_max, "mean_pair_latency_ms": sum(dev_busy) / len(dev_busy),
                 "gpu_launches": int(launches), "roofline": roofline, "hamming_Gcmp_per_s": gcmp, "ransac_two_view": ransac,
-                "ransac_scoring": ransac_scoring, "allpairs64": ap64, "inliers_equal_oracle": inliers_equal_oracle, "cpu_baseline": cpu,
+                "ransac_scoring": ransac_scoring, "allpairs64": ap64, "track256": tr256, "inliers_equal_oracle": inliers_equal_oracle, "cpu_baseline": cpu,
                 "clocks": sampler.summary()}
         print(json.dumps(line), flush=True)
     if world > 1:

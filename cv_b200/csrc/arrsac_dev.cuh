@@ -148,6 +148,59 @@ __device__ void ars_sample_block(ArrsacCtl *ctl, const uint32_t *raw, uint32_t l
     __syncthreads();
 }
 
+// The same samples, CTA-parallel, for the big initial batch (no index map).  A sample without a repeat consumes exactly K draws, so
+// thread t takes sample h0 + t from draws [p0 + t*K, p0 + (t+1)*K) -- right as long as no earlier sample of the turn met a repeat
+// (probability K(K-1)/2n per sample).  Samples in front of the first repeat are committed, the thread that owns it redoes its sample
+// draw by draw (the reference's loop) and the next turn starts behind it.  The tail of the staged stream goes to ars_sample_block.
+__device__ void ars_sample_block_par(ArrsacCtl *ctl, const uint32_t *raw, uint32_t len, uint32_t K, uint32_t count, uint32_t *out,
+                                     uint32_t *win, uint32_t *sh /* 4 shared words */) {
+    const uint32_t nraw = ctl->nraw, tid = threadIdx.x;
+    if (tid == 0) { sh[0] = 0; *(uint64_t *)(sh + 2) = ctl->rng_pos; }
+    __syncthreads();
+    while (true) {
+        const uint32_t h0 = sh[0];
+        const uint64_t p0 = *(const uint64_t *)(sh + 2);
+        if (h0 >= count) break;
+        const uint32_t m = min((uint32_t)blockDim.x, count - h0);
+        if (p0 + (uint64_t)(m + 8) * K > nraw) break;               // not enough staged draws for a whole turn (+ slack for the redo)
+        __syncthreads();                                            // everyone has read sh[0] / the position
+        if (tid == 0) sh[1] = m;
+        __syncthreads();
+        uint32_t loc[8];
+        if (tid < m) {
+            bool dup = false;
+            for (uint32_t k = 0; k < K; k++) {
+                loc[k] = raw[p0 + (uint64_t)tid * K + k] % len;
+                for (uint32_t j = 0; j < k; j++) dup |= loc[j] == loc[k];
+            }
+            if (dup) atomicMin(&sh[1], tid);
+        }
+        __syncthreads();
+        const uint32_t f = sh[1];
+        if (tid < f)
+            for (uint32_t k = 0; k < K; k++) out[(size_t)(h0 + tid) * K + k] = loc[k];
+        if (f < m && tid == f) {
+            uint64_t pos = p0 + (uint64_t)f * K;
+            for (uint32_t c = 0; c < K;) {
+                const uint32_t s = ars_raw_at(ctl, raw, pos) % len;
+                pos++;
+                bool dup = false;
+                for (uint32_t j = 0; j < c; j++) dup |= loc[j] == s;
+                if (!dup) { loc[c] = s; out[(size_t)(h0 + f) * K + c] = s; c++; }
+            }
+            sh[0] = h0 + f + 1; *(uint64_t *)(sh + 2) = pos;
+        } else if (f >= m && tid == 0) {
+            sh[0] = h0 + m; *(uint64_t *)(sh + 2) = p0 + (uint64_t)m * K;
+        }
+        __syncthreads();
+    }
+    const uint32_t hdone = sh[0];
+    __syncthreads();
+    if (tid == 0) ctl->rng_pos = *(const uint64_t *)(sh + 2);
+    __syncthreads();
+    if (hdone < count) ars_sample_block(ctl, raw, len, K, count - hdone, out + (size_t)hdone * K, nullptr, win, sh);
+}
+
 // ---- k_ars_begin ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_begin(ArrsacCtl *ctl, ArrsacParams P, const uint32_t *n_dev, uint32_t n_host,
                                                             const uint32_t *raw, uint32_t *samples0) {
@@ -164,7 +217,7 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_begin(ArrsacCtl *ctl, Arrsa
     }
     __syncthreads();
     if (n < P.K || P.H0 == 0) return;
-    ars_sample_block(ctl, raw, n, P.K, P.H0, samples0, nullptr, win, sh);
+    ars_sample_block_par(ctl, raw, n, P.K, P.H0, samples0, win, sh);
 }
 
 // ---- k_ars_estimate ------------------------------------------------------------------------------------------------------
@@ -624,7 +677,11 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
                     const unsigned vb = __ballot_sync(full, viol), eb = __ballot_sync(full, e2);
                     const uint32_t fv = vb ? (uint32_t)__ffs(vb) - 1 : 32u, fe = eb ? (uint32_t)__ffs(eb) - 1 : 32u;
                     if (fv < 32 && fv <= fe) {                                 // walked under a state that is not its own
-                        if (lane == fv) { walk_position(jj, true, db); ctl->stat_repairs++; }
+                        // every violating position in front of the epsilon event is walked again at once, each with the exact delta
+                        // its CURRENT predecessors give it: the first of them is final (everything in front of it is), the others are
+                        // final unless a repaired predecessor changed its outcome -- then their delta no longer equals the one they
+                        // were walked with (box = that single value) and they come back as violations in the next turn
+                        if (viol && lane <= fe) { walk_position(jj, true, db); atomicAdd(&ctl->stat_repairs, 1u); }
                         __syncwarp();
                         continue;
                     }

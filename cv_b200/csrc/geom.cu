@@ -22,14 +22,14 @@ namespace {
 // (below) produce the same bits whatever the compiler would contract.
 __device__ __forceinline__ void jacobi_cs(double app, double aqq, double apq, double &c, double &s) {
     const double theta = __ddiv_rn(__dsub_rn(aqq, app), __dmul_rn(2.0, apq));
-    const double t = __ddiv_rn(theta >= 0.0 ? 1.0 : -1.0, __dadd_rn(fabs(theta), __dsqrt_rn(__fma_rn(theta, theta, 1.0))));
-    c = __ddiv_rn(1.0, __dsqrt_rn(__fma_rn(t, t, 1.0)));
+    const double t = __ddiv_rn(theta >= 0.0 ? 1.0 : -1.0, __dadd_rn(fabs(theta), __dsqrt_rn(__dadd_rn(__dmul_rn(theta, theta), 1.0))));
+    c = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(__dmul_rn(t, t), 1.0)));
     s = __dmul_rn(t, c);
 }
 __device__ __forceinline__ void jacobi_rot(double &x, double &y, double c, double s) {
     const double a = x, b = y;
-    x = __fma_rn(c, a, -__dmul_rn(s, b));
-    y = __fma_rn(s, a, __dmul_rn(c, b));
+    x = __dsub_rn(__dmul_rn(c, a), __dmul_rn(s, b));
+    y = __dadd_rn(__dmul_rn(s, a), __dmul_rn(c, b));
 }
 
 template <int N>
@@ -42,8 +42,8 @@ __device__ bool sym_eigen(const double *Ain, double eps, int max_sweeps, double 
     for (int sweep = 0; sweep < max_sweeps; sweep++) {
         double off = 0.0, diag = 0.0;
         for (int i = 0; i < N; i++) {
-            diag = __fma_rn(A[i * N + i], A[i * N + i], diag);
-            for (int j = i + 1; j < N; j++) off = __fma_rn(A[i * N + j], A[i * N + j], off);
+            diag = __dadd_rn(diag, __dmul_rn(A[i * N + i], A[i * N + i]));
+            for (int j = i + 1; j < N; j++) off = __dadd_rn(off, __dmul_rn(A[i * N + j], A[i * N + j]));
         }
         if (off <= eps * eps * diag || off == 0.0) {
             for (int i = 0; i < N; i++) d[i] = A[i * N + i];
@@ -75,8 +75,8 @@ __device__ bool sym_eigen9_lanes(double *A, double *V, int lane, unsigned mask, 
     for (int sweep = 0; sweep < max_sweeps; sweep++) {
         double off = 0.0, diag = 0.0;
         for (int i = 0; i < N; i++) {
-            diag = __fma_rn(A[i * N + i], A[i * N + i], diag);
-            for (int j = i + 1; j < N; j++) off = __fma_rn(A[i * N + j], A[i * N + j], off);
+            diag = __dadd_rn(diag, __dmul_rn(A[i * N + i], A[i * N + i]));
+            for (int j = i + 1; j < N; j++) off = __dadd_rn(off, __dmul_rn(A[i * N + j], A[i * N + j]));
         }
         if (off <= eps * eps * diag || off == 0.0) return true;
         for (int p = 0; p < N - 1; p++)
@@ -154,7 +154,7 @@ __device__ __forceinline__ void eight_point_row(const double *a, const double *b
 }
 __device__ __forceinline__ double eight_point_gram(const double *D /* [8][9] */, int r, int c) {
     double s = 0.0;
-    for (int i = 0; i < 8; i++) s = __fma_rn(D[i * 9 + r], D[i * 9 + c], s);
+    for (int i = 0; i < 8; i++) s = __dadd_rn(s, __dmul_rn(D[i * 9 + r], D[i * 9 + c]));
     return s;
 }
 // the four poses from the eigenvectors (V column-stacked, d = diagonal after convergence)

@@ -8,33 +8,10 @@ import pytest
 
 import cv_b200
 from oracle import pyoracle as O
-from tests.geom_util import rot_from_euler, rot_angle, unit, world_homog
+from tests.geom_util import rot_angle, world_homog
+from tests.synth import helix_track, landmark_observations as _landmark_observations
 
 pytestmark = pytest.mark.gpu
-
-
-def helix_track(seed, n_poses, n_points, visible, outlier_frac, noise_px=0.3, focal=1000.0):
-    rng = np.random.default_rng(seed)
-    cloud = rng.uniform(-3, 3, (n_points, 3)) + np.array([0, 0, 0.0])
-    frames = []
-    for f in range(n_poses):
-        ang = 2 * np.pi * f / 64.0
-        centre = np.array([9 * np.cos(ang), 9 * np.sin(ang), -2 + 4.0 * f / max(n_poses - 1, 1)])
-        fwd = unit(-centre); up = np.array([0, 0, 1.0]); right = unit(np.cross(fwd, up)); dwn = np.cross(fwd, right)
-        R = np.stack([right, dwn, fwd]) @ rot_from_euler(*rng.uniform(-0.02, 0.02, 3))       # world -> camera rotation
-        t = -R @ centre
-        cam = cloud @ R.T + t
-        vis = np.where((cam[:, 2] > 1.0) & (np.abs(cam[:, 0] / cam[:, 2]) < 0.9) & (np.abs(cam[:, 1] / cam[:, 2]) < 0.5))[0]
-        vis = rng.choice(vis, min(visible, len(vis)), replace=False)
-        px = cam[vis, :2] / cam[vis, 2:3] + rng.normal(0, noise_px / focal, (len(vis), 2))
-        bearing = unit(np.concatenate([px, np.ones((len(vis), 1))], 1))
-        good = np.ones(len(vis), bool)
-        bad = rng.choice(len(vis), int(outlier_frac * len(vis)), replace=False)
-        bearing[bad] = unit(np.concatenate([rng.uniform(-0.9, 0.9, (len(bad), 1)), rng.uniform(-0.5, 0.5, (len(bad), 1)),
-                                            np.ones((len(bad), 1))], 1))
-        good[bad] = False
-        frames.append(dict(R=R, t=t, ids=vis, bearing=bearing, good=good))
-    return cloud, frames
 
 
 def _register(frames, cloud, seed, init, cand, use_oracle):
@@ -49,23 +26,6 @@ def _register(frames, cloud, seed, init, cand, use_oracle):
                    .max_candidate_hypotheses(cand).estimations_per_block(256))
             out.append(ars.model_inliers(cv_b200.LambdaTwist(), fr["bearing"], world))
     return out
-
-
-def _landmark_observations(frames, regs, min_obs=3):
-    """Observations (pose, bearing) of every landmark seen as an inlier in >= min_obs registered frames."""
-    obs = {}
-    for fr, reg in zip(frames, regs):
-        if reg is None:
-            continue
-        for i in reg[2]:
-            obs.setdefault(int(fr["ids"][i]), []).append(((reg[0], reg[1]), fr["bearing"][i]))
-    ids = sorted(l for l, v in obs.items() if len(v) >= min_obs)
-    poses, bearings, offsets = [], [], [0]
-    for l in ids:
-        for p, b in obs[l]:
-            poses.append(p); bearings.append(b)
-        offsets.append(len(poses))
-    return ids, poses, np.array(bearings), offsets
 
 
 def test_track_reduced_matches_cpu_port():
