@@ -244,11 +244,17 @@ def track256(rank, world, ctxs):
     t0 = time.perf_counter()
     sweep(0, F)
     t_reg = time.perf_counter() - t0
-    ids, poses, bearings, offsets = landmark_observations(frames, regs)
+    # feature tracks of bounded length (the first 8 inlier observations of a landmark): the reference's cheirality rule
+    # (cv-geom/src/triangulation.rs:120-127) rejects a landmark as soon as ONE of its views sees it from the far side of the world
+    # origin, which over four full turns of the orbit would be nearly every landmark
+    ids, poses, bearings, offsets = landmark_observations(frames, regs, max_obs=8)
+    from cv_b200.geom import POSE_DTYPE
+    parr = np.zeros(len(poses), POSE_DTYPE)
+    parr["r"] = np.array([p[0] for p in poses]).reshape(-1, 9); parr["t"] = np.array([p[1] for p in poses]).reshape(-1, 3)
     tri = cv_b200.LinearEigenTriangulator()
-    tri.triangulate_batch(poses, bearings, offsets)
+    tri.triangulate_batch(parr, bearings, offsets)
     t0 = time.perf_counter()
-    pts, ok = tri.triangulate_batch(poses, bearings, offsets)
+    pts, ok = tri.triangulate_batch(parr, bearings, offsets)
     t_tri = time.perf_counter() - t0
     inl = [0 if r is None else len(r[2]) for r in regs]
     good = [float(fr["good"][r[2]].mean()) for fr, r in zip(frames, regs) if r is not None and len(r[2])]
@@ -257,7 +263,7 @@ def track256(rank, world, ctxs):
     return {"frames": F, "matches_per_frame": 2000, "outlier_fraction": 0.2, "registered": int(sum(r is not None for r in regs)),
             "inliers_per_frame_mean": float(np.mean(inl)), "inlier_purity_mean": float(np.mean(good)) if good else None,
             "registration_ms_total": t_reg * 1e3, "registrations_per_s": F / t_reg, "host_threads": nthreads,
-            "landmarks": len(ids), "observations": len(poses), "triangulated_ok": int(ok.sum()), "triangulation_ms": t_tri * 1e3,
+            "landmarks": len(ids), "observations": len(poses), "max_observations_per_landmark": 8, "triangulated_ok": int(ok.sum()), "triangulation_ms": t_tri * 1e3,
             "landmarks_per_s": len(ids) / t_tri if t_tri > 0 else None, "median_landmark_error": float(np.median(err)),
             "arrsac": {"threshold": 1e-5, "initialization_hypotheses": 16384, "max_candidate_hypotheses": 1024, "estimations_per_block": 256},
             "timing": "host API (host pointers in, results on the host), wall clock, this rank's replica"}

@@ -42,6 +42,8 @@ struct ArrsacCtl {
     cvb_pose winner;
     uint32_t n_inliers, overflow;
     uint32_t stat_chunks, stat_pass;
+    uint32_t stat_walk_us, stat_commit_us;   // SPRT: time in the chunk walks / in the commit turns (globaltimer)
+    uint32_t stat_perm_us, stat_turns;       // SPRT: time in the ordering step in front of the walks; commit turns in total
 };
 
 struct ArrsacParams {            // launch-constant configuration (by value)
@@ -58,6 +60,7 @@ struct ArrsacParams {            // launch-constant configuration (by value)
     int row0;
 };
 
+__device__ __forceinline__ unsigned long long ars_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ uint64_t ars_rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
 __device__ uint32_t ars_rng_next_u32(cvb_rng *r) {
     if (r->kind == 0) {
@@ -161,7 +164,8 @@ __device__ void ars_sample_block_par(ArrsacCtl *ctl, const uint32_t *raw, uint32
         const uint32_t h0 = sh[0];
         const uint64_t p0 = *(const uint64_t *)(sh + 2);
         if (h0 >= count) break;
-        const uint32_t m = min((uint32_t)blockDim.x, count - h0);
+        // a turn commits the samples in front of its first repeat (one in ~2n / K(K-1) samples): wider turns mostly compute discards
+        const uint32_t m = min(min((uint32_t)blockDim.x, 256u), count - h0);
         if (p0 + (uint64_t)(m + 8) * K > nraw) break;               // not enough staged draws for a whole turn (+ slack for the redo)
         __syncthreads();                                            // everyone has read sh[0] / the position
         if (tid == 0) sh[1] = m;
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_begin(ArrsacCtl *ctl, Arrsa
         ctl->init_n = min(P.bs * P.ib, n);
         ctl->Mv = 0; ctl->npass = 0; ctl->Hn = 0; ctl->cur = 0; ctl->blk_lo = ctl->blk_hi = ctl->acc_hi = 0;
         ctl->n_new = 0; ctl->worst = 0; ctl->found = 0; ctl->iters = 0; ctl->n_inliers = 0; ctl->overflow = 0;
-        ctl->stat_chunks = 0; ctl->stat_pass = 0; ctl->q_count = 0; ctl->q_count2 = 0; ctl->stat_lazy = 0; ctl->stat_units0 = 0; ctl->stat_units2 = 0; ctl->stat_repairs = 0; ctl->stat_pad = 0;
+        ctl->stat_chunks = 0; ctl->stat_pass = 0; ctl->q_count = 0; ctl->q_count2 = 0; ctl->stat_lazy = 0; ctl->stat_units0 = 0; ctl->stat_units2 = 0; ctl->stat_repairs = 0; ctl->stat_pad = 0; ctl->stat_walk_us = 0; ctl->stat_commit_us = 0; ctl->stat_perm_us = 0; ctl->stat_turns = 0;
         ctl->done = (n < P.K || P.H0 == 0) ? 1u : 0u;
     }
     __syncthreads();
@@ -236,10 +240,11 @@ __global__ void __launch_bounds__(128) k_ars_estimate(const ArrsacCtl *ctl, int 
     nposes[h] = (uint8_t)n;
 }
 
-// Eight-point with EIGHT_LANES lanes per hypothesis, the 9x9 matrix and its eigenvectors in shared memory (32 hypotheses per CTA).
+// Eight-point with EIGHT_LANES lanes per hypothesis, the 9x9 matrix and its eigenvectors in shared memory (128 / EIGHT_LANES hypotheses per CTA).
 // The chain of 36 rotations x ~8 sweeps is what a block of the hypothesis loop waits for: a rotation is the FP64 divide / square-root
 // sequence (every lane) followed by the column and row updates (split over the lanes).  (A nine-lane version with the matrix in
 // REGISTERS and shuffles was measured slower than one thread; shared memory keeps the element exchange off the critical path.)
+template <int EIGHT_LANES>
 __global__ void __launch_bounds__(128) k_ars_estimate8(const ArrsacCtl *ctl, int phase, uint32_t H_init, const double *__restrict__ a,
                                                        const double *__restrict__ b, const uint32_t *__restrict__ samples,
                                                        cvb_pose *poses, uint8_t *nposes) {
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(128) k_ars_estimate8(const ArrsacCtl *ctl, int
     if (h >= H) return;                                          // whole lane groups leave together
     const unsigned mask = ((1u << EIGHT_LANES) - 1u) << ((threadIdx.x & 31) / EIGHT_LANES * EIGHT_LANES);
     cvb_pose out[4];
-    const int n = eight_point_lanes(a, b, samples + (size_t)h * 8, out, sh + g * EIGHT_SH, lane, mask);
+    const int n = eight_point_lanes<EIGHT_LANES>(a, b, samples + (size_t)h * 8, out, sh + g * EIGHT_SH, lane, mask);
     if (lane == 0) {
         for (int k = 0; k < n; k++) poses[(size_t)h * 4 + k] = out[k];
         nposes[h] = (uint8_t)n;
@@ -449,74 +454,138 @@ __device__ uint32_t ars_popc_range(const uint32_t *row, uint32_t lo, uint32_t hi
     return c;
 }
 
-// SPRT walk of one model over its initialisation mask (the reference's inner loop, f32 in data order).  words[w * stride] = mask
-// word w; words at and beyond `avail` have not been computed by the scoring kernels (two-stage initial scoring): the walk
-// evaluates such a word itself, stores it (walk copy and global row) and moves `avail` on.  Returns tested (the 1-based datum
-// at which the ratio exceeded the threshold) or 0 when the model passes.
+// SPRT walk of one model over its initialisation mask (the reference's inner loop, f32 in data order): ONE pass that carries the exact
+// likelihood ratio for delta = dl and, beside it, both corners of ARS_NBOX nested boxes of delta values dl (1 -+ width) (two boxes,
+// widths 1/4 and 1/128: the 1024-thread CTA has 64 registers per thread, and four boxes = 9 chains + 18 multipliers spilled).
+//   * f32 multiplication and division are monotone, so for every delta inside a box the ratio lies between the box's lower and upper
+//     corner at every datum (upper corner: delta_hi / eps on inliers, (1 - delta_lo) / (1 - eps) on outliers; lower corner the other way).
+//   * the exact walk stops at datum T (ratio > thr) or passes.  A box is VALID for this model when its upper corner does not stop in
+//     front of T and its lower corner stops at T as well (or, for a passing model, when the upper corner never stops): the outcome
+//     (T, inliers up to T) then holds for every delta in the box.  The widest valid box is returned ([dl, dl] when none is).
+// words[w * stride] = mask word w; words at and beyond `avail` have not been computed by the scoring kernels (two-stage initial scoring):
+// the walk evaluates such a word itself, stores it (walk copy and global row) and moves `avail` on.  *tested_out = the 1-based datum at
+// which the ratio exceeded the threshold, 0 when the model passes; *inl_out = inliers up to there.
 struct ArsLazy { const cvb_pose *pose; const double *a, *b; double thr; uint32_t *grow; uint32_t *counter; uint32_t *steps; };
-template <int RES>
-__device__ uint32_t ars_sprt_walk(uint32_t *words, uint32_t stride, uint32_t init_n, float pos, float neg, float thr, uint32_t *inl_out,
-                                  uint32_t &avail, const ArsLazy &L) {
-    float ratio = 1.0f;
-    uint32_t inl = 0;
-    for (uint32_t w = 0; w * 32 < init_n; w++) {
-        const uint32_t cnt = min(32u, init_n - w * 32);
-        if (w >= avail) {
-            uint32_t bits = 0;
-            for (uint32_t k = 0; k < cnt; k++)
-                if (ars_inlier<RES>(*L.pose, L.a, L.b, w * 32 + k, L.thr)) bits |= 1u << k;
-            words[w * stride] = bits;
-            L.grow[w] = bits;
-            avail = w + 1;
-            atomicAdd(L.counter, 1u);
-        }
-        const uint32_t x = words[w * stride];
-        if (ratio == 0.0f) { inl += __popc(cnt < 32 ? (x & ((1u << cnt) - 1)) : x); continue; }   // 0 * finite stays 0: never rejected
-        for (uint32_t k = 0; k < cnt; k++) {
-            if ((x >> k) & 1u) { inl++; ratio *= pos; }
-            else ratio *= neg;
-            if (ratio > thr) { *inl_out = inl; return w * 32 + k + 1; }
-        }
-    }
-    *inl_out = inl;
-    return 0;
+#ifndef ARS_NBOX
+#define ARS_NBOX 2
+#endif
+__device__ __forceinline__ float ars_box_width(int i) {
+    constexpr float W0 = 0.25f, WS = ARS_NBOX == 2 ? 0.03125f : (ARS_NBOX == 3 ? 0.125f : 0.25f);   // 1/4, 1/128 | 1/4, 1/32, 1/256 | 1/4 .. 1/256
+    float w = W0;
+    for (int k = 0; k < i; k++) w *= WS;
+    return w;
 }
-
-// Both corners of a box in one pass (ratio_hi >= ratio_lo at every datum by monotonicity): returns true when the two walks stop at the
-// same datum (the outcome then holds for the whole box); *tested / *inl_out as in ars_sprt_walk.
+// Out of line on purpose: inlined into the 1024-thread kernel (64 registers per thread, a dozen live pointers) the multipliers and
+// ratios were spilled and every step reloaded them from local memory; as a function the walk has the register file to itself.
+// Returns (tested << 16 | inliers, index of the widest valid box or ARS_NBOX).
 template <int RES>
-__device__ bool ars_sprt_walk_box(uint32_t *words, uint32_t stride, uint32_t init_n, float pos_hi, float neg_hi, float pos_lo, float neg_lo,
-                                  float thr, uint32_t *tested, uint32_t *inl_out, uint32_t &avail, const ArsLazy &L) {
-    float rh = 1.0f, rl = 1.0f;
-    uint32_t inl = 0;
-    for (uint32_t w = 0; w * 32 < init_n; w++) {
+__device__ __noinline__ uint2 ars_sprt_walk_multi(uint32_t *words, uint32_t stride, uint32_t init_n, float dl, float eps, float one_m_eps, float thr,
+                                                  uint32_t avail, const ArsLazy *L) {
+    constexpr int NB = ARS_NBOX;
+    const float pe = dl / eps, ne = (1.0f - dl) / one_m_eps;
+    float ph[NB], nh[NB], pl[NB], nl[NB];
+    bool dead[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        const float wdt = ars_box_width(i);
+        const float lo = dl * (1.0f - wdt), hi = dl * (1.0f + wdt);
+        dead[i] = !(hi < 1.0f);                     // keeps every multiplier positive (the monotonicity argument needs it)
+        ph[i] = dead[i] ? pe : hi / eps; nh[i] = dead[i] ? ne : (1.0f - lo) / one_m_eps;
+        pl[i] = dead[i] ? pe : lo / eps; nl[i] = dead[i] ? ne : (1.0f - hi) / one_m_eps;
+    }
+    float re = 1.0f, rh[NB], rl[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) rh[i] = rl[i] = 1.0f;
+    uint32_t inl = 0, tested = 0;
+    bool stopped = false;
+    for (uint32_t w = 0; w * 32 < init_n && !stopped; w++) {
         const uint32_t cnt = min(32u, init_n - w * 32);
         if (w >= avail) {
             uint32_t bits = 0;
             for (uint32_t k = 0; k < cnt; k++)
-                if (ars_inlier<RES>(*L.pose, L.a, L.b, w * 32 + k, L.thr)) bits |= 1u << k;
+                if (ars_inlier<RES>(*L->pose, L->a, L->b, w * 32 + k, L->thr)) bits |= 1u << k;
             words[w * stride] = bits;
-            L.grow[w] = bits;
+            L->grow[w] = bits;
             avail = w + 1;
-            atomicAdd(L.counter, 1u);
+            atomicAdd(L->counter, 1u);
         }
         const uint32_t x = words[w * stride];
-        if (rh == 0.0f) { inl += __popc(cnt < 32 ? (x & ((1u << cnt) - 1)) : x); continue; }      // rl <= rh: both stay 0, never rejected
-        for (uint32_t k = 0; k < cnt; k++) {
+        // 0 * finite stays 0: once every chain has underflowed nothing can stop any more
+        bool all0 = re == 0.0f;
+#pragma unroll
+        for (int i = 0; i < NB; i++) all0 = all0 && rh[i] == 0.0f;
+        if (all0) {
+            inl += __popc(cnt < 32 ? (x & ((1u << cnt) - 1)) : x);
+            continue;
+        }
+        uint32_t k = 0;
+        // four data per turn: the products are the sequential ones (same order), only the threshold tests are gathered
+        for (; k + 4 <= cnt && !stopped; k += 4) {
+            const uint32_t q = (x >> k) & 15u;
+            const bool b0 = q & 1u, b1 = q & 2u, b2 = q & 4u, b3 = q & 8u;
+            const float e1 = re * (b0 ? pe : ne), e2 = e1 * (b1 ? pe : ne), e3 = e2 * (b2 ? pe : ne), e4 = e3 * (b3 ? pe : ne);
+            float h1[NB], h2[NB], h3[NB], h4[NB], l1[NB], l2[NB], l3[NB], l4[NB];
+#pragma unroll
+            for (int i = 0; i < NB; i++) {
+                h1[i] = rh[i] * (b0 ? ph[i] : nh[i]); h2[i] = h1[i] * (b1 ? ph[i] : nh[i]);
+                h3[i] = h2[i] * (b2 ? ph[i] : nh[i]); h4[i] = h3[i] * (b3 ? ph[i] : nh[i]);
+                l1[i] = rl[i] * (b0 ? pl[i] : nl[i]); l2[i] = l1[i] * (b1 ? pl[i] : nl[i]);
+                l3[i] = l2[i] * (b2 ? pl[i] : nl[i]); l4[i] = l3[i] * (b3 ? pl[i] : nl[i]);
+            }
+            if (!(fmaxf(fmaxf(e1, e2), fmaxf(e3, e4)) > thr)) {          // the exact walk goes on (no NaN: every factor is finite and positive)
+#pragma unroll
+                for (int i = 0; i < NB; i++) {
+                    dead[i] |= fmaxf(fmaxf(h1[i], h2[i]), fmaxf(h3[i], h4[i])) > thr;      // upper corner stops in front of the exact walk
+                    rh[i] = h4[i]; rl[i] = l4[i];
+                }
+                re = e4;
+                inl += __popc(q);
+                continue;
+            }
+            const int jstop = e1 > thr ? 1 : (e2 > thr ? 2 : (e3 > thr ? 3 : 4));      // first datum of the turn at which the exact ratio stops
+            tested = w * 32 + k + jstop;
+            inl += __popc(q & ((1u << jstop) - 1u));
+#pragma unroll
+            for (int i = 0; i < NB; i++) {
+                const bool early = (jstop > 1 && h1[i] > thr) || (jstop > 2 && h2[i] > thr) || (jstop > 3 && h3[i] > thr);
+                const float lj = jstop == 1 ? l1[i] : (jstop == 2 ? l2[i] : (jstop == 3 ? l3[i] : l4[i]));
+                dead[i] |= early || !(lj > thr);                           // ... or the lower corner does not stop here
+            }
+            stopped = true;
+        }
+        for (; k < cnt && !stopped; k++) {                                 // tail of a partial word
             const bool in = (x >> k) & 1u;
             inl += in ? 1u : 0u;
-            rh *= in ? pos_hi : neg_hi;
-            rl *= in ? pos_lo : neg_lo;
-            if (rh > thr) {                      // the upper corner stops here; the box is decided iff the lower corner stops here too
-                *tested = w * 32 + k + 1; *inl_out = inl;
-                atomicAdd(L.steps, w * 32 + k + 1);
-                return rl > thr;
+            re *= in ? pe : ne;
+#pragma unroll
+            for (int i = 0; i < NB; i++) { rh[i] *= in ? ph[i] : nh[i]; rl[i] *= in ? pl[i] : nl[i]; }
+            if (re > thr) {
+                tested = w * 32 + k + 1; stopped = true;
+#pragma unroll
+                for (int i = 0; i < NB; i++) dead[i] |= !(rl[i] > thr);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NB; i++) dead[i] |= rh[i] > thr;
             }
         }
     }
-    *tested = 0; *inl_out = inl;                 // the upper corner passes, hence the lower corner as well
-    atomicAdd(L.steps, init_n);
-    return true;
+    atomicAdd(L->steps, stopped ? tested : init_n);
+    uint32_t box = NB;
+#pragma unroll
+    for (int i = NB - 1; i >= 0; i--)
+        if (!dead[i]) box = (uint32_t)i;
+    return make_uint2((tested << 16) | inl, box);
+}
+
+// both minima of a pair of block-wide values in one pass (ARS_BOOK_NT threads)
+__device__ void ars_block_min2(uint32_t &a, uint32_t &b, uint32_t *sm /* 64 */) {
+    const unsigned full = 0xffffffffu;
+    for (int o = 16; o; o >>= 1) { a = min(a, __shfl_xor_sync(full, a, o)); b = min(b, __shfl_xor_sync(full, b, o)); }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = a; sm[32 + (threadIdx.x >> 5)] = b; }
+    __syncthreads();
+    a = sm[threadIdx.x & 31]; b = sm[32 + (threadIdx.x & 31)];
+    for (int o = 16; o; o >>= 1) { a = min(a, __shfl_xor_sync(full, a, o)); b = min(b, __shfl_xor_sync(full, b, o)); }
 }
 
 // inclusive block-wide max scan (ARS_BOOK_NT threads)
@@ -572,22 +641,28 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
         s_eps = P.eps0; s_delta = P.delta0; s_best = 0; s_cursor = 0; s_npass = 0; s_rej_inl = 0; s_rej_tested = 0; s_chunks = 0;
     }
     __syncthreads();
-    // B. adaptive SPRT.  A chunk of models is walked concurrently; every model gets its OWN box of delta values around the current
-    // one (the widest of +-1/4, 1/16, 1/64, 1/256 for which the walks at both corners stop at the same datum -- f32 multiplication
-    // is monotone, so the outcome is then the same for every delta inside; epsilon is fixed inside a chunk).  Prefix sums over the
-    // chunk give the exact delta in front of every model.  The first model whose delta lies outside its box is walked again by its
-    // thread with that exact delta (everything in front of it is final) and the sums are redone; models are committed up to the
-    // first one that raises epsilon (the next chunk starts behind it).
-    //  * models are assigned to threads with the long walks (models the scoring kernels gave all their mask words) first, so that a
-    //    warp of quickly rejected models costs a few instructions instead of waiting for one long walk among its lanes;
-    //  * the chunk doubles (64 .. NT) while it is committed whole and restarts small after an epsilon change.
+    // B. adaptive SPRT.  A chunk of up to NT models is walked concurrently under the state (epsilon, delta) in front of the chunk; the
+    // one-pass walk returns every model's outcome together with the widest BOX of delta values for which that outcome is certain
+    // (ars_sprt_walk_multi; epsilon is fixed inside a chunk).  Block-wide prefix sums over the outcomes give the delta in front of every
+    // position.  Positions whose delta lies outside their box are walked again -- all of them at once, each with the delta its current
+    // predecessors give it -- and the sums are redone: the first such position is final after one turn (everything in front of it is),
+    // a later one unless a repaired predecessor changed its outcome, in which case its delta leaves its new box and it comes back.
+    // When no position in front of the first epsilon-raising model violates its box, everything up to and including that model is
+    // committed by the positions' own threads, and the next chunk starts behind it.
+    //  * for the walk, models are assigned to threads with the long walks (models the scoring kernels gave all their mask words)
+    //    first, so that a warp of quickly rejected models costs a few instructions instead of waiting for one long walk among its lanes.
     uint32_t *smw = (uint32_t *)keys;                    // [8][NT] mask words by chunk position (keys[] is free until phase C)
-    __shared__ float o_lo[ARS_BOOK_NT], o_hi[ARS_BOOK_NT];
+    __shared__ float o_lo[ARS_BOOK_NT], o_hi[ARS_BOOK_NT], o_d[ARS_BOOK_NT];
     __shared__ uint32_t o_ti[ARS_BOOK_NT];               // outcome by position: tested << 16 | inliers at the stop (init_n < 8192)
     __shared__ uint16_t perm[ARS_BOOK_NT];
+    //  * the chunk doubles (64 .. NT) while it is committed whole and restarts small behind an epsilon change: models walked under a
+    //    stale (smaller) epsilon survive longer than they will, and those the two-stage scoring gave one mask word would evaluate the
+    //    missing words themselves, one predicate after the other.
     __shared__ uint32_t s_chunk;
+    __shared__ unsigned long long s_t_walk, s_t_commit, s_t_perm;
+    __shared__ uint32_t s_turns;
     const bool words_in_smem = P.W0 <= 8;
-    if (tid == 0) s_chunk = 64;
+    if (tid == 0) { s_chunk = 64; s_t_walk = 0; s_t_commit = 0; s_t_perm = 0; s_turns = 0; }
     __syncthreads();
     while (true) {
         const uint32_t c0 = s_cursor;
@@ -596,7 +671,8 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
         const uint32_t best0 = s_best, np0 = s_npass;
         const unsigned long long ri0 = s_rej_inl, rt0 = s_rej_tested;
         const uint32_t j = tid, cnt = min(s_chunk, Mv - c0);
-        (void)np0;
+        unsigned long long t_a = 0;
+        if (tid == 0) t_a = ars_globaltimer();
         const float one_m_eps = 1.0f - eps;
         // 1. positions with all mask words first
         {
@@ -607,8 +683,9 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
             if (j < cnt) perm[rdy ? x - 1 : tot[0] + y - 1] = (uint16_t)j;
             __syncthreads();
         }
+        if (tid == 0) { const unsigned long long t_b = ars_globaltimer(); s_t_perm += t_b - t_a; t_a = t_b; }
         // 2. thread t walks position perm[t]
-        auto walk_position = [&](uint32_t pos, bool exact_only, float dl) {
+        auto walk_position = [&](uint32_t pos, float dl) {
             const uint32_t id = vm[c0 + pos];
             uint32_t *grow = masks0 + (size_t)id * P.W0, *row = grow;
             uint32_t stride = 1;
@@ -618,101 +695,66 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
                 row = smw + pos; stride = NT;
             }
             const ArsLazy LZ = {poses0 + id, a, b, P.thr, grow, &ctl->stat_lazy, &ctl->stat_pad};
-            uint32_t tested = 0, inl = 0;
+            const uint2 res = ars_sprt_walk_multi<RES>(row, stride, init_n, dl, eps, one_m_eps, P.lr_thr, avail, &LZ);
             float blo = dl, bhi = dl;
-            bool boxed = false;
-            if (!exact_only) {
-                float wdt = 0.25f;
-                for (int t = 0; t < 4 && !boxed; t++, wdt *= 0.25f) {
-                    const float lo = dl * (1.0f - wdt), hi = dl * (1.0f + wdt);
-                    if (!(hi < 1.0f)) continue;           // keeps both multipliers positive (the monotonicity argument needs it)
-                    uint32_t t1 = 0;
-                    if (ars_sprt_walk_box<RES>(row, stride, init_n, hi / eps, (1.0f - lo) / one_m_eps, lo / eps, (1.0f - hi) / one_m_eps, P.lr_thr,
-                                               &t1, &inl, avail, LZ)) { boxed = true; tested = t1; blo = lo; bhi = hi; }
-                }
-            }
-            if (!boxed) tested = ars_sprt_walk<RES>(row, stride, init_n, dl / eps, (1.0f - dl) / one_m_eps, P.lr_thr, &inl, avail, LZ);
-            o_ti[pos] = (tested << 16) | inl;
+            if (res.y < ARS_NBOX) { const float wdt = ars_box_width((int)res.y); blo = dl * (1.0f - wdt); bhi = dl * (1.0f + wdt); }
+            o_ti[pos] = res.x;
             o_lo[pos] = blo; o_hi[pos] = bhi;
         };
-        if (tid < cnt) { const uint32_t pos = perm[tid]; walk_position(pos, pos == 0, delta); }
+        if (tid < cnt) walk_position(perm[tid], delta);
         __syncthreads();
-        // 3. warp 0 commits the chunk in order, 32 positions at a time, carrying the exact state (rejected sums, delta, passes) in
-        //    registers: warp scans give the state in front of every lane's position; the first position whose delta is outside
-        //    its box is walked again by its lane with that exact delta (everything in front of it is final) and the group is
-        //    redone; the chunk ends behind the first model that raises epsilon.  No block-wide barrier inside.
-        if (tid < 32) {
-            const unsigned full = 0xffffffffu;
-            const uint32_t lane = tid;
-            unsigned long long ri = ri0, rt = rt0;
-            float dcur = delta;
-            uint32_t np = np0, ce = cnt, ev_inl = 0;
-            bool eps_event = false;
-            for (uint32_t g0 = 0; g0 < cnt && !eps_event; g0 += 32) {
-                const uint32_t jj = g0 + lane;
-                const bool hv = jj < cnt;
-                const uint32_t lastl_all = min(31u, cnt - g0 - 1);
-                while (true) {
-                    const uint32_t oti = hv ? o_ti[jj] : 0u;
-                    const uint32_t tested = oti >> 16, inl = oti & 0xffffu;
-                    const bool pass = hv && tested == 0, rej = hv && tested != 0;
-                    uint32_t a_ri = rej ? inl : 0, a_rt = rej ? tested : 0, a_pc = pass ? 1 : 0;
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t x = __shfl_up_sync(full, a_ri, o), y = __shfl_up_sync(full, a_rt, o), z = __shfl_up_sync(full, a_pc, o);
-                        if ((int)lane >= o) { a_ri += x; a_rt += y; a_pc += z; }
-                    }
-                    float dj = 0.0f;                                           // delta estimate right after this position (valid ones only)
-                    if (rej) {
-                        const float d = (float)(ri + a_ri) / (float)(rt + a_rt);
-                        if (d > 0.0f && d < eps) dj = d;
-                    }
-                    uint32_t lv_inc = dj != 0.0f ? lane + 1 : 0u;              // 1-based lane of the last valid estimate in [0, lane]
-                    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(full, lv_inc, o); if ((int)lane >= o) lv_inc = max(lv_inc, x); }
-                    uint32_t lv_exc = __shfl_up_sync(full, lv_inc, 1);
-                    if (lane == 0) lv_exc = 0;
-                    float db = __shfl_sync(full, dj, lv_exc ? lv_exc - 1 : 0);
-                    if (!lv_exc) db = dcur;
-                    const bool viol = hv && !(db >= o_lo[jj] && db <= o_hi[jj]);
-                    const bool e2 = pass && inl > best0;
-                    const unsigned vb = __ballot_sync(full, viol), eb = __ballot_sync(full, e2);
-                    const uint32_t fv = vb ? (uint32_t)__ffs(vb) - 1 : 32u, fe = eb ? (uint32_t)__ffs(eb) - 1 : 32u;
-                    if (fv < 32 && fv <= fe) {                                 // walked under a state that is not its own
-                        // every violating position in front of the epsilon event is walked again at once, each with the exact delta
-                        // its CURRENT predecessors give it: the first of them is final (everything in front of it is), the others are
-                        // final unless a repaired predecessor changed its outcome -- then their delta no longer equals the one they
-                        // were walked with (box = that single value) and they come back as violations in the next turn
-                        if (viol && lane <= fe) { walk_position(jj, true, db); atomicAdd(&ctl->stat_repairs, 1u); }
-                        __syncwarp();
-                        continue;
-                    }
-                    const uint32_t lastl = min(fe, lastl_all);
-                    if (pass && lane <= lastl) { const uint32_t p = np + a_pc - 1; pass_id[p] = vm[c0 + jj]; pass_inl[p] = inl; }
-                    ri += __shfl_sync(full, a_ri, lastl); rt += __shfl_sync(full, a_rt, lastl); np += __shfl_sync(full, a_pc, lastl);
-                    const uint32_t lvl = __shfl_sync(full, lv_inc, lastl);
-                    const float dl = __shfl_sync(full, dj, lvl ? lvl - 1 : 0);
-                    if (lvl) dcur = dl;
-                    const uint32_t einl = __shfl_sync(full, inl, fe < 32 ? fe : 0);
-                    if (fe < 32) { eps_event = true; ev_inl = einl; ce = g0 + fe + 1; }
-                    break;
-                }
+        if (tid == 0) { const unsigned long long t_b = ars_globaltimer(); s_t_walk += t_b - t_a; t_a = t_b; }
+        // 3. commit: thread j owns position j
+        const bool hv = j < cnt;
+        while (true) {
+            const uint32_t oti = hv ? o_ti[j] : 0u;
+            const uint32_t tested = oti >> 16, inl = oti & 0xffffu;
+            const bool pass = hv && tested == 0, rej = hv && tested != 0;
+            uint32_t a_ri = rej ? inl : 0, a_rt = rej ? tested : 0, a_pc = pass ? 1 : 0;
+            if (tid == 0) s_turns++;
+            ars_scan3(a_ri, a_rt, a_pc, sm, tot);                             // inclusive: rejected inliers / tested data / passes
+            float dj = 0.0f;                                                   // delta estimate right behind this position (valid ones only)
+            if (rej) {
+                const float d = (float)(ri0 + a_ri) / (float)(rt0 + a_rt);
+                if (d > 0.0f && d < eps) dj = d;
             }
-            if (lane == 0) {                                                   // publish the state behind position ce - 1
-                s_rej_inl = ri; s_rej_tested = rt;
-                s_npass = np;
-                s_cursor = c0 + ce;
+            o_d[j] = dj;
+            __syncthreads();
+            // 1-based position of the last valid estimate in front of position j
+            const uint32_t lv_exc = ars_scan_max((j > 0 && j <= cnt && o_d[j - 1] != 0.0f) ? j : 0u, sm);
+            const float db = lv_exc ? o_d[lv_exc - 1] : delta;                 // delta in front of this position
+            const bool viol = hv && !(db >= o_lo[j] && db <= o_hi[j]);
+            const bool e2 = pass && inl > best0;
+            uint32_t fv = viol ? j : (uint32_t)NT, fe = e2 ? j : (uint32_t)NT;
+            ars_block_min2(fv, fe, sm);
+            if (fv < NT && fv <= fe) {                                         // walked under a state that is not their own
+                if (viol && j <= fe) { walk_position(j, db); atomicAdd(&ctl->stat_repairs, 1u); }
+                __syncthreads();
+                continue;
+            }
+            const uint32_t last = min(fe, cnt - 1);
+            if (pass && j <= last) { const uint32_t p = np0 + a_pc - 1; pass_id[p] = vm[c0 + j]; pass_inl[p] = inl; }
+            if (j == last) {                                                   // publish the state behind position `last`
+                s_rej_inl = ri0 + a_ri; s_rej_tested = rt0 + a_rt;
+                s_npass = np0 + a_pc;
+                s_cursor = c0 + last + 1;
                 s_chunks++;
-                s_delta = dcur;
-                if (eps_event) {
-                    s_best = ev_inl;
-                    const float e = (float)ev_inl / (float)init_n;
+                s_delta = dj != 0.0f ? dj : db;
+                s_chunk = fe < NT ? 64u : min((uint32_t)NT, 2u * cnt);
+                if (fe < NT) {
+                    s_best = inl;
+                    const float e = (float)inl / (float)init_n;
                     if (e > eps && e < 1.0f) s_eps = e; else if (e >= 1.0f) s_eps = 0.999f;
                 }
-                s_chunk = eps_event ? 64u : min((uint32_t)NT, 2u * cnt);
             }
+            break;
         }
         __syncthreads();
+        if (tid == 0) s_t_commit += ars_globaltimer() - t_a;
     }
     __syncthreads();
+    if (tid == 0) { ctl->stat_walk_us = (uint32_t)(s_t_walk / 1000); ctl->stat_commit_us = (uint32_t)(s_t_commit / 1000);
+                    ctl->stat_perm_us = (uint32_t)(s_t_perm / 1000); ctl->stat_turns = s_turns; }
     // C. stable top-max_cand by inliers: threshold from a histogram, ordered compaction, bitonic on (inliers desc, order asc)
     const uint32_t npass = s_npass;
     uint32_t *hist = (uint32_t *)keys;      // init_n + 1 <= 32 * W0 + 1 bins (host guarantees <= 2 * ARS_SORT_CAP)

@@ -64,14 +64,29 @@ __device__ bool sym_eigen(const double *Ain, double eps, int max_sweeps, double 
     return false;
 }
 
-// The same 9x9 eigensolver shared by JL lanes of a warp (`mask` = those lanes, `lane` = 0..JL-1), A and V in shared memory: every lane
-// forms the rotation, the lanes split the nine column / row updates (they are independent inside a rotation).  Bit-identical to
-// sym_eigen<9>: same operations on every element, same order of the convergence sums.
+// The 9x9 eigensolver of the eight-point estimator: Jacobi in round-robin (tournament) order, restated on the checker's side as
+// ref_sym_eigen9_rr.  A sweep is nine rounds; round r rotates the four DISJOINT index pairs {(r + k) mod 9, (r - k) mod 9}, k = 1..4:
+// the angles come from the matrix in front of the round, then all column rotations (A and V), then all row rotations.  Disjoint pairs
+// touch disjoint columns / rows, so JL = 1, 2 or 4 lanes (`mask` = those lanes, `lane` = 0..JL-1; A and V in shared memory, or thread
+// local for JL = 1) each take their share of a round's pairs and produce the bits of the sequential order.  A sweep costs nine
+// dependent rotation set-ups instead of 36, and the set-up itself is quotient-free: with d = aqq - app, h = 2 apq,
+// w = |d| + sqrt(d^2 + h^2), n = sqrt(w^2 + h^2): c = w / n, s = +-|h| / n (two square roots and one level of division on the chain).
+__device__ __forceinline__ void jacobi_cs_rr(double app, double aqq, double apq, double &c, double &s) {
+    const double d = __dsub_rn(aqq, app), h = __dmul_rn(2.0, apq);
+    const double w = __dadd_rn(fabs(d), __dsqrt_rn(__dadd_rn(__dmul_rn(d, d), __dmul_rn(h, h))));
+    const double n = __dsqrt_rn(__dadd_rn(__dmul_rn(w, w), __dmul_rn(h, h)));
+    const bool pos = d == 0.0 || ((d > 0.0) == (h > 0.0));
+    c = __ddiv_rn(w, n);
+    s = __ddiv_rn(pos ? fabs(h) : -fabs(h), n);
+}
 template <int JL>
-__device__ bool sym_eigen9_lanes(double *A, double *V, int lane, unsigned mask, double eps, int max_sweeps) {
-    constexpr int N = 9;
+__device__ bool sym_eigen9_rr(double *A, double *V, int lane, unsigned mask, double eps, int max_sweeps) {
+    // JL = 1, 2, 4: a lane owns 4 / JL pairs of a round and all nine rows / columns of their updates;
+    // JL = 8, 16: SUB = JL / 4 lanes share a pair (each forms the rotation itself) and split the nine rows / columns
+    constexpr int N = 9, SUB = JL > 4 ? JL / 4 : 1, PL = JL >= 4 ? 1 : 4 / JL, PSTEP = JL / SUB;
+    const int lp = lane / SUB, sub = lane % SUB;
     for (int e = lane; e < N * N; e += JL) V[e] = (e / N == e % N) ? 1.0 : 0.0;
-    __syncwarp(mask);
+    if (JL > 1) __syncwarp(mask);
     for (int sweep = 0; sweep < max_sweeps; sweep++) {
         double off = 0.0, diag = 0.0;
         for (int i = 0; i < N; i++) {
@@ -79,21 +94,40 @@ __device__ bool sym_eigen9_lanes(double *A, double *V, int lane, unsigned mask, 
             for (int j = i + 1; j < N; j++) off = __dadd_rn(off, __dmul_rn(A[i * N + j], A[i * N + j]));
         }
         if (off <= eps * eps * diag || off == 0.0) return true;
-        for (int p = 0; p < N - 1; p++)
-            for (int q = p + 1; q < N; q++) {
-                const double apq = A[p * N + q], app = A[p * N + p], aqq = A[q * N + q];
-                __syncwarp(mask);                                  // every lane has read the pivot block before anyone writes it
-                if (apq == 0.0) continue;
-                double c, s;
-                jacobi_cs(app, aqq, apq, c, s);
-                for (int k = lane; k < N; k += JL) {
-                    jacobi_rot(A[k * N + p], A[k * N + q], c, s);
-                    jacobi_rot(V[k * N + p], V[k * N + q], c, s);
-                }
-                __syncwarp(mask);
-                for (int k = lane; k < N; k += JL) jacobi_rot(A[p * N + k], A[q * N + k], c, s);
-                __syncwarp(mask);
+        for (int r = 0; r < N; r++) {
+            int P[PL], Q[PL];
+            bool act[PL];
+            double Cc[PL], Ss[PL];
+#pragma unroll
+            for (int i = 0; i < PL; i++) {
+                const int k = 1 + lp + i * PSTEP;
+                int a = r + k, b = r + N - k;
+                if (a >= N) a -= N;
+                if (b >= N) b -= N;
+                P[i] = min(a, b); Q[i] = max(a, b);
+                const double apq = A[P[i] * N + Q[i]];
+                act[i] = apq != 0.0;
+                if (act[i]) jacobi_cs_rr(A[P[i] * N + P[i]], A[Q[i] * N + Q[i]], apq, Cc[i], Ss[i]);
             }
+            // every lane has read its pivot block before a lane of the same pair rewrites it (lanes of OTHER pairs never touch it:
+            // they write their own pairs' columns only)
+            if (SUB > 1) __syncwarp(mask);
+#pragma unroll
+            for (int i = 0; i < PL; i++) {
+                if (!act[i]) continue;
+                for (int k = sub; k < N; k += SUB) {
+                    jacobi_rot(A[k * N + P[i]], A[k * N + Q[i]], Cc[i], Ss[i]);
+                    jacobi_rot(V[k * N + P[i]], V[k * N + Q[i]], Cc[i], Ss[i]);
+                }
+            }
+            if (JL > 1) __syncwarp(mask);
+#pragma unroll
+            for (int i = 0; i < PL; i++) {
+                if (!act[i]) continue;
+                for (int k = sub; k < N; k += SUB) jacobi_rot(A[P[i] * N + k], A[Q[i] * N + k], Cc[i], Ss[i]);
+            }
+            if (JL > 1) __syncwarp(mask);
+        }
     }
     return false;
 }
@@ -184,19 +218,20 @@ __device__ int eight_point(const double *a, const double *b, const uint32_t *idx
     for (int i = 0; i < 8; i++) eight_point_row(a, b, idx[i], D + 9 * i);
     for (int r = 0; r < 9; r++)
         for (int c = 0; c < 9; c++) EtE[r * 9 + c] = eight_point_gram(D, r, c);
-    if (!sym_eigen<9>(EtE, 1e-12, 1000, d, V)) return 0;
+    if (!sym_eigen9_rr<1>(EtE, V, 0, 0u, 1e-12, 1000)) return 0;
+    for (int i = 0; i < 9; i++) d[i] = EtE[i * 9 + i];
     return eight_point_poses(d, V, out);
 }
 // JL lanes per hypothesis; sh = 163 doubles of shared memory of this hypothesis (A | V, the design matrix lives in V's place first)
-#define EIGHT_LANES 4
 #define EIGHT_SH 163
+template <int JL>
 __device__ int eight_point_lanes(const double *a, const double *b, const uint32_t *idx, cvb_pose *out, double *sh, int lane, unsigned mask) {
     double *A = sh, *V = sh + 81;
-    for (int i = lane; i < 8; i += EIGHT_LANES) eight_point_row(a, b, idx[i], V + 9 * i);
+    for (int i = lane; i < 8; i += JL) eight_point_row(a, b, idx[i], V + 9 * i);
     __syncwarp(mask);
-    for (int e = lane; e < 81; e += EIGHT_LANES) A[e] = eight_point_gram(V, e / 9, e % 9);
+    for (int e = lane; e < 81; e += JL) A[e] = eight_point_gram(V, e / 9, e % 9);
     __syncwarp(mask);
-    const bool ok = sym_eigen9_lanes<EIGHT_LANES>(A, V, lane, mask, 1e-12, 1000);
+    const bool ok = sym_eigen9_rr<JL>(A, V, lane, mask, 1e-12, 1000);
     __syncwarp(mask);
     int n = 0;
     if (ok && lane == 0) {
@@ -1455,7 +1490,8 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
     P.thr = cfg->inlier_threshold; P.row0 = row0;
     // two-stage initial scoring only where a predicate is expensive (CameraToCamera residual); CVB_ARS_EAGER=1 scores everything up front
     { const char *env = getenv("CVB_ARS_EAGER"); const bool eager = (env && env[0] == '1') || kind_res(kind) == 1;
-      P.prefix = eager ? P.H0 : std::min<uint32_t>(P.H0, 64); P.cmin = 2; }
+      P.prefix = eager ? P.H0 : std::min<uint32_t>(P.H0, 64); P.cmin = 2;
+      if (const char *cm = getenv("CVB_ARS_CMIN")) P.cmin = (uint32_t)std::max(0, atoi(cm)); }
     if (P.max_cand == 0 || P.rows > ARS_SORT_CAP)
         return cvb_set_error(ctx, CVB_EUNSUPPORTED, "max_candidate_hypotheses + estimations_per_block * %u must be in 1..%u", P.MM, ARS_SORT_CAP);
     if ((uint64_t)P.bs * P.ib + 1 > 2ull * ARS_SORT_CAP) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "block_size * initialization_blocks too large");
@@ -1530,7 +1566,10 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
     auto estimate = [&](int phase, uint32_t H, const uint32_t *samples, cvb_pose *poses, uint8_t *nposes) -> int {
         if (H == 0) return 0;
         CVB_PROF(ctx, phase == 0 ? "k_ars_estimate_init" : "k_ars_estimate_block", 0);
-        if (kind == 0) k_ars_estimate8<<<cdiv(H, 128 / EIGHT_LANES), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes);
+        // the big initial batch is bound by FP64 issue (4 lanes per hypothesis waste the fewest slots); a block's 64 hypotheses
+        // are a latency chain in front of the next scoring (16 lanes: the shortest chain)
+        if (kind == 0 && phase == 0) k_ars_estimate8<4><<<cdiv(H, 128 / 4), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes);
+        else if (kind == 0) k_ars_estimate8<16><<<cdiv(H, 128 / 16), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes);
         else if (kind == 1) k_ars_estimate<1><<<cdiv(H, 128), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
         else k_ars_estimate<2><<<cdiv(H, 128), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
         CVB_LAUNCH_CHECK(ctx);
@@ -1891,12 +1930,15 @@ int cvb_arrsac_commit_rng(cvb_ctx *ctx, cvb_rng *rng, uint32_t *stats_out) {
     ArrsacCtl h;
     int rc = arrsac_commit_rng(ctx, rng, &h);
     if (rc) return rc;
+    if (getenv("CVB_ARS_DEBUG"))
+        fprintf(stderr, "[arrsac] n %u models %u pass %u chunks %u turns %u repairs %u lazy %u | sprt us: order %u walk %u commit %u | block iterations %u\n", h.n, h.Mv, h.npass,
+                h.stat_chunks, h.stat_turns, h.stat_repairs, h.stat_lazy, h.stat_perm_us, h.stat_walk_us, h.stat_commit_us, h.iters);
     if (stats_out) {   // 16 words (13..15 reserved): n, valid initial models, SPRT passes, SPRT commit rounds, block iterations, draws, inliers, found, 32-datum units
                        // scored in stage 1 / stage 2, predicates resolved exactly from the queues, mask words computed by the SPRT itself, SPRT repairs
         stats_out[0] = h.n; stats_out[1] = h.Mv; stats_out[2] = h.npass; stats_out[3] = h.stat_chunks; stats_out[4] = h.iters;
         stats_out[5] = (uint32_t)h.rng_pos; stats_out[6] = h.n_inliers; stats_out[7] = h.found;
         stats_out[8] = h.stat_units0; stats_out[9] = h.stat_units2; stats_out[10] = h.q_count + h.q_count2; stats_out[11] = h.stat_lazy;
-        stats_out[12] = h.stat_repairs; stats_out[13] = h.stat_pad /* data walked by the box walks */; stats_out[14] = stats_out[15] = 0;
+        stats_out[12] = h.stat_repairs; stats_out[13] = h.stat_pad /* data walked by the box walks */; stats_out[14] = h.stat_walk_us; stats_out[15] = h.stat_commit_us;
     }
     return 0;
 }

@@ -228,6 +228,7 @@ def _geom():
     if not _geom_ready:
         dp = C.POINTER(C.c_double)
         L.ref_sym_eigen.argtypes = [C.c_int, dp, C.c_double, C.c_int, dp, dp]
+        L.ref_sym_eigen9_rr.argtypes = [dp, C.c_double, C.c_int, dp, dp]
         L.ref_eight_point_essential.argtypes = [dp, dp, C.c_double, C.c_int, dp]
         L.ref_essential_poses.argtypes = [dp, C.c_double, C.c_int, C.POINTER(Pose)]
         L.ref_eight_point.argtypes = [dp, dp, C.POINTER(Pose)]
@@ -270,6 +271,15 @@ def sym_eigen(A, eps=1e-12, iters=1000):
     A = np.ascontiguousarray(A, np.float64); n = A.shape[0]
     d = np.zeros(n); V = np.zeros((n, n))
     ok = _geom().ref_sym_eigen(n, _dp(A), eps, iters, _dp(d), _dp(V))
+    return ok, d, V
+
+
+def sym_eigen9_rr(A, eps=1e-12, iters=1000):
+    """the round-robin Jacobi of the eight-point estimator (ref_geom.c)"""
+    A = np.ascontiguousarray(A, np.float64)
+    assert A.shape == (9, 9)
+    d = np.zeros(9); V = np.zeros((9, 9))
+    ok = _geom().ref_sym_eigen9_rr(_dp(A), eps, iters, _dp(d), _dp(V))
     return ok, d, V
 
 

@@ -74,6 +74,79 @@ int ref_sym_eigen(int n, const double *Ain, double eps, int max_sweeps, double *
     return 0;
 }
 
+/* The 9 x 9 eigensolver of the eight-point estimator: Jacobi in ROUND-ROBIN (tournament) order.  A sweep is nine rounds; round r
+ * rotates the four disjoint index pairs {(r + k) mod 9, (r - k) mod 9}, k = 1..4 (index r rests; every pair of a sweep occurs exactly
+ * once because 2 is invertible mod 9).  The four angles of a round are taken from the matrix in front of the round, then the column
+ * rotations of all four pairs are applied (to A and to V), then the row rotations: disjoint pairs touch disjoint columns / rows, so
+ * the result does not depend on the order inside a phase -- which is what lets the four rotations of a round run concurrently on the
+ * device with identical bits.  The rotation is formed without the quotient theta: with d = aqq - app, h = 2 apq,
+ *   w = |d| + sqrt(d^2 + h^2),  n = sqrt(w^2 + h^2),  c = w / n,  s = +-|h| / n   (sign of theta = d / h, + for theta = 0)
+ * which is the textbook t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), c = 1 / sqrt(t^2 + 1), s = t c with two square roots and one
+ * level of division on the dependent path instead of two square roots and three divisions.
+ * (The reference calls nalgebra's symmetric_eigen, a tridiagonal QR iteration; every Jacobi variant is a restatement whose
+ * eigenvectors agree with it to rounding, eigenvector signs being normalised downstream: essential.rs:139-143.) */
+int ref_sym_eigen9_rr(const double *Ain, double eps, int max_sweeps, double *d, double *V) {
+    enum { n = 9 };
+    double A[81];
+    memcpy(A, Ain, sizeof(A));
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) V[i * n + j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < n; i++) {
+            diag += A[i * n + i] * A[i * n + i];
+            for (int j = i + 1; j < n; j++) off += A[i * n + j] * A[i * n + j];
+        }
+        if (off <= eps * eps * diag || off == 0.0) {
+            for (int i = 0; i < n; i++) d[i] = A[i * n + i];
+            return 1;
+        }
+        for (int r = 0; r < n; r++) {
+            int P[4], Q[4], act[4];
+            double C[4], S[4];
+            for (int k = 1; k <= 4; k++) {
+                const int a = (r + k) % n, b = (r + n - k) % n;
+                const int p = a < b ? a : b, q = a < b ? b : a;
+                P[k - 1] = p; Q[k - 1] = q;
+                const double apq = A[p * n + q];
+                act[k - 1] = apq != 0.0;
+                if (!act[k - 1]) continue;
+                const double dd = A[q * n + q] - A[p * n + p], h = 2.0 * apq;
+                const double w = fabs(dd) + sqrt(dd * dd + h * h);
+                const double nn = sqrt(w * w + h * h);
+                const int pos = dd == 0.0 || ((dd > 0.0) == (h > 0.0));
+                C[k - 1] = w / nn;
+                S[k - 1] = (pos ? fabs(h) : -fabs(h)) / nn;
+            }
+            for (int i = 0; i < 4; i++) {
+                if (!act[i]) continue;
+                const int p = P[i], q = Q[i];
+                const double c = C[i], s2 = S[i];
+                for (int k = 0; k < n; k++) {
+                    const double akp = A[k * n + p], akq = A[k * n + q];
+                    A[k * n + p] = c * akp - s2 * akq;
+                    A[k * n + q] = s2 * akp + c * akq;
+                    const double vkp = V[k * n + p], vkq = V[k * n + q];
+                    V[k * n + p] = c * vkp - s2 * vkq;
+                    V[k * n + q] = s2 * vkp + c * vkq;
+                }
+            }
+            for (int i = 0; i < 4; i++) {
+                if (!act[i]) continue;
+                const int p = P[i], q = Q[i];
+                const double c = C[i], s2 = S[i];
+                for (int k = 0; k < n; k++) {
+                    const double apk = A[p * n + k], aqk = A[q * n + k];
+                    A[p * n + k] = c * apk - s2 * aqk;
+                    A[q * n + k] = s2 * apk + c * aqk;
+                }
+            }
+        }
+    }
+    for (int i = 0; i < n; i++) d[i] = A[i * n + i];
+    return 0;
+}
+
 static void mat3_mul(const double *a, const double *b, double *o) {
     double r[9];
     for (int i = 0; i < 3; i++)
@@ -141,7 +214,7 @@ int ref_eight_point_essential(const double *a, const double *b, double eps, int 
             for (int i = 0; i < 8; i++) s += A[i][r] * A[i][c];
             EtE[r * 9 + c] = s;
         }
-    if (!ref_sym_eigen(9, EtE, eps, iters, d, V)) return 0;
+    if (!ref_sym_eigen9_rr(EtE, eps, iters, d, V)) return 0;
     int best = 0;
     for (int i = 1; i < 9; i++)
         if (d[i] < d[best]) best = i;

@@ -15,6 +15,7 @@ typedef struct {
 } ref_arrsac_cfg;
 
 int ref_sym_eigen(int n, const double *A, double eps, int max_sweeps, double *d, double *V);
+int ref_sym_eigen9_rr(const double *A, double eps, int max_sweeps, double *d, double *V);
 int ref_svd3(const double *M, double eps, int max_iter, double *U, double *s, double *Vt);
 int ref_eight_point_essential(const double *a, const double *b, double eps, int iters, double *E);
 int ref_essential_poses(const double *E, double eps, int iters, ref_pose out[4]);

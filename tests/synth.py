@@ -89,14 +89,17 @@ def helix_track(seed, n_poses, n_points, visible, outlier_frac, noise_px=0.3, fo
     return cloud, frames
 
 
-def landmark_observations(frames, regs, min_obs=3):
-    """Observations (pose, bearing) of every landmark seen as an inlier in >= min_obs registered frames."""
+def landmark_observations(frames, regs, min_obs=3, max_obs=None):
+    """Observations (pose, bearing) of every landmark seen as an inlier in >= min_obs registered frames (at most the first
+    `max_obs` of them: a feature track of bounded length)."""
     obs = {}
     for fr, reg in zip(frames, regs):
         if reg is None:
             continue
         for i in reg[2]:
-            obs.setdefault(int(fr["ids"][i]), []).append(((reg[0], reg[1]), fr["bearing"][i]))
+            lst = obs.setdefault(int(fr["ids"][i]), [])
+            if max_obs is None or len(lst) < max_obs:
+                lst.append(((reg[0], reg[1]), fr["bearing"][i]))
     ids = sorted(l for l, v in obs.items() if len(v) >= min_obs)
     poses, bearings, offsets = [], [], [0]
     for l in ids:
@@ -104,5 +107,3 @@ def landmark_observations(frames, regs, min_obs=3):
             poses.append(p); bearings.append(b)
         offsets.append(len(poses))
     return ids, poses, np.array(bearings), offsets
-
-

@@ -29,6 +29,21 @@ def test_sym_eigen_matches_numpy():
             assert np.allclose(V.T @ V, np.eye(n), atol=1e-12)
 
 
+def test_round_robin_jacobi_matches_numpy():
+    # the eight-point estimator's 9x9 eigensolver (tournament order, quotient-free rotation), incl. the rank-8 Gram matrices it meets
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        M = rng.standard_normal((9, 9 if trial % 2 else 8)); A = M @ M.T
+        ok, d, V = O.sym_eigen9_rr(A)
+        assert ok
+        assert np.allclose(np.sort(d), np.linalg.eigvalsh(A), rtol=1e-10, atol=1e-10)
+        assert np.allclose(A @ V, V * d, atol=1e-9)
+        assert np.allclose(V.T @ V, np.eye(9), atol=1e-12)
+        ok2, d2, V2 = O.sym_eigen(A)
+        i, j = np.argmin(d), np.argmin(d2)
+        assert abs(abs(V[:, i] @ V2[:, j]) - 1.0) < 1e-9        # same null direction as the cyclic order
+
+
 def test_eight_point_randomized_reference_test():
     # eight-point/tests/random.rs: Vector3::new_random() is uniform [0,1) per component
     rng = np.random.default_rng(1)
