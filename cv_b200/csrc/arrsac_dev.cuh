@@ -184,14 +184,25 @@ __device__ void ars_sample_block_par(ArrsacCtl *ctl, const uint32_t *raw, uint32
         if (tid < f)
             for (uint32_t k = 0; k < K; k++) out[(size_t)(h0 + tid) * K + k] = loc[k];
         if (f < m && tid == f) {
-            uint64_t pos = p0 + (uint64_t)f * K;
-            for (uint32_t c = 0; c < K;) {
+            // the reference's loop over this sample: its first K draws are the ones already reduced in loc[] (consumed in order, repeats
+            // dropped), further draws come from the stream one at a time
+            uint32_t t[8];
+            for (uint32_t k = 0; k < K; k++) t[k] = loc[k];
+            uint64_t pos = p0 + (uint64_t)f * K + K;
+            uint32_t c = 0;
+            for (uint32_t k = 0; k < K; k++) {
+                bool dup = false;
+                for (uint32_t j = 0; j < c; j++) dup |= loc[j] == t[k];
+                if (!dup) loc[c++] = t[k];
+            }
+            while (c < K) {
                 const uint32_t s = ars_raw_at(ctl, raw, pos) % len;
                 pos++;
                 bool dup = false;
                 for (uint32_t j = 0; j < c; j++) dup |= loc[j] == s;
-                if (!dup) { loc[c] = s; out[(size_t)(h0 + f) * K + c] = s; c++; }
+                if (!dup) loc[c++] = s;
             }
+            for (uint32_t k = 0; k < K; k++) out[(size_t)(h0 + f) * K + k] = loc[k];
             sh[0] = h0 + f + 1; *(uint64_t *)(sh + 2) = pos;
         } else if (f >= m && tid == 0) {
             sh[0] = h0 + m; *(uint64_t *)(sh + 2) = p0 + (uint64_t)m * K;

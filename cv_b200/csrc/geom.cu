@@ -1575,9 +1575,11 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
         CVB_LAUNCH_CHECK(ctx);
         return 0;
     };
-    // the initial scoring fills the machine; a block's scoring is a few thousand warp-units: a grid of the whole machine would
-    // spend more time scheduling empty CTAs (76 launches per pair) than computing
-    const uint32_t sgrid_full = (uint32_t)ctx->num_sms * 4, sgrid_block = 48;
+    // the initial scoring fills the machine (4 CTAs per SM); a block scores ~200 k predicates: measured per pair (76 launches, most
+    // of them idle because the loop is over) 1.23 ms on 48 CTAs, 0.88 ms on 148, 0.79 ms on 296 -- an idle launch costs the same
+    const uint32_t sgrid_full = (uint32_t)ctx->num_sms * 4;
+    uint32_t sgrid_block = (uint32_t)ctx->num_sms * 2;
+    if (const char *e = getenv("CVB_ARS_SGRID")) sgrid_block = (uint32_t)std::max(1, atoi(e));
     auto score = [&](int phase) -> int {
         const uint32_t sgrid = phase == 1 ? sgrid_block : sgrid_full;
         CVB_PROF(ctx, phase == 1 ? "k_ars_score_block" : "k_ars_score_init", 0);
