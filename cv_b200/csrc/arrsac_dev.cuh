@@ -7,16 +7,19 @@
 // ~3 stream synchronisations per 64-datum block.  Here nothing returns to the host between enqueue and result:
 //
 //   k_ars_begin     minimal samples of all initial hypotheses from a pre-generated stream of raw u32 draws (the modulo and
-//                   the rejection of repeats need n, which may only exist on the device); one warp, 32 draws per step
-//   k_ars_estimate  eight-point / P3P / five-point per hypothesis (k_estimate's device functions)
+//                   the rejection of repeats need n, which may only exist on the device); one CTA, 256 samples per turn, a turn
+//                   commits the samples in front of its first repeat (ars_sample_block_par)
+//   k_ars_estimate  eight-point / P3P / five-point per hypothesis (k_estimate's device functions); k_ars_estimate8<L>: eight-point
+//                   with L lanes per hypothesis on the round-robin Jacobi (geom.cu: sym_eigen9_rr)
 //   k_ars_score     one warp per (model, 32 data): inlier bits by ballot.  CameraToCamera bits come from the exact-predicate
 //                   filter (c2c_filter.cuh) with the Jacobi evaluation as fallback
-//   k_ars_sprt      one CTA: the adaptive SPRT over all initial models in order.  1024 models are walked concurrently under a
-//                   BOX of possible (epsilon, delta) states; f32 multiplication is monotone, so a model whose walk ends at the
-//                   same datum for both corners of the box has that outcome for every state inside.  Prefix sums over the
-//                   chunk then give the exact state in front of every model; everything up to the first model whose state
-//                   leaves the box (or whose corners disagree, or which raises epsilon) is committed, and the next chunk starts
-//                   there with a new box.  Then: stable top-max_candidate selection (histogram + ordered compaction + bitonic).
+//   k_ars_sprt      one CTA: the adaptive SPRT over all initial models in order.  Up to 1024 models are walked concurrently under
+//                   the state in front of the chunk; a walk carries the exact likelihood ratio and both corners of nested BOXES of
+//                   delta values -- f32 multiplication is monotone, so a model whose corners stop where the exact walk stops has
+//                   that outcome for every delta inside the box.  Block-wide prefix sums then give the exact state in front of
+//                   every model; models whose state leaves their box are walked again (all at once), everything up to the first
+//                   model that raises epsilon is committed, and the next chunk starts behind it.  Then: stable top-max_candidate
+//                   selection (histogram + ordered compaction + bitonic).
 //   k_ars_book      one CTA per block of data: accept the new hypotheses that beat the bar, stable sort, truncate, termination
 //                   test, add the next block's inliers, stable sort, halve, inlier pool of the best, next minimal samples.
 //   k_ars_final     inlier list of the winner.
@@ -429,11 +432,16 @@ __device__ uint32_t ars_block_min(uint32_t v, uint32_t *sm /* 32 */) {
 }
 __device__ uint32_t ars_block_max(uint32_t v, uint32_t *sm) { return ~ars_block_min(~v, sm); }
 
-// ascending bitonic sort of the first P2 (power of two) u64 keys in shared memory
+// ascending bitonic sort of the first P2 (power of two) u64 keys in shared memory.  Element i belongs to thread i mod blockDim.x, so
+// the partners of a stage with distance j < 32 live in the same warp: such a stage needs a block barrier only when the stage in
+// front of it crossed warps (of the 66 stages of 2 048 keys, 21 cross warps).
 __device__ void ars_bitonic(uint64_t *keys, uint32_t P2) {
+    bool prev_wide = true;
     for (uint32_t k = 2; k <= P2; k <<= 1)
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            __syncthreads();
+            const bool wide = j >= 32;
+            if (wide || prev_wide) __syncthreads(); else __syncwarp();
+            prev_wide = wide;
             for (uint32_t i = threadIdx.x; i < P2; i += blockDim.x) {
                 const uint32_t l = i ^ j;
                 if (l > i) {

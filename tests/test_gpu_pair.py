@@ -165,3 +165,33 @@ def test_two_view_frames_equals_separate_calls():
     assert (owant is None) == (want is None)
     if want is not None:
         assert np.array_equal(want[2], owant[2])
+
+
+def test_graph_replay_of_a_run_equals_eager_and_oracle(monkeypatch):
+    # the consensus run is captured into a CUDA graph the second time the same (configuration, buffers) key is seen and replayed
+    # afterwards: call 1 eager, call 2 capture + launch, calls 3-4 replay -- with a continuing generator every call draws new samples,
+    # and every call must equal the oracle continuing from the same state; CVB_ARS_NO_GRAPH=1 (a fresh context) gives the same results
+    rng = np.random.default_rng(77)
+    R, t, a, b, good = two_view_scene(rng, 900, outlier_frac=0.3, noise=2e-4)
+    cfg = dict(initialization_hypotheses=512, max_candidate_hypotheses=128)
+    ars = cv_b200.Arrsac(1e-6, cv_b200.Xoshiro256PlusPlus(5)).initialization_hypotheses(512).max_candidate_hypotheses(128)
+    orng = O.rng_xoshiro(5)
+    results = []
+    for call in range(4):
+        got = ars.model_inliers(cv_b200.EightPoint(), a, b)
+        want = O.arrsac(O.arrsac_cfg(1e-6, **cfg), 0, a, b, orng)
+        assert (got is None) == (want is None)
+        if got is not None:
+            assert np.array_equal(got[2], want[2]), call
+            assert np.allclose(got[0], want[0], rtol=1e-6, atol=1e-12) and np.allclose(got[1], want[1], rtol=1e-6, atol=1e-12)
+        assert [int(x) for x in ars.rng.state.s] == [int(x) for x in orng.s], call
+        results.append(None if got is None else got[2])
+    monkeypatch.setenv("CVB_ARS_NO_GRAPH", "1")
+    ctx = cv_b200.Context(0)
+    ars2 = cv_b200.Arrsac(1e-6, cv_b200.Xoshiro256PlusPlus(5), ctx=ctx).initialization_hypotheses(512).max_candidate_hypotheses(128)
+    for call in range(4):
+        got = ars2.model_inliers(cv_b200.EightPoint(), a, b)
+        assert (got is None) == (results[call] is None)
+        if got is not None:
+            assert np.array_equal(got[2], results[call])
+    ctx.close()
