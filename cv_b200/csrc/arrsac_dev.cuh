@@ -258,8 +258,8 @@ __global__ void __launch_bounds__(128) k_ars_estimate(const ArrsacCtl *ctl, int 
 // The chain of 36 rotations x ~8 sweeps is what a block of the hypothesis loop waits for: a rotation is the FP64 divide / square-root
 // sequence (every lane) followed by the column and row updates (split over the lanes).  (A nine-lane version with the matrix in
 // REGISTERS and shuffles was measured slower than one thread; shared memory keeps the element exchange off the critical path.)
-template <int EIGHT_LANES>
-__global__ void __launch_bounds__(128) k_ars_estimate8(const ArrsacCtl *ctl, int phase, uint32_t H_init, const double *__restrict__ a,
+template <int EIGHT_LANES, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_ars_estimate8(const ArrsacCtl *ctl, int phase, uint32_t H_init, const double *__restrict__ a,
                                                        const double *__restrict__ b, const uint32_t *__restrict__ samples,
                                                        cvb_pose *poses, uint8_t *nposes) {
     if (ctl->done) return;

@@ -3,7 +3,7 @@
 //
 // ARRSAC consumes only that one bit per (hypothesis, datum).  The reference obtains it from a full 4x4 symmetric
 // eigen-decomposition (residual_c2c in geom.cu restates it with cyclic Jacobi: ~6 k FP64 instructions).  This filter
-// decides the same bit with ~0.8 k instructions whenever the decision is provably insensitive to rounding, and
+// decides the same bit with ~25 instructions for most outliers (epipolar pre-test) and ~0.8 k instructions otherwise, whenever the decision is provably insensitive to rounding, and
 // returns "undecided" otherwise; the caller then runs the exact routine.  It is an exact-predicate filter in the
 // computational-geometry sense, not an approximation of the result:
 //
@@ -97,6 +97,19 @@ C2C_HD int c2c_inlier_filter(const double *R, const double *t, const double *a, 
     const double tt = 1.0 + (t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
     const double s_lo = 8.0 * tt * thr, s_hi = fmin(1024.0 * s_lo, 0.01);
     if (!(s_hi >= 16.0 * s_lo) || !(thr > 0.0)) return -1;      // contraction <= 1/15 per step, or no filter
+    // (0) epipolar pre-test (~25 instructions; decides the bulk of the predicates of a wrong hypothesis).  Whatever point X the
+    //     reference triangulates, its bearings a' (first camera) and b' (second camera) are coplanar with the baseline:
+    //     b'^T [t]x R a' = 0.  The residual is sin^2(alpha/2) + sin^2(beta/2) with alpha = angle(a, a'), beta = angle(b, b'), and
+    //     |a - a'| = 2 sin(alpha/2), |b - b'| = 2 sin(beta/2), ||[t]x R|| = |t|, so
+    //       |b^T [t]x R a| = |b^T E a - b'^T E a'| <= |t| (|a - a'| + |b - b'|) <= 2 sqrt(2) |t| sqrt(residual),
+    //     i.e. residual >= e^2 / (8 |t|^2).  With a 6 % margin (rounding of e is ~1e-16 |t|): certain outlier.
+    {
+        const double ra0 = C2C_FMA(R[2], a[2], C2C_FMA(R[1], a[1], R[0] * a[0])), ra1 = C2C_FMA(R[5], a[2], C2C_FMA(R[4], a[1], R[3] * a[0])),
+                     ra2 = C2C_FMA(R[8], a[2], C2C_FMA(R[7], a[1], R[6] * a[0]));
+        const double c0 = C2C_FMA(t[1], ra2, -(t[2] * ra1)), c1 = C2C_FMA(t[2], ra0, -(t[0] * ra2)), c2 = C2C_FMA(t[0], ra1, -(t[1] * ra0));
+        const double e = C2C_FMA(b[2], c2, C2C_FMA(b[1], c1, b[0] * c0));
+        if (e * e > 8.5 * (tt - 1.0) * thr + 1e-28) return 0;
+    }
     // D = sum over the two views of (M - b b^T M)^T (M - b b^T M), M = [I | 0] resp. [R | t]   (pose.rs:256-277)
     double D[16];
     {

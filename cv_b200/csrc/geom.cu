@@ -1582,17 +1582,20 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
             CVB_PROF(ctx, phase == 0 ? "k_ars_estimate_init" : "k_ars_estimate_block", 0);
             // the big initial batch is bound by FP64 issue (4 lanes per hypothesis waste the fewest slots); a block's 64 hypotheses
             // are a latency chain in front of the next scoring (16 lanes: the shortest chain)
-            if (kind == 0 && phase == 0) k_ars_estimate8<4><<<cdiv(H, 128 / 4), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes);
-            else if (kind == 0) k_ars_estimate8<16><<<cdiv(H, 128 / 16), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes);
+            // (8 lanes, or 16 lanes at 64 registers, measured the same 0.137-0.140 ms for the initial batch)
+            if (kind == 0 && phase == 0) k_ars_estimate8<4, 5><<<cdiv(H, 128 / 4), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes);
+            else if (kind == 0) k_ars_estimate8<16, 5><<<cdiv(H, 128 / 16), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes);
             else if (kind == 1) k_ars_estimate<1><<<cdiv(H, 128), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
             else k_ars_estimate<2><<<cdiv(H, 128), 128, 0, st>>>(ctl, phase, H, a_dev, b_dev, samples, poses, nposes, row0);
             CVB_LAUNCH_CHECK(ctx);
             return 0;
         };
-        // the initial scoring fills the machine (4 CTAs per SM); a block scores ~200 k predicates: measured per pair (76 launches, most
-        // of them idle because the loop is over) 1.23 ms on 48 CTAs, 0.88 ms on 148, 0.79 ms on 296 -- an idle launch costs the same
-        const uint32_t sgrid_full = (uint32_t)ctx->num_sms * 4;
-        uint32_t sgrid_block = (uint32_t)ctx->num_sms * 2;
+        // the initial scoring fills the machine (4 CTAs per SM).  A block scores ~200 k predicates; measured on B200 per pair (76 launches,
+    // most of them idle because the loop is over): 1.23 ms on 48 CTAs, 0.88 ms on 148, 0.79 ms on 296 for ONE context -- but 16
+    // pipelined contexts reach 1 678 / 1 660 / 1 629 frames/s: the small grid costs the least SM time (more units per warp, the
+    // exact-fallback stragglers amortised), and the step is bound by SM time, not by a pair's latency.  CVB_ARS_SGRID overrides.
+    const uint32_t sgrid_full = (uint32_t)ctx->num_sms * 4;
+        uint32_t sgrid_block = 48;
         if (const char *e = getenv("CVB_ARS_SGRID")) sgrid_block = (uint32_t)std::max(1, atoi(e));
         auto score = [&](int phase) -> int {
             const uint32_t sgrid = phase == 1 ? sgrid_block : sgrid_full;

@@ -88,3 +88,23 @@ def test_filter_declines_large_thresholds_and_degenerate_input(filt):
     exact = np.array([O.residual_c2c(np.eye(3), np.zeros(3), a[i], a[i]) < 1e-7 for i in range(50)])
     d = out[0] >= 0
     assert np.array_equal(out[0][d] == 1, exact[d])
+
+
+def test_epipolar_lower_bound_of_the_residual():
+    # the filter's pre-test rests on residual >= (b^T [t]x R a)^2 / (8 |t|^2) for whatever point the reference triangulates;
+    # checked here against the exact evaluation on hypotheses of every quality, with matches from perfect to random
+    rng = np.random.default_rng(11)
+    worst = np.inf
+    for trial in range(6):
+        R, t, a, b, good = two_view_scene(rng, 200, outlier_frac=0.4, noise=[0.0, 1e-5, 1e-4, 1e-3, 1e-2, 0.1][trial])
+        poses = _poses(a, b, rng, 6) + [(R, t), (R, 3.0 * t), (R, 1e-3 * t)]
+        for Rm, tm in poses:
+            E = np.cross(np.eye(3), tm).T @ Rm if False else np.array([[0, -tm[2], tm[1]], [tm[2], 0, -tm[0]], [-tm[1], tm[0], 0]]) @ Rm
+            e = np.einsum("ij,jk,ik->i", b, E, a)
+            for i in range(len(a)):
+                res = O.residual_c2c(Rm, tm, a[i], b[i])
+                bound = e[i] ** 2 / (8.0 * (tm @ tm))
+                assert res >= bound * (1 - 1e-9) - 1e-15, (trial, i, res, bound)
+                if bound > 1e-12:
+                    worst = min(worst, res / bound)
+    assert worst >= 1.0 - 1e-9
