@@ -20,6 +20,7 @@ from .optimize import (observation_losses, single_view_simple_optimize_l2, singl
                        three_view_adaptive_optimize_l2, three_view_optimize_l2_batch, three_view_simple_optimize_l2,
                        tri_landmarks_robust)
 from .sfm_match import landmark_matches  # noqa: F401
+from . import checkpoint  # noqa: F401  (bincode record images of the VSlamData checkpoint)
 from .pair import Intrinsics, TwoViewBuffers, two_view_frames  # noqa: F401
 
 __version__ = "0.1.0"

@@ -342,7 +342,7 @@ int build_tables(cvb_ctx *ctx, AkazeWorkspace *ws) {
     std::vector<int> oct(MAX_EVO, 0);
     for (size_t i = 0; i < ws->evo.size(); i++) oct[i] = (int)ws->evo[i].octave;
     CVB_CUDA(ctx, cudaMemcpyAsync(ws->evo_octave, oct.data(), sizeof(int) * MAX_EVO, cudaMemcpyHostToDevice, ctx->stream));
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     return 0;
 }
 
@@ -351,7 +351,7 @@ int build_workspace(cvb_ctx *ctx, AkazeWorkspace *ws, const cvb_akaze_cfg *cfg, 
 int ensure_workspace(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, uint32_t batch, uint32_t w, uint32_t h, unsigned cap_out) {
     AkazeWorkspace *ws = ctx->akaze;
     if (ws && same_cfg(ws->cfg, *cfg) && ws->w == w && ws->h == h && ws->batch >= batch && ws->cap_out >= cap_out) return 0;
-    if (ws) { cudaStreamSynchronize(ctx->stream); akaze_workspace_free(ws); ctx->akaze = nullptr; }
+    if (ws) { cvb_wait(ctx, ctx->stream); akaze_workspace_free(ws); ctx->akaze = nullptr; }
     if (cfg->descriptor_channels < 1 || cfg->descriptor_channels > 3) return cvb_set_error(ctx, CVB_EINVAL, "descriptor_channels must be 1..3");
     if (cfg->contrast_factor_num_bins < 1 || cfg->contrast_factor_num_bins > 8192) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "contrast_factor_num_bins must be 1..8192");
     if (cfg->num_sublevels < 1) return cvb_set_error(ctx, CVB_EINVAL, "num_sublevels must be >= 1");
@@ -361,7 +361,7 @@ int ensure_workspace(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, uint32_t batch, uin
     // the workspace is published on the context only when it is complete: a failed build must not satisfy the
     // fast path of the next call with identical arguments
     int rc = build_workspace(ctx, ws, cfg, batch, w, h, cap_out);
-    if (rc) { cudaStreamSynchronize(ctx->stream); akaze_workspace_free(ws); return rc; }
+    if (rc) { cvb_wait(ctx, ctx->stream); akaze_workspace_free(ws); return rc; }
     ctx->akaze = ws;
     return 0;
 }
@@ -438,7 +438,7 @@ int build_workspace(cvb_ctx *ctx, AkazeWorkspace *ws, const cvb_akaze_cfg *cfg, 
             if (!ok) ws->use_tma = false;        // e.g. a level width that is not a multiple of 4 floats: every kernel keeps the classic path
         }
         CVB_CUDA(ctx, cudaMemcpyAsync(ws->tmaps, hm.data(), sizeof(CUtensorMap) * hm.size(), cudaMemcpyHostToDevice, ctx->stream));
-        CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     }
     {
         std::vector<unsigned char> te((size_t)std::max(ws->table.total_tiles, 1), 0);
@@ -459,7 +459,7 @@ int build_workspace(cvb_ctx *ctx, AkazeWorkspace *ws, const cvb_akaze_cfg *cfg, 
         rc = dalloc(ctx, ws, &ws->extrema_mask, (size_t)B * std::max(words, 1));
         if (rc) return rc;
         CVB_CUDA(ctx, cudaMemcpyAsync(ws->tile_evo, te.data(), te.size(), cudaMemcpyHostToDevice, ctx->stream));
-        CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     }
     CVB_CUDA(ctx, cudaMemsetAsync(ws->overflow, 0, sizeof(unsigned), ctx->stream));
     CVB_CUDA(ctx, cudaMemsetAsync(ws->inv_k, 0, sizeof(float) * B * MAX_EVO, ctx->stream));
@@ -825,7 +825,7 @@ int cvb_akaze_dev_overflow(cvb_ctx *ctx, uint32_t *flag_out) {
     if (!hs) return cvb_set_error(ctx, CVB_ENOMEM, "page-locked scratch");
     CVB_CUDA(ctx, cudaMemcpyAsync(hs, ws->overflow, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     CVB_CUDA(ctx, cudaMemsetAsync(ws->overflow, 0, sizeof(unsigned), ctx->stream));
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     *flag_out = hs[0];
     return 0;
 }
@@ -848,7 +848,7 @@ int cvb_akaze_extract_batch(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, const float 
     if (!hs) return cvb_set_error(ctx, CVB_ENOMEM, "page-locked scratch");
     CVB_CUDA(ctx, cudaMemcpyAsync(hs, ws->n_out, sizeof(unsigned) * batch, cudaMemcpyDeviceToHost, st));
     CVB_CUDA(ctx, cudaMemcpyAsync(hs + batch, ws->overflow, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    CVB_CUDA(ctx, cudaStreamSynchronize(st));
+    CVB_CUDA(ctx, cvb_wait(ctx, st));
     const unsigned ovf = hs[batch];
     for (uint32_t b = 0; b < batch; b++) n_out[b] = hs[b];
     if (ovf) {
@@ -864,7 +864,7 @@ int cvb_akaze_extract_batch(cvb_ctx *ctx, const cvb_akaze_cfg *cfg, const float 
         CVB_CUDA(ctx, cudaMemcpyAsync(desc_out + (size_t)b * cap * 64, ws->desc_out + (size_t)b * cap_dev * 64, (size_t)n * 64,
                                       cudaMemcpyDeviceToHost, st));
     }
-    CVB_CUDA(ctx, cudaStreamSynchronize(st));
+    CVB_CUDA(ctx, cvb_wait(ctx, st));
     return 0;
 }
 
@@ -902,7 +902,7 @@ int cvb_akaze_debug_plane(cvb_ctx *ctx, uint32_t frame, uint32_t i, uint32_t pla
     if (plane >= 6) return cvb_set_error(ctx, CVB_EINVAL, "bad plane");
     const EvoHost &e = ws->evo[i];
     if (plane == 1 && i == 0) plane = 0;   // Lsmooth_0 is Lt_0 (lib.rs:201)
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     CVB_CUDA(ctx, cudaMemcpy(out, planes[plane] + (size_t)frame * ws->plane_floats + e.off, sizeof(float) * (size_t)e.w * e.h,
                              cudaMemcpyDeviceToHost));
     return 0;
@@ -912,7 +912,7 @@ int cvb_akaze_debug_contrast(cvb_ctx *ctx, uint32_t frame, double *k_out) {
     if (!ctx || !k_out) return CVB_EINVAL;
     AkazeWorkspace *ws = ctx->akaze;
     if (!ws || !ws->has_run || frame >= ws->batch) return cvb_set_error(ctx, CVB_EINVAL, "bad frame");
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     CVB_CUDA(ctx, cudaMemcpy(k_out, ws->kc + frame, sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -921,7 +921,7 @@ int cvb_akaze_debug_stage(cvb_ctx *ctx, uint32_t frame, uint32_t stage, cvb_keyp
     if (!ctx || !n_out) return CVB_EINVAL;
     AkazeWorkspace *ws = ctx->akaze;
     if (!ws || !ws->has_run || frame >= ws->batch) return cvb_set_error(ctx, CVB_EINVAL, "bad frame");
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     std::vector<cvb_keypoint> res;
     if (stage == 0) {
         unsigned n = 0;

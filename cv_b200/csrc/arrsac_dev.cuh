@@ -852,8 +852,10 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_book(ArrsacCtl *ctl, Arrsac
                                                            cvb_pose *tposes, uint32_t *tinl, uint32_t *tmasks,
                                                            const cvb_pose *__restrict__ newposes, const uint8_t *__restrict__ nposes_new,
                                                            const uint32_t *__restrict__ newmask, uint32_t *__restrict__ pool,
-                                                           uint32_t *__restrict__ samples_new) {
-    if (ctl->done) return;
+                                                           uint32_t *__restrict__ samples_new, unsigned long long loop_cond) {
+    // loop_cond: the handle of the graph's WHILE node when the block loop is a device-side loop (0 = unrolled launches);
+    // the node re-runs its body while the value is non-zero, so the loop's end is the one thing this kernel has to report
+    if (ctl->done) { if (loop_cond && threadIdx.x == 0) cudaGraphSetConditional(loop_cond, 0); return; }
     __shared__ __align__(8) uint32_t sm[96];
     __shared__ uint32_t tot[3];
     extern __shared__ __align__(16) unsigned char ars_dyn[];     // ARS_BOOK_SMEM bytes
@@ -899,6 +901,7 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_book(ArrsacCtl *ctl, Arrsac
                 const uint32_t src = e_src[(uint32_t)keys[0] & 0xffffu];
                 ctl->winner = src < P.rows ? tp[src] : newposes[src - P.rows];
             }
+            if (loop_cond) cudaGraphSetConditional(loop_cond, 0);
         }
         return;
     }

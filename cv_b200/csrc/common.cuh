@@ -18,6 +18,7 @@ struct cvb_ctx {
     std::string err;
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_wait = nullptr;   // blocking-sync event of cvb_wait
     int num_sms = 148;
     AkazeWorkspace *akaze = nullptr;
     MatchWorkspace *match = nullptr;
@@ -36,6 +37,9 @@ struct cvb_ctx {
 };
 
 cudaEvent_t cvb_prof_event(cvb_ctx *ctx);
+// Host wait for a stream.  Default: the thread sleeps on a blocking-sync event (a service runs one host thread per context and
+// several ranks per box; spinning threads take the cores the launching threads need).  CVB_SYNC=spin: cudaStreamSynchronize.
+cudaError_t cvb_wait(cvb_ctx *ctx, cudaStream_t st);
 void *cvb_pinned(cvb_ctx *ctx, size_t bytes);   // >= bytes of page-locked scratch (nullptr on failure); valid until the next call
 struct CvbProfScope {
     cvb_ctx *ctx; const char *name; double bytes; cudaEvent_t e0 = nullptr;

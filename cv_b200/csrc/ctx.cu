@@ -25,9 +25,21 @@ cudaEvent_t cvb_prof_event(cvb_ctx *ctx) {
     return ctx->prof_pool[ctx->prof_used++];
 }
 
+cudaError_t cvb_wait(cvb_ctx *ctx, cudaStream_t st) {
+    static const bool spin = [] { const char *e = getenv("CVB_SYNC"); return e && !strcmp(e, "spin"); }();
+    if (spin || !ctx) return cudaStreamSynchronize(st);
+    if (!ctx->ev_wait) {
+        const cudaError_t e = cudaEventCreateWithFlags(&ctx->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) { ctx->ev_wait = nullptr; cudaGetLastError(); return cudaStreamSynchronize(st); }
+    }
+    const cudaError_t e = cudaEventRecord(ctx->ev_wait, st);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ctx->ev_wait);
+}
+
 void *cvb_pinned(cvb_ctx *ctx, size_t bytes) {
     if (ctx->pinned && ctx->pinned_bytes >= bytes) return ctx->pinned;
-    if (ctx->pinned) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
+    if (ctx->pinned) { cvb_wait(ctx, ctx->stream); cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
     const size_t n = std::max<size_t>(bytes, 64 * 1024);
     if (cudaHostAlloc(&ctx->pinned, n, cudaHostAllocDefault) != cudaSuccess) { ctx->pinned = nullptr; return nullptr; }
     ctx->pinned_bytes = n;
@@ -38,7 +50,7 @@ extern "C" {
 
 int cvb_ctx_profile(cvb_ctx *ctx, int enable) {
     if (!ctx) return CVB_EINVAL;
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     ctx->prof = enable != 0;
     ctx->prof_recs.clear();
     ctx->prof_used = 0;
@@ -48,7 +60,7 @@ int cvb_ctx_profile(cvb_ctx *ctx, int enable) {
 // Text report: one line per kernel name: "name launches total_ms algorithmic_bytes"
 int cvb_ctx_profile_report(cvb_ctx *ctx, char *buf, size_t cap) {
     if (!ctx || !buf || !cap) return CVB_EINVAL;
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     struct Agg { const char *name; int n; double ms, bytes; };
     std::vector<Agg> agg;
     for (auto &r : ctx->prof_recs) {
@@ -99,12 +111,13 @@ int cvb_ctx_create(int device, cvb_ctx **out) { return cvb_ctx_create_on_stream(
 void cvb_ctx_destroy(cvb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    cvb_wait(ctx, ctx->stream);
     akaze_workspace_free(ctx->akaze);
     match_workspace_free(ctx->match);
     geom_workspace_free(ctx->geom);
     pair_workspace_free(ctx->pair);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev_wait) cudaEventDestroy(ctx->ev_wait);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -114,7 +127,7 @@ void cvb_ctx_destroy(cvb_ctx *ctx) {
 
 int cvb_ctx_sync(cvb_ctx *ctx) {
     if (!ctx) return CVB_EINVAL;
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     return 0;
 }
 

@@ -1192,7 +1192,7 @@ struct DevBuf {
     size_t bytes = 0;
     int ensure(cvb_ctx *ctx, size_t need) {
         if (need <= bytes && p) return 0;
-        if (p) { cudaStreamSynchronize(ctx->stream); cudaFree(p); p = nullptr; bytes = 0; }
+        if (p) { cvb_wait(ctx, ctx->stream); cudaFree(p); p = nullptr; bytes = 0; }
         size_t n = std::max<size_t>(need, 256);
         cudaError_t e = cudaMalloc(&p, n);
         if (e != cudaSuccess) return cvb_set_error(ctx, CVB_ENOMEM, "cudaMalloc(%zu): %s", n, cudaGetErrorString(e));
@@ -1221,10 +1221,15 @@ struct ArsWorkspace {
         ArrsacParams P; int kind, row0; const void *a, *b, *n_dev; uint32_t n_host, nmax, cap, nb; const void *model, *inl, *ninl, *found;
         const void *ws[21];
     };
-    struct GraphEntry { GraphKey key; cudaGraphExec_t exec; uint64_t launches; };
+    struct GraphEntry { GraphKey key; cudaGraphExec_t exec; uint64_t launches; bool loop; };
+    bool last_loop = false;         // the pending run went through a WHILE-node graph (its body's launches are counted at commit)
     std::vector<GraphEntry> graphs;
     std::vector<GraphKey> seen;
     int use_graph = -1;             // CVB_NO_GRAPH=1 / CVB_ARS_NO_GRAPH=1 disable
+    // the block loop as a WHILE node of the graph (body: score, book, estimate; k_ars_book clears the condition at the loop's
+    // end) instead of one unrolled body per possible data block.  CVB_ARS_WHILE=0 keeps the unrolled graph.
+    int use_while = -1;
+    cudaStream_t body_stream = nullptr;
 };
 struct GeomWorkspace {
     DevBuf a, b, samples, poses, nposes, out, masks, offsets, ok;
@@ -1242,6 +1247,7 @@ void geom_workspace_free(GeomWorkspace *g) {
         if (w->h_raw) cudaFreeHost(w->h_raw);
         if (w->h_res) cudaFreeHost(w->h_res);
         if (w->up_done) cudaEventDestroy(w->up_done);
+        if (w->body_stream) cudaStreamDestroy(w->body_stream);
         for (auto &ge : w->graphs) cudaGraphExecDestroy(ge.exec);
         delete w;
     }
@@ -1295,7 +1301,7 @@ int estimate_dev(cvb_ctx *ctx, int kind, const uint32_t *samples, uint32_t H, st
     }
     nposes.resize(H);
     CVB_CUDA(ctx, cudaMemcpyAsync(nposes.data(), g->nposes.p, H, cudaMemcpyDeviceToHost, ctx->stream));
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     return 0;
 }
 
@@ -1322,7 +1328,7 @@ int masks_dev(cvb_ctx *ctx, int kind, const cvb_pose *poses_dev, uint32_t m, uin
         CVB_LAUNCH_CHECK(ctx);
     }
     CVB_CUDA(ctx, cudaMemcpyAsync(masks.data(), g->masks.p, sizeof(uint32_t) * (size_t)m * words, cudaMemcpyDeviceToHost, ctx->stream));
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     return 0;
 }
 
@@ -1533,13 +1539,13 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
     // page-locked staging: [ArrsacCtl header | raw draws]
     const size_t hdr = (sizeof(ArrsacCtl) + 15) / 16 * 16, stage_bytes = hdr + sizeof(uint32_t) * (size_t)nraw;
     if (w->h_raw_cap < stage_bytes) {
-        if (w->h_raw) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(w->h_raw); w->h_raw = nullptr; w->h_raw_cap = 0; }
+        if (w->h_raw) { cvb_wait(ctx, ctx->stream); cudaFreeHost(w->h_raw); w->h_raw = nullptr; w->h_raw_cap = 0; }
         if (cudaHostAlloc((void **)&w->h_raw, stage_bytes, cudaHostAllocDefault) != cudaSuccess) return cvb_set_error(ctx, CVB_ENOMEM, "page-locked staging");
         w->h_raw_cap = stage_bytes;
     }
     if (!w->h_res && cudaHostAlloc((void **)&w->h_res, sizeof(ArrsacCtl) + sizeof(cvb_pose) + 64, cudaHostAllocDefault) != cudaSuccess)
         return cvb_set_error(ctx, CVB_ENOMEM, "page-locked staging");
-    if (!w->up_done) CVB_CUDA(ctx, cudaEventCreateWithFlags(&w->up_done, cudaEventDisableTiming));
+    if (!w->up_done) CVB_CUDA(ctx, cudaEventCreateWithFlags(&w->up_done, cudaEventDisableTiming | cudaEventBlockingSync));
     else CVB_CUDA(ctx, cudaEventSynchronize(w->up_done));       // previous upload has left the staging buffer
     {
         cvb_rng g = *rng;
@@ -1563,7 +1569,7 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
         cudaFuncSetAttribute(k_ars_sprt<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr_set = true;
     }
-    bool capturing = false;
+    bool capturing = false, while_loop = false;
     // everything the stream sees, from the upload of the draw stream to the copy of the control block back
     auto enqueue = [&]() -> int {
         CVB_CUDA(ctx, cudaMemcpyAsync(w->ctl.p, w->h_raw, sizeof(ArrsacCtl), cudaMemcpyHostToDevice, st));
@@ -1641,15 +1647,46 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
         const uint32_t n_bound = n_dev ? P.NMAX : std::min(n_host, P.NMAX);
         const uint32_t init_n = std::min(P.bs * P.ib, n_bound);
         const uint32_t nb = n_bound > init_n ? cdiv(n_bound - init_n, P.bs) : 0;
+        auto book = [&](unsigned long long cond) -> int {
+            CVB_PROF(ctx, "k_ars_book", 0);
+            k_ars_book<<<1, ARS_BOOK_NT, ARS_BOOK_SMEM, st>>>(ctl, P, raw, (cvb_pose *)w->tposes.p, (uint32_t *)w->tinl.p, (uint32_t *)w->tmasks.p,
+                                                              (const cvb_pose *)w->newposes.p, (const uint8_t *)w->nposes_new.p,
+                                                              (const uint32_t *)w->newmask.p, (uint32_t *)w->pool.p, (uint32_t *)w->samples_new.p, cond);
+            CVB_LAUNCH_CHECK(ctx);
+            return 0;
+        };
+        if (capturing && while_loop) {
+            // device-side loop: one WHILE node whose body is one block iteration; k_ars_book ends it (block nb at the latest: lo >= n)
+            cudaStreamCaptureStatus cs;
+            cudaGraph_t g = nullptr;
+            const cudaGraphNode_t *deps = nullptr;
+            size_t ndeps = 0;
+            CVB_CUDA(ctx, cudaStreamGetCaptureInfo(st, &cs, nullptr, &g, &deps, &ndeps));
+            cudaGraphConditionalHandle cond;
+            CVB_CUDA(ctx, cudaGraphConditionalHandleCreate(&cond, g, 1, cudaGraphCondAssignDefault));
+            cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+            np.conditional.handle = cond;
+            np.conditional.type = cudaGraphCondTypeWhile;
+            np.conditional.size = 1;
+            cudaGraphNode_t node;
+            CVB_CUDA(ctx, cudaGraphAddNode(&node, g, deps, ndeps, &np));
+            cudaGraph_t body = np.conditional.phGraph_out[0];
+            const cudaStream_t outer = st;
+            st = w->body_stream;
+            CVB_CUDA(ctx, cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+            rc = score(1);
+            if (!rc) rc = book(cond);
+            if (!rc && nb && P.G) rc = estimate(1, P.G, (const uint32_t *)w->samples_new.p, (cvb_pose *)w->newposes.p, (uint8_t *)w->nposes_new.p);
+            cudaGraph_t same_body = nullptr;
+            const cudaError_t be = cudaStreamEndCapture(st, &same_body);
+            st = outer;
+            if (rc) return rc;
+            CVB_CUDA(ctx, be);
+            CVB_CUDA(ctx, cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies));
+        } else
         for (uint32_t it = 0; it <= nb; it++) {
             if ((rc = score(1))) return rc;
-            {
-                CVB_PROF(ctx, "k_ars_book", 0);
-                k_ars_book<<<1, ARS_BOOK_NT, ARS_BOOK_SMEM, st>>>(ctl, P, raw, (cvb_pose *)w->tposes.p, (uint32_t *)w->tinl.p, (uint32_t *)w->tmasks.p,
-                                                                  (const cvb_pose *)w->newposes.p, (const uint8_t *)w->nposes_new.p,
-                                                                  (const uint32_t *)w->newmask.p, (uint32_t *)w->pool.p, (uint32_t *)w->samples_new.p);
-                CVB_LAUNCH_CHECK(ctx);
-            }
+            if ((rc = book(0))) return rc;
             if (it < nb && P.G)
                 if ((rc = estimate(1, P.G, (const uint32_t *)w->samples_new.p, (cvb_pose *)w->newposes.p, (uint8_t *)w->nposes_new.p))) return rc;
         }
@@ -1688,6 +1725,7 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
             CVB_CUDA(ctx, cudaGraphLaunch(ge.exec, st));
             CVB_CUDA(ctx, cudaEventRecord(w->up_done, st));       // replay: the staging buffer is free when the run is over
             ctx->launches += ge.launches;
+            w->last_loop = ge.loop;
             w->pending = true;
             return 0;
         }
@@ -1701,15 +1739,32 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
         return 0;
     }
     const uint64_t l0 = ctx->launches;
-    capturing = true;
-    CVB_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    rc = enqueue();
-    cudaGraph_t graph = nullptr;
-    cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    capturing = false;
+    if (w->use_while < 0) {
+        const char *e = getenv("CVB_ARS_WHILE");
+        w->use_while = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (w->use_while && !w->body_stream && cudaStreamCreateWithFlags(&w->body_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        w->use_while = 0;
+    }
     cudaGraphExec_t exec = nullptr;
-    if (!rc && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&exec, graph, 0);
-    if (graph) cudaGraphDestroy(graph);
+    cudaError_t ce = cudaSuccess;
+    for (int attempt = 0; attempt < 2 && !exec; attempt++) {
+        ctx->launches = l0;
+        capturing = true;
+        while_loop = w->use_while != 0;
+        CVB_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue();
+        cudaGraph_t graph = nullptr;
+        ce = cudaStreamEndCapture(st, &graph);
+        capturing = false;
+        if (!rc && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (exec || !while_loop) break;
+        cudaGetLastError();                                        // the WHILE node is not available: capture the unrolled loop instead
+        w->use_while = 0;
+        exec = nullptr;
+    }
     if (rc) return rc;
     if (ce != cudaSuccess || !exec) {                              // capture not possible: eager from now on
         cudaGetLastError();
@@ -1720,7 +1775,8 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
         return 0;
     }
     if (w->graphs.size() >= 16) { cudaGraphExecDestroy(w->graphs.front().exec); w->graphs.erase(w->graphs.begin()); }
-    w->graphs.push_back({key, exec, ctx->launches - l0});
+    w->graphs.push_back({key, exec, ctx->launches - l0, while_loop});
+    w->last_loop = while_loop;
     CVB_CUDA(ctx, cudaGraphLaunch(exec, st));
     CVB_CUDA(ctx, cudaEventRecord(w->up_done, st));
     w->pending = true;
@@ -1734,6 +1790,8 @@ int arrsac_commit_rng(cvb_ctx *ctx, cvb_rng *rng, ArrsacCtl *stats_out = nullptr
     if (!w->pending) return cvb_set_error(ctx, CVB_EINVAL, "no device ARRSAC run to commit");
     const ArrsacCtl *h = (const ArrsacCtl *)w->h_res;
     if (stats_out) *stats_out = *h;
+    if (w->last_loop) ctx->launches += 3ull * h->iters;           // the WHILE body ran iters + 1 times, the capture counted it once
+    w->last_loop = false;
     w->pending = false;
     if (!rng) return 0;
     const uint64_t used = h->rng_pos;
@@ -1771,7 +1829,7 @@ int arrsac_host(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const double 
     unsigned char *hs = (unsigned char *)cvb_pinned(ctx, res_bytes);
     if (!hs) return cvb_set_error(ctx, CVB_ENOMEM, "page-locked scratch");
     CVB_CUDA(ctx, cudaMemcpyAsync(hs, rd, res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     if ((rc = arrsac_commit_rng(ctx, rng))) return rc;
     const uint32_t c = *(const uint32_t *)(hs + sizeof(cvb_pose));
     *found = *(const int32_t *)(hs + sizeof(cvb_pose) + 4);
@@ -1811,7 +1869,7 @@ int residuals_host(cvb_ctx *ctx, int kind, const cvb_pose *poses, uint32_t m, co
         CVB_LAUNCH_CHECK(ctx);
     }
     CVB_CUDA(ctx, cudaMemcpyAsync(out, g->out.p, sizeof(double) * (size_t)m * n, cudaMemcpyDeviceToHost, ctx->stream));
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     return 0;
 }
 
@@ -1840,7 +1898,7 @@ int download_poses_updates(cvb_ctx *ctx, GeomWorkspace *g, cvb_pose *poses_out, 
     if (!hs) return cvb_set_error(ctx, CVB_ENOMEM, "page-locked scratch");
     CVB_CUDA(ctx, cudaMemcpyAsync(hs, g->out.p, pb, cudaMemcpyDeviceToHost, ctx->stream));
     CVB_CUDA(ctx, cudaMemcpyAsync(hs + pb, g->ok.p, ub, cudaMemcpyDeviceToHost, ctx->stream));
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     memcpy(poses_out, hs, pb);
     if (updates_out) memcpy(updates_out, hs + pb, ub);
     return 0;
@@ -1947,7 +2005,7 @@ int cvb_triangulate_linear_eigen(cvb_ctx *ctx, const cvb_pose *poses, const doub
     }
     CVB_CUDA(ctx, cudaMemcpyAsync(xyzw_out, g->out.p, sizeof(double) * 4 * (size_t)L, cudaMemcpyDeviceToHost, ctx->stream));
     CVB_CUDA(ctx, cudaMemcpyAsync(ok_out, g->ok.p, L, cudaMemcpyDeviceToHost, ctx->stream));
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     return 0;
 }
 
@@ -2008,7 +2066,7 @@ int cvb_arrsac_p3p_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, const double *be
 }
 int cvb_arrsac_commit_rng(cvb_ctx *ctx, cvb_rng *rng, uint32_t *stats_out) {
     if (!ctx) return CVB_EINVAL;
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     ArrsacCtl h;
     int rc = arrsac_commit_rng(ctx, rng, &h);
     if (rc) return rc;
@@ -2104,7 +2162,7 @@ int cvb_observation_losses(cvb_ctx *ctx, const cvb_pose *poses, const double *be
         CVB_LAUNCH_CHECK(ctx);
     }
     CVB_CUDA(ctx, cudaMemcpyAsync(loss_out, g->out.p, sizeof(double) * (size_t)nobs, cudaMemcpyDeviceToHost, ctx->stream));
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     return 0;
 }
 
@@ -2125,7 +2183,7 @@ int cvb_tri_landmarks_robust(cvb_ctx *ctx, const cvb_pose *first_pose, const cvb
         CVB_LAUNCH_CHECK(ctx);
     }
     CVB_CUDA(ctx, cudaMemcpyAsync(robust_out, g->ok.p, n, cudaMemcpyDeviceToHost, ctx->stream));
-    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CVB_CUDA(ctx, cvb_wait(ctx, ctx->stream));
     return 0;
 }
 

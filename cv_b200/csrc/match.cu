@@ -402,7 +402,7 @@ namespace {
 template <typename T>
 int grow(cvb_ctx *ctx, T **p, size_t *have, size_t need) {
     if (*have >= need && *p) return 0;
-    if (*p) { cudaStreamSynchronize(ctx->stream); cudaFree(*p); *p = nullptr; }
+    if (*p) { cvb_wait(ctx, ctx->stream); cudaFree(*p); *p = nullptr; }
     size_t n = std::max<size_t>(need, 1);
     cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
     if (e != cudaSuccess) { *have = 0; return cvb_set_error(ctx, CVB_ENOMEM, "cudaMalloc(%zu): %s", n * sizeof(T), cudaGetErrorString(e)); }
@@ -582,7 +582,7 @@ int cvb_hamming_knn(cvb_ctx *ctx, const uint8_t *q, uint32_t n, const uint8_t *d
     if (rc) return rc;
     CVB_CUDA(ctx, cudaMemcpyAsync(idx, ws->idx, sizeof(uint32_t) * (size_t)n * k, cudaMemcpyDeviceToHost, st));
     CVB_CUDA(ctx, cudaMemcpyAsync(dist, ws->dist, sizeof(uint32_t) * (size_t)n * k, cudaMemcpyDeviceToHost, st));
-    CVB_CUDA(ctx, cudaStreamSynchronize(st));
+    CVB_CUDA(ctx, cvb_wait(ctx, st));
     return 0;
 }
 
@@ -680,7 +680,7 @@ int cvb_hash_bag(cvb_ctx *ctx, const uint8_t *desc, uint32_t n, const uint8_t *c
     CVB_CUDA(ctx, cudaMemcpyAsync(n_slot, hn, 4, cudaMemcpyHostToDevice, st));
     if ((rc = cvb_hash_bag_dev(ctx, ws->q, n_slot, n, ws->db, ncode, hash_dev))) return rc;
     CVB_CUDA(ctx, cudaMemcpyAsync(hn + 4, hash_dev, ncode / 8, cudaMemcpyDeviceToHost, st));
-    CVB_CUDA(ctx, cudaStreamSynchronize(st));
+    CVB_CUDA(ctx, cvb_wait(ctx, st));
     memcpy(hash_out, hn + 4, ncode / 8);
     return 0;
 }
@@ -712,7 +712,7 @@ int cvb_match_symmetric(cvb_ctx *ctx, const uint8_t *a, uint32_t n, const uint8_
     const uint32_t *flag = (const uint32_t *)cvb_pinned(ctx, sizeof(uint32_t) * (size_t)n);
     if (!flag) return cvb_set_error(ctx, CVB_ENOMEM, "page-locked scratch");
     CVB_CUDA(ctx, cudaMemcpyAsync((void *)flag, ws->flag, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
-    CVB_CUDA(ctx, cudaStreamSynchronize(st));
+    CVB_CUDA(ctx, cvb_wait(ctx, st));
     uint32_t cnt = 0;
     for (uint32_t i = 0; i < n; i++)
         if (flag[i] != 0xffffffffu) {

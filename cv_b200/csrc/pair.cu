@@ -33,7 +33,7 @@ ResLayout res_layout(uint32_t cap) {
 
 template <typename T>
 int regrow(cvb_ctx *ctx, T **p, size_t n) {
-    if (*p) { cudaStreamSynchronize(ctx->stream); cudaFree(*p); *p = nullptr; }
+    if (*p) { cvb_wait(ctx, ctx->stream); cudaFree(*p); *p = nullptr; }
     cudaError_t e = cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T));
     if (e != cudaSuccess) return cvb_set_error(ctx, CVB_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
     return 0;

@@ -120,3 +120,22 @@ def test_suppression_kernel_variants_agree():
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         outs.append(subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=600).stdout.strip())
     assert outs[0].startswith("3425 ") and all(o == outs[0] for o in outs), outs
+
+
+def test_extract_from_8_and_16_bit_images_follows_from_dynamic():
+    # Akaze::extract -> GrayFloatImage::from_dynamic (akaze/src/image.rs:45-69): u8 / 255f32, u16 / 65535f32, both single f32 divisions
+    im8 = np.load(os.path.join(GOLDEN, "kitti_0000000000.npz"))["image"]
+    assert im8.dtype == np.uint8
+    ak = cv_b200.Akaze(0.01)
+    kps, d = ak.extract(im8)
+    assert len(d) == 399                       # the reference's own golden goes through this entry (estimate_pose.rs:28-41)
+    okp, odesc = O.Akaze(detector_threshold=0.01).extract(im8.astype(np.float32) / np.float32(255))
+    assert kps.tobytes() == okp.tobytes() and np.array_equal(d, odesc)
+    im16 = im8.astype(np.uint16) * np.uint16(257) + np.uint16(3)          # not a multiple of the 8-bit levels
+    kps16, d16 = ak.extract(im16)
+    okp, odesc = O.Akaze(detector_threshold=0.01).extract(im16.astype(np.float32) / np.float32(65535))
+    assert len(d16) > 0 and kps16.tobytes() == okp.tobytes() and np.array_equal(d16, odesc)
+    with pytest.raises(TypeError):
+        ak.extract(im8.astype(np.float64))     # image.rs:107: any other pixel type panics upstream
+    with pytest.raises(ValueError):
+        ak.extract(np.zeros((8, 8, 3), np.uint8))
