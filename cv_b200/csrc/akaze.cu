@@ -300,6 +300,24 @@ int build_tables(cvb_ctx *ctx, AkazeWorkspace *ws) {
         int n = 0;
         while (ang1 < two_pi && n < 64) { ot.ang1[n++] = ang1; ang1 = ang1 + 0.15f; }
         ot.nwin = n;
+        // upper window ends with the reference's expression, and the structure k_refine_orient relies on: the non-wrapping
+        // windows come first and both ends ascend inside each group
+        const float PI = 3.14159265358979323846f;
+        int nn = 0;
+        for (int i = 0; i < n; i++) {
+            const volatile float a1 = ot.ang1[i];
+            const volatile float up = a1 + PI / 3.0f, dn = a1 - 5.0f * PI / 3.0f;
+            ot.ang2[i] = up > two_pi ? dn : up;
+            if (ot.ang1[i] < ot.ang2[i]) nn = i + 1;
+        }
+        ot.nn = nn;
+        bool ok = true;
+        for (int i = 0; i < n; i++) {
+            if ((i < nn) != (ot.ang1[i] < ot.ang2[i])) ok = false;
+            if (i + 1 < n && !(ot.ang1[i] < ot.ang1[i + 1])) ok = false;
+            if (i + 1 < n && i + 1 != nn && !(ot.ang2[i] < ot.ang2[i + 1])) ok = false;
+        }
+        if (!ok) return cvb_set_error(ctx, CVB_EUNSUPPORTED, "orientation window table is not ordered as expected");
     }
     CVB_CUDA(ctx, cudaMemcpyAsync(ws->ot, &ot, sizeof(ot), cudaMemcpyHostToDevice, ctx->stream));
     // descriptor tables (descriptors.rs:64-96,117-124,188-201)

@@ -1434,6 +1434,8 @@ __global__ void __launch_bounds__(NT) k_filter_upper(const cvb_keypoint *__restr
 struct OrientTables {
     int nwin;                 // number of sliding windows (ang1 = 0, += 0.15f while < 2pi)
     float ang1[64];
+    float ang2[64];           // the window's upper end: ang1 + pi/3, or ang1 - 5pi/3 once that passes 2pi (scale_space_extrema.rs:262-266)
+    int nn;                   // windows [0, nn) do not wrap (ang1 < ang2), windows [nn, nwin) do; both tables ascend inside each group
     signed char di[109], dj[109];
     float gw[109];            // GAUSS25[id[j+6]][id[i+6]]
 };
@@ -1446,12 +1448,35 @@ __global__ void __launch_bounds__(NT) k_refine_orient(const cvb_keypoint *__rest
                                                       const OrientTables *__restrict__ OT,
                                                       cvb_keypoint *__restrict__ refined,
                                                       unsigned char *__restrict__ valid) {
-    __shared__ float s_rx[NT / 32][112], s_ry[NT / 32][112], s_an[NT / 32][112];
+    // Window membership is decided once per SAMPLE instead of once per (window, sample): both window ends ascend with the window
+    // index inside the non-wrapping and the wrapping group, so the windows that hold an angle are index ranges whose ends are
+    // counts of table entries below the angle -- found from an arithmetic guess and corrected with the reference's own
+    // comparisons (exact whatever the guess).  The 42 windows of a sample become one 64-bit mask; a lane then adds the samples
+    // of its two windows in sample order, as before.
+    __shared__ float2 s_r[NT / 32][112];
+    __shared__ uint2 s_m[NT / 32][112];
+    __shared__ float s_a1[64], s_a2[64];
     const int b = blockIdx.y;
     const unsigned n = ncache[b];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const float PI = 3.14159265358979323846f;
     const float two_pi = 2.0f * PI;
+    const int nwin = OT->nwin, nn = OT->nn;
+    if (threadIdx.x < 64) { s_a1[threadIdx.x] = OT->ang1[threadIdx.x]; s_a2[threadIdx.x] = OT->ang2[threadIdx.x]; }
+    __syncthreads();
+    auto count_lt = [](const float *A, int cnt, float v, int g) {        // #{i < cnt : A[i] < v}, A ascending
+        g = min(max(g, 0), cnt);
+        while (g < cnt && A[g] < v) g++;
+        while (g > 0 && !(A[g - 1] < v)) g--;
+        return g;
+    };
+    auto count_le = [](const float *A, int cnt, float v, int g) {        // #{i < cnt : A[i] <= v}
+        g = min(max(g, 0), cnt);
+        while (g < cnt && A[g] <= v) g++;
+        while (g > 0 && !(A[g - 1] <= v)) g--;
+        return g;
+    };
+    auto bits = [](int lo, int hi) -> unsigned long long { return hi > lo ? ((~0ull >> (64 - (hi - lo))) << lo) : 0ull; };
     for (unsigned q = blockIdx.x * (NT / 32) + wid; q < n; q += gridDim.x * (NT / 32)) {
         const size_t gi = (size_t)b * capk + q;
         if (!keep[gi]) { if (lane == 0) valid[gi] = 0; continue; }
@@ -1494,31 +1519,42 @@ __global__ void __launch_bounds__(NT) k_refine_orient(const cvb_keypoint *__rest
             iy = iy > ev.h - 1 ? ev.h - 1 : iy;
             float gwt = OT->gw[idx];
             float rx = gwt * PX[iy * w + ix], ry = gwt * PY[iy * w + ix];
-            s_rx[wid][idx] = rx; s_ry[wid][idx] = ry;
-            s_an[wid][idx] = dlm::fast_atan2_equiv(ry, rx);
+            s_r[wid][idx] = make_float2(rx, ry);
+            const float ang = dlm::fast_atan2_equiv(ry, rx);
+            unsigned long long m = 0ull;
+            if (ang == ang) {                        // (a NaN angle is in no window: every comparison of the reference is false)
+                // scale_space_extrema.rs:268-271 per window w:  (a1 < a2 && a1 < ang && ang < a2) || (a2 < a1 && ((ang > 0 && ang < a2) || (ang > a1 && ang < 2pi)))
+                const int g = (int)(ang * (1.0f / 0.15f));
+                const int hi = count_lt(s_a1, nwin, ang, g + 1);                       // a1[w] < ang  <=>  w < hi
+                const int c2 = count_le(s_a2, nn, ang, g - 6);                         // ang < a2[w]  <=>  w >= c2        (w < nn)
+                m = bits(c2, min(hi, nn));
+                if (ang > 0.f) m |= bits(nn + count_le(s_a2 + nn, nwin - nn, ang, g + 1), nwin);   // ang < a2[w], wrapping windows
+                if (ang < two_pi) m |= bits(nn, hi);                                   // a1[w] < ang, wrapping windows
+            }
+            s_m[wid][idx] = make_uint2((unsigned)m, (unsigned)(m >> 32));
         }
         __syncwarp();
         float best_val = 0.f, best_sx = 0.f, best_sy = 0.f;
         int best_w = 0x7fffffff;
-        // two consecutive windows per lane in ONE pass over the samples (42 windows -> lanes 0..20; one window per lane needed a
-        // second, mostly idle pass for windows 32..41); each window still adds its samples in sample order
-        for (int wa = 2 * lane; wa < OT->nwin; wa += 64) {
-            const int wb = wa + 1;
-            const bool hasb = wb < OT->nwin;
-            const float a1 = OT->ang1[wa], b1 = hasb ? OT->ang1[wb] : 0.f;
-            const float a2 = (a1 + PI / 3.0f > two_pi) ? a1 - 5.0f * PI / 3.0f : a1 + PI / 3.0f;
-            const float b2 = (b1 + PI / 3.0f > two_pi) ? b1 - 5.0f * PI / 3.0f : b1 + PI / 3.0f;
+        // two consecutive windows per lane in ONE pass over the samples (42 windows -> lanes 0..20); each window adds its samples
+        // in sample order.  (The tables hold at most 64 windows.)
+        {
+            const int wa = 2 * lane, wb = wa + 1;
+            const unsigned *mw = reinterpret_cast<const unsigned *>(&s_m[wid][0]) + (lane >> 4);
+            const int sh = wa & 31;
             float sxa = 0.f, sya = 0.f, sxb = 0.f, syb = 0.f;
+#pragma unroll 4
             for (int k = 0; k < 109; k++) {
-                const float ang = s_an[wid][k], rx = s_rx[wid][k], ry = s_ry[wid][k];
-                const bool ina = (a1 < a2 && a1 < ang && ang < a2) || (a2 < a1 && ((ang > 0.f && ang < a2) || (ang > a1 && ang < two_pi)));
-                const bool inb = (b1 < b2 && b1 < ang && ang < b2) || (b2 < b1 && ((ang > 0.f && ang < b2) || (ang > b1 && ang < two_pi)));
-                if (ina) { sxa += rx; sya += ry; }
-                if (inb) { sxb += rx; syb += ry; }
+                const unsigned mb = mw[2 * k] >> sh;
+                const float2 r = s_r[wid][k];
+                if (mb & 1u) { sxa += r.x; sya += r.y; }
+                if (mb & 2u) { sxb += r.x; syb += r.y; }
             }
-            const float va = sxa * sxa + sya * sya;
-            if (va > best_val) { best_val = va; best_sx = sxa; best_sy = sya; best_w = wa; }
-            if (hasb) {
+            if (wa < nwin) {
+                const float va = sxa * sxa + sya * sya;
+                if (va > best_val) { best_val = va; best_sx = sxa; best_sy = sya; best_w = wa; }
+            }
+            if (wb < nwin) {
                 const float vb = sxb * sxb + syb * syb;
                 if (vb > best_val) { best_val = vb; best_sx = sxb; best_sy = syb; best_w = wb; }
             }

@@ -710,7 +710,8 @@ __global__ void __launch_bounds__(ARS_BOOK_NT) k_ars_sprt(ArrsacCtl *ctl, Arrsac
             uint32_t stride = 1;
             uint32_t avail = ars_ready(grow[0], init_n, id / P.MM, P) ? P.W0 : 1u;     // words the scoring kernels computed
             if (words_in_smem) {
-                for (uint32_t w = 0; w < avail; w++) smw[w * NT + pos] = grow[w];
+                const uint32_t wn = min(avail, (init_n + 31) >> 5);       // words behind the data count were never written (nor are they walked)
+                for (uint32_t w = 0; w < wn; w++) smw[w * NT + pos] = grow[w];
                 row = smw + pos; stride = NT;
             }
             const ArsLazy LZ = {poses0 + id, a, b, P.thr, grow, &ctl->stat_lazy, &ctl->stat_pad};

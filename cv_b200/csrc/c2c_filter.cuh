@@ -3,7 +3,7 @@
 //
 // ARRSAC consumes only that one bit per (hypothesis, datum).  The reference obtains it from a full 4x4 symmetric
 // eigen-decomposition (residual_c2c in geom.cu restates it with cyclic Jacobi: ~6 k FP64 instructions).  This filter
-// decides the same bit with ~25 instructions for most outliers (epipolar pre-test) and ~0.8 k instructions otherwise, whenever the decision is provably insensitive to rounding, and
+// decides the same bit with ~25-40 instructions for most outliers (epipolar and cheirality pre-tests) and ~0.8 k instructions otherwise, whenever the decision is provably insensitive to rounding, and
 // returns "undecided" otherwise; the caller then runs the exact routine.  It is an exact-predicate filter in the
 // computational-geometry sense, not an approximation of the result:
 //
@@ -15,7 +15,7 @@
 //       (Sylvester's law of inertia).  Exactly one negative pivot at s_lo and exactly one at s_hi = min(1024 s_lo, 0.01)
 //       (>= 16 s_lo, else the filter declines) gives l1 < s_lo < s_hi < l2: inverse iteration with shift s_lo then contracts
 //       the error by <= s_lo / (s_hi - s_lo) <= 1/15 per step (1e-3 at the production threshold 1e-7), and a final step that
-//       moves the unit vector by < 1e-11 certifies the eigenvector to ~1e-12.
+//       turns the vector by < 1e-11 certifies the eigenvector to ~1e-12.
 //   (3) the residual of that eigenvector is computed with the reference's formula; if it is further from the threshold
 //       than 1e-11 + 1e-4 thr (orders of magnitude above the rounding of either evaluation) the comparison is decided.
 //   Anything else (tiny pivots, l2 < s_hi, non-finite values, slow convergence, residual inside the band, thresholds so
@@ -35,8 +35,10 @@
 // separate roundings.  Both are valid evaluations of the same bounds.
 #if defined(__CUDA_ARCH__)
 #define C2C_FMA(a, b, c) fma((a), (b), (c))
+#define C2C_RSQRT(a) rsqrt(a)
 #else
 #define C2C_FMA(a, b, c) ((a) * (b) + (c))
+#define C2C_RSQRT(a) (1.0 / sqrt(a))
 #endif
 
 // LDL^T of the symmetric 4x4 matrix m (full storage, row-major) minus s*I.  d[] = pivots, l[] = the six multipliers
@@ -84,11 +86,13 @@ C2C_HD void c2c_ldl4_solve(const double *id, const double *l, double *x) {
     x[0] = C2C_FMA(-l[2], x[3], C2C_FMA(-l[1], x[2], C2C_FMA(-l[0], x[1], x[0])));
 }
 
-C2C_HD double c2c_normalise4(double *x) {
-    const double n = sqrt(C2C_FMA(x[3], x[3], C2C_FMA(x[2], x[2], C2C_FMA(x[1], x[1], x[0] * x[0]))));
-    const double in = 1.0 / n;
+C2C_HD double c2c_dot4(const double *x, const double *y) {
+    return C2C_FMA(x[3], y[3], C2C_FMA(x[2], y[2], C2C_FMA(x[1], y[1], x[0] * y[0])));
+}
+
+C2C_HD void c2c_normalise4(double *x) {
+    const double in = C2C_RSQRT(c2c_dot4(x, x));
     x[0] *= in; x[1] *= in; x[2] *= in; x[3] *= in;
-    return n;
 }
 
 // R row-major 3x3, t[3]: the CameraToCamera pose; a, b: unit bearings of the match.
@@ -109,6 +113,21 @@ C2C_HD int c2c_inlier_filter(const double *R, const double *t, const double *a, 
         const double c0 = C2C_FMA(t[1], ra2, -(t[2] * ra1)), c1 = C2C_FMA(t[2], ra0, -(t[0] * ra2)), c2 = C2C_FMA(t[0], ra1, -(t[1] * ra0));
         const double e = C2C_FMA(b[2], c2, C2C_FMA(b[1], c1, b[0] * c0));
         if (e * e > 8.5 * (tt - 1.0) * thr + 1e-28) return 0;
+        // (0b) cheirality pre-test (~12 more instructions).  An essential matrix yields four poses with the SAME epipolar error; three of
+        //     them put the point behind a camera, and the reference finds that out only through the full evaluation (its residual
+        //     is then ~1).  Whatever X it triangulates: p = from_homogeneous(X) has unit xyz p^ and w >= 0, q = R p^ + w t, q^ = q / |q|,
+        //     residual = ((1 - a.p^) + (1 - b.q^)) / 2.  residual < thr forces |a - p^|^2 + |b - q^|^2 < 4 thr.  With u' = R p^, b' = q^:
+        //       u' + w t = |q| b'   =>   w (u' x t) = |q| (u' x b')  and  (u' x b') = w (b' x t)          (cross with u', with b')
+        //     hence  (u' x t).(u' x b') = t.b' - (u'.b')(t.u') >= 0   and   (u' x b').(b' x t) = (u'.b')(t.b') - t.u' >= 0.
+        //     Replacing u', b' by u = R a, b moves either expression by at most 2 |t| (|a - p^| + |b - q^|) <= 5.66 |t| sqrt(thr);
+        //     a value below -10 |t| sqrt(thr) therefore excludes an inlier.  (Only for small thresholds: the bound is linearised.)
+        if (thr <= 1e-4) {
+            const double tb = C2C_FMA(t[2], b[2], C2C_FMA(t[1], b[1], t[0] * b[0])), ub = C2C_FMA(ra2, b[2], C2C_FMA(ra1, b[1], ra0 * b[0])),
+                         tu = C2C_FMA(t[2], ra2, C2C_FMA(t[1], ra1, t[0] * ra0));
+            const double c1 = C2C_FMA(-ub, tu, tb), c2 = C2C_FMA(ub, tb, -tu);
+            const double lim2 = 100.0 * (tt - 1.0) * thr;
+            if ((c1 < 0.0 && c1 * c1 > lim2) || (c2 < 0.0 && c2 * c2 > lim2)) return 0;
+        }
     }
     // D = sum over the two views of (M - b b^T M)^T (M - b b^T M), M = [I | 0] resp. [R | t]   (pose.rs:256-277)
     double D[16];
@@ -136,37 +155,44 @@ C2C_HD int c2c_inlier_filter(const double *R, const double *t, const double *a, 
     if (c_lo != 1) return -1;
     if (c2c_ldl4(D, s_hi, dh, lh, ih) != 1) return -1; // need l2 > s_hi for the contraction bound
     id[3] = 1.0 / d[3];
-    // inverse iteration with shift s_lo.  Three solves without normalisation (growth <= 1 / |l1 - s_lo| per solve, harmless in
-    // f64), one normalisation, then a checked step: the unit vector must not move by more than 1e-11
+    // inverse iteration with shift s_lo.  Four solves without normalisation (growth <= 1 / |l1 - s_lo| per solve, harmless in
+    // f64; error <= 1e-12 at the production threshold), one normalisation, then a checked step y = (D - s_lo I)^-1 x: the
+    // direction must not turn by more than 1e-11, measured without a square root or a division as
+    //   sin^2(angle(x, y)) = |y - (x.y) x|^2 / |y|^2 <= 1e-22        (|x| = 1).
+    // Everything behind this point is independent of the scale of the eigenvector (from_homogeneous divides by |xyz|), so the
+    // accepted iterate is used as it is; only a rejected one is normalised for the next turn.  Non-finite values fail the test.
     double x[4] = {0.5, 0.5, 0.5, 0.5};
     c2c_ldl4_solve(id, l, x);
     c2c_ldl4_solve(id, l, x);
     c2c_ldl4_solve(id, l, x);
+    c2c_ldl4_solve(id, l, x);
     c2c_normalise4(x);
-    double delta2 = 1.0;
-    for (int it = 0; it < 4 && delta2 > 1e-22; it++) {
-        double y[4] = {x[0], x[1], x[2], x[3]};
+    double y[4], yy = 0.0;
+    int certified = 0;
+    for (int it = 0; it < 4; it++) {
+        y[0] = x[0]; y[1] = x[1]; y[2] = x[2]; y[3] = x[3];
         c2c_ldl4_solve(id, l, y);
-        c2c_normalise4(y);
-        // the shifted operator has a negative dominant eigenvalue when l1 < s_lo: successive iterates alternate in sign
-        const double sg = (x[0] * y[0] + x[1] * y[1] + x[2] * y[2] + x[3] * y[3]) < 0.0 ? -1.0 : 1.0;
-        double e = 0.0;
-        for (int k = 0; k < 4; k++) { const double df = sg * y[k] - x[k]; e = C2C_FMA(df, df, e); x[k] = sg * y[k]; }
-        delta2 = e;
+        const double xy = c2c_dot4(x, y);
+        yy = c2c_dot4(y, y);
+        double r2 = 0.0;
+        for (int k = 0; k < 4; k++) { const double r = C2C_FMA(-xy, x[k], y[k]); r2 = C2C_FMA(r, r, r2); }
+        if (r2 <= 1e-22 * yy) { certified = 1; break; }
+        const double in = C2C_RSQRT(yy);
+        for (int k = 0; k < 4; k++) x[k] = y[k] * in;
     }
-    if (!(delta2 <= 1e-22)) return -1;
+    if (!certified) return -1;
     // pose.rs:284-295: from_homogeneous (sign of w, unit xyz), transform, cosine distances
-    double p[4] = {x[0], x[1], x[2], x[3]};
+    double p[4] = {y[0], y[1], y[2], y[3]};
     if (signbit(p[3])) { p[0] = -p[0]; p[1] = -p[1]; p[2] = -p[2]; p[3] = -p[3]; }
-    const double pn = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
-    if (!(pn > 1e-9)) return -1;
-    const double ipn = 1.0 / pn;
+    const double pp = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+    if (!(pp > 1e-18 * yy)) return -1;
+    const double ipn = C2C_RSQRT(pp);
     p[0] *= ipn; p[1] *= ipn; p[2] *= ipn; p[3] *= ipn;
     double q[3];
     for (int r = 0; r < 3; r++) q[r] = R[3 * r] * p[0] + R[3 * r + 1] * p[1] + R[3 * r + 2] * p[2] + t[r] * p[3];
-    const double qn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
-    if (!(qn > 1e-9)) return -1;
-    const double res = 0.5 * (1.0 - (a[0] * p[0] + a[1] * p[1] + a[2] * p[2]) + 1.0 - (b[0] * q[0] + b[1] * q[1] + b[2] * q[2]) / qn);
+    const double qq = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+    if (!(qq > 1e-18)) return -1;
+    const double res = 0.5 * (1.0 - (a[0] * p[0] + a[1] * p[1] + a[2] * p[2]) + 1.0 - (b[0] * q[0] + b[1] * q[1] + b[2] * q[2]) * C2C_RSQRT(qq));
     if (!isfinite(res)) return -1;
     if (fabs(res - thr) <= 1e-11 + 1e-4 * thr) return -1;
     return res < thr ? 1 : 0;

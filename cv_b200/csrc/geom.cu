@@ -814,7 +814,8 @@ __global__ void __launch_bounds__(256) k_residuals(const cvb_pose *__restrict__ 
     if (MODE == 0) { if (in) out[(size_t)p * out_stride + i] = r; }
     else {
         const unsigned bits = __ballot_sync(0xffffffffu, in && r < thr);
-        if ((threadIdx.x & 31) == 0) masks[(size_t)p * words + ((i - i0) >> 5)] = bits;
+        // warps behind the data count own no mask word (a row has cdiv(i1 - i0, 32) words, the CTA covers 8)
+        if ((threadIdx.x & 31) == 0 && ((i - i0) >> 5) < words) masks[(size_t)p * words + ((i - i0) >> 5)] = bits;
     }
 }
 
@@ -1567,6 +1568,8 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
         cudaFuncSetAttribute(k_ars_book, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ARS_BOOK_SMEM);
         cudaFuncSetAttribute(k_ars_sprt<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         cudaFuncSetAttribute(k_ars_sprt<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(k_ars_score<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_ars_score<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
     bool capturing = false, while_loop = false;
@@ -1603,15 +1606,20 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
     const uint32_t sgrid_full = (uint32_t)ctx->num_sms * 4;
         uint32_t sgrid_block = 48;
         if (const char *e = getenv("CVB_ARS_SGRID")) sgrid_block = (uint32_t)std::max(1, atoi(e));
+        // CVB_ARS_SCORE_SMEM: unused dynamic shared memory per scoring CTA, a residency limiter.  The kernel needs 128 registers per
+        // thread, so two CTAs take an SM's whole register file and nothing of another context can run beside them although they
+        // only use the FP64 pipe; > half of the SM's shared memory leaves one CTA per SM and half the registers to other kernels.
+        size_t score_smem = 0;
+        if (const char *e = getenv("CVB_ARS_SCORE_SMEM")) score_smem = (size_t)std::max(0, atoi(e));
         auto score = [&](int phase) -> int {
             const uint32_t sgrid = phase == 1 ? sgrid_block : sgrid_full;
             CVB_PROF(ctx, phase == 1 ? "k_ars_score_block" : "k_ars_score_init", 0);
             if (res == 0)
-                k_ars_score<0><<<sgrid, 256, 0, st>>>(ctl, (uint2 *)w->queue.p, P, phase, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p,
+                k_ars_score<0><<<sgrid, 256, score_smem, st>>>(ctl, (uint2 *)w->queue.p, P, phase, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p,
                                                       (uint32_t *)w->masks0.p, (const cvb_pose *)w->tposes.p, (uint32_t *)w->tmasks.p,
                                                       (const cvb_pose *)w->newposes.p, (const uint8_t *)w->nposes_new.p, (uint32_t *)w->newmask.p);
             else
-                k_ars_score<1><<<sgrid, 256, 0, st>>>(ctl, (uint2 *)w->queue.p, P, phase, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p,
+                k_ars_score<1><<<sgrid, 256, score_smem, st>>>(ctl, (uint2 *)w->queue.p, P, phase, a_dev, b_dev, (const cvb_pose *)w->poses0.p, (const uint8_t *)w->nposes0.p,
                                                       (uint32_t *)w->masks0.p, (const cvb_pose *)w->tposes.p, (uint32_t *)w->tmasks.p,
                                                       (const cvb_pose *)w->newposes.p, (const uint8_t *)w->nposes_new.p, (uint32_t *)w->newmask.p);
             CVB_LAUNCH_CHECK(ctx);
