@@ -108,3 +108,28 @@ def test_epipolar_lower_bound_of_the_residual():
                 if bound > 1e-12:
                     worst = min(worst, res / bound)
     assert worst >= 1.0 - 1e-9
+
+
+def test_cheirality_bound_of_the_residual(filt):
+    # the second pre-test: residual < thr forces c1 = t.b - (u.b)(t.u) and c2 = (u.b)(t.b) - t.u (u = R a) above -5.66 |t| sqrt(thr);
+    # the filter rejects below -10 |t| sqrt(thr).  Checked against the exact evaluation on the four poses of true and estimated
+    # essential matrices (three of the four are wrong-cheirality poses with the same epipolar error), and on scaled translations.
+    rng = np.random.default_rng(12)
+    nrej = ntot = 0
+    for trial, thr in enumerate([1e-9, 1e-7, 1e-6, 1e-5, 1e-4, 1e-7]):
+        R, t, a, b, good = two_view_scene(rng, 150, outlier_frac=0.3, noise=[0.0, 1e-5, 1e-4, 3e-4, 1e-3, 1e-2][trial])
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        Rt = R @ (2.0 * np.outer(t, t) - np.eye(3))                 # the twisted pair of the true pose (rotation by pi about t)
+        poses = _poses(a, b, rng, 5) + [(R, t), (R, -t), (Rt, t), (Rt, -t), (R, 5.0 * t), (R, -1e-2 * t)]
+        for Rm, tm in poses:
+            u = a @ Rm.T
+            tb, ub, tu = b @ tm, np.einsum("ij,ij->i", u, b), u @ tm
+            c1, c2 = tb - ub * tu, ub * tb - tu
+            lim = 10.0 * np.linalg.norm(tm) * np.sqrt(thr)
+            certain = (c1 < -lim) | (c2 < -lim)
+            for i in np.nonzero(certain)[0]:
+                assert not (O.residual_c2c(Rm, tm, a[i], b[i]) < thr), (trial, i, c1[i], c2[i])
+            nrej += int(certain.sum()); ntot += len(a)
+        # and the filter as a whole stays consistent with the exact predicate on these poses
+        _check(filt, poses, a, b, thr)
+    assert nrej > 0.3 * ntot          # the bound does decide the wrong poses (this is what makes it worth its 12 instructions)
