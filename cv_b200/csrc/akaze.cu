@@ -108,7 +108,6 @@ struct AkazeWorkspace {
     double *g2 = nullptr;
     unsigned long long *gmax = nullptr;
     unsigned *hist = nullptr, *npoints = nullptr;
-    double *cthr = nullptr;    // per frame: the g2 thresholds of the contrast histogram's bin edges (nbins + 1)
     double *kc = nullptr;
     float *inv_k = nullptr;
     int *evo_octave = nullptr;
@@ -400,7 +399,7 @@ int build_workspace(cvb_ctx *ctx, AkazeWorkspace *ws, const cvb_akaze_cfg *cfg, 
     DA(Lt, B * PF); DA(Lsm, B * PF); DA(Lx, B * PF); DA(Ly, B * PF); DA(Lflow, B * PF); DA(Ldet, B * PF);
     DA(tmpA, B * ws->p0); DA(tmpB, B * ws->p0); DA(tmpC, B * ws->p0);
     DA(g2, B * ws->p0);
-    DA(gmax, B); DA(hist, B * cfg->contrast_factor_num_bins); DA(cthr, B * (cfg->contrast_factor_num_bins + 1)); DA(npoints, B); DA(kc, B); DA(inv_k, B * MAX_EVO);
+    DA(gmax, B); DA(hist, B * cfg->contrast_factor_num_bins); DA(npoints, B); DA(kc, B); DA(inv_k, B * MAX_EVO);
     DA(evo_octave, MAX_EVO);
     DA(rowcount, B * R); DA(rowoff, B * R); DA(ncand, B);
     DA(cand, B * ws->capc);
@@ -628,10 +627,7 @@ int run_extract_eager(cvb_ctx *ctx, const float *images, unsigned B, cvb_keypoin
     {
         unsigned blocks = std::min<unsigned>(cdiv((unsigned)P0, NT), (unsigned)ctx->num_sms * 8);
         { CVB_PROF(ctx, "k_contrast_hist", 4.0 * W * H * B);
-        k_contrast_thresholds<<<B, NT, 0, st>>>(ws->gmax, nbins, ws->cthr);
-        CVB_LAUNCH_CHECK(ctx);
-        k_contrast_hist<<<dim3(blocks, 1, B), NT, sizeof(double) * (nbins + 1) + sizeof(unsigned) * nbins, st>>>(ws->g2, ws->gmax, ws->cthr, ws->hist,
-                                                                                                                 ws->npoints, (int)P0, P0, nbins);
+        k_contrast_hist<<<dim3(blocks, 1, B), NT, sizeof(unsigned) * nbins, st>>>(ws->g2, ws->gmax, ws->hist, ws->npoints, (int)P0, P0, nbins);
         CVB_LAUNCH_CHECK(ctx); }
         { CVB_PROF(ctx, "k_contrast_final", 0);
         k_contrast_final<<<B, 32, 0, st>>>(ws->gmax, ws->hist, ws->npoints, nbins, ws->cfg.contrast_percentile, ws->evo_octave, E, ws->kc, ws->inv_k);

@@ -145,63 +145,25 @@ __global__ void k_half_size(const float *__restrict__ in, float *__restrict__ ou
     out[(size_t)blockIdx.z * out_bstride + (size_t)y * hw + x] = v;
 }
 
-// contrast_factor.rs:35-48 histogram of floor(nbins * modg/hmax) over interior pixels with modg != 0.
-// The reference's bin is a chain of correctly rounded monotone operations of g2 = modg^2 (f64 sqrt, division by hmax > 0,
-// multiplication by nbins, floor), so bin(v) >= k  <=>  v >= T_k for one f64 threshold T_k per bin edge.  k_contrast_thresholds finds
-// the T_k of a frame by bisection over the bit patterns of the non-negative doubles with the reference's own expression (nbins x 63
-// evaluations); the histogram kernel then bins a pixel with a float guess corrected by exact f64 comparisons against the table
-// instead of an FP64 square root and division per pixel (the kernel was FP64-pipe bound: ~45 FP64 instructions per pixel).
-__device__ __forceinline__ long long contrast_bin(double v, double hmax, int nbins) {
-    return (long long)floor((double)nbins * (sqrt(v) / hmax));
-}
-
-__global__ void __launch_bounds__(NT) k_contrast_thresholds(const unsigned long long *__restrict__ gmax, int nbins, double *__restrict__ T) {
-    const int b = blockIdx.x;
-    const unsigned long long gbits = gmax[b];
-    const double hmax = sqrt(__longlong_as_double((long long)gbits));
-    for (int k = threadIdx.x; k <= nbins; k += NT) {
-        double out = 0.0;
-        if (k > 0) {
-            if (!(hmax > 0.0)) out = __longlong_as_double(0x7ff0000000000000ll);        // no gradient anywhere: nothing is binned
-            else {
-                unsigned long long lo = 0ull, hi = gbits;                               // bin(0) = 0 < k <= nbins = bin(gmax)
-                while (hi - lo > 1ull) {
-                    const unsigned long long mid = lo + (hi - lo) / 2ull;
-                    if (contrast_bin(__longlong_as_double((long long)mid), hmax, nbins) >= (long long)k) hi = mid; else lo = mid;
-                }
-                out = __longlong_as_double((long long)hi);
-            }
-        }
-        T[(size_t)b * (nbins + 1) + k] = out;
-    }
-}
-
+// contrast_factor.rs:35-48 histogram of floor(nbins * modg/hmax) over interior pixels with modg != 0
 __global__ void __launch_bounds__(NT) k_contrast_hist(const double *__restrict__ g2, const unsigned long long *gmax,
-                                                      const double *__restrict__ T, unsigned *hist, unsigned *npoints, int n,
-                                                      size_t bstride, int nbins) {
-    extern __shared__ __align__(8) unsigned char s_dyn[];
-    double *s_T = reinterpret_cast<double *>(s_dyn);                      // [nbins + 1]
-    unsigned *s_hist = reinterpret_cast<unsigned *>(s_T + nbins + 1);     // [nbins]
+                                                      unsigned *hist, unsigned *npoints, int n, size_t bstride, int nbins) {
+    extern __shared__ unsigned s_hist[];
     for (int i = threadIdx.x; i < nbins; i += NT) s_hist[i] = 0;
-    for (int i = threadIdx.x; i <= nbins; i += NT) s_T[i] = T[(size_t)blockIdx.z * (nbins + 1) + i];
     __syncthreads();
     const double hmax = sqrt(__longlong_as_double((long long)gmax[blockIdx.z]));
-    const float scale = (float)((double)nbins / hmax);                    // for the guess only
     const double *p = g2 + (size_t)blockIdx.z * bstride;
     unsigned cnt = 0;
     for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT) {
-        const double v = p[i];
-        if (v < 0.0 || v == 0.0) continue;                                // outside the interior / modg == 0
-        int g = 0;
-        if (v == v) {                                                     // (a NaN went to bin 0 through the conversion before, and still does)
-            g = (int)(sqrtf((float)v) * scale);
-            g = min(max(g, 0), nbins);
-            while (g < nbins && v >= s_T[g + 1]) g++;
-            while (g > 0 && v < s_T[g]) g--;
-            if (g == nbins) g -= 1;
+        double v = p[i];
+        if (v < 0.0) continue;
+        double modg = sqrt(v);
+        if (modg != 0.0) {
+            long long bin = (long long)floor((double)nbins * (modg / hmax));
+            if (bin == nbins) bin -= 1;
+            if (bin >= 0 && bin < nbins) atomicAdd(&s_hist[bin], 1u);
+            cnt++;
         }
-        atomicAdd(&s_hist[g], 1u);
-        cnt++;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nbins; i += NT)
