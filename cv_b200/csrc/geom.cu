@@ -1680,8 +1680,8 @@ int arrsac_run_dev(cvb_ctx *ctx, const cvb_arrsac_cfg *cfg, int kind, const doub
             CVB_CUDA(ctx, cudaGraphAddNode(&node, g, deps, ndeps, &np));
             cudaGraph_t body = np.conditional.phGraph_out[0];
             const cudaStream_t outer = st;
-            st = w->body_stream;
-            CVB_CUDA(ctx, cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+            CVB_CUDA(ctx, cudaStreamBeginCaptureToGraph(w->body_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+            st = w->body_stream;                     // the launch helpers below capture into the body (restored before any return)
             rc = score(1);
             if (!rc) rc = book(cond);
             if (!rc && nb && P.G) rc = estimate(1, P.G, (const uint32_t *)w->samples_new.p, (cvb_pose *)w->newposes.p, (uint8_t *)w->nposes_new.p);
