@@ -1678,24 +1678,31 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_descriptors(const cvb_keypo
         const float xf = kp.x / ratio, yf = kp.y / ratio;
         const float co = dlm::cosf_glibc(kp.angle), si = dlm::sinf_glibc(kp.angle);
         bool oob = false;
+        const bool kmajor = fabsf(co) >= fabsf(si);
         // lattice gathers in batches: all addresses, then all loads, then the arithmetic (a rolled loop would pay one L2
         // round trip per iteration)
         constexpr int GB = 7;
         for (int p0 = lane; p0 < nl * nl; p0 += 32 * GB) {
             size_t g[GB];
+            int slot[GB];
             float vt[GB], vx[GB], vy[GB];
 #pragma unroll
             for (int u = 0; u < GB; u++) {
                 const int p = p0 + 32 * u;
                 g[u] = (size_t)-1;
                 if (p < nl * nl) {
-                    const int ki = p / nl, lj = p - ki * nl;
+                    // consecutive lanes take consecutive lattice steps along the axis that advances mostly in x for this keypoint's
+                    // rotation (k when |cos| >= |sin|, else l), so a warp-wide gather touches a few 32-byte sectors per image row
+                    // instead of one per lane; every point still lands in its own slot ki * nl + lj
+                    const int qa = p / nl, qb = p - qa * nl;
+                    const int ki = kmajor ? qb : qa, lj = kmajor ? qa : qb;
                     const float kf = (float)(ki - pattern), lf = (float)(lj - pattern);
                     const float sample_y = yf + (lf * co * scale + kf * si * scale);
                     const float sample_x = xf + (-lf * si * scale + kf * co * scale);
                     const float ry_ = roundf(sample_y), rx_ = roundf(sample_x);
                     if (!(rx_ >= 0.f && rx_ < (float)W) || !(ry_ >= 0.f && ry_ < (float)H)) oob = true;
                     else g[u] = (size_t)(int)ry_ * W + (int)rx_;
+                    slot[u] = ki * nl + lj;
                 }
             }
 #pragma unroll
@@ -1708,8 +1715,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_descriptors(const cvb_keypo
             }
 #pragma unroll
             for (int u = 0; u < GB; u++) {
-                const int p = p0 + 32 * u;
                 if (g[u] == (size_t)-1) continue;
+                const int p = slot[u];
                 s_lat[wid][0][p] = vt[u];
                 if (nch > 1) {
                     const float rx = vx[u], ry = vy[u];
