@@ -73,6 +73,9 @@ int cvb_ctx_create(int device, cvb_ctx **out);
  * e.g. torch.cuda.current_stream().cuda_stream, so the caller can time it with its own events. */
 int cvb_ctx_create_on_stream(int device, void *cuda_stream, cvb_ctx **out);
 void cvb_ctx_destroy(cvb_ctx *ctx);
+/* Waits for the context's stream.  This and every other blocking call of the library SLEEPS on a blocking-sync CUDA event while the
+ * GPU works (one host thread per context, several processes per box: waiting threads must not take the cores of the launching
+ * ones); the environment variable CVB_SYNC=spin selects spinning waits (cudaStreamSynchronize) for a latency-critical single caller. */
 int cvb_ctx_sync(cvb_ctx *ctx);
 const char *cvb_last_error(const cvb_ctx *ctx);
 const char *cvb_version(void);
