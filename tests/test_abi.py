@@ -89,3 +89,35 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in src.lower(), os.path.join(dirpath, f)
+
+
+def test_rust_bindings_are_generated_from_the_current_header():
+    """bindings/rust: the sys crate is what scripts/gen_rust_sys.py produces from include/cvb200.h (and the shim what it assembles from
+    INTEGRATION.md); every exported symbol is declared exactly once with the header's parameter count; repr(C) structs keep the
+    header's field order.  (No Rust toolchain in the image: this is the drift check the bindings get instead of a compile.)"""
+    import importlib.util
+    import re
+    spec = importlib.util.spec_from_file_location("gen_rust_sys", os.path.join(ROOT, "scripts", "gen_rust_sys.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    header = open(os.path.join(ROOT, "include", "cvb200.h")).read()
+    text, protos = gen.generate(header)
+    assert open(gen.OUT).read() == text, "stale: python scripts/gen_rust_sys.py"
+    assert open(gen.SHIM_OUT).read() == gen.generate_shim(), "stale: python scripts/gen_rust_sys.py"
+    from cv_b200._lib import ABI_SYMBOLS
+    declared = re.findall(r"pub fn (cvb_\w+)\((.*?)\)(?: -> [^;]+)?;", text)
+    assert sorted(n for n, _ in declared) == sorted(ABI_SYMBOLS)
+    plain = gen.strip_comments(header)
+    for name, params in declared:
+        cargs = re.search(r"\b" + name + r"\s*\(([^;{]*?)\)\s*;", plain, flags=re.S).group(1)
+        cn = 0 if cargs.strip() in ("", "void") else cargs.count(",") + 1
+        rn = 0 if not params.strip() else params.count(",") + 1
+        assert cn == rn, (name, cn, rn)
+    # struct layout: field names in header order, pointer-free PODs
+    for cname, fields in gen.parse(header)[2]:
+        body = re.search(r"pub struct " + cname + r" \{(.*?)\n\}", text, flags=re.S).group(1)
+        assert [f for f, _ in fields] == re.findall(r"pub (\w+):", body), cname
+    # every extern the safe shim calls exists in the sys crate
+    shim = open(gen.SHIM_OUT).read()
+    called = set(re.findall(r"\b(cvb_[a-z0-9_]+)\s*\(", shim))
+    assert called and called <= set(ABI_SYMBOLS), sorted(called - set(ABI_SYMBOLS))
